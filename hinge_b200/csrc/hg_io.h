@@ -1,0 +1,90 @@
+// Host-side readers for the file formats at the drop-in boundary:
+//   DAZZ_DB stub/index/track files, DALIGNER .las files, the INI config.
+// Formats follow /root/reference/src/include/DB.h:214-303,
+// /root/reference/src/include/align.h:126-132,332-337 and
+// /root/reference/src/lib/ini.c; the code is written from the format, it
+// shares nothing with the reference's readers.
+#ifndef HG_IO_H
+#define HG_IO_H
+#include <stdint.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "hg_params.h"
+
+namespace hg {
+
+// Reads of a (trimmed) DAZZ_DB, indexed the way DALIGNER numbers them.
+struct ReadDB {
+    int32_t n_read = 0;
+    std::vector<int32_t> rlen;
+    bool has_qv = false;          // `qual` track present and in sync
+    std::vector<int64_t> qv_off;  // n_read + 1 offsets into qv
+    std::vector<uint8_t> qv;      // one intrinsic QV per tspace tile
+    std::string error;
+
+    // Mirrors LAInterface::openDB + getReadNumber + getQV
+    // (/root/reference/src/lib/LAInterface.cpp:133-185,2556-2558,4369-4494).
+    // Returns 0 on success; on failure `error` says why (the reference exits 1).
+    int open(const std::string& db_name);
+};
+
+// A whole .las file as a struct of arrays (the layout the kernels consume).
+struct LasFile {
+    int64_t novl = 0;
+    int32_t tspace = 0;
+    int32_t tbytes = 1;  // 1 if tspace <= 125 (align.h:58 TRACE_XOVR), else 2
+    std::vector<int32_t> aread, bread, abpos, aepos, bbpos, bepos, diffs, flags;
+    std::vector<int64_t> trace_off;  // novl + 1 byte offsets into trace
+    std::vector<uint8_t> trace;      // raw trace bytes, (diff, bdelta) pairs
+    std::string error;
+
+    // Mirrors LAInterface::openAlignmentFile + getOverlap(0, n_read)
+    // (/root/reference/src/lib/LAInterface.cpp:595-621,1519-1634).
+    int open(const std::string& las_name, bool want_trace);
+};
+
+// inih-compatible INI reader (/root/reference/src/lib/ini.c, INIReader.cpp):
+// ';' starts a comment only after whitespace, so "1000;" keeps its ';' and
+// strtol stops there, while "true;" fails the boolean match and falls back to
+// the default.
+class Ini {
+public:
+    // <0: file could not be opened (the only case the reference treats as fatal)
+    int load(const std::string& path);
+    long get_integer(const std::string& section, const std::string& name, long def) const;
+    double get_real(const std::string& section, const std::string& name, double def) const;
+    bool get_boolean(const std::string& section, const std::string& name, bool def) const;
+    const std::string& text() const { return text_; }
+
+private:
+    std::string get(const std::string& section, const std::string& name) const;
+    std::map<std::string, std::string> values_;
+    std::string text_;
+};
+
+void load_filter_params(const Ini& ini, bool has_qv, hg_filter_params* p);
+void load_layout_params(const Ini& ini, hg_layout_params* p);
+
+// Buffered text emitter for the line-oriented outputs (integers separated by
+// single characters); much faster than iostream, same bytes.
+class TextOut {
+public:
+    explicit TextOut(const std::string& path);
+    ~TextOut();
+    bool ok() const { return fp_ != nullptr; }
+    void put_int(long v);
+    void put_char(char c);
+    void put_str(const char* s);
+    void close();
+
+private:
+    void flush();
+    void* fp_ = nullptr;
+    std::vector<char> buf_;
+    size_t len_ = 0;
+};
+
+}  // namespace hg
+#endif
