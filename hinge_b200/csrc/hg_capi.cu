@@ -1,0 +1,437 @@
+// C ABI (include/hinge_b200.h): context, ingest, the filter stage.
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "hg_ctx.h"
+
+using namespace hg;
+
+namespace hg {
+
+int set_err(hg_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+int cuda_check(hg_ctx* c, cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return HG_OK;
+    return set_err(c, e == cudaErrorMemoryAllocation ? HG_ERR_NOMEM : HG_ERR_CUDA,
+                   std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+}  // namespace hg
+
+RecView hg_ctx::rec_view() const {
+    RecView v;
+    v.novl = novl;
+    v.aread = d_aread; v.bread = d_bread; v.abpos = d_abpos; v.aepos = d_aepos;
+    v.bbpos = d_bbpos; v.bepos = d_bepos; v.flags = d_flags;
+    v.trace_off = d_trace_off; v.trace = d_trace; v.tbytes = tbytes;
+    v.read_off = d_read_off;
+    return v;
+}
+
+ReadView hg_ctx::read_view() const {
+    ReadView v;
+    v.n_read = n_read;
+    v.r_lo = a_lo;
+    v.r_hi = a_hi;
+    v.rlen = d_rlen;
+    v.qvmask = d_qvmask;
+    return v;
+}
+
+static void free_overlaps(hg_ctx* c) {
+    if (!c->adopted) {
+        cudaFree(c->d_aread); cudaFree(c->d_bread); cudaFree(c->d_abpos); cudaFree(c->d_aepos);
+        cudaFree(c->d_bbpos); cudaFree(c->d_bepos); cudaFree(c->d_flags);
+        cudaFree(c->d_trace_off); cudaFree(c->d_trace);
+    }
+    c->d_aread = c->d_bread = c->d_abpos = c->d_aepos = c->d_bbpos = c->d_bepos = c->d_flags = nullptr;
+    c->d_trace_off = nullptr;
+    c->d_trace = nullptr;
+    c->novl = 0;
+    c->has_trace = false;
+}
+
+extern "C" {
+
+const char* hg_version(void) { return "hinge_b200 0.1 (sm_100a)"; }
+
+const char* hg_last_error(const hg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int hg_ctx_create(int device, void* stream, hg_ctx** out) {
+    if (!out) return HG_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        fprintf(stderr, "hinge_b200: no usable CUDA device (%s); there is no CPU fallback\n",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+        return HG_ERR_CUDA;
+    }
+    hg_ctx* c = new hg_ctx();
+    c->device = device;
+    c->stream = (cudaStream_t)stream;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete c;
+        return HG_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+    c->fs.num_sms = c->num_sms;
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    int rc = dev_alloc(c, &c->d_err, 4, "err flag");
+    if (rc == HG_OK) rc = dev_alloc(c, &c->fs.scal, 8, "scalars");
+    if (rc == HG_OK) rc = dev_alloc(c, &c->fs.counters, 8, "counters");
+    if (rc == HG_OK) rc = dev_alloc(c, &c->fs.med_hist, 4097 + 4096, "median histogram");
+    if (rc != HG_OK) {
+        hg_ctx_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return HG_OK;
+}
+
+void hg_ctx_destroy(hg_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    free_overlaps(c);
+    cudaFree(c->d_rlen); cudaFree(c->d_qvmask); cudaFree(c->d_read_off); cudaFree(c->d_err);
+    FilterScratch& s = c->fs;
+    cudaFree(s.cov_sum); cudaFree(s.cov_maxbin); cudaFree(s.self_cnt); cudaFree(s.mean_cov);
+    cudaFree(s.med_hist); cudaFree(s.scal); cudaFree(s.mask); cudaFree(s.cmask); cudaFree(s.rflags);
+    cudaFree(s.anno_ref); cudaFree(s.anno_pool); cudaFree(s.counters); cudaFree(s.work_list);
+    cudaFree(s.big_list); cudaFree(s.big_scratch); cudaFree(s.hinge_keep); cudaFree(s.hinge_scratch);
+    cudaFree(c->d_cov0); cudaFree(c->d_cov0_off);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+}
+
+int hg_set_option(hg_ctx* c, int option, int64_t value) {
+    if (!c) return HG_ERR_ARG;
+    if (option == HG_OPT_KEEP_COVERAGE) {
+        c->keep_cov = value != 0;
+        return HG_OK;
+    }
+    return set_err(c, HG_ERR_ARG, "unknown option");
+}
+
+int hg_set_reads(hg_ctx* c, int32_t n_read, const int32_t* rlen, const int64_t* qv_off,
+                 const uint8_t* qv, int32_t tspace) {
+    if (!c || n_read <= 0 || !rlen) return set_err(c, HG_ERR_ARG, "hg_set_reads: bad arguments");
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    c->n_read = n_read;
+    c->tspace = tspace;
+    c->h_rlen.assign(rlen, rlen + n_read);
+    {
+        std::vector<int> srt(c->h_rlen);
+        std::sort(srt.begin(), srt.end());
+        c->max_rlen = srt.back();
+        c->rlen_q999 = srt[(size_t)((double)(n_read - 1) * 0.999)];
+        if (srt.front() < 0) return set_err(c, HG_ERR_INPUT, "negative read length");
+    }
+    HG_TRY(dev_alloc(c, &c->d_rlen, n_read, "rlen"));
+    HG_TRY(dev_alloc(c, &c->d_qvmask, n_read, "qv mask"));
+    HG_TRY(cuda_check(c, cudaMemcpyAsync(c->d_rlen, rlen, sizeof(int) * n_read, cudaMemcpyHostToDevice, st), "rlen H2D"));
+    c->has_qv = qv_off != nullptr && qv != nullptr;
+    if (c->has_qv) {
+        int64_t* d_off = nullptr;
+        uint8_t* d_qv = nullptr;
+        const int64_t nq = qv_off[n_read];
+        HG_TRY(dev_alloc(c, &d_off, (size_t)n_read + 1, "qv offsets"));
+        int rc = dev_alloc(c, &d_qv, (size_t)nq, "qv");
+        if (rc == HG_OK) rc = cuda_check(c, cudaMemcpyAsync(d_off, qv_off, 8 * ((size_t)n_read + 1), cudaMemcpyHostToDevice, st), "qv_off H2D");
+        if (rc == HG_OK && nq > 0) rc = cuda_check(c, cudaMemcpyAsync(d_qv, qv, (size_t)nq, cudaMemcpyHostToDevice, st), "qv H2D");
+        if (rc == HG_OK) {
+            launch_qv_mask(n_read, d_off, d_qv, tspace, c->d_qvmask, st);
+            rc = cuda_check(c, cudaStreamSynchronize(st), "qv mask");
+        }
+        cudaFree(d_off);
+        cudaFree(d_qv);
+        HG_TRY(rc);
+    } else {
+        HG_TRY(cuda_check(c, cudaMemsetAsync(c->d_qvmask, 0, sizeof(int2) * n_read, st), "qv mask"));
+    }
+    // per-read buffers
+    FilterScratch& s = c->fs;
+    HG_TRY(dev_alloc(c, &s.cov_sum, n_read, "cov_sum"));
+    HG_TRY(dev_alloc(c, &s.cov_maxbin, n_read, "cov_maxbin"));
+    HG_TRY(dev_alloc(c, &s.self_cnt, n_read, "self_cnt"));
+    HG_TRY(dev_alloc(c, &s.mean_cov, n_read, "mean_cov"));
+    HG_TRY(dev_alloc(c, &s.mask, n_read, "mask"));
+    HG_TRY(dev_alloc(c, &s.cmask, n_read, "cmask"));
+    HG_TRY(dev_alloc(c, &s.rflags, n_read, "rflags"));
+    HG_TRY(dev_alloc(c, &s.anno_ref, n_read, "anno_ref"));
+    HG_TRY(dev_alloc(c, &s.work_list, n_read, "work_list"));
+    HG_TRY(dev_alloc(c, &s.big_list, n_read, "big_list"));
+    HG_TRY(dev_alloc(c, &c->d_read_off, (size_t)n_read + 1, "read_off"));
+    cudaMemsetAsync(s.mean_cov, 0xff, sizeof(int) * n_read, st);
+    cudaMemsetAsync(s.rflags, 0, n_read, st);
+    s.anno_cap = 0;
+    c->a_lo = 0;
+    c->a_hi = n_read;
+    c->filter_done = false;
+    return cuda_check(c, cudaStreamSynchronize(st), "hg_set_reads");
+}
+
+static int alloc_anno_pool(hg_ctx* c, int cap) {
+    FilterScratch& s = c->fs;
+    HG_TRY(dev_alloc(c, &s.anno_pool, cap, "annotation pool"));
+    HG_TRY(dev_alloc(c, &s.hinge_keep, cap, "hinge flags"));
+    s.anno_cap = cap;
+    return HG_OK;
+}
+
+int hg_set_overlaps(hg_ctx* c, int64_t novl, const int32_t* aread, const int32_t* bread,
+                    const int32_t* abpos, const int32_t* aepos, const int32_t* bbpos,
+                    const int32_t* bepos, const int32_t* diffs, const int32_t* flags,
+                    const int64_t* trace_off, const uint8_t* trace, int32_t tbytes, int32_t where,
+                    int32_t a_lo, int32_t a_hi) {
+    (void)diffs;  // part of the record layout, read by no stage
+    if (!c || c->n_read <= 0) return set_err(c, HG_ERR_ARG, "hg_set_overlaps: call hg_set_reads first");
+    if (novl < 0 || (novl > 0 && (!aread || !bread || !abpos || !aepos || !bbpos || !bepos || !flags)))
+        return set_err(c, HG_ERR_ARG, "hg_set_overlaps: null column");
+    if (a_lo < 0 || a_hi > c->n_read || a_lo >= a_hi)
+        return set_err(c, HG_ERR_ARG, "hg_set_overlaps: bad read range");
+    if (novl == 0) return set_err(c, HG_ERR_NO_ALIGNMENTS, "No alignments!");
+    if (tbytes != 1 && tbytes != 2) return set_err(c, HG_ERR_ARG, "tbytes must be 1 or 2");
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    free_overlaps(c);
+    c->novl = novl;
+    c->a_lo = a_lo;
+    c->a_hi = a_hi;
+    c->tbytes = tbytes;
+    c->has_trace = trace_off != nullptr && trace != nullptr;
+    int first_a = 0, last_a = 0;
+    if (where == HG_MEM_DEVICE) {
+        c->adopted = true;
+        const int32_t* cols[7] = {aread, bread, abpos, aepos, bbpos, bepos, flags};
+        for (int i = 0; i < 7; i++)
+            if (((uintptr_t)cols[i]) & 15)
+                return set_err(c, HG_ERR_ARG, "device columns must be 16-byte aligned");
+        c->d_aread = (int32_t*)aread; c->d_bread = (int32_t*)bread; c->d_abpos = (int32_t*)abpos;
+        c->d_aepos = (int32_t*)aepos; c->d_bbpos = (int32_t*)bbpos; c->d_bepos = (int32_t*)bepos;
+        c->d_flags = (int32_t*)flags;
+        c->d_trace_off = (int64_t*)trace_off;
+        c->d_trace = (uint8_t*)trace;
+        HG_TRY(cuda_check(c, cudaMemcpyAsync(&first_a, aread, 4, cudaMemcpyDeviceToHost, st), "D2H"));
+        HG_TRY(cuda_check(c, cudaMemcpyAsync(&last_a, aread + (novl - 1), 4, cudaMemcpyDeviceToHost, st), "D2H"));
+        HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "D2H"));
+    } else {
+        c->adopted = false;
+        const size_t nb = sizeof(int32_t) * (size_t)novl;
+        int32_t** dst[7] = {&c->d_aread, &c->d_bread, &c->d_abpos, &c->d_aepos,
+                            &c->d_bbpos, &c->d_bepos, &c->d_flags};
+        const int32_t* src[7] = {aread, bread, abpos, aepos, bbpos, bepos, flags};
+        for (int i = 0; i < 7; i++) {
+            HG_TRY(dev_alloc(c, dst[i], (size_t)novl + 8, "overlap column"));
+            HG_TRY(cuda_check(c, cudaMemcpyAsync(*dst[i], src[i], nb, cudaMemcpyHostToDevice, st), "overlap H2D"));
+        }
+        if (c->has_trace) {
+            const int64_t tb = trace_off[novl];
+            HG_TRY(dev_alloc(c, &c->d_trace_off, (size_t)novl + 1, "trace offsets"));
+            HG_TRY(dev_alloc(c, &c->d_trace, (size_t)tb + 16, "trace"));
+            HG_TRY(cuda_check(c, cudaMemcpyAsync(c->d_trace_off, trace_off, 8 * ((size_t)novl + 1), cudaMemcpyHostToDevice, st), "trace_off H2D"));
+            if (tb > 0) HG_TRY(cuda_check(c, cudaMemcpyAsync(c->d_trace, trace, (size_t)tb, cudaMemcpyHostToDevice, st), "trace H2D"));
+        }
+        first_a = aread[0];
+        last_a = aread[novl - 1];
+    }
+    c->r_begin = first_a;
+    c->r_end = last_a;
+    // CSR + validation + deepest pile-up
+    cudaMemsetAsync(c->d_err, 0, sizeof(int) * 4, st);
+    launch_csr_validate(c->rec_view(), c->read_view(), c->d_read_off, c->d_err, st);
+    launch_max_pileup(c->d_read_off, c->n_read, c->d_err + 1, st);
+    int h[2] = {0, 0};
+    HG_TRY(cuda_check(c, cudaMemcpyAsync(h, c->d_err, 8, cudaMemcpyDeviceToHost, st), "D2H"));
+    HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "csr build"));
+    if (h[0])
+        return set_err(c, HG_ERR_INPUT,
+                       "overlap records are not sorted by A-read or violate 0 <= abpos < aepos <= "
+                       "rlen[aread], 0 <= bbpos <= bepos <= rlen[bread]");
+    c->max_pileup = h[1];
+
+    // scratch that depends on the shape of the data
+    FilterScratch& s = c->fs;
+    if (s.anno_cap == 0) HG_TRY(alloc_anno_pool(c, 2 * (a_hi - a_lo) + (1 << 16)));
+    // K4: one slot of 32 B per pile-up record and warp
+    s.hinge_cap = std::max(c->max_pileup, 32);
+    {
+        const size_t slot = (size_t)s.hinge_cap * 32;
+        size_t warps = (size_t)c->num_sms * 16;
+        const size_t budget = (size_t)768 << 20;
+        if (warps * slot > budget) warps = std::max<size_t>(4, budget / slot);
+        warps = std::max<size_t>(4, warps & ~(size_t)3);
+        s.hinge_warps = (int)warps;
+        HG_TRY(dev_alloc(c, &s.hinge_scratch, warps * slot, "hinge scratch"));
+    }
+    c->filter_done = false;
+    return HG_OK;
+}
+
+static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
+    if (p->reso <= 0 || p->coverage_fraction == 0)
+        return set_err(c, HG_ERR_ARG, "reso must be > 0 and coverage_frac_repeat_annotation != 0");
+    c->fp = *p;
+    c->filter_params_set = true;
+    FilterScratch& s = c->fs;
+    auto bins = [&](int rlen) { return (rlen + std::max(p->cut_off, 0)) / p->reso + 3; };
+    mask_anno_configure(s, bins(c->rlen_q999));
+    if (bins(c->max_rlen) > s.nb_cap || c->max_pileup > 32000) {
+        s.big_slot_words = (bins(c->max_rlen) + 31) & ~31;
+        s.big_warps = 64;
+        HG_TRY(dev_alloc(c, &s.big_scratch, (size_t)s.big_warps * s.big_slot_words, "big-read scratch"));
+    } else {
+        s.big_slot_words = 0;
+    }
+    return HG_OK;
+}
+
+int hg_filter_phase1(hg_ctx* c, const hg_filter_params* p) {
+    if (!c || !p || c->novl <= 0) return set_err(c, HG_ERR_ARG, "hg_filter: no overlaps loaded");
+    cudaSetDevice(c->device);
+    HG_TRY(configure_filter(c, p));
+    cudaEventRecord(c->ev0, c->stream);
+    launch_cov_estimate(c->rec_view(), c->read_view(), c->fp, c->r_begin, c->r_end, c->fs, c->stream);
+    return cuda_check(c, cudaGetLastError(), "filter phase 1");
+}
+
+int hg_filter_phase2(hg_ctx* c) {
+    if (!c || !c->filter_params_set) return set_err(c, HG_ERR_ARG, "phase2 before phase1");
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    FilterScratch& s = c->fs;
+    int* cov0 = nullptr;
+    if (c->keep_cov) {
+        // profile lengths are known after phase 1: lay the dump out as a CSR
+        std::vector<int> maxbin(c->n_read);
+        HG_TRY(cuda_check(c, cudaMemcpyAsync(maxbin.data(), s.cov_maxbin, sizeof(int) * c->n_read, cudaMemcpyDeviceToHost, st), "D2H"));
+        HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "D2H"));
+        c->h_cov0_off.assign((size_t)c->n_read + 1, 0);
+        for (int i = 0; i < c->n_read; i++) {
+            const bool in = i >= c->a_lo && i < c->a_hi && i >= c->r_begin && i <= c->r_end;
+            c->h_cov0_off[i + 1] = c->h_cov0_off[i] + (in ? maxbin[i] + 1 : 0);
+        }
+        HG_TRY(dev_alloc(c, &c->d_cov0, (size_t)c->h_cov0_off[c->n_read], "coverage dump"));
+        HG_TRY(dev_alloc(c, &c->d_cov0_off, (size_t)c->n_read + 1, "coverage offsets"));
+        HG_TRY(cuda_check(c, cudaMemcpyAsync(c->d_cov0_off, c->h_cov0_off.data(), 8 * ((size_t)c->n_read + 1), cudaMemcpyHostToDevice, st), "H2D"));
+        cov0 = c->d_cov0;
+    }
+    launch_median(c->read_view(), c->fp, s, st);
+    launch_mask_anno(c->rec_view(), c->read_view(), c->fp, c->r_begin, c->r_end, s, cov0,
+                     c->d_cov0_off, st);
+    return cuda_check(c, cudaGetLastError(), "filter phase 2");
+}
+
+int hg_filter_phase3(hg_ctx* c, hg_filter_summary* out) {
+    if (!c || !c->filter_params_set) return set_err(c, HG_ERR_ARG, "phase3 before phase1");
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    FilterScratch& s = c->fs;
+    launch_hinge_call(c->rec_view(), c->read_view(), c->fp, s, st);
+    cudaEventRecord(c->ev1, st);
+    int cnt[8], scal[8];
+    HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, s.counters, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
+    HG_TRY(cuda_check(c, cudaMemcpyAsync(scal, s.scal, sizeof scal, cudaMemcpyDeviceToHost, st), "D2H"));
+    HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "filter"));
+    if (cnt[2]) return HG_RETRY_POOL;  // annotation pool overflow: hg_filter grows it and reruns
+    c->filter_done = true;
+    if (out) {
+        out->r_begin = c->r_begin;
+        out->r_end = c->r_end;
+        out->cov_est = scal[0];
+        out->min_cov = scal[1];
+        out->n_annotations = cnt[0];
+        out->n_hinges = -1;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        out->ms_device = ms;
+    }
+    return HG_OK;
+}
+
+int hg_filter(hg_ctx* c, const hg_filter_params* p, hg_filter_summary* out) {
+    for (int attempt = 0; attempt < 8; attempt++) {
+        HG_TRY(hg_filter_phase1(c, p));
+        HG_TRY(hg_filter_phase2(c));
+        const int rc = hg_filter_phase3(c, out);
+        if (rc != HG_RETRY_POOL) return rc;
+        // the annotation pool was too small for this data: grow and run again
+        int used = 0;
+        cudaMemcpy(&used, c->fs.counters, sizeof(int), cudaMemcpyDeviceToHost);
+        HG_TRY(alloc_anno_pool(c, std::max(used + (1 << 16), c->fs.anno_cap * 2)));
+    }
+    return set_err(c, HG_ERR_NOMEM, "annotation pool kept overflowing");
+}
+
+int hg_device_buffer(hg_ctx* c, int which, void** dptr, int64_t* bytes) {
+    if (!c || !dptr || !bytes || c->n_read <= 0) return HG_ERR_ARG;
+    switch (which) {
+        case HG_BUF_MEAN_COV: *dptr = c->fs.mean_cov; *bytes = 4ll * c->n_read; return HG_OK;
+        case HG_BUF_MASK: *dptr = c->fs.mask; *bytes = 8ll * c->n_read; return HG_OK;
+        case HG_BUF_READ_FLAGS: *dptr = c->fs.rflags; *bytes = c->n_read; return HG_OK;
+        default: return set_err(c, HG_ERR_ARG, "unknown buffer");
+    }
+}
+
+int hg_filter_fetch(hg_ctx* c, int32_t* mask, int32_t* cmask, uint8_t* flags, int64_t* anno_off,
+                    int32_t* anno_pos, int32_t* anno_type, uint8_t* hinge_keep) {
+    if (!c || !c->filter_done) return set_err(c, HG_ERR_ARG, "hg_filter_fetch: run hg_filter first");
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    FilterScratch& s = c->fs;
+    const int n = c->n_read;
+    if (mask) HG_TRY(cuda_check(c, cudaMemcpyAsync(mask, s.mask, 8ull * n, cudaMemcpyDeviceToHost, st), "D2H"));
+    if (cmask) HG_TRY(cuda_check(c, cudaMemcpyAsync(cmask, s.cmask, 8ull * n, cudaMemcpyDeviceToHost, st), "D2H"));
+    if (flags) HG_TRY(cuda_check(c, cudaMemcpyAsync(flags, s.rflags, n, cudaMemcpyDeviceToHost, st), "D2H"));
+    if (anno_off) {
+        int used = 0;
+        std::vector<int2> ref(n);
+        HG_TRY(cuda_check(c, cudaMemcpyAsync(&used, s.counters, 4, cudaMemcpyDeviceToHost, st), "D2H"));
+        HG_TRY(cuda_check(c, cudaMemcpyAsync(ref.data(), s.anno_ref, 8ull * n, cudaMemcpyDeviceToHost, st), "D2H"));
+        HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "D2H"));
+        std::vector<int2> pool((size_t)std::max(used, 1));
+        std::vector<uint8_t> keep((size_t)std::max(used, 1));
+        if (used > 0) {
+            HG_TRY(cuda_check(c, cudaMemcpyAsync(pool.data(), s.anno_pool, 8ull * used, cudaMemcpyDeviceToHost, st), "D2H"));
+            HG_TRY(cuda_check(c, cudaMemcpyAsync(keep.data(), s.hinge_keep, used, cudaMemcpyDeviceToHost, st), "D2H"));
+            HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "D2H"));
+        }
+        // the pool is filled in completion order; hand it back in read order
+        int64_t o = 0;
+        for (int i = 0; i < n; i++) {
+            anno_off[i] = o;
+            for (int k = 0; k < ref[i].y; k++, o++) {
+                if (anno_pos) anno_pos[o] = pool[ref[i].x + k].x;
+                if (anno_type) anno_type[o] = pool[ref[i].x + k].y;
+                if (hinge_keep) hinge_keep[o] = keep[ref[i].x + k];
+            }
+        }
+        anno_off[n] = o;
+    }
+    return cuda_check(c, cudaStreamSynchronize(st), "hg_filter_fetch");
+}
+
+int hg_filter_coverage(hg_ctx* c, int64_t* cov_off, int32_t* cov, int64_t* n_bins) {
+    if (!c || !c->filter_done || !c->keep_cov)
+        return set_err(c, HG_ERR_ARG, "hg_filter_coverage: set HG_OPT_KEEP_COVERAGE before hg_filter");
+    const int64_t total = c->h_cov0_off[c->n_read];
+    if (n_bins) *n_bins = total;
+    if (cov_off) memcpy(cov_off, c->h_cov0_off.data(), 8 * ((size_t)c->n_read + 1));
+    if (cov && total > 0) {
+        cudaSetDevice(c->device);
+        HG_TRY(cuda_check(c, cudaMemcpyAsync(cov, c->d_cov0, 4ull * total, cudaMemcpyDeviceToHost, c->stream), "D2H"));
+        HG_TRY(cuda_check(c, cudaStreamSynchronize(c->stream), "D2H"));
+    }
+    return HG_OK;
+}
+
+}  // extern "C"

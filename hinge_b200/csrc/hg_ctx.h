@@ -1,0 +1,74 @@
+// The context behind the C ABI: device buffers, stream, per-stage scratch.
+#ifndef HG_CTX_H
+#define HG_CTX_H
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/hinge_b200.h"
+#include "hg_device.cuh"
+#include "hg_filter.h"
+
+struct hg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int num_sms = 148;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // reads
+    int n_read = 0, tspace = 100, max_rlen = 0, rlen_q999 = 0;
+    bool has_qv = false;
+    int* d_rlen = nullptr;
+    int2* d_qvmask = nullptr;
+    std::vector<int> h_rlen;
+
+    // overlaps (owned copies unless adopted)
+    int64_t novl = 0;
+    bool adopted = false;
+    int32_t *d_aread = nullptr, *d_bread = nullptr, *d_abpos = nullptr, *d_aepos = nullptr;
+    int32_t *d_bbpos = nullptr, *d_bepos = nullptr, *d_flags = nullptr;
+    int64_t* d_trace_off = nullptr;
+    uint8_t* d_trace = nullptr;
+    int tbytes = 1;
+    bool has_trace = false;
+    int64_t* d_read_off = nullptr;
+    int* d_err = nullptr;
+    int a_lo = 0, a_hi = 0, r_begin = 0, r_end = -1, max_pileup = 0;
+
+    // filter
+    hg::FilterScratch fs;
+    hg_filter_params fp;
+    bool filter_params_set = false, filter_done = false;
+    int keep_cov = 0;
+    int* d_cov0 = nullptr;
+    int64_t* d_cov0_off = nullptr;
+    std::vector<int64_t> h_cov0_off;
+
+    hg::RecView rec_view() const;
+    hg::ReadView read_view() const;
+};
+
+namespace hg {
+int set_err(hg_ctx* c, int code, const std::string& msg);
+int cuda_check(hg_ctx* c, cudaError_t e, const char* what);
+template <typename T>
+int dev_alloc(hg_ctx* c, T** p, size_t n, const char* what) {
+    if (*p) {
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    if (n == 0) n = 1;
+    return cuda_check(c, cudaMalloc((void**)p, n * sizeof(T)), what);
+}
+}  // namespace hg
+
+#define HG_TRY(x)                \
+    do {                         \
+        int _rc = (x);           \
+        if (_rc != HG_OK) return _rc; \
+    } while (0)
+
+#endif

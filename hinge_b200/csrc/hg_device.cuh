@@ -1,0 +1,102 @@
+// Device-side views and small helpers shared by the kernels (sm_100a).
+#ifndef HG_DEVICE_CUH
+#define HG_DEVICE_CUH
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hg_params.h"
+
+namespace hg {
+
+// Overlap records resident in HBM as a struct of arrays (the layout named by
+// BASELINE.json north_star) plus the CSR that groups them by A-read.
+struct RecView {
+    int64_t novl;
+    const int32_t* __restrict__ aread;
+    const int32_t* __restrict__ bread;
+    const int32_t* __restrict__ abpos;
+    const int32_t* __restrict__ aepos;
+    const int32_t* __restrict__ bbpos;
+    const int32_t* __restrict__ bepos;
+    const int32_t* __restrict__ flags;
+    const int64_t* __restrict__ trace_off;
+    const uint8_t* __restrict__ trace;
+    int32_t tbytes;
+    const int64_t* __restrict__ read_off;  // n_read + 1, global read ids
+};
+
+struct ReadView {
+    int32_t n_read;
+    int32_t r_lo, r_hi;      // reads owned by this context
+    const int32_t* __restrict__ rlen;
+    const int2* __restrict__ qvmask;  // (start, end) of the longest good-QV run
+};
+
+// bin of an event position on the 40-bp grid: profileCoverage emits entry i
+// once every event with pos < i*reso has been consumed
+// (/root/reference/src/lib/LAInterface.cpp:4309-4317)
+__device__ __forceinline__ int cov_bin(int e, int reso) { return e < 0 ? 0 : e / reso + 1; }
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan(T v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane_id() >= d) v += o;
+    }
+    return v;
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
+// Two signed counters packed in one word: low half = profile without cut-off,
+// high half = profile with cut-off.  Sums of packed words stay decodable while
+// both halves fit their width, so ONE shared-memory histogram and ONE warp scan
+// serve both coverage profiles.
+template <typename W>
+struct Packed;
+template <>
+struct Packed<uint32_t> {
+    static constexpr int kMaxCount = 32000;  // pile-ups deeper than this use the 64-bit path
+    static __device__ __forceinline__ uint32_t one_lo() { return 1u; }
+    static __device__ __forceinline__ uint32_t one_hi() { return 1u << 16; }
+    static __device__ __forceinline__ int lo(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
+    static __device__ __forceinline__ int hi(uint32_t v) {
+        return ((int32_t)(v - (uint32_t)(int32_t)(int16_t)(v & 0xffffu))) >> 16;
+    }
+    static __device__ __forceinline__ void add(uint32_t* p, uint32_t v) { atomicAdd(p, v); }
+};
+template <>
+struct Packed<unsigned long long> {
+    static constexpr int kMaxCount = 2000000000;
+    typedef unsigned long long W;
+    static __device__ __forceinline__ W one_lo() { return 1ull; }
+    static __device__ __forceinline__ W one_hi() { return 1ull << 32; }
+    static __device__ __forceinline__ int lo(W v) { return (int)(int32_t)(v & 0xffffffffull); }
+    static __device__ __forceinline__ int hi(W v) {
+        return (int)(((long long)(v - (W)(long long)(int32_t)(v & 0xffffffffull))) >> 32);
+    }
+    static __device__ __forceinline__ void add(W* p, W v) { atomicAdd(p, v); }
+};
+
+}  // namespace hg
+#endif

@@ -1,0 +1,814 @@
+// Kernels of the `hinge filter` stage (sm_100a, integer / index work, no tensor
+// cores).  Reference behaviour: /root/reference/src/filter/filter.cpp:529-1098.
+//
+//   K0 csr_validate    .las order + invariants, CSR offsets by A-read
+//   K0 qv_mask         longest good-QV run per read          (filter.cpp:340-369)
+//   K1 cov_accum       flat streaming pass: per-read sum / length of the
+//                      coverage profile without building it  (filter.cpp:588-656)
+//   K1 median_*        median of the per-read means -> MIN_COV (filter.cpp:660-678)
+//   K2 mask_anno       one warp per A-read: packed coverage histogram in shared
+//                      memory + warp scan -> coverage mask, repeat annotation,
+//                      hinge pre-test                          (filter.cpp:696-865)
+//   K4 hinge_call      one warp per annotated read: order-exact pile-up sort and
+//                      bridged / unbridged walk                (filter.cpp:867-1066)
+#include <stdio.h>
+
+#include "hg_device.cuh"
+#include "hg_filter.h"
+#include "hg_order.h"
+
+namespace hg {
+
+// ------------------------------------------------------------------ K0
+
+__global__ void k_csr_validate(RecView rv, ReadView rd, int64_t* read_off, int* err) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > rv.novl) return;
+    const int prev = k == 0 ? rd.r_lo - 1 : rv.aread[k - 1];
+    int cur = k == rv.novl ? rd.r_hi - 1 : rv.aread[k];
+    if (k < rv.novl) {
+        const int a = rv.aread[k], b = rv.bread[k];
+        bool ok = a >= rd.r_lo && a < rd.r_hi && b >= 0 && b < rd.n_read && a >= prev;
+        if (ok) {
+            const int as = rv.abpos[k], ae = rv.aepos[k], bs = rv.bbpos[k], be = rv.bepos[k];
+            ok = as >= 0 && as < ae && ae <= rd.rlen[a] && bs >= 0 && bs <= be && be <= rd.rlen[b];
+        }
+        if (!ok) {
+            atomicExch(err, 1);
+            return;
+        }
+    }
+    // every read in (prev, cur] starts at record k
+    for (int r = max(prev + 1, rd.r_lo); r <= cur; r++) read_off[r] = k;
+    if (k == rv.novl) {
+        for (int r = 0; r < rd.r_lo; r++) read_off[r] = 0;  // reads of other shards: empty
+        for (int r = rd.r_hi; r <= rd.n_read; r++) read_off[r] = rv.novl;
+    }
+}
+
+// filter.cpp:340-369: a tile is good when its QV < 40 (filter.cpp:311); a bad
+// tile or the LAST tile closes the current run; keep the strictly longest run.
+__global__ void k_qv_mask(int n_read, const int64_t* __restrict__ qv_off,
+                          const uint8_t* __restrict__ qv, int tspace, int2* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_read) return;
+    const int64_t o = qv_off[i];
+    const int n = (int)(qv_off[i + 1] - o);
+    int s = 0, e = 0, best = 0, bs = 0, be = 0;
+    for (int j = 0; j < n; j++) {
+        const bool good = qv[o + j] < 40;
+        if (good && j < n - 1) {
+            e++;
+        } else {
+            if (e - s > best) {
+                be = e;
+                bs = s;
+                best = e - s;
+            }
+            s = j + 1;
+            e = j + 1;
+        }
+    }
+    out[i] = make_int2(bs * tspace, be * tspace);
+}
+
+// ------------------------------------------------------------------ K1
+
+// The mean of read i's profile needs no histogram:
+//   sum_j cov[j] = sum_records (bin(aepos) - bin(abpos)),  length = max bin(aepos) + 1
+// so the coverage estimate is one flat, coalesced pass over (aread, bread, abpos,
+// aepos): 16 B per record, int4 loads, warp segmented reduction by A-read, one
+// atomic per (warp, read).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_cov_accum(RecView rv, int reso, unsigned long long* __restrict__ cov_sum,
+            int* __restrict__ cov_maxbin, int* __restrict__ self_cnt) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k0 = t * VEC;
+    int a[VEC], b[VEC], s[VEC], e[VEC];
+    bool vec_loaded = false;
+    if constexpr (VEC == 4) {
+        if (k0 + 4 <= rv.novl) {
+            const int4 va = __ldg(reinterpret_cast<const int4*>(rv.aread + k0));
+            const int4 vb = __ldg(reinterpret_cast<const int4*>(rv.bread + k0));
+            const int4 vs = __ldg(reinterpret_cast<const int4*>(rv.abpos + k0));
+            const int4 ve = __ldg(reinterpret_cast<const int4*>(rv.aepos + k0));
+            a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w;
+            b[0] = vb.x; b[1] = vb.y; b[2] = vb.z; b[3] = vb.w;
+            s[0] = vs.x; s[1] = vs.y; s[2] = vs.z; s[3] = vs.w;
+            e[0] = ve.x; e[1] = ve.y; e[2] = ve.z; e[3] = ve.w;
+            vec_loaded = true;
+        }
+    }
+    if (!vec_loaded) {
+#pragma unroll
+        for (int i = 0; i < VEC; i++) {
+            const int64_t k = k0 + i;
+            const bool in = k < rv.novl;
+            a[i] = in ? rv.aread[k] : -2;
+            b[i] = in ? rv.bread[k] : -1;
+            s[i] = in ? rv.abpos[k] : 0;
+            e[i] = in ? rv.aepos[k] : 0;
+        }
+    }
+    int key = -2, mx = -1;
+    long long acc = 0;
+#pragma unroll
+    for (int i = 0; i < VEC; i++) {
+        if (a[i] != key) {
+            if (key >= 0) {  // a read ended inside this thread's records
+                if (acc) atomicAdd(&cov_sum[key], (unsigned long long)acc);
+                if (mx >= 0) atomicMax(&cov_maxbin[key], mx);
+            }
+            key = a[i];
+            acc = 0;
+            mx = -1;
+        }
+        if (a[i] >= 0) {
+            if (a[i] != b[i]) {
+                const int be = cov_bin(e[i], reso);
+                acc += be - cov_bin(s[i], reso);
+                mx = max(mx, be);
+            } else {
+                atomicAdd(&self_cnt[a[i]], 1);
+            }
+        }
+    }
+    // warp segmented reduction of the tails (keys are non-decreasing across lanes)
+    const int lane = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int okey = __shfl_up_sync(0xffffffffu, key, d);
+        const long long oacc = __shfl_up_sync(0xffffffffu, acc, d);
+        const int omx = __shfl_up_sync(0xffffffffu, mx, d);
+        if (lane >= d && okey == key) {
+            acc += oacc;
+            mx = max(mx, omx);
+        }
+    }
+    const int nkey = __shfl_down_sync(0xffffffffu, key, 1);
+    if (key >= 0 && (lane == 31 || nkey != key)) {
+        if (acc) atomicAdd(&cov_sum[key], (unsigned long long)acc);
+        if (mx >= 0) atomicMax(&cov_maxbin[key], mx);
+    }
+}
+
+// filter.cpp:642-656 (mean over reads >= 5000 bp inside [r_begin, r_end]) and
+// filter.cpp:552-561 (self-match reads; float accumulation in record order).
+__global__ void k_cov_finalize(RecView rv, ReadView rd, int r_begin, int r_end,
+                               const unsigned long long* __restrict__ cov_sum,
+                               const int* __restrict__ cov_maxbin,
+                               const int* __restrict__ self_cnt, int* __restrict__ mean_cov,
+                               uint8_t* __restrict__ rflags) {
+    const int i = rd.r_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rd.r_hi) return;
+    const int len0 = cov_maxbin[i] + 1;
+    const int mean = (int)((long long)cov_sum[i] / (long long)max(1, len0));
+    const int rl = rd.rlen[i];
+    mean_cov[i] = (rl >= 5000 && i >= r_begin && i <= r_end) ? mean : -1;
+    uint8_t f = 0;
+    if (self_cnt[i] > 0) {
+        float cov = 0.0f;
+        for (int64_t k = rv.read_off[i]; k < rv.read_off[i + 1]; k++) {
+            if (rv.bread[k] != i) continue;
+            cov = __fadd_rn(cov, (float)(rv.aepos[k] - rv.abpos[k]));
+            // B span is strand-invariant: (blen-bbpos) - (blen-bepos) = bepos - bbpos
+            cov = __fadd_rn(cov, (float)(rv.bepos[k] - rv.bbpos[k]));
+        }
+        cov = __fdiv_rn(cov, (float)rl);
+        if ((double)cov > 4.5 && rl > 10000) f |= kFlagSelf;
+    }
+    rflags[i] = f;
+}
+
+// Median by counting: per-read means are small integers, so a 4096-bin
+// shared-memory histogram resolves the rank exactly; means >= 4095 (coverage
+// in the thousands) take the generic three-digit radix select below.
+__global__ void k_median_hist(const int* __restrict__ mean_cov, int n_read,
+                              unsigned int* __restrict__ hist /*4096 + 1*/) {
+    __shared__ unsigned int sh[4096];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    unsigned int valid = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_read; i += gridDim.x * blockDim.x) {
+        const int v = mean_cov[i];
+        if (v >= 0) {
+            atomicAdd(&sh[min(v, 4095)], 1u);
+            valid++;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+    valid = (unsigned int)warp_sum((int)valid);
+    if (lane_id() == 0 && valid) atomicAdd(&hist[4096], valid);
+}
+
+// scal: [0] cov_est  [1] MIN_COV  [2] radix prefix  [3] radix rank  [4] need radix pass
+__global__ void k_median_pick(const unsigned int* __restrict__ hist, int est_cov, int min_cov,
+                              int* __restrict__ scal) {
+    // single thread: 4096 adds, negligible next to the launch itself
+    if (threadIdx.x || blockIdx.x) return;
+    const unsigned int m = hist[4096];
+    unsigned int rank = m / 2, run = 0;  // filter.cpp:660 median_id = size / 2
+    int cov_est = 0, need = 0;
+    if (m > 0) {
+        int v = 0;
+        for (; v < 4096; v++) {
+            if (run + hist[v] > rank) break;
+            run += hist[v];
+        }
+        if (v >= 4095) {  // inside the overflow bin: resolve with the radix passes
+            need = 1;
+            scal[3] = (int)(rank - run);
+        }
+        cov_est = v;
+    }
+    scal[2] = 0;
+    scal[4] = need;
+    if (!need) {
+        if (est_cov != 0) cov_est = est_cov;  // filter.cpp:671
+        scal[0] = cov_est;
+        scal[1] = max(min_cov, cov_est / 3);  // filter.cpp:677-678
+    }
+}
+
+// Generic fallback, three passes (digits 12/10/10 bits of v - 4095, high to low).
+__global__ void k_median_radix(const int* __restrict__ mean_cov, int n_read, int pass,
+                               unsigned int* __restrict__ dig /*4096*/, int* __restrict__ scal) {
+    if (!scal[4]) return;
+    const int shift = pass == 0 ? 20 : (pass == 1 ? 10 : 0);
+    const int bits = pass == 0 ? 12 : 10;
+    const unsigned int prefix = (unsigned int)scal[2];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_read; i += gridDim.x * blockDim.x) {
+        const int v = mean_cov[i];
+        if (v < 4095) continue;
+        const unsigned int u = (unsigned int)(v - 4095);
+        const unsigned int hi = pass == 0 ? 0u : (u >> (shift + bits));
+        if (hi != prefix) continue;
+        atomicAdd(&dig[(u >> shift) & ((1u << bits) - 1u)], 1u);
+    }
+}
+__global__ void k_median_radix_pick(int pass, unsigned int* __restrict__ dig, int est_cov,
+                                    int min_cov, int* __restrict__ scal) {
+    if (threadIdx.x || blockIdx.x || !scal[4]) return;
+    const int bits = pass == 0 ? 12 : 10;
+    unsigned int rank = (unsigned int)scal[3], run = 0;
+    unsigned int d = 0;
+    for (; d < (1u << bits); d++) {
+        if (run + dig[d] > rank) break;
+        run += dig[d];
+    }
+    scal[3] = (int)(rank - run);
+    scal[2] = (int)(((unsigned int)scal[2] << bits) | d);
+    for (unsigned int i = 0; i < 4096; i++) dig[i] = 0;
+    if (pass == 2) {
+        int cov_est = (int)((unsigned int)scal[2] + 4095u);
+        if (est_cov != 0) cov_est = est_cov;
+        scal[0] = cov_est;
+        scal[1] = max(min_cov, cov_est / 3);
+    }
+}
+
+// ------------------------------------------------------------------ K2
+
+struct MaskAnnoOut {
+    int2* mask;        // .mas
+    int2* cmask;       // .cmas (bin coordinates)
+    uint8_t* rflags;   // kFlag*
+    int2* anno_ref;    // (offset into pool, count) per read
+    int2* anno_pool;   // (pos, type)
+    int anno_cap;
+    int* counters;     // [0] pool used  [1] work-list length  [2] overflow flag  [3] big-list length
+    int* work_list;    // reads that need hinge calling
+    int* big_list;     // reads whose profile does not fit the shared-memory path
+    int* cov0;         // optional dump of the cut-off-free profile (coverage.txt)
+    const int64_t* cov0_off;
+};
+
+// One warp owns one read.  `hist` holds `nbz` packed words (shared memory on
+// the fast path, global scratch for very long reads / very deep pile-ups).
+template <typename W>
+__device__ void mask_anno_read(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
+                               const int MIN_COV, const int read, W* hist, const int nbz,
+                               const MaskAnnoOut& out) {
+    typedef Packed<W> PK;
+    const int lane = lane_id();
+    const int reso = P.reso;
+    const int64_t o0 = rv.read_off[read], o1 = rv.read_off[read + 1];
+
+    for (int j = lane; j < nbz; j += 32) hist[j] = 0;
+    __syncwarp();
+
+    // ---- scatter the four events of every record (A == B records are inactive,
+    //      filter.cpp:538-547); profileCoverage, LAInterface.cpp:4298-4320
+    int m0 = -1, mc = -1;
+    for (int64_t k = o0 + lane; k < o1; k += 32) {
+        const int b = __ldg(rv.bread + k);
+        if (b == read) continue;
+        const int as = __ldg(rv.abpos + k), ae = __ldg(rv.aepos + k);
+        const int b_s0 = cov_bin(as, reso), b_e0 = cov_bin(ae, reso);
+        const int b_sc = cov_bin(as + P.cut_off, reso), b_ec = cov_bin(ae - P.cut_off, reso);
+        PK::add(&hist[b_s0], PK::one_lo());
+        PK::add(&hist[b_e0], (W)0 - PK::one_lo());
+        PK::add(&hist[b_sc], PK::one_hi());
+        PK::add(&hist[b_ec], (W)0 - PK::one_hi());
+        m0 = max(m0, b_e0);
+        mc = max(mc, max(b_sc, b_ec));
+    }
+    const int L0 = warp_max(m0) + 1;  // profile lengths (0 for an empty pile-up)
+    const int LC = warp_max(mc) + 1;
+    __syncwarp();
+
+    // ---- prefix sums in place + longest run of covered bins (filter.cpp:696-728).
+    // A bin is "zero" when covC - MIN_COV <= 0; the run between two consecutive
+    // zeros p < z scores 40 * (z - p - 2); bin 0 acts as a zero; strict '>' keeps
+    // the earliest of the longest runs.
+    W carry = 0;
+    int last_zero = 0;
+    unsigned long long best = 0;  // (gap << 32) | ~z  -> max gap, then smallest z
+    for (int base = 0; base < nbz; base += 32) {
+        const int j = base + lane;
+        W v = j < nbz ? hist[j] : 0;
+        v = warp_incl_scan(v) + carry;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+        if (j < nbz) hist[j] = v;
+        const bool zero = j < LC && !(PK::hi(v) > MIN_COV);
+        const unsigned zm = __ballot_sync(0xffffffffu, zero);
+        if (zero) {
+            const unsigned below = zm & ((1u << lane) - 1u);
+            const int p = below ? base + 31 - __clz(below) : last_zero;
+            const int gap = j - p;
+            if (gap >= 3) {
+                const unsigned long long cand =
+                    ((unsigned long long)gap << 32) | (unsigned)(0x7fffffff - j);
+                if (cand > best) best = cand;
+            }
+        }
+        if (zm) last_zero = base + 31 - __clz(zm);
+    }
+    best = warp_max_u64(best);
+    __syncwarp();
+    int maxstart = 0, maxend = 0, msc = 0, mec = 0;
+    if (best) {
+        const int gap = (int)(best >> 32), z = 0x7fffffff - (int)(best & 0xffffffffu), p = z - gap;
+        msc = p + 1;
+        mec = z - 1;
+        maxstart = reso * (p + 1);
+        maxend = reso * (z - 1);
+    }
+
+    // ---- telomere / coverage-imbalance flag (filter.cpp:731-760)
+    uint8_t flags = out.rflags[read] & kFlagSelf;
+    if (P.delete_telomere) {
+        int limit, div;
+        if (mec - msc + 1 > 20) {
+            limit = 10;
+            div = 10;
+        } else {
+            limit = (mec - msc) / 2;
+            div = limit;
+        }
+        int sc = 0, ec = 0;
+        for (int t = lane; t < limit; t += 32) {
+            sc += max(PK::hi(hist[msc + t]), MIN_COV);  // clamped value + MIN_COV
+            ec += max(PK::hi(hist[mec - t]), MIN_COV);
+        }
+        sc = warp_sum(sc);
+        ec = warp_sum(ec);
+        if (div == 0) {
+            sc = 0;
+            ec = 0;
+        } else {
+            sc /= div;
+            ec /= div;
+        }
+        if (sc >= 10 * ec || ec >= 10 * sc) flags |= kFlagCov;
+    } else {
+        flags = 0;  // .self.flag is only written with del_telomere (filter.cpp:757-765)
+    }
+
+    // ---- final mask (filter.cpp:777-788)
+    const int2 q = rd.qvmask[read];
+    int2 mk;
+    if (P.use_qv_mask && P.use_coverage_mask)
+        mk = make_int2(max(maxstart, q.x), min(maxend, q.y));
+    else if (P.use_coverage_mask && !P.use_qv_mask)
+        mk = make_int2(maxstart, maxend);
+    else
+        mk = q;
+
+    // ---- optional dump of the profile for .coverage.txt (filter.cpp:599-602)
+    if (out.cov0) {
+        int* dst = out.cov0 + out.cov0_off[read];
+        for (int j = lane; j < L0; j += 32) dst[j] = PK::lo(hist[j]);
+    }
+
+    // ---- hinge pre-test: mean coverage near both mask ends (filter.cpp:842-865)
+    const int NHR = P.no_hinge_region;
+    int cs = 0, ns = 0, ce = 0, ne = 0;
+    {
+        // bins with  mk.x <= 40 j <= mk.x + NHR
+        int jlo = mk.x <= 0 ? 0 : (mk.x + reso - 1) / reso;
+        int jhi = mk.x + NHR < 0 ? -1 : min((mk.x + NHR) / reso, L0 - 1);
+        for (int j = jlo + lane; j <= jhi; j += 32) {
+            cs += PK::lo(hist[j]);
+            ns++;
+        }
+        // bins with  mk.y - NHR <= 40 j <= mk.y
+        jlo = mk.y - NHR <= 0 ? 0 : (mk.y - NHR + reso - 1) / reso;
+        jhi = mk.y < 0 ? -1 : min(mk.y / reso, L0 - 1);
+        for (int j = jlo + lane; j <= jhi; j += 32) {
+            ce += PK::lo(hist[j]);
+            ne++;
+        }
+        cs = warp_sum(cs);
+        ns = warp_sum(ns);
+        ce = warp_sum(ce);
+        ne = warp_sum(ne);
+    }
+    // float on purpose: 0/0 = NaN makes the '< 10' test false (filter.cpp:861-865)
+    const float avg_end = __fdiv_rn((float)ce, (float)ne);
+    const float avg_start = __fdiv_rn((float)cs, (float)ns);
+    const bool skip_hinges = fabsf(__fsub_rn(avg_end, avg_start)) < 10.0f;
+
+    // ---- repeat annotation from the coverage gradient (filter.cpp:796-813);
+    // entries are compacted in place over the histogram words they came from
+    const int jn = max(L0 - 2, 0);
+    int cnt = 0;
+    for (int base = 0; base < jn; base += 32) {
+        const int j = base + lane;
+        int type = 0;
+        if (j < jn) {
+            const int pos = reso * j;
+            if (pos >= mk.x + NHR && pos <= mk.y - NHR) {
+                const int c0 = PK::lo(hist[j]);
+                const int g = PK::lo(hist[j + 1]) - c0;
+                const int thr = min(max((c0 + MIN_COV) / P.coverage_fraction,
+                                        P.min_repeat_annotation_threshold),
+                                    P.max_repeat_annotation_threshold);
+                type = g > thr ? 1 : (g < -thr ? -1 : 0);
+            }
+        }
+        const unsigned am = __ballot_sync(0xffffffffu, type != 0);
+        __syncwarp();
+        if (type != 0) {
+            const int slot = cnt + __popc(am & ((1u << lane) - 1u));
+            hist[slot] = (W)(((unsigned)(reso * j) << 2) | (unsigned)(type + 1));
+        }
+        cnt += __popc(am);
+        __syncwarp();
+    }
+
+    // ---- merge pass (filter.cpp:817-829), lane 0: +1,+1 closer than the gap
+    // threshold drops the later one; -1,-1 drops the earlier one
+    int kept = 0;
+    if (lane == 0 && cnt > 0) {
+        const int GAP = P.repeat_annotation_gap_threshold;
+        unsigned cur = (unsigned)hist[0];
+        for (int k = 1; k < cnt; k++) {
+            const unsigned nxt = (unsigned)hist[k];
+            const int ct = (int)(cur & 3u) - 1, nt = (int)(nxt & 3u) - 1;
+            const int gap = (int)(nxt >> 2) - (int)(cur >> 2);
+            if (ct == 1 && nt == 1 && gap < GAP) {
+                continue;  // erase next
+            } else if (ct == -1 && nt == -1 && gap < GAP) {
+                cur = nxt;  // erase current
+            } else {
+                hist[kept++] = (W)cur;
+                cur = nxt;
+            }
+        }
+        hist[kept++] = (W)cur;
+    }
+    kept = __shfl_sync(0xffffffffu, kept, 0);
+    int off = 0;
+    if (lane == 0 && kept > 0) {
+        off = atomicAdd(&out.counters[0], kept);
+        if (off + kept > out.anno_cap) {
+            atomicExch(&out.counters[2], 1);
+            off = -1;
+        }
+    }
+    off = __shfl_sync(0xffffffffu, off, 0);
+    __syncwarp();
+    if (kept > 0 && off >= 0)
+        for (int k = lane; k < kept; k += 32) {
+            const unsigned w = (unsigned)hist[k];
+            out.anno_pool[off + k] = make_int2((int)(w >> 2), (int)(w & 3u) - 1);
+        }
+    if (lane == 0) {
+        out.mask[read] = mk;
+        out.cmask[read] = make_int2(msc, mec);
+        out.rflags[read] = flags | (skip_hinges ? kFlagSkipHinge : 0);
+        out.anno_ref[read] = make_int2(off, kept);
+        if (kept > 0 && !skip_hinges && off >= 0) out.work_list[atomicAdd(&out.counters[1], 1)] = read;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ int bins_needed(int rlen, const hg_filter_params& P) {
+    return (rlen + max(P.cut_off, 0)) / P.reso + 3;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_mask_anno(RecView rv, ReadView rd, hg_filter_params P, const int* __restrict__ scal,
+            int r_begin, int r_end, int nb_cap, MaskAnnoOut out) {
+    extern __shared__ uint32_t sh[];  // WARPS x nb_cap packed histogram words
+    const int warp = threadIdx.x >> 5;
+    uint32_t* hist = sh + (size_t)warp * nb_cap;
+    const int MIN_COV = scal[1];
+    const int lo = max(rd.r_lo, r_begin), hi = min(rd.r_hi, r_end + 1);
+    for (int read = lo + blockIdx.x * WARPS + warp; read < hi; read += gridDim.x * WARPS) {
+        const int nbz = bins_needed(rd.rlen[read], P);
+        const int64_t n = rv.read_off[read + 1] - rv.read_off[read];
+        if (nbz > nb_cap || n > Packed<uint32_t>::kMaxCount) {
+            if (lane_id() == 0) out.big_list[atomicAdd(&out.counters[3], 1)] = read;
+            continue;
+        }
+        mask_anno_read<uint32_t>(rv, rd, P, MIN_COV, read, hist, nbz, out);
+    }
+}
+
+// Slow path for reads longer than nb_cap bins or deeper than 32000 records:
+// 64-bit packed words in a global scratch slot per warp.
+__global__ void __launch_bounds__(128)
+k_mask_anno_big(RecView rv, ReadView rd, hg_filter_params P, const int* __restrict__ scal,
+                MaskAnnoOut out, unsigned long long* scratch, int slot_words) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int MIN_COV = scal[1];
+    const int nbig = out.counters[3];
+    for (int w = warp; w < nbig; w += nwarps) {
+        const int read = out.big_list[w];
+        const int nbz = bins_needed(rd.rlen[read], P);
+        mask_anno_read<unsigned long long>(rv, rd, P, MIN_COV, read,
+                                           scratch + (size_t)warp * slot_words, nbz, out);
+    }
+}
+
+// ------------------------------------------------------------------ K4
+
+struct KeyIdx {
+    int key, idx;
+};
+struct GreaterKey {
+    __device__ bool operator()(const KeyIdx& a, const KeyIdx& b) const { return a.key > b.key; }
+};
+struct FirstAsc {
+    __device__ bool operator()(const int2& a, const int2& b) const { return a.x < b.x; }
+};
+struct FirstDesc {
+    __device__ bool operator()(const int2& a, const int2& b) const { return a.x > b.x; }
+};
+
+// One warp per annotated read.  Scratch slot layout (cap records each):
+//   KeyIdx ord[cap] | int2 ends[cap] | int4 rec[cap] = (astart, aend, left_oh, right_oh)
+__global__ void __launch_bounds__(128)
+k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict__ mask,
+             const int2* __restrict__ anno_ref, const int2* __restrict__ anno_pool,
+             const int* __restrict__ counters, const int* __restrict__ work_list,
+             uint8_t* __restrict__ hinge_keep, uint8_t* scratch, int cap) {
+    const int lane = lane_id();
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const size_t slot = (size_t)cap * (sizeof(KeyIdx) + sizeof(int2) + sizeof(int4));
+    uint8_t* base = scratch + (size_t)warp * slot;
+    int4* rec = reinterpret_cast<int4*>(base);
+    KeyIdx* ord = reinterpret_cast<KeyIdx*>(base + (size_t)cap * sizeof(int4));
+    int2* ends = reinterpret_cast<int2*>(base + (size_t)cap * (sizeof(int4) + sizeof(KeyIdx)));
+    const int nwork = counters[1];
+    const int THETA = P.theta, HTL = P.hinge_tolerance_length, HBL = P.hinge_bin_length;
+
+    for (int w = warp; w < nwork; w += nwarps) {
+        const int read = work_list[w];
+        const int64_t o0 = rv.read_off[read], o1 = rv.read_off[read + 1];
+        const int2 mk = mask[read];
+        // ---- gather the active pile-up in file order (filter.cpp:537-548, 877-890)
+        int n = 0;
+        for (int64_t kb = o0; kb < o1; kb += 32) {
+            const int64_t k = kb + lane;
+            bool act = false;
+            int as = 0, ae = 0, lo = 0, ro = 0, key = 0;
+            if (k < o1) {
+                const int b = rv.bread[k];
+                if (b != read) {
+                    act = true;
+                    as = rv.abpos[k];
+                    ae = rv.aepos[k];
+                    const int comp = rv.flags[k] & 1;
+                    int bs = rv.bbpos[k], be = rv.bepos[k];
+                    if (comp) {  // LAInterface.cpp:1619-1626
+                        const int bl = rd.rlen[b];
+                        const int t = bl - be;
+                        be = bl - bs;
+                        bs = t;
+                    }
+                    const int2 mb = mask[b];
+                    const int r0 = max(mb.y - be, 0), l0 = max(bs - mb.x, 0);
+                    ro = comp ? l0 : r0;
+                    lo = comp ? r0 : l0;
+                    key = (ae - as) + (be - bs);
+                }
+            }
+            const unsigned am = __ballot_sync(0xffffffffu, act);
+            if (act) {
+                const int s = n + __popc(am & ((1u << lane) - 1u));
+                rec[s] = make_int4(as, ae, lo, ro);
+                ord[s].key = key;
+                ord[s].idx = s;
+            }
+            n += __popc(am);
+        }
+        __syncwarp();
+        // ---- the pile-up order the reference sees: std::sort by total length,
+        // descending, unstable (filter.cpp:565-567)
+        if (lane == 0) std_sort_exact(ord, n, GreaterKey());
+        __syncwarp();
+
+        const int2 ar = anno_ref[read];
+        for (int j = 0; j < ar.y; j++) {
+            const int2 an = anno_pool[ar.x + j];
+            const int apos = an.x;
+            const bool out_hinge = an.y == -1;
+            // ---- reads starting / ending at the annotation, in pile-up order
+            int support = 0;
+            for (int kb = 0; kb < n; kb += 32) {
+                const int k = kb + lane;
+                bool sel = false;
+                int2 e = make_int2(0, 0);
+                if (k < n) {
+                    const int4 r = rec[ord[k].idx];
+                    if (out_hinge) {
+                        sel = r.w > THETA && r.y > apos - HTL && r.y < apos + HTL;
+                        e = make_int2(r.x, r.z);
+                    } else {
+                        sel = r.z > THETA && r.x > apos - HTL && r.x < apos + HTL;
+                        e = make_int2(r.y, r.w);
+                    }
+                }
+                const unsigned sm = __ballot_sync(0xffffffffu, sel);
+                if (sel) ends[support + __popc(sm & ((1u << lane) - 1u))] = e;
+                support += __popc(sm);
+            }
+            __syncwarp();
+            uint8_t keep = 0;
+            if (lane == 0 && support >= P.hinge_min_support) {
+                if (out_hinge)
+                    std_sort_exact(ends, support, FirstAsc());
+                else
+                    std_sort_exact(ends, support, FirstDesc());
+                // ---- bridged / unbridged walk (filter.cpp:916-965, 1013-1065)
+                bool bridged = true;
+                int considered = 0, to_end = 0;
+                const int first0 = ends[0].x;
+                for (int id = 0; id < support; ++id) {
+                    const int f = ends[id].x, oh = ends[id].y;
+                    const int dist_end = out_hinge ? f - mk.x : mk.y - f;
+                    const int dist0 = out_hinge ? f - first0 : first0 - f;
+                    if (dist_end < HBL) {
+                        considered++;
+                        to_end++;
+                        if (to_end > P.hinge_read_unbridged_threshold ||
+                            (considered > P.hinge_read_unbridged_threshold && dist0 > HBL)) {
+                            bridged = false;
+                            break;
+                        }
+                    } else if (oh < THETA) {
+                        considered++;
+                        if (to_end > P.hinge_read_unbridged_threshold ||
+                            (considered > P.hinge_read_unbridged_threshold && dist0 > HBL)) {
+                            bridged = false;
+                            break;
+                        }
+                    } else if (oh > THETA) {
+                        considered++;
+                        int pl = 1;
+                        for (int id1 = id + 1; id1 < support; id1++) {
+                            const int g = out_hinge ? ends[id1].x - f : f - ends[id1].x;
+                            if (g < HBL)
+                                pl++;
+                            else
+                                break;
+                        }
+                        if (pl > P.hinge_bin_pileup_threshold) {
+                            bridged = true;
+                            break;
+                        }
+                    }
+                }
+                keep = (!bridged && support > P.hinge_min_support) ? 1 : 0;
+            }
+            if (lane == 0) hinge_keep[ar.x + j] = keep;
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void k_max_pileup(const int64_t* __restrict__ read_off, int n_read, int* out_max) {
+    int m = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_read; i += gridDim.x * blockDim.x)
+        m = max(m, (int)min((int64_t)0x7fffffff, read_off[i + 1] - read_off[i]));
+    m = warp_max(m);
+    if (lane_id() == 0 && m > 0) atomicMax(out_max, m);
+}
+
+// ------------------------------------------------------------------ launchers
+
+static inline int ceil_div64(int64_t a, int b) { return (int)((a + b - 1) / b); }
+
+void launch_csr_validate(const RecView& rv, const ReadView& rd, int64_t* read_off, int* err,
+                         cudaStream_t st) {
+    k_csr_validate<<<ceil_div64(rv.novl + 1, 256), 256, 0, st>>>(rv, rd, read_off, err);
+}
+
+void launch_qv_mask(int n_read, const int64_t* qv_off, const uint8_t* qv, int tspace, int2* out,
+                    cudaStream_t st) {
+    k_qv_mask<<<ceil_div64(n_read, 128), 128, 0, st>>>(n_read, qv_off, qv, tspace, out);
+}
+
+void launch_cov_estimate(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
+                         int r_begin, int r_end, FilterScratch& s, cudaStream_t st) {
+    cudaMemsetAsync(s.cov_sum, 0, sizeof(unsigned long long) * rd.n_read, st);
+    cudaMemsetAsync(s.cov_maxbin, 0xff, sizeof(int) * rd.n_read, st);
+    cudaMemsetAsync(s.self_cnt, 0, sizeof(int) * rd.n_read, st);
+    const bool aligned = (((uintptr_t)rv.aread | (uintptr_t)rv.bread | (uintptr_t)rv.abpos |
+                           (uintptr_t)rv.aepos) & 15) == 0;
+    if (rv.novl > 0) {
+        if (aligned)
+            k_cov_accum<4><<<ceil_div64((rv.novl + 3) / 4, 256), 256, 0, st>>>(
+                rv, P.reso, s.cov_sum, s.cov_maxbin, s.self_cnt);
+        else
+            k_cov_accum<1><<<ceil_div64(rv.novl, 256), 256, 0, st>>>(rv, P.reso, s.cov_sum,
+                                                                      s.cov_maxbin, s.self_cnt);
+    }
+    const int owned = rd.r_hi - rd.r_lo;
+    if (owned > 0)
+        k_cov_finalize<<<ceil_div64(owned, 256), 256, 0, st>>>(rv, rd, r_begin, r_end, s.cov_sum,
+                                                               s.cov_maxbin, s.self_cnt,
+                                                               s.mean_cov, s.rflags);
+}
+
+void launch_median(const ReadView& rd, const hg_filter_params& P, FilterScratch& s,
+                   cudaStream_t st) {
+    cudaMemsetAsync(s.med_hist, 0, sizeof(unsigned int) * (4097 + 4096), st);
+    k_median_hist<<<148 * 2, 256, 0, st>>>(s.mean_cov, rd.n_read, s.med_hist);
+    k_median_pick<<<1, 32, 0, st>>>(s.med_hist, P.est_cov, P.min_cov, s.scal);
+    for (int pass = 0; pass < 3; pass++) {  // no-ops unless the median is >= 4095
+        k_median_radix<<<148, 256, 0, st>>>(s.mean_cov, rd.n_read, pass, s.med_hist + 4097, s.scal);
+        k_median_radix_pick<<<1, 32, 0, st>>>(pass, s.med_hist + 4097, P.est_cov, P.min_cov, s.scal);
+    }
+}
+
+int mask_anno_configure(FilterScratch& s, int nb_cap) {
+    // shared memory per CTA = warps x nb_cap words; as many CTAs per SM as fit
+    nb_cap = (nb_cap + 31) & ~31;
+    const int max_words = (200 * 1024) / (4 * kMaskAnnoWarps);
+    if (nb_cap > max_words) nb_cap = max_words;
+    const int smem = nb_cap * 4 * kMaskAnnoWarps;
+    cudaFuncSetAttribute(k_mask_anno<kMaskAnnoWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         smem);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mask_anno<kMaskAnnoWarps>,
+                                                  kMaskAnnoWarps * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    s.nb_cap = nb_cap;
+    s.mask_anno_grid = s.num_sms * per_sm;
+    return per_sm;
+}
+
+void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
+                      int r_begin, int r_end, FilterScratch& s, int* cov0, const int64_t* cov0_off,
+                      cudaStream_t st) {
+    MaskAnnoOut out;
+    out.mask = s.mask; out.cmask = s.cmask; out.rflags = s.rflags; out.anno_ref = s.anno_ref;
+    out.anno_pool = s.anno_pool; out.anno_cap = s.anno_cap; out.counters = s.counters;
+    out.work_list = s.work_list; out.big_list = s.big_list; out.cov0 = cov0; out.cov0_off = cov0_off;
+    cudaMemsetAsync(s.counters, 0, sizeof(int) * 8, st);
+    cudaMemsetAsync(s.mask, 0, sizeof(int2) * rd.n_read, st);
+    cudaMemsetAsync(s.cmask, 0, sizeof(int2) * rd.n_read, st);
+    cudaMemsetAsync(s.anno_ref, 0, sizeof(int2) * rd.n_read, st);
+    cudaMemsetAsync(s.hinge_keep, 0, (size_t)s.anno_cap, st);
+    const int smem = s.nb_cap * 4 * kMaskAnnoWarps;
+    k_mask_anno<kMaskAnnoWarps><<<s.mask_anno_grid, kMaskAnnoWarps * 32, smem, st>>>(
+        rv, rd, P, s.scal, r_begin, r_end, s.nb_cap, out);
+    if (s.big_slot_words > 0)
+        k_mask_anno_big<<<s.big_warps / 4, 128, 0, st>>>(rv, rd, P, s.scal, out, s.big_scratch,
+                                                         s.big_slot_words);
+}
+
+void launch_max_pileup(const int64_t* read_off, int n_read, int* out_max, cudaStream_t st) {
+    cudaMemsetAsync(out_max, 0, sizeof(int), st);
+    k_max_pileup<<<148 * 2, 256, 0, st>>>(read_off, n_read, out_max);
+}
+
+void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
+                       FilterScratch& s, cudaStream_t st) {
+    if (s.hinge_cap <= 0) return;
+    k_hinge_call<<<s.hinge_warps / 4, 128, 0, st>>>(rv, rd, P, s.mask, s.anno_ref, s.anno_pool,
+                                                    s.counters, s.work_list, s.hinge_keep,
+                                                    s.hinge_scratch, s.hinge_cap);
+}
+
+}  // namespace hg

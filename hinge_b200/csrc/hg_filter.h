@@ -1,0 +1,65 @@
+// Host-visible declarations of the filter-stage kernels' launchers.
+#ifndef HG_FILTER_H
+#define HG_FILTER_H
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hg_params.h"
+
+namespace hg {
+
+struct RecView;
+struct ReadView;
+
+enum : uint8_t { kFlagCov = 1, kFlagSelf = 2, kFlagSkipHinge = 4 };
+
+constexpr int kMaskAnnoWarps = 8;  // warps (= reads in flight) per CTA of K2
+
+// Device buffers of one filter run (all sized at hg_set_reads / hg_set_overlaps).
+struct FilterScratch {
+    int num_sms = 148;
+    // K1
+    unsigned long long* cov_sum = nullptr;  // n_read
+    int* cov_maxbin = nullptr;              // n_read
+    int* self_cnt = nullptr;                // n_read
+    int* mean_cov = nullptr;                // n_read, -1 = not part of the estimate
+    unsigned int* med_hist = nullptr;       // 4097 + 4096
+    int* scal = nullptr;                    // 8: cov_est, MIN_COV, radix state
+    // K2
+    int2* mask = nullptr;      // n_read
+    int2* cmask = nullptr;     // n_read
+    uint8_t* rflags = nullptr; // n_read
+    int2* anno_ref = nullptr;  // n_read
+    int2* anno_pool = nullptr;
+    int anno_cap = 0;
+    int* counters = nullptr;   // 8
+    int* work_list = nullptr;  // n_read
+    int* big_list = nullptr;   // n_read
+    int nb_cap = 0;            // histogram words per warp on the shared-memory path
+    int mask_anno_grid = 0;
+    unsigned long long* big_scratch = nullptr;
+    int big_slot_words = 0, big_warps = 0;
+    // K4
+    uint8_t* hinge_keep = nullptr;  // anno_cap
+    uint8_t* hinge_scratch = nullptr;
+    int hinge_cap = 0, hinge_warps = 0;
+};
+
+void launch_csr_validate(const RecView& rv, const ReadView& rd, int64_t* read_off, int* err,
+                         cudaStream_t st);
+void launch_qv_mask(int n_read, const int64_t* qv_off, const uint8_t* qv, int tspace, int2* out,
+                    cudaStream_t st);
+void launch_cov_estimate(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
+                         int r_begin, int r_end, FilterScratch& s, cudaStream_t st);
+void launch_median(const ReadView& rd, const hg_filter_params& P, FilterScratch& s,
+                   cudaStream_t st);
+int mask_anno_configure(FilterScratch& s, int nb_cap);  // picks grid from occupancy
+void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
+                      int r_begin, int r_end, FilterScratch& s, int* cov0, const int64_t* cov0_off,
+                      cudaStream_t st);
+void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
+                       FilterScratch& s, cudaStream_t st);
+void launch_max_pileup(const int64_t* read_off, int n_read, int* out_max, cudaStream_t st);
+
+}  // namespace hg
+#endif

@@ -1,0 +1,281 @@
+// File-level drivers behind `hinge filter | maximal | layout`: same flags,
+// inputs, outputs and exit codes as the reference executables
+// (/root/reference/src/filter/filter.cpp:168-1123, maximal/maximal.cpp:238-905,
+// layout/hinging.cpp:616-2156), with the compute done through the C ABI.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/hinge_b200.h"
+#include "hg_host.h"
+#include "hg_io.h"
+
+namespace hg {
+
+// cmdline.h-style options: --name value | --name=value | -c value | --flag
+bool parse_args(int argc, char** argv, bool layout, Args* a, std::string* err) {
+    struct Opt {
+        const char* name;
+        char shortc;
+        std::string* dst;
+        bool* flag;
+    };
+    std::vector<Opt> opts = {
+        {"db", 'b', &a->db, nullptr},         {"las", 'l', &a->las, nullptr},
+        {"paf", 'p', &a->paf, nullptr},       {"config", 'c', &a->config, nullptr},
+        {"fasta", 'f', &a->fasta, nullptr},   {"prefix", 'x', &a->prefix, nullptr},
+        {"log", 'g', &a->log, nullptr},       {"mlas", 0, nullptr, &a->mlas},
+        {"debug", 0, nullptr, &a->debug},
+    };
+    if (layout)
+        opts.push_back({"out", 'o', &a->out, nullptr});
+    else
+        opts.push_back({"restrictreads", 'r', &a->restrictreads, nullptr});
+    bool have_prefix = false, have_out = false;
+    for (int i = 1; i < argc; i++) {
+        std::string s = argv[i];
+        const Opt* o = nullptr;
+        std::string value;
+        bool has_value = false;
+        if (s.size() > 2 && s[0] == '-' && s[1] == '-') {
+            std::string name = s.substr(2);
+            size_t eq = name.find('=');
+            if (eq != std::string::npos) {
+                value = name.substr(eq + 1);
+                name.resize(eq);
+                has_value = true;
+            }
+            for (const Opt& c : opts)
+                if (name == c.name) o = &c;
+        } else if (s.size() == 2 && s[0] == '-') {
+            for (const Opt& c : opts)
+                if (c.shortc && s[1] == c.shortc) o = &c;
+        }
+        if (!o) {
+            *err = "undefined option: " + s;
+            return false;
+        }
+        if (o->flag) {
+            *o->flag = true;
+            continue;
+        }
+        if (!has_value) {
+            if (i + 1 >= argc) {
+                *err = std::string("option needs value: --") + o->name;
+                return false;
+            }
+            value = argv[++i];
+        }
+        *o->dst = value;
+        if (o->dst == &a->prefix) have_prefix = true;
+        if (o->dst == &a->out) have_out = true;
+    }
+    if (layout && (!have_prefix || !have_out)) {  // hinging.cpp:627-628: required options
+        *err = std::string("need option: --") + (!have_prefix ? "prefix" : "out");
+        return false;
+    }
+    return true;
+}
+
+static void say(const char* fmt, const std::string& s = std::string()) {
+    printf("[hinge_b200] ");
+    printf(fmt, s.c_str());
+    printf("\n");
+    fflush(stdout);
+}
+
+// Flag-combination checks shared by the three stages (filter.cpp:212-241).
+int check_inputs(const Args& a, std::string* las_name) {
+    const bool db_and_las = !a.db.empty() && !a.las.empty();
+    const bool db_or_las = !a.db.empty() || !a.las.empty();
+    const bool fa_and_paf = !a.fasta.empty() && !a.paf.empty();
+    const bool fa_or_paf = !a.fasta.empty() || !a.paf.empty();
+    if (db_or_las && fa_or_paf) {
+        fprintf(stderr, "Pass in either a db and a las or a fasta and a paf\n");
+        return 1;
+    }
+    if (!fa_and_paf && !db_and_las) {
+        fprintf(stderr, "Pass in at least one of the following two combinations: a db and a las or a fasta and a paf\n");
+        return 1;
+    }
+    if (fa_and_paf) {
+        fprintf(stderr, "hinge_b200: the fasta + paf input path is outside the B200 hot path (DESIGN.md, out of scope)\n");
+        return 1;
+    }
+    if (a.mlas) {
+        fprintf(stderr, "hinge_b200: --mlas is not supported: merge the parts with LAmerge; the reference's multi-part "
+                        "results differ from its single-file results (SURVEY.md section 5)\n");
+        return 1;
+    }
+    *las_name = a.las;
+    if (las_name->size() < 4 || las_name->compare(las_name->size() - 4, 4, ".las") != 0) *las_name += ".las";
+    return 0;
+}
+
+int load_inputs(const Args& a, bool want_trace, Ini* ini, ReadDB* db, LasFile* las) {
+    std::string las_name;
+    int rc = check_inputs(a, &las_name);
+    if (rc) return rc;
+    if (db->open(a.db) != 0) {  // LAInterface::openDB exits 1
+        fprintf(stderr, "%s\n", db->error.c_str());
+        return 1;
+    }
+    say("# Reads: %s", std::to_string(db->n_read));
+    if (ini->load(a.config) < 0) {  // filter.cpp:371-375
+        fprintf(stderr, "Can't load %s\n", a.config.c_str());
+        return 1;
+    }
+    if (las->open(las_name, want_trace) != 0) {
+        fprintf(stderr, "%s\n", las->error.c_str());
+        return 1;
+    }
+    say("# Alignments: %s", std::to_string(las->novl));
+    if (las->novl == 0) {  // filter.cpp:505-508
+        fprintf(stderr, "No alignments!\n");
+        return 1;
+    }
+    return 0;
+}
+
+int open_context(const ReadDB& db, const LasFile& las, bool with_trace, hg_ctx** ctx) {
+    int rc = hg_ctx_create(0, nullptr, ctx);
+    if (rc != HG_OK) {
+        fprintf(stderr, "hinge_b200: cannot create a CUDA context (status %d)\n", rc);
+        return rc;
+    }
+    rc = hg_set_reads(*ctx, db.n_read, db.rlen.data(), db.has_qv ? db.qv_off.data() : nullptr,
+                      db.has_qv ? db.qv.data() : nullptr, las.tspace);
+    if (rc == HG_OK)
+        rc = hg_set_overlaps(*ctx, las.novl, las.aread.data(), las.bread.data(), las.abpos.data(),
+                             las.aepos.data(), las.bbpos.data(), las.bepos.data(), las.diffs.data(),
+                             las.flags.data(), with_trace ? las.trace_off.data() : nullptr,
+                             with_trace ? las.trace.data() : nullptr, las.tbytes, HG_MEM_HOST, 0,
+                             db.n_read);
+    if (rc != HG_OK) fprintf(stderr, "hinge_b200: %s\n", hg_last_error(*ctx));
+    return rc;
+}
+
+static void touch(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "w");
+    if (f) fclose(f);
+}
+
+}  // namespace hg
+
+using namespace hg;
+
+extern "C" int hg_main_filter(int argc, char** argv) {
+    mkdir("log", S_IRWXU | S_IRWXG | S_IROTH | S_IXOTH);  // filter.cpp:170
+    Args a;
+    std::string err;
+    if (!parse_args(argc, argv, false, &a, &err)) {
+        fprintf(stderr, "%s\n", err.c_str());
+        return 1;
+    }
+    if (!a.restrictreads.empty()) {
+        fprintf(stderr, "hinge_b200: --restrictreads (a debugging aid, filter.cpp:317-331) is not supported\n");
+        return 1;
+    }
+    say("Reads filtering");
+    Ini ini;
+    ReadDB db;
+    LasFile las;
+    int rc = load_inputs(a, false, &ini, &db, &las);
+    if (rc) return rc;
+    hg_filter_params fp;
+    load_filter_params(ini, db.has_qv, &fp);
+
+    hg_ctx* ctx = nullptr;
+    if (open_context(db, las, false, &ctx) != HG_OK) {
+        hg_ctx_destroy(ctx);
+        return 1;
+    }
+    const bool want_cov = getenv("HINGE_B200_SKIP_COVERAGE_TXT") == nullptr;
+    hg_set_option(ctx, HG_OPT_KEEP_COVERAGE, want_cov);
+    hg_filter_summary sum;
+    rc = hg_filter(ctx, &fp, &sum);
+    if (rc != HG_OK) {
+        fprintf(stderr, "hinge_b200: filter failed: %s\n", hg_last_error(ctx));
+        hg_ctx_destroy(ctx);
+        return 1;
+    }
+    say("Estimated median coverage: %s", std::to_string(sum.cov_est));
+
+    const int n = db.n_read;
+    std::vector<int32_t> mask(2 * (size_t)n), cmask(2 * (size_t)n);
+    std::vector<uint8_t> flags(n);
+    std::vector<int64_t> anno_off((size_t)n + 1);
+    std::vector<int32_t> apos((size_t)sum.n_annotations + 1), atype((size_t)sum.n_annotations + 1);
+    std::vector<uint8_t> keep((size_t)sum.n_annotations + 1);
+    rc = hg_filter_fetch(ctx, mask.data(), cmask.data(), flags.data(), anno_off.data(), apos.data(),
+                         atype.data(), keep.data());
+    std::vector<int64_t> cov_off;
+    std::vector<int32_t> cov;
+    if (rc == HG_OK && want_cov) {
+        int64_t nb = 0;
+        cov_off.resize((size_t)n + 1);
+        rc = hg_filter_coverage(ctx, cov_off.data(), nullptr, &nb);
+        cov.resize((size_t)nb + 1);
+        if (rc == HG_OK) rc = hg_filter_coverage(ctx, nullptr, cov.data(), &nb);
+    }
+    if (rc != HG_OK) {
+        fprintf(stderr, "hinge_b200: fetching results failed: %s\n", hg_last_error(ctx));
+        hg_ctx_destroy(ctx);
+        return 1;
+    }
+    hg_ctx_destroy(ctx);
+
+    const std::string& x = a.prefix;
+    {  // filter.cpp:449-457 opens all of these, some stay empty
+        touch(x + ".homologous.txt");
+        touch(x + ".filtered.fasta");
+        touch("debug.txt");
+        TextOut fcov(x + ".coverage.txt"), fmask(x + ".mas"), fcmask(x + ".cmas");
+        TextOut frep(x + ".repeat.txt"), fhg(x + ".hinges.txt");
+        TextOut fcf(x + ".cov.flag"), fsf(x + ".self.flag");
+        int64_t hinges = 0;
+        for (int i = sum.r_begin; i <= sum.r_end; i++) {
+            if (want_cov) {  // filter.cpp:599-602
+                fcov.put_str("read ");
+                fcov.put_int(i);
+                fcov.put_char(' ');
+                for (int64_t k = cov_off[i]; k < cov_off[i + 1]; k++) {
+                    fcov.put_int((long)(k - cov_off[i]) * fp.reso);
+                    fcov.put_char(',');
+                    fcov.put_int(cov[k]);
+                    fcov.put_char(' ');
+                }
+                fcov.put_char('\n');
+            }
+            fcmask.put_int(i); fcmask.put_char(' '); fcmask.put_int(cmask[2 * i]); fcmask.put_char(' ');
+            fcmask.put_int(cmask[2 * i + 1]); fcmask.put_char('\n');
+            fmask.put_int(i); fmask.put_char(' '); fmask.put_int(mask[2 * i]); fmask.put_char(' ');
+            fmask.put_int(mask[2 * i + 1]); fmask.put_char('\n');
+            if (flags[i] & 1) { fcf.put_int(i); fcf.put_char('\n'); }
+            if (flags[i] & 2) { fsf.put_int(i); fsf.put_char('\n'); }
+            frep.put_int(i);  // filter.cpp:1078-1085
+            frep.put_char(' ');
+            for (int64_t k = anno_off[i]; k < anno_off[i + 1]; k++) {
+                frep.put_int(apos[k]); frep.put_char(' '); frep.put_int(atype[k]); frep.put_char(' ');
+            }
+            frep.put_char('\n');
+            if (i < sum.r_end) {  // filter.cpp:1091: the last read gets no line
+                fhg.put_int(i);
+                fhg.put_char(' ');
+                for (int64_t k = anno_off[i]; k < anno_off[i + 1]; k++)
+                    if (keep[k]) {
+                        fhg.put_int(apos[k]); fhg.put_char(' '); fhg.put_int(atype[k]); fhg.put_char(' ');
+                        hinges++;
+                    }
+                fhg.put_char('\n');
+            }
+        }
+        say("Number of hinges before filtering: %s", std::to_string(sum.n_annotations));
+        say("Number of hinges: %s", std::to_string(hinges));
+    }
+    return 0;
+}

@@ -1,0 +1,181 @@
+// Order-exact restatements of two libstdc++ routines whose implementation-
+// defined element order leaks into the reference's results:
+//
+//   * std::sort (introsort; unstable).  The reference sorts every pile-up with
+//     compare_overlap (filter.cpp:565-567), the hinge-call end lists with
+//     pairAscend/pairDescend (filter.cpp:914,1010), each (A,B) pair's overlaps
+//     (maximal.cpp:647-654,791; hinging.cpp:534) and the extension candidates
+//     with compare_overlap_weight (hinging.cpp:1066-1071).  Ties are common
+//     (64 % of reads), so a kernel that wants the reference's
+//     bytes has to reproduce the exact permutation, not just "a" sorted order.
+//   * std::unordered_map<int, T> iteration order (maximal.cpp:789,
+//     hinging.cpp:532): decides the pre-sort order of candidate extensions.
+//
+// Both are restated from the published algorithm of GCC 13's libstdc++
+// (bits/stl_algo.h: __introsort_loop / __final_insertion_sort / __heap_select;
+// bits/hashtable.h + hashtable_policy.h: _Prime_rehash_policy), compile for
+// host and device, and are checked element-for-element against the real
+// library in tests/test_order_exact.py.
+#ifndef HG_ORDER_H
+#define HG_ORDER_H
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HG_HD __host__ __device__ __forceinline__
+#else
+#define HG_HD inline
+#endif
+
+namespace hg {
+
+// ---------------------------------------------------------------- std::sort
+
+template <class T, class Less>
+HG_HD void os_unguarded_linear_insert(T* a, int last, Less less) {
+    T val = a[last];
+    int next = last - 1;
+    while (less(val, a[next])) {
+        a[last] = a[next];
+        last = next;
+        --next;
+    }
+    a[last] = val;
+}
+
+template <class T, class Less>
+HG_HD void os_insertion_sort(T* a, int first, int last, Less less) {
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        if (less(a[i], a[first])) {
+            T val = a[i];
+            for (int k = i; k > first; --k) a[k] = a[k - 1];
+            a[first] = val;
+        } else {
+            os_unguarded_linear_insert(a, i, less);
+        }
+    }
+}
+
+template <class T, class Less>
+HG_HD void os_push_heap(T* a, int first, int hole, int top, T value, Less less) {
+    int parent = (hole - 1) / 2;
+    while (hole > top && less(a[first + parent], value)) {
+        a[first + hole] = a[first + parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    a[first + hole] = value;
+}
+
+template <class T, class Less>
+HG_HD void os_adjust_heap(T* a, int first, int hole, int len, T value, Less less) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (less(a[first + child], a[first + (child - 1)])) child--;
+        a[first + hole] = a[first + child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        a[first + hole] = a[first + (child - 1)];
+        hole = child - 1;
+    }
+    os_push_heap(a, first, hole, top, value, less);
+}
+
+// std::__partial_sort(first, last, last): make_heap + sort_heap
+template <class T, class Less>
+HG_HD void os_heap_sort(T* a, int first, int last, Less less) {
+    const int len = last - first;
+    if (len >= 2) {
+        int parent = (len - 2) / 2;
+        while (true) {
+            T value = a[first + parent];
+            os_adjust_heap(a, first, parent, len, value, less);
+            if (parent == 0) break;
+            parent--;
+        }
+    }
+    while (last - first > 1) {
+        --last;
+        T value = a[last];
+        a[last] = a[first];
+        os_adjust_heap(a, first, 0, last - first, value, less);
+    }
+}
+
+template <class T>
+HG_HD void os_swap(T* a, int i, int j) {
+    T t = a[i];
+    a[i] = a[j];
+    a[j] = t;
+}
+
+// Exactly the permutation std::sort(a, a + n, less) produces (GCC 13).
+template <class T, class Less>
+HG_HD void std_sort_exact(T* a, int n, Less less) {
+    if (n <= 0) return;
+    // __introsort_loop; the recursion on the right part is replaced by an
+    // explicit stack (disjoint ranges commute, so the result is identical)
+    int stack_first[64], stack_last[64], stack_depth[64];
+    int sp = 0;
+    int lg = 0;
+    for (unsigned v = (unsigned)n; v > 1; v >>= 1) lg++;
+    stack_first[0] = 0;
+    stack_last[0] = n;
+    stack_depth[0] = 2 * lg;
+    sp = 1;
+    while (sp > 0) {
+        --sp;
+        int first = stack_first[sp], last = stack_last[sp], depth = stack_depth[sp];
+        while (last - first > 16) {
+            if (depth == 0) {
+                os_heap_sort(a, first, last, less);
+                break;
+            }
+            --depth;
+            // __move_median_to_first(first, first+1, mid, last-1)
+            const int mid = first + (last - first) / 2;
+            const int x = first + 1, y = mid, z = last - 1;
+            if (less(a[x], a[y])) {
+                if (less(a[y], a[z])) os_swap(a, first, y);
+                else if (less(a[x], a[z])) os_swap(a, first, z);
+                else os_swap(a, first, x);
+            } else if (less(a[x], a[z])) {
+                os_swap(a, first, x);
+            } else if (less(a[y], a[z])) {
+                os_swap(a, first, z);
+            } else {
+                os_swap(a, first, y);
+            }
+            // __unguarded_partition(first+1, last, pivot = first)
+            int lo = first + 1, hi = last;
+            while (true) {
+                while (less(a[lo], a[first])) ++lo;
+                --hi;
+                while (less(a[first], a[hi])) --hi;
+                if (!(lo < hi)) break;
+                os_swap(a, lo, hi);
+                ++lo;
+            }
+            const int cut = lo;
+            stack_first[sp] = cut;  // right part: later
+            stack_last[sp] = last;
+            stack_depth[sp] = depth;
+            ++sp;
+            last = cut;
+        }
+    }
+    // __final_insertion_sort
+    if (n > 16) {
+        os_insertion_sort(a, 0, 16, less);
+        for (int i = 16; i != n; ++i) os_unguarded_linear_insert(a, i, less);
+    } else {
+        os_insertion_sort(a, 0, n, less);
+    }
+}
+
+}  // namespace hg
+#endif

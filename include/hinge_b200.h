@@ -1,0 +1,172 @@
+/* hinge_b200 — C ABI of the B200-native HINGE hot path.
+ *
+ * HINGE has no in-process plugin interface: its hot path sits behind three
+ * executables (`hinge filter | maximal | layout`, /root/reference/src/hinge:9-17)
+ * that talk through files.  This header is the FFI surface a maintainer binds
+ * instead of (or from inside) those executables; every entry point names the
+ * reference code it replaces.  Plain pointers and sizes only; all integers are
+ * int32 unless stated; offsets are int64.  Functions return 0 (HG_OK) or a
+ * negative hg_status; nothing throws, nothing falls back to the CPU: without a
+ * CUDA device every compute call returns HG_ERR_CUDA.
+ *
+ * Threading: a context is bound to one device and one stream; use one context
+ * per thread / per GPU.  Host buffers passed in are only read during the call.
+ */
+#ifndef HINGE_B200_H
+#define HINGE_B200_H
+#include <stdint.h>
+
+#include "../hinge_b200/csrc/hg_params.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hg_ctx hg_ctx;
+
+typedef enum hg_status {
+    HG_OK = 0,
+    HG_ERR_CUDA = -1,      /* no device / CUDA runtime error (see hg_last_error) */
+    HG_ERR_ARG = -2,       /* bad argument or call order */
+    HG_ERR_INPUT = -3,     /* overlap records violate the .las invariants */
+    HG_ERR_NOMEM = -4,
+    HG_ERR_IO = -5,        /* file-level helpers: unreadable DB / .las / INI */
+    HG_ERR_NO_ALIGNMENTS = -6 /* reference: "No alignments!", exit 1 (filter.cpp:505-508) */
+} hg_status;
+
+enum { HG_MEM_HOST = 0, HG_MEM_DEVICE = 1 };
+
+/* positive, non-fatal: the variable-size annotation pool was too small; the
+ * phase-level caller grows it (hg_filter does this itself) and reruns */
+#define HG_RETRY_POOL 1
+
+enum hg_option {
+    HG_OPT_KEEP_COVERAGE = 1 /* keep the 40-bp coverage profiles (.coverage.txt) */
+};
+
+enum hg_buffer { /* per-read device arrays a sharded run exchanges between phases */
+    HG_BUF_MEAN_COV = 1,  /* int32[n_read], -1 = not part of the estimate      */
+    HG_BUF_MASK = 2,      /* int32[n_read][2], the .mas intervals               */
+    HG_BUF_READ_FLAGS = 3 /* uint8[n_read]                                       */
+};
+
+/* ---- context ---------------------------------------------------------- */
+
+/* `stream` is a cudaStream_t (NULL = the legacy default stream). */
+int hg_ctx_create(int device, void* stream, hg_ctx** out);
+void hg_ctx_destroy(hg_ctx* ctx);
+const char* hg_last_error(const hg_ctx* ctx);
+const char* hg_version(void);
+int hg_set_option(hg_ctx* ctx, int option, int64_t value);
+/* Device address and size of a per-read array (rows of reads outside the
+ * context's [a_lo, a_hi) are the caller's to fill, e.g. by an NCCL all-gather). */
+int hg_device_buffer(hg_ctx* ctx, int which, void** dptr, int64_t* bytes);
+
+/* ---- inputs ----------------------------------------------------------- */
+
+/* Reads of the (trimmed) DAZZ_DB: lengths and the optional `qual` track.
+ * Replaces LAInterface::openDB/getRead/getQV as used by the stages
+ * (lib/LAInterface.cpp:133-185,1195-1286,4369-4494); only rlen and the QV tiles
+ * are consumed.  qv_off/qv may be NULL (no track => coverage mask only,
+ * filter.cpp:304-305).  Host pointers. */
+int hg_set_reads(hg_ctx* ctx, int32_t n_read, const int32_t* rlen, const int64_t* qv_off,
+                 const uint8_t* qv, int32_t tspace);
+
+/* Overlap records as a struct of arrays, sorted by (aread, bread, abpos) like
+ * a LAsort-ed .las.  Replaces LAInterface::getOverlap + LOverlap
+ * (lib/LAInterface.cpp:1519-1634): B coordinates are passed exactly as stored
+ * in the file (complement-strand coordinates when flags&1); the flip to the
+ * forward strand happens on the device.  `diffs` is part of the layout but no
+ * stage reads it (may be NULL).  trace_off/trace (raw (diff,bdelta) bytes, tbytes
+ * = 1 or 2 per value) are needed by hg_maximal/hg_layout only and may be NULL
+ * for hg_filter.  `where` = HG_MEM_HOST copies to the device on the context's
+ * stream; HG_MEM_DEVICE adopts 16-byte aligned device pointers without a copy
+ * (they must stay valid until replaced).
+ *
+ * A context may own just a slice of the reads: pass the records whose aread is
+ * in [a_lo, a_hi) and that range; n_read arrays stay global. */
+int hg_set_overlaps(hg_ctx* ctx, int64_t novl, const int32_t* aread, const int32_t* bread,
+                    const int32_t* abpos, const int32_t* aepos, const int32_t* bbpos,
+                    const int32_t* bepos, const int32_t* diffs, const int32_t* flags,
+                    const int64_t* trace_off, const uint8_t* trace, int32_t tbytes, int32_t where,
+                    int32_t a_lo, int32_t a_hi);
+
+/* ---- hinge filter (filter.cpp:529-1098) -------------------------------- */
+
+typedef struct hg_filter_summary {
+    int32_t r_begin, r_end;  /* first / last A-read with records (filter.cpp:516-517) */
+    int32_t cov_est;         /* median of per-read mean coverage (filter.cpp:660-671) */
+    int32_t min_cov;         /* max(min_cov, cov_est/3)      (filter.cpp:677-678) */
+    int64_t n_annotations;   /* "Number of hinges before filtering" */
+    int64_t n_hinges;        /* "Number of hinges" (reads r_begin..r_end-1) */
+    float ms_device;         /* device time of the whole stage, CUDA events */
+} hg_filter_summary;
+
+/* One call = the whole stage on the device, no host round trip in between:
+ * coverage estimate -> masks -> repeat annotation -> hinge calls. */
+int hg_filter(hg_ctx* ctx, const hg_filter_params* params, hg_filter_summary* out);
+
+/* The same stage split at its two global dependencies, for contexts that own
+ * a slice of the reads: exchange (all-gather) the named device array between
+ * the calls.  hg_filter == phase1; phase2; phase3 on one context. */
+int hg_filter_phase1(hg_ctx* ctx, const hg_filter_params* params); /* -> HG_BUF_MEAN_COV */
+int hg_filter_phase2(hg_ctx* ctx);                                 /* -> HG_BUF_MASK     */
+int hg_filter_phase3(hg_ctx* ctx, hg_filter_summary* out);         /* hinge calls        */
+
+/* Results of the last filter run, copied to caller-owned host arrays (any may
+ * be NULL).  mask/cmask: 2 ints per read (.mas / .cmas lines, filter.cpp:775-788);
+ * flags: bit0 = .cov.flag, bit1 = .self.flag; anno_off: n_read+1 offsets into
+ * anno_pos/anno_type (.repeat.txt); hinge_keep[k] = 1 if annotation k is a
+ * called hinge (.hinges.txt). */
+int hg_filter_fetch(hg_ctx* ctx, int32_t* mask, int32_t* cmask, uint8_t* flags, int64_t* anno_off,
+                    int32_t* anno_pos, int32_t* anno_type, uint8_t* hinge_keep);
+/* Coverage profiles at 40 bp (the .coverage.txt payload, filter.cpp:599-602);
+ * needs HG_OPT_KEEP_COVERAGE set before hg_filter.  cov_off gets n_read+1
+ * offsets, cov one int per bin; call with cov == NULL first to learn *n_bins. */
+int hg_filter_coverage(hg_ctx* ctx, int64_t* cov_off, int32_t* cov, int64_t* n_bins);
+
+/* ---- maximal reads (maximal.cpp:524-878) ------------------------------- */
+
+/* mask: 2 ints per read (the .mas content); NULL = use the masks of the last
+ * hg_filter on this context.  maximal_out: n_read bytes, 1 = read survives
+ * (.max); contained_by (may be NULL): containing read per read or -1
+ * (.contained.txt). */
+int hg_maximal(hg_ctx* ctx, const hg_layout_params* params, const int32_t* mask,
+               uint8_t* maximal_out, int32_t* contained_by, float* ms_device);
+
+/* ---- layout: candidate extensions + best-overlap selection ------------- */
+
+typedef struct hg_edge {      /* one line of .edges.hinges (hinging.cpp:188-248) */
+    int32_t a, b, length, comp, type, weight;
+    int32_t eff_a[2], eff_b[2];   /* trimmed match on A / B            */
+    int32_t read_a[2], read_b[2]; /* effective (masked) read intervals */
+    int32_t raw_a[2], raw_b[2];   /* untrimmed match, B on its forward strand */
+    int32_t hinge_pos;            /* .edges.hinges2 */
+} hg_edge;
+
+/* Everything `hinge layout` computes from the records: classification of the
+ * top-two overlaps per maximal pair (hinging.cpp:473-602), weight ordering
+ * (:1066-1071), hinge bookkeeping and hinge graph (:1180-1691) and the
+ * best-overlap scoring loop (:1911-2148).  Inputs are the inter-stage files'
+ * content: mask (2 ints/read), maximal (1 byte/read), repeat annotations and
+ * hinges as CSR (off has n_read+1 entries; pos/type per entry).  Results are
+ * written by the hg_layout_write_* helpers or fetched with hg_layout_edges. */
+int hg_layout(hg_ctx* ctx, const hg_layout_params* params, const int32_t* mask,
+              const uint8_t* maximal, const int64_t* rep_off, const int32_t* rep_pos,
+              const int32_t* rep_type, const int64_t* hin_off, const int32_t* hin_pos,
+              const int32_t* hin_type, float* ms_device);
+int hg_layout_edges(hg_ctx* ctx, hg_edge* edges, int64_t capacity, int64_t* n_edges);
+
+/* ---- file-level drivers: what the three executables do ------------------ */
+
+/* Same flags, inputs, outputs and exit conventions as Reads_filter,
+ * get_maximal_reads and hinging (filter.cpp:168, maximal.cpp:238,
+ * hinging.cpp:616).  Return value is the process exit code. */
+int hg_main_filter(int argc, char** argv);
+int hg_main_maximal(int argc, char** argv);
+int hg_main_layout(int argc, char** argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
