@@ -44,6 +44,8 @@ ReadView hg_ctx::read_view() const {
 }
 
 static void free_overlaps(hg_ctx* c) {
+    c->cap_novl = 0;
+    c->cap_trace = 0;
     if (!c->adopted) {
         cudaFree(c->d_aread); cudaFree(c->d_bread); cudaFree(c->d_abpos); cudaFree(c->d_aepos);
         cudaFree(c->d_bbpos); cudaFree(c->d_bepos); cudaFree(c->d_flags);
@@ -102,8 +104,12 @@ void hg_ctx_destroy(hg_ctx* c) {
     free_overlaps(c);
     cudaFree(c->d_rlen); cudaFree(c->d_qvmask); cudaFree(c->d_read_off); cudaFree(c->d_err);
     FilterScratch& s = c->fs;
-    cudaFree(s.cov_sum); cudaFree(s.cov_maxbin); cudaFree(s.self_cnt); cudaFree(s.mean_cov);
-    cudaFree(s.med_hist); cudaFree(s.scal); cudaFree(s.mask); cudaFree(s.cmask); cudaFree(s.rflags);
+    cudaFree(s.cov_sum); cudaFree(s.cov_maxbin); cudaFree(s.self_cnt);
+    if (!c->ext_mean_cov) cudaFree(s.mean_cov);
+    if (!c->ext_mask) cudaFree(s.mask);
+    for (int i = 0; i < hg_ctx::kMarks; i++)
+        if (c->marks[i]) cudaEventDestroy(c->marks[i]);
+    cudaFree(s.med_hist); cudaFree(s.scal); cudaFree(s.cmask); cudaFree(s.rflags);
     cudaFree(s.anno_ref); cudaFree(s.anno_pool); cudaFree(s.counters); cudaFree(s.work_list);
     cudaFree(s.big_list); cudaFree(s.big_scratch); cudaFree(s.hinge_keep); cudaFree(s.hinge_scratch);
     cudaFree(c->d_cov0); cudaFree(c->d_cov0_off);
@@ -116,6 +122,12 @@ int hg_set_option(hg_ctx* c, int option, int64_t value) {
     if (!c) return HG_ERR_ARG;
     if (option == HG_OPT_KEEP_COVERAGE) {
         c->keep_cov = value != 0;
+        return HG_OK;
+    }
+    if (option == HG_OPT_PROFILE) {
+        c->profile = value != 0;
+        if (c->profile && !c->marks[0])
+            for (int i = 0; i < hg_ctx::kMarks; i++) cudaEventCreate(&c->marks[i]);
         return HG_OK;
     }
     return set_err(c, HG_ERR_ARG, "unknown option");
@@ -163,6 +175,8 @@ int hg_set_reads(hg_ctx* c, int32_t n_read, const int32_t* rlen, const int64_t* 
     HG_TRY(dev_alloc(c, &s.cov_sum, n_read, "cov_sum"));
     HG_TRY(dev_alloc(c, &s.cov_maxbin, n_read, "cov_maxbin"));
     HG_TRY(dev_alloc(c, &s.self_cnt, n_read, "self_cnt"));
+    if (c->ext_mean_cov) { s.mean_cov = nullptr; c->ext_mean_cov = false; }
+    if (c->ext_mask) { s.mask = nullptr; c->ext_mask = false; }
     HG_TRY(dev_alloc(c, &s.mean_cov, n_read, "mean_cov"));
     HG_TRY(dev_alloc(c, &s.mask, n_read, "mask"));
     HG_TRY(dev_alloc(c, &s.cmask, n_read, "cmask"));
@@ -177,6 +191,7 @@ int hg_set_reads(hg_ctx* c, int32_t n_read, const int32_t* rlen, const int64_t* 
     c->a_lo = 0;
     c->a_hi = n_read;
     c->filter_done = false;
+    c->shape_version++;
     return cuda_check(c, cudaStreamSynchronize(st), "hg_set_reads");
 }
 
@@ -203,7 +218,10 @@ int hg_set_overlaps(hg_ctx* c, int64_t novl, const int32_t* aread, const int32_t
     if (tbytes != 1 && tbytes != 2) return set_err(c, HG_ERR_ARG, "tbytes must be 1 or 2");
     cudaSetDevice(c->device);
     cudaStream_t st = c->stream;
-    free_overlaps(c);
+    // host-path buffers are kept across calls when the new batch fits
+    const bool reuse = where == HG_MEM_HOST && !c->adopted && c->d_aread != nullptr &&
+                       novl <= c->cap_novl;
+    if (!reuse) free_overlaps(c);
     c->novl = novl;
     c->a_lo = a_lo;
     c->a_hi = a_hi;
@@ -231,13 +249,17 @@ int hg_set_overlaps(hg_ctx* c, int64_t novl, const int32_t* aread, const int32_t
                             &c->d_bbpos, &c->d_bepos, &c->d_flags};
         const int32_t* src[7] = {aread, bread, abpos, aepos, bbpos, bepos, flags};
         for (int i = 0; i < 7; i++) {
-            HG_TRY(dev_alloc(c, dst[i], (size_t)novl + 8, "overlap column"));
+            if (!reuse) HG_TRY(dev_alloc(c, dst[i], (size_t)novl + 8, "overlap column"));
             HG_TRY(cuda_check(c, cudaMemcpyAsync(*dst[i], src[i], nb, cudaMemcpyHostToDevice, st), "overlap H2D"));
         }
+        if (!reuse) c->cap_novl = novl;
         if (c->has_trace) {
             const int64_t tb = trace_off[novl];
-            HG_TRY(dev_alloc(c, &c->d_trace_off, (size_t)novl + 1, "trace offsets"));
-            HG_TRY(dev_alloc(c, &c->d_trace, (size_t)tb + 16, "trace"));
+            if (!reuse || !c->d_trace_off) HG_TRY(dev_alloc(c, &c->d_trace_off, (size_t)c->cap_novl + 1, "trace offsets"));
+            if (!c->d_trace || tb > c->cap_trace) {
+                HG_TRY(dev_alloc(c, &c->d_trace, (size_t)tb + 16, "trace"));
+                c->cap_trace = tb;
+            }
             HG_TRY(cuda_check(c, cudaMemcpyAsync(c->d_trace_off, trace_off, 8 * ((size_t)novl + 1), cudaMemcpyHostToDevice, st), "trace_off H2D"));
             if (tb > 0) HG_TRY(cuda_check(c, cudaMemcpyAsync(c->d_trace, trace, (size_t)tb, cudaMemcpyHostToDevice, st), "trace H2D"));
         }
@@ -271,17 +293,25 @@ int hg_set_overlaps(hg_ctx* c, int64_t novl, const int32_t* aread, const int32_t
         if (warps * slot > budget) warps = std::max<size_t>(4, budget / slot);
         warps = std::max<size_t>(4, warps & ~(size_t)3);
         s.hinge_warps = (int)warps;
-        HG_TRY(dev_alloc(c, &s.hinge_scratch, warps * slot, "hinge scratch"));
+        if (warps * slot > c->cap_hinge_scratch) {
+            HG_TRY(dev_alloc(c, &s.hinge_scratch, warps * slot, "hinge scratch"));
+            c->cap_hinge_scratch = warps * slot;
+        }
     }
     c->filter_done = false;
+    c->shape_version++;
     return HG_OK;
 }
 
 static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
     if (p->reso <= 0 || p->coverage_fraction == 0)
         return set_err(c, HG_ERR_ARG, "reso must be > 0 and coverage_frac_repeat_annotation != 0");
+    if (c->filter_params_set && c->configured_shape == c->shape_version &&
+        memcmp(&c->fp, p, sizeof(*p)) == 0)
+        return HG_OK;  // same parameters, same data shape: launch configuration is still valid
     c->fp = *p;
     c->filter_params_set = true;
+    c->configured_shape = c->shape_version;
     FilterScratch& s = c->fs;
     auto bins = [&](int rlen) { return (rlen + std::max(p->cut_off, 0)) / p->reso + 3; };
     mask_anno_configure(s, bins(c->rlen_q999));
@@ -300,7 +330,9 @@ int hg_filter_phase1(hg_ctx* c, const hg_filter_params* p) {
     cudaSetDevice(c->device);
     HG_TRY(configure_filter(c, p));
     cudaEventRecord(c->ev0, c->stream);
+    c->mark(0);
     launch_cov_estimate(c->rec_view(), c->read_view(), c->fp, c->r_begin, c->r_end, c->fs, c->stream);
+    c->mark(1);
     return cuda_check(c, cudaGetLastError(), "filter phase 1");
 }
 
@@ -325,9 +357,12 @@ int hg_filter_phase2(hg_ctx* c) {
         HG_TRY(cuda_check(c, cudaMemcpyAsync(c->d_cov0_off, c->h_cov0_off.data(), 8 * ((size_t)c->n_read + 1), cudaMemcpyHostToDevice, st), "H2D"));
         cov0 = c->d_cov0;
     }
+    c->mark(2);
     launch_median(c->read_view(), c->fp, s, st);
+    c->mark(3);
     launch_mask_anno(c->rec_view(), c->read_view(), c->fp, c->r_begin, c->r_end, s, cov0,
                      c->d_cov0_off, st);
+    c->mark(4);
     return cuda_check(c, cudaGetLastError(), "filter phase 2");
 }
 
@@ -336,7 +371,9 @@ int hg_filter_phase3(hg_ctx* c, hg_filter_summary* out) {
     cudaSetDevice(c->device);
     cudaStream_t st = c->stream;
     FilterScratch& s = c->fs;
+    c->mark(5);
     launch_hinge_call(c->rec_view(), c->read_view(), c->fp, s, st);
+    c->mark(6);
     cudaEventRecord(c->ev1, st);
     int cnt[8], scal[8];
     HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, s.counters, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
@@ -370,6 +407,33 @@ int hg_filter(hg_ctx* c, const hg_filter_params* p, hg_filter_summary* out) {
         HG_TRY(alloc_anno_pool(c, std::max(used + (1 << 16), c->fs.anno_cap * 2)));
     }
     return set_err(c, HG_ERR_NOMEM, "annotation pool kept overflowing");
+}
+
+// ms[0..3] = coverage estimate (K1), median, mask + annotation (K2), hinge calls (K4)
+int hg_filter_kernel_times(hg_ctx* c, float* ms, int n) {
+    if (!c || !c->profile || !c->filter_done) return set_err(c, HG_ERR_ARG, "profiling is off");
+    const int pairs[4][2] = {{0, 1}, {2, 3}, {3, 4}, {5, 6}};
+    for (int i = 0; i < n && i < 4; i++) cudaEventElapsedTime(&ms[i], c->marks[pairs[i][0]], c->marks[pairs[i][1]]);
+    return HG_OK;
+}
+
+int64_t hg_launch_count(void) { return hg::g_launches; }
+
+int hg_bind_buffer(hg_ctx* c, int which, void* dptr, int64_t bytes) {
+    if (!c || !dptr || c->n_read <= 0) return HG_ERR_ARG;
+    if (which == HG_BUF_MEAN_COV && bytes >= 4ll * c->n_read) {
+        if (!c->ext_mean_cov) cudaFree(c->fs.mean_cov);
+        c->fs.mean_cov = (int*)dptr;
+        c->ext_mean_cov = true;
+        return HG_OK;
+    }
+    if (which == HG_BUF_MASK && bytes >= 8ll * c->n_read) {
+        if (!c->ext_mask) cudaFree(c->fs.mask);
+        c->fs.mask = (int2*)dptr;
+        c->ext_mask = true;
+        return HG_OK;
+    }
+    return set_err(c, HG_ERR_ARG, "hg_bind_buffer: unknown buffer or too small");
 }
 
 int hg_device_buffer(hg_ctx* c, int which, void** dptr, int64_t* bytes) {

@@ -37,21 +37,34 @@ struct hg_ctx {
     int64_t* d_read_off = nullptr;
     int* d_err = nullptr;
     int a_lo = 0, a_hi = 0, r_begin = 0, r_end = -1, max_pileup = 0;
+    int64_t cap_novl = 0, cap_trace = 0;  // capacity of the owned record buffers
+    size_t cap_hinge_scratch = 0;
 
     // filter
     hg::FilterScratch fs;
     hg_filter_params fp;
     bool filter_params_set = false, filter_done = false;
+    int shape_version = 0, configured_shape = -1;
     int keep_cov = 0;
     int* d_cov0 = nullptr;
     int64_t* d_cov0_off = nullptr;
     std::vector<int64_t> h_cov0_off;
+
+    // per-kernel timing (HG_OPT_PROFILE): events between the launches of a stage
+    static constexpr int kMarks = 16;
+    bool profile = false;
+    cudaEvent_t marks[kMarks] = {};
+    void mark(int i) {
+        if (profile) cudaEventRecord(marks[i], stream);
+    }
+    bool ext_mean_cov = false, ext_mask = false;  // bound to caller-owned memory
 
     hg::RecView rec_view() const;
     hg::ReadView read_view() const;
 };
 
 namespace hg {
+extern int64_t g_launches;  // kernels launched by this library (all contexts)
 int set_err(hg_ctx* c, int code, const std::string& msg);
 int cuda_check(hg_ctx* c, cudaError_t e, const char* what);
 template <typename T>

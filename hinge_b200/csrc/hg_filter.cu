@@ -19,6 +19,8 @@
 
 namespace hg {
 
+int64_t g_launches = 0;
+
 // ------------------------------------------------------------------ K0
 
 __global__ void k_csr_validate(RecView rv, ReadView rd, int64_t* read_off, int* err) {
@@ -721,11 +723,13 @@ static inline int ceil_div64(int64_t a, int b) { return (int)((a + b - 1) / b); 
 void launch_csr_validate(const RecView& rv, const ReadView& rd, int64_t* read_off, int* err,
                          cudaStream_t st) {
     k_csr_validate<<<ceil_div64(rv.novl + 1, 256), 256, 0, st>>>(rv, rd, read_off, err);
+    g_launches += 1;
 }
 
 void launch_qv_mask(int n_read, const int64_t* qv_off, const uint8_t* qv, int tspace, int2* out,
                     cudaStream_t st) {
     k_qv_mask<<<ceil_div64(n_read, 128), 128, 0, st>>>(n_read, qv_off, qv, tspace, out);
+    g_launches += 1;
 }
 
 void launch_cov_estimate(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
@@ -743,6 +747,7 @@ void launch_cov_estimate(const RecView& rv, const ReadView& rd, const hg_filter_
             k_cov_accum<1><<<ceil_div64(rv.novl, 256), 256, 0, st>>>(rv, P.reso, s.cov_sum,
                                                                       s.cov_maxbin, s.self_cnt);
     }
+    g_launches += (rv.novl > 0) + 1;
     const int owned = rd.r_hi - rd.r_lo;
     if (owned > 0)
         k_cov_finalize<<<ceil_div64(owned, 256), 256, 0, st>>>(rv, rd, r_begin, r_end, s.cov_sum,
@@ -753,6 +758,7 @@ void launch_cov_estimate(const RecView& rv, const ReadView& rd, const hg_filter_
 void launch_median(const ReadView& rd, const hg_filter_params& P, FilterScratch& s,
                    cudaStream_t st) {
     cudaMemsetAsync(s.med_hist, 0, sizeof(unsigned int) * (4097 + 4096), st);
+    g_launches += 8;
     k_median_hist<<<148 * 2, 256, 0, st>>>(s.mean_cov, rd.n_read, s.med_hist);
     k_median_pick<<<1, 32, 0, st>>>(s.med_hist, P.est_cov, P.min_cov, s.scal);
     for (int pass = 0; pass < 3; pass++) {  // no-ops unless the median is >= 4095
@@ -791,6 +797,7 @@ void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_par
     cudaMemsetAsync(s.anno_ref, 0, sizeof(int2) * rd.n_read, st);
     cudaMemsetAsync(s.hinge_keep, 0, (size_t)s.anno_cap, st);
     const int smem = s.nb_cap * 4 * kMaskAnnoWarps;
+    g_launches += 1 + (s.big_slot_words > 0);
     k_mask_anno<kMaskAnnoWarps><<<s.mask_anno_grid, kMaskAnnoWarps * 32, smem, st>>>(
         rv, rd, P, s.scal, r_begin, r_end, s.nb_cap, out);
     if (s.big_slot_words > 0)
@@ -801,11 +808,13 @@ void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_par
 void launch_max_pileup(const int64_t* read_off, int n_read, int* out_max, cudaStream_t st) {
     cudaMemsetAsync(out_max, 0, sizeof(int), st);
     k_max_pileup<<<148 * 2, 256, 0, st>>>(read_off, n_read, out_max);
+    g_launches += 1;
 }
 
 void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
                        FilterScratch& s, cudaStream_t st) {
     if (s.hinge_cap <= 0) return;
+    g_launches += 1;
     k_hinge_call<<<s.hinge_warps / 4, 128, 0, st>>>(rv, rd, P, s.mask, s.anno_ref, s.anno_pool,
                                                     s.counters, s.work_list, s.hinge_keep,
                                                     s.hinge_scratch, s.hinge_cap);

@@ -41,7 +41,8 @@ enum { HG_MEM_HOST = 0, HG_MEM_DEVICE = 1 };
 #define HG_RETRY_POOL 1
 
 enum hg_option {
-    HG_OPT_KEEP_COVERAGE = 1 /* keep the 40-bp coverage profiles (.coverage.txt) */
+    HG_OPT_KEEP_COVERAGE = 1, /* keep the 40-bp coverage profiles (.coverage.txt) */
+    HG_OPT_PROFILE = 2        /* record CUDA events between the kernels of a stage */
 };
 
 enum hg_buffer { /* per-read device arrays a sharded run exchanges between phases */
@@ -61,6 +62,14 @@ int hg_set_option(hg_ctx* ctx, int option, int64_t value);
 /* Device address and size of a per-read array (rows of reads outside the
  * context's [a_lo, a_hi) are the caller's to fill, e.g. by an NCCL all-gather). */
 int hg_device_buffer(hg_ctx* ctx, int which, void** dptr, int64_t* bytes);
+/* Make the context use caller-owned device memory for a per-read array (so a
+ * framework tensor can be all-gathered in place); call after hg_set_reads. */
+int hg_bind_buffer(hg_ctx* ctx, int which, void* dptr, int64_t bytes);
+/* Device time of the filter kernels of the last run (needs HG_OPT_PROFILE):
+ * ms[0] coverage estimate, [1] median, [2] mask + annotation, [3] hinge calls. */
+int hg_filter_kernel_times(hg_ctx* ctx, float* ms, int n);
+/* Number of kernels this library has launched so far (process-wide). */
+int64_t hg_launch_count(void);
 
 /* ---- inputs ----------------------------------------------------------- */
 
