@@ -39,7 +39,8 @@ class LayoutParamsC(C.Structure):
 
 class FilterSummaryC(C.Structure):
     _fields_ = [("r_begin", i32), ("r_end", i32), ("cov_est", i32), ("min_cov", i32),
-                ("n_annotations", i64), ("n_hinges", i64), ("ms_device", C.c_float)]
+                ("n_annotations", i64), ("n_hinges", i64), ("ms_device", C.c_float),
+                ("n_exact_order", i32)]
 
 
 class EdgeC(C.Structure):

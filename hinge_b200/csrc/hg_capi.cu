@@ -284,10 +284,10 @@ int hg_set_overlaps(hg_ctx* c, int64_t novl, const int32_t* aread, const int32_t
     // scratch that depends on the shape of the data
     FilterScratch& s = c->fs;
     if (s.anno_cap == 0) HG_TRY(alloc_anno_pool(c, 2 * (a_hi - a_lo) + (1 << 16)));
-    // K4: one slot of 32 B per pile-up record and warp
-    s.hinge_cap = std::max(c->max_pileup, 32);
+    // K4: one slot of 40 B per pile-up record and warp
+    s.hinge_cap = (std::max(c->max_pileup, 32) + 3) & ~3;  // keeps every slot 16-byte aligned
     {
-        const size_t slot = (size_t)s.hinge_cap * 32;
+        const size_t slot = (size_t)s.hinge_cap * 40;
         size_t warps = (size_t)c->num_sms * 16;
         const size_t budget = (size_t)768 << 20;
         if (warps * slot > budget) warps = std::max<size_t>(4, budget / slot);
@@ -304,8 +304,8 @@ int hg_set_overlaps(hg_ctx* c, int64_t novl, const int32_t* aread, const int32_t
 }
 
 static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
-    if (p->reso <= 0 || p->coverage_fraction == 0)
-        return set_err(c, HG_ERR_ARG, "reso must be > 0 and coverage_frac_repeat_annotation != 0");
+    if (p->reso != kReso || p->coverage_fraction == 0)
+        return set_err(c, HG_ERR_ARG, "reso is fixed at 40 (filter.cpp:386) and coverage_frac_repeat_annotation must be != 0");
     if (c->filter_params_set && c->configured_shape == c->shape_version &&
         memcmp(&c->fp, p, sizeof(*p)) == 0)
         return HG_OK;  // same parameters, same data shape: launch configuration is still valid
@@ -388,6 +388,7 @@ int hg_filter_phase3(hg_ctx* c, hg_filter_summary* out) {
         out->min_cov = scal[1];
         out->n_annotations = cnt[0];
         out->n_hinges = -1;
+        out->n_exact_order = cnt[4];
         float ms = 0;
         cudaEventElapsedTime(&ms, c->ev0, c->ev1);
         out->ms_device = ms;
@@ -481,7 +482,10 @@ int hg_filter_fetch(hg_ctx* c, int32_t* mask, int32_t* cmask, uint8_t* flags, in
         }
         anno_off[n] = o;
     }
-    return cuda_check(c, cudaStreamSynchronize(st), "hg_filter_fetch");
+    HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "hg_filter_fetch"));
+    if (flags)  // internal bits (hinge pre-test) stay inside the library
+        for (int i = 0; i < n; i++) flags[i] &= (kFlagCov | kFlagSelf);
+    return HG_OK;
 }
 
 int hg_filter_coverage(hg_ctx* c, int64_t* cov_off, int32_t* cov, int64_t* n_bins) {

@@ -32,6 +32,11 @@ struct ReadView {
     const int2* __restrict__ qvmask;  // (start, end) of the longest good-QV run
 };
 
+// Resolution of coverage profiles, masks and annotations: hard-coded in the
+// reference (filter.cpp:386 `int reso = 40`), a compile-time constant here so
+// the divisions become multiplies.
+constexpr int kReso = 40;
+
 // bin of an event position on the 40-bp grid: profileCoverage emits entry i
 // once every event with pos < i*reso has been consumed
 // (/root/reference/src/lib/LAInterface.cpp:4309-4317)

@@ -83,7 +83,7 @@ __global__ void k_qv_mask(int n_read, const int64_t* __restrict__ qv_off,
 // atomic per (warp, read).
 template <int VEC>
 __global__ void __launch_bounds__(256)
-k_cov_accum(RecView rv, int reso, unsigned long long* __restrict__ cov_sum,
+k_cov_accum(RecView rv, unsigned long long* __restrict__ cov_sum,
             int* __restrict__ cov_maxbin, int* __restrict__ self_cnt) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t k0 = t * VEC;
@@ -114,7 +114,7 @@ k_cov_accum(RecView rv, int reso, unsigned long long* __restrict__ cov_sum,
         }
     }
     int key = -2, mx = -1;
-    long long acc = 0;
+    unsigned acc = 0;  // per-warp partial: <= 128 records x bins, far below 2^32
 #pragma unroll
     for (int i = 0; i < VEC; i++) {
         if (a[i] != key) {
@@ -128,8 +128,8 @@ k_cov_accum(RecView rv, int reso, unsigned long long* __restrict__ cov_sum,
         }
         if (a[i] >= 0) {
             if (a[i] != b[i]) {
-                const int be = cov_bin(e[i], reso);
-                acc += be - cov_bin(s[i], reso);
+                const int be = cov_bin(e[i], kReso);
+                acc += (unsigned)(be - cov_bin(s[i], kReso));
                 mx = max(mx, be);
             } else {
                 atomicAdd(&self_cnt[a[i]], 1);
@@ -141,7 +141,7 @@ k_cov_accum(RecView rv, int reso, unsigned long long* __restrict__ cov_sum,
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const int okey = __shfl_up_sync(0xffffffffu, key, d);
-        const long long oacc = __shfl_up_sync(0xffffffffu, acc, d);
+        const unsigned oacc = __shfl_up_sync(0xffffffffu, acc, d);
         const int omx = __shfl_up_sync(0xffffffffu, mx, d);
         if (lane >= d && okey == key) {
             acc += oacc;
@@ -296,7 +296,7 @@ __device__ void mask_anno_read(const RecView& rv, const ReadView& rd, const hg_f
                                const MaskAnnoOut& out) {
     typedef Packed<W> PK;
     const int lane = lane_id();
-    const int reso = P.reso;
+    constexpr int reso = kReso;
     const int64_t o0 = rv.read_off[read], o1 = rv.read_off[read + 1];
 
     for (int j = lane; j < nbz; j += 32) hist[j] = 0;
@@ -510,7 +510,7 @@ __device__ void mask_anno_read(const RecView& rv, const ReadView& rd, const hg_f
 }
 
 __device__ __forceinline__ int bins_needed(int rlen, const hg_filter_params& P) {
-    return (rlen + max(P.cut_off, 0)) / P.reso + 3;
+    return (rlen + max(P.cut_off, 0)) / kReso + 3;
 }
 
 template <int WARPS>
@@ -565,21 +565,127 @@ struct FirstDesc {
     __device__ bool operator()(const int2& a, const int2& b) const { return a.x > b.x; }
 };
 
-// One warp per annotated read.  Scratch slot layout (cap records each):
-//   KeyIdx ord[cap] | int2 ends[cap] | int4 rec[cap] = (astart, aend, left_oh, right_oh)
+// One pile-up record as the hinge call sees it (filter.cpp:877-890): A interval,
+// overhangs of B beyond the match w.r.t. B's mask (swapped for complemented
+// matches) and the sort key of compare_overlap (LAInterface.cpp:4884).
+struct PileRec {
+    int as, ae, lo, ro, key;
+    bool active;
+};
+__device__ __forceinline__ PileRec load_pile_rec(const RecView& rv, const ReadView& rd,
+                                                 const int2* __restrict__ mask, int read, int64_t k) {
+    PileRec r;
+    const int b = __ldg(rv.bread + k);
+    r.active = b != read;  // A == B records are inactive (filter.cpp:538-547)
+    r.as = __ldg(rv.abpos + k);
+    r.ae = __ldg(rv.aepos + k);
+    const int comp = __ldg(rv.flags + k) & 1;
+    int bs = __ldg(rv.bbpos + k), be = __ldg(rv.bepos + k);
+    if (comp) {  // B to its forward strand, LAInterface.cpp:1619-1626
+        const int bl = __ldg(rd.rlen + b);
+        const int t = bl - be;
+        be = bl - bs;
+        bs = t;
+    }
+    const int2 mb = mask[b];
+    const int r0 = max(mb.y - be, 0), l0 = max(bs - mb.x, 0);
+    r.ro = comp ? l0 : r0;
+    r.lo = comp ? r0 : l0;
+    r.key = (r.ae - r.as) + (be - bs);
+    return r;
+}
+
+// Selection test of one record for one annotation (filter.cpp:894-907, 991-1003):
+// out-hinge (-1): B keeps going right of its match and ends on A at the
+// annotation -> (astart, left overhang); in-hinge (+1) mirrored.
+__device__ __forceinline__ bool hinge_select(const PileRec& r, bool out_hinge, int apos, int THETA,
+                                             int HTL, int2* e) {
+    if (out_hinge) {
+        *e = make_int2(r.as, r.lo);
+        return r.ro > THETA && r.ae > apos - HTL && r.ae < apos + HTL;
+    }
+    *e = make_int2(r.ae, r.ro);
+    return r.lo > THETA && r.as > apos - HTL && r.as < apos + HTL;
+}
+
+// Bridged / unbridged walk over the sorted end list (filter.cpp:916-965,
+// 1013-1065); returns true when the annotation is a hinge.
+__device__ bool hinge_walk(const int2* ends, int support, bool out_hinge, int2 mk,
+                           const hg_filter_params& P) {
+    const int THETA = P.theta, HBL = P.hinge_bin_length, U = P.hinge_read_unbridged_threshold;
+    bool bridged = true;
+    int considered = 0, to_end = 0;
+    const int first0 = ends[0].x;
+    for (int id = 0; id < support; ++id) {
+        const int f = ends[id].x, oh = ends[id].y;
+        const int dist_end = out_hinge ? f - mk.x : mk.y - f;
+        const int dist0 = out_hinge ? f - first0 : first0 - f;
+        if (dist_end < HBL) {
+            considered++;
+            to_end++;
+            if (to_end > U || (considered > U && dist0 > HBL)) {
+                bridged = false;
+                break;
+            }
+        } else if (oh < THETA) {
+            considered++;
+            if (to_end > U || (considered > U && dist0 > HBL)) {
+                bridged = false;
+                break;
+            }
+        } else if (oh > THETA) {
+            considered++;
+            int pl = 1;
+            for (int id1 = id + 1; id1 < support; id1++) {
+                const int g = out_hinge ? ends[id1].x - f : f - ends[id1].x;
+                if (g < HBL)
+                    pl++;
+                else
+                    break;
+            }
+            if (pl > P.hinge_bin_pileup_threshold) {
+                bridged = true;
+                break;
+            }
+        }
+    }
+    return !bridged && support > P.hinge_min_support;
+}
+
+// What the walk can tell apart: reads reaching the mask end (1), small overhang
+// (2), internal (3), overhang == theta (0, ignored by the reference's if-chain).
+__device__ __forceinline__ int hinge_class(int2 e, bool out_hinge, int2 mk, int THETA, int HBL) {
+    const int dist_end = out_hinge ? e.x - mk.x : mk.y - e.x;
+    if (dist_end < HBL) return 1;
+    return e.y < THETA ? 2 : (e.y > THETA ? 3 : 0);
+}
+
+// One warp per annotated read.  The reference feeds the walk with the selected
+// records in the order left by two unstable std::sorts (pile-up by length, then
+// the end list by position).  The walk only distinguishes entries by (position,
+// class), so whenever no two selected entries share a position with different
+// classes ANY sort by position yields the reference's result: that is the fast
+// path (warp rank sort, no pile-up sort at all).  Otherwise the annotation goes
+// through the order-exact path: libstdc++'s introsort restated (hg_order.h) on
+// the pile-up and on the end list.
+//
+// Scratch slot per warp (cap = deepest pile-up):
+//   int4 rec[cap] | KeyIdx ord[cap] | int2 ends[cap] | int2 sorted[cap]
+constexpr int kHingeSlotBytesPerRec = 16 + 8 + 8 + 8;
+
 __global__ void __launch_bounds__(128)
 k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict__ mask,
              const int2* __restrict__ anno_ref, const int2* __restrict__ anno_pool,
-             const int* __restrict__ counters, const int* __restrict__ work_list,
+             int* __restrict__ counters, const int* __restrict__ work_list,
              uint8_t* __restrict__ hinge_keep, uint8_t* scratch, int cap) {
     const int lane = lane_id();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const size_t slot = (size_t)cap * (sizeof(KeyIdx) + sizeof(int2) + sizeof(int4));
-    uint8_t* base = scratch + (size_t)warp * slot;
+    uint8_t* base = scratch + (size_t)warp * cap * kHingeSlotBytesPerRec;
     int4* rec = reinterpret_cast<int4*>(base);
-    KeyIdx* ord = reinterpret_cast<KeyIdx*>(base + (size_t)cap * sizeof(int4));
-    int2* ends = reinterpret_cast<int2*>(base + (size_t)cap * (sizeof(int4) + sizeof(KeyIdx)));
+    KeyIdx* ord = reinterpret_cast<KeyIdx*>(base + (size_t)cap * 16);
+    int2* ends = reinterpret_cast<int2*>(base + (size_t)cap * 24);
+    int2* sorted = reinterpret_cast<int2*>(base + (size_t)cap * 32);
     const int nwork = counters[1];
     const int THETA = P.theta, HTL = P.hinge_tolerance_length, HBL = P.hinge_bin_length;
 
@@ -587,68 +693,22 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
         const int read = work_list[w];
         const int64_t o0 = rv.read_off[read], o1 = rv.read_off[read + 1];
         const int2 mk = mask[read];
-        // ---- gather the active pile-up in file order (filter.cpp:537-548, 877-890)
-        int n = 0;
-        for (int64_t kb = o0; kb < o1; kb += 32) {
-            const int64_t k = kb + lane;
-            bool act = false;
-            int as = 0, ae = 0, lo = 0, ro = 0, key = 0;
-            if (k < o1) {
-                const int b = rv.bread[k];
-                if (b != read) {
-                    act = true;
-                    as = rv.abpos[k];
-                    ae = rv.aepos[k];
-                    const int comp = rv.flags[k] & 1;
-                    int bs = rv.bbpos[k], be = rv.bepos[k];
-                    if (comp) {  // LAInterface.cpp:1619-1626
-                        const int bl = rd.rlen[b];
-                        const int t = bl - be;
-                        be = bl - bs;
-                        bs = t;
-                    }
-                    const int2 mb = mask[b];
-                    const int r0 = max(mb.y - be, 0), l0 = max(bs - mb.x, 0);
-                    ro = comp ? l0 : r0;
-                    lo = comp ? r0 : l0;
-                    key = (ae - as) + (be - bs);
-                }
-            }
-            const unsigned am = __ballot_sync(0xffffffffu, act);
-            if (act) {
-                const int s = n + __popc(am & ((1u << lane) - 1u));
-                rec[s] = make_int4(as, ae, lo, ro);
-                ord[s].key = key;
-                ord[s].idx = s;
-            }
-            n += __popc(am);
-        }
-        __syncwarp();
-        // ---- the pile-up order the reference sees: std::sort by total length,
-        // descending, unstable (filter.cpp:565-567)
-        if (lane == 0) std_sort_exact(ord, n, GreaterKey());
-        __syncwarp();
-
         const int2 ar = anno_ref[read];
+        bool have_exact_order = false;
+        int n_exact = 0;
         for (int j = 0; j < ar.y; j++) {
             const int2 an = anno_pool[ar.x + j];
             const int apos = an.x;
             const bool out_hinge = an.y == -1;
-            // ---- reads starting / ending at the annotation, in pile-up order
+            // ---- select in file order
             int support = 0;
-            for (int kb = 0; kb < n; kb += 32) {
-                const int k = kb + lane;
+            for (int64_t kb = o0; kb < o1; kb += 32) {
+                const int64_t k = kb + lane;
                 bool sel = false;
                 int2 e = make_int2(0, 0);
-                if (k < n) {
-                    const int4 r = rec[ord[k].idx];
-                    if (out_hinge) {
-                        sel = r.w > THETA && r.y > apos - HTL && r.y < apos + HTL;
-                        e = make_int2(r.x, r.z);
-                    } else {
-                        sel = r.z > THETA && r.x > apos - HTL && r.x < apos + HTL;
-                        e = make_int2(r.y, r.w);
-                    }
+                if (k < o1) {
+                    const PileRec r = load_pile_rec(rv, rd, mask, read, k);
+                    sel = r.active && hinge_select(r, out_hinge, apos, THETA, HTL, &e);
                 }
                 const unsigned sm = __ballot_sync(0xffffffffu, sel);
                 if (sel) ends[support + __popc(sm & ((1u << lane) - 1u))] = e;
@@ -656,51 +716,82 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
             }
             __syncwarp();
             uint8_t keep = 0;
-            if (lane == 0 && support >= P.hinge_min_support) {
-                if (out_hinge)
-                    std_sort_exact(ends, support, FirstAsc());
-                else
-                    std_sort_exact(ends, support, FirstDesc());
-                // ---- bridged / unbridged walk (filter.cpp:916-965, 1013-1065)
-                bool bridged = true;
-                int considered = 0, to_end = 0;
-                const int first0 = ends[0].x;
-                for (int id = 0; id < support; ++id) {
-                    const int f = ends[id].x, oh = ends[id].y;
-                    const int dist_end = out_hinge ? f - mk.x : mk.y - f;
-                    const int dist0 = out_hinge ? f - first0 : first0 - f;
-                    if (dist_end < HBL) {
-                        considered++;
-                        to_end++;
-                        if (to_end > P.hinge_read_unbridged_threshold ||
-                            (considered > P.hinge_read_unbridged_threshold && dist0 > HBL)) {
-                            bridged = false;
-                            break;
+            if (support >= P.hinge_min_support) {  // filter.cpp:910, 1005
+                // ---- stable rank sort by position (ascending for out-hinges, descending for
+                // in-hinges) and detection of position ties the walk could tell apart
+                bool danger = support > 1024;
+                if (!danger) {
+                    for (int i = lane; i < support; i += 32) {
+                        const int2 me = ends[i];
+                        int rank = 0;
+                        for (int t = 0; t < support; t++) {
+                            const int x = ends[t].x;
+                            const bool before = out_hinge ? x < me.x : x > me.x;
+                            rank += (before || (x == me.x && t < i)) ? 1 : 0;
                         }
-                    } else if (oh < THETA) {
-                        considered++;
-                        if (to_end > P.hinge_read_unbridged_threshold ||
-                            (considered > P.hinge_read_unbridged_threshold && dist0 > HBL)) {
-                            bridged = false;
-                            break;
+                        sorted[rank] = me;
+                    }
+                    __syncwarp();
+                    bool d = false;
+                    for (int i = lane; i + 1 < support; i += 32) {
+                        const int2 a = sorted[i], b = sorted[i + 1];
+                        d = d || (a.x == b.x && hinge_class(a, out_hinge, mk, THETA, HBL) !=
+                                                    hinge_class(b, out_hinge, mk, THETA, HBL));
+                    }
+                    danger = __any_sync(0xffffffffu, d);
+                }
+                if (!danger) {
+                    if (lane == 0) keep = hinge_walk(sorted, support, out_hinge, mk, P) ? 1 : 0;
+                } else {
+                    // ---- order-exact path.  Pile-up in file order, then std::sort by total
+                    // length, descending (filter.cpp:565-567), once per read
+                    if (!have_exact_order) {
+                        int n = 0;
+                        for (int64_t kb = o0; kb < o1; kb += 32) {
+                            const int64_t k = kb + lane;
+                            PileRec r;
+                            r.active = false;
+                            if (k < o1) r = load_pile_rec(rv, rd, mask, read, k);
+                            const unsigned am = __ballot_sync(0xffffffffu, r.active);
+                            if (r.active) {
+                                const int s = n + __popc(am & ((1u << lane) - 1u));
+                                rec[s] = make_int4(r.as, r.ae, r.lo, r.ro);
+                                ord[s].key = r.key;
+                                ord[s].idx = s;
+                            }
+                            n += __popc(am);
                         }
-                    } else if (oh > THETA) {
-                        considered++;
-                        int pl = 1;
-                        for (int id1 = id + 1; id1 < support; id1++) {
-                            const int g = out_hinge ? ends[id1].x - f : f - ends[id1].x;
-                            if (g < HBL)
-                                pl++;
-                            else
-                                break;
+                        __syncwarp();
+                        if (lane == 0) std_sort_exact(ord, n, GreaterKey());
+                        __syncwarp();
+                        have_exact_order = true;
+                        n_exact = n;
+                    }
+                    int sup2 = 0;
+                    for (int kb = 0; kb < n_exact; kb += 32) {
+                        const int k = kb + lane;
+                        bool sel = false;
+                        int2 e = make_int2(0, 0);
+                        if (k < n_exact) {
+                            const int4 q = rec[ord[k].idx];
+                            PileRec r;
+                            r.as = q.x; r.ae = q.y; r.lo = q.z; r.ro = q.w; r.key = 0; r.active = true;
+                            sel = hinge_select(r, out_hinge, apos, THETA, HTL, &e);
                         }
-                        if (pl > P.hinge_bin_pileup_threshold) {
-                            bridged = true;
-                            break;
-                        }
+                        const unsigned sm = __ballot_sync(0xffffffffu, sel);
+                        if (sel) ends[sup2 + __popc(sm & ((1u << lane) - 1u))] = e;
+                        sup2 += __popc(sm);
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (out_hinge)
+                            std_sort_exact(ends, sup2, FirstAsc());  // filter.cpp:914
+                        else
+                            std_sort_exact(ends, sup2, FirstDesc());  // filter.cpp:1010
+                        keep = hinge_walk(ends, sup2, out_hinge, mk, P) ? 1 : 0;
+                        atomicAdd(&counters[4], 1);
                     }
                 }
-                keep = (!bridged && support > P.hinge_min_support) ? 1 : 0;
             }
             if (lane == 0) hinge_keep[ar.x + j] = keep;
             __syncwarp();
@@ -742,9 +833,9 @@ void launch_cov_estimate(const RecView& rv, const ReadView& rd, const hg_filter_
     if (rv.novl > 0) {
         if (aligned)
             k_cov_accum<4><<<ceil_div64((rv.novl + 3) / 4, 256), 256, 0, st>>>(
-                rv, P.reso, s.cov_sum, s.cov_maxbin, s.self_cnt);
+                rv, s.cov_sum, s.cov_maxbin, s.self_cnt);
         else
-            k_cov_accum<1><<<ceil_div64(rv.novl, 256), 256, 0, st>>>(rv, P.reso, s.cov_sum,
+            k_cov_accum<1><<<ceil_div64(rv.novl, 256), 256, 0, st>>>(rv, s.cov_sum,
                                                                       s.cov_maxbin, s.self_cnt);
     }
     g_launches += (rv.novl > 0) + 1;

@@ -109,6 +109,7 @@ typedef struct hg_filter_summary {
     int64_t n_annotations;   /* "Number of hinges before filtering" */
     int64_t n_hinges;        /* "Number of hinges" (reads r_begin..r_end-1) */
     float ms_device;         /* device time of the whole stage, CUDA events */
+    int32_t n_exact_order;   /* annotations that needed the order-exact sort path */
 } hg_filter_summary;
 
 /* One call = the whole stage on the device, no host round trip in between:

@@ -1,0 +1,81 @@
+"""Array-level parity of hg_filter (C ABI, through the Python mirror) with the
+oracle on in-memory synthetic batches, including tie-heavy data that drives the
+hinge call through its order-exact sort path, sharded runs, and edge cases."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def _run_both(built, synth_kw, a_ranges=None):
+    import hgsynth
+    import oraclelib
+    from hinge_b200 import api
+
+    s = hgsynth.Synth(**synth_kw)
+    s.generate(want_trace=False, threads=4)
+    cols = {k: v.copy() for k, v in s.cols().items()}
+    rlen, qv_off, qv = s.rlen.copy(), s.qv_off.copy(), s.qv.copy()
+    orc = oraclelib.Oracle(rlen, qv_off, qv, 100, cols)
+    want = orc.filter()
+    orc.close()
+    ctx = api.Context(0)
+    ctx.set_reads(rlen, qv_off, qv, 100)
+    ctx.set_overlaps(len(cols["aread"]), cols)
+    summ = ctx.filter(api.FilterParams())
+    got = ctx.filter_fetch(int(summ.n_annotations))
+    ctx.close()
+    s.close()
+    return got, want, summ
+
+
+def _assert_equal(got, want, summ):
+    assert (summ.r_begin, summ.r_end, summ.cov_est, summ.min_cov) == tuple(want["summary"])
+    for k in ("mask", "cmask", "flags", "anno_off", "anno_pos", "anno_type", "hinge_keep"):
+        np.testing.assert_array_equal(got[k], want[k], err_msg=k)
+
+
+def test_filter_arrays_match_oracle(built):
+    got, want, summ = _run_both(built, dict(genome_len=600000, coverage=40.0, seed=77, n_families=4))
+    _assert_equal(got, want, summ)
+    assert want["hinge_keep"].sum() > 0, "fixture should call hinges"
+
+
+def test_tie_heavy_data_uses_order_exact_path(built):
+    # no end jitter: every repeat-induced alignment starts exactly on the repeat
+    # boundary, and reads longer than the repeats see both boundaries, so end lists
+    # are full of equal positions with different overhang classes
+    got, want, summ = _run_both(built, dict(genome_len=500000, coverage=60.0, seed=5, n_families=8, jitter=0,
+                                           read_mean=8000, read_sd=2500, read_min=2000,
+                                           rep_min_len=1500, rep_max_len=3500, rep_min_copies=3,
+                                           rep_max_copies=6))
+    _assert_equal(got, want, summ)
+    assert summ.n_exact_order > 0, "expected position ties that need the order-exact sort"
+
+
+def test_long_reads_take_the_big_histogram_path(built):
+    # a few reads far longer than the 99.9th percentile exceed the shared-memory histogram
+    got, want, summ = _run_both(built, dict(genome_len=400000, coverage=30.0, seed=9, read_mean=4000,
+                                           read_sd=6000, read_min=1000, read_max=120000, n_families=2))
+    _assert_equal(got, want, summ)
+
+
+def test_records_out_of_order_are_rejected(built):
+    from hinge_b200 import api, HingeError
+
+    rlen = np.array([5000, 6000, 7000], np.int32)
+    cols = {"aread": np.array([1, 0], np.int32), "bread": np.array([0, 1], np.int32),
+            "abpos": np.array([0, 0], np.int32), "aepos": np.array([2000, 2000], np.int32),
+            "bbpos": np.array([0, 0], np.int32), "bepos": np.array([2000, 2000], np.int32),
+            "flags": np.array([0, 0], np.int32)}
+    ctx = api.Context(0)
+    ctx.set_reads(rlen)
+    with pytest.raises(HingeError):
+        ctx.set_overlaps(2, cols)
+    ctx.close()

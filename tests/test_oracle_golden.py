@@ -1,0 +1,34 @@
+"""The oracle is only worth something if it IS the reference: its output files
+must equal, byte for byte, what the unmodified reference binaries wrote for the
+committed fixtures (tests/golden, made by make_golden.py), and — where the
+reference binaries are available (oracle/_ref) — what they write for fresh
+synthetic inputs."""
+import pytest
+
+import hingetest as ht
+
+ALL = ht.FILTER_OUT + ht.MAXIMAL_OUT + ht.LAYOUT_OUT
+
+
+@pytest.mark.parametrize("name", ht.FIXTURES)
+def test_oracle_reproduces_golden(built, tmp_path, name):
+    root, _ = ht.materialize(name, str(tmp_path))
+    for stage in ("filter", "maximal", "layout"):
+        ht.run_stage("oracle", stage, str(tmp_path), root, "ora")
+    ht.assert_matches_golden(name, str(tmp_path), "ora", ALL)
+
+
+@pytest.mark.skipif(not ht.have_reference(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("args", [
+    ["--genome", 500000, "--cov", 35, "--seed", 101, "--families", 4],
+    ["--genome", 400000, "--cov", 50, "--seed", 202, "--jitter", 0, "--read-mean", 7000, "--read-sd", 2500,
+     "--read-min", 2000, "--rep-min", 1500, "--rep-max", 3500, "--copies-min", 3, "--copies-max", 5,
+     "--families", 6],
+])
+def test_oracle_equals_reference_on_fresh_synthetic(built, tmp_path, args):
+    ht.synth(str(tmp_path), args, "S")
+    for stage in ("filter", "maximal", "layout"):
+        ht.run_stage("reference", stage, str(tmp_path), "S", "S", out="S")
+    for stage in ("filter", "maximal", "layout"):
+        ht.run_stage("oracle", stage, str(tmp_path), "S", "ora")
+    ht.assert_same_files(str(tmp_path), "ora", "S", ALL)
