@@ -115,6 +115,7 @@ void hg_ctx_destroy(hg_ctx* c) {
     cudaFree(c->d_cov0); cudaFree(c->d_cov0_off);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    free_layout_result(c->layout);
     delete c;
 }
 

@@ -11,6 +11,11 @@
 #include "hg_device.cuh"
 #include "hg_filter.h"
 
+namespace hg {
+struct LayoutResult;
+void free_layout_result(LayoutResult* r);
+}
+
 struct hg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -58,6 +63,8 @@ struct hg_ctx {
         if (profile) cudaEventRecord(marks[i], stream);
     }
     bool ext_mean_cov = false, ext_mask = false;  // bound to caller-owned memory
+
+    hg::LayoutResult* layout = nullptr;  // result of the last hg_layout
 
     hg::RecView rec_view() const;
     hg::ReadView read_view() const;

@@ -1,0 +1,569 @@
+// Kernels of the `hinge maximal` and `hinge layout` stages (sm_100a).
+//
+//   K5 classify_pairs   per (A,B) pair: top two overlaps by total length, trim to
+//                       both reads' masks along the trace, classify
+//                       (maximal.cpp:65-134,780-858; hinging.cpp:473-602;
+//                        LAInterface.cpp:4552-4683,4721-4781)
+//   K5 contain_*        containment recurrence of maximal.cpp:780-858 as a
+//                       monotone fixed point over ascending read ids
+//   K6 sort_candidates  order-exact weight sort of each read's extension
+//                       candidates                     (hinging.cpp:1066-1071)
+//   K6 hinge_graph      hinge kill pass + hinge-graph edges through the trace
+//                       (hinging.cpp:1262-1321,1365-1640; LAInterface.cpp:4498-4546)
+//   K6 best_extension   the best-overlap scoring loop  (hinging.cpp:1911-2148)
+#include "hg_device.cuh"
+#include "hg_layout.h"
+#include "hg_order.h"
+
+namespace hg {
+
+extern int64_t g_launches;
+
+// ------------------------------------------------------------------ classification
+
+struct Match {
+    int as, ae, bs, be, comp;     // raw match, B on its forward strand
+    int eas, eae, ebs, ebe;       // trimmed to the masks
+    int type, weight, length;
+    bool active;
+};
+
+__device__ __forceinline__ int trace_value(const RecView& rv, int64_t off, int k) {
+    if (rv.tbytes == 1) return rv.trace[off + k];
+    return reinterpret_cast<const uint16_t*>(rv.trace + off)[k];
+}
+
+// ProcessAlignment = trim_overlap + AddTypesAsymmetric
+// (maximal.cpp:65-134; LAInterface.cpp:4552-4683, 4721-4781).
+__device__ Match classify_record(const RecView& rv, const int* __restrict__ rlen,
+                                 const int2* __restrict__ mask, int64_t k, int a, int b,
+                                 const hg_layout_params& P) {
+    Match m;
+    m.as = rv.abpos[k];
+    m.ae = rv.aepos[k];
+    m.comp = rv.flags[k] & 1;
+    m.bs = rv.bbpos[k];
+    m.be = rv.bepos[k];
+    if (m.comp) {
+        const int bl = rlen[b];
+        const int t = bl - m.be;
+        m.be = bl - m.bs;
+        m.bs = t;
+    }
+    const int2 EA = mask[a], EB = mask[b];
+    m.eas = m.as; m.eae = m.ae; m.ebs = m.bs; m.ebe = m.be;
+    const int64_t toff = rv.trace_off[k];
+    const int tlen = (int)((rv.trace_off[k + 1] - toff) / rv.tbytes);
+    const int inner = max(tlen / 2 - 1, 0);
+    const int npts = inner + 2;
+    const int sign = 1 - 2 * m.comp;
+    int start_idx = npts, end_idx = 0;
+    bool have_start = false;
+    int pa = m.as, pb = m.comp ? m.be : m.bs;
+    for (int idx = 0; idx < npts; idx++) {
+        if (idx == npts - 1) {
+            pa = m.ae;
+            pb = m.comp ? m.bs : m.be;
+        } else if (idx > 0) {
+            pa = (pa / 100 + 1) * 100;  // next multiple of 100 (LAInterface.cpp:4584-4587)
+            pb += sign * trace_value(rv, toff, 2 * (idx - 1) + 1);
+        }
+        if (!m.comp) {
+            if (!have_start && pa >= EA.x && pb >= EB.x) {
+                m.eas = pa; m.ebs = pb; start_idx = idx; have_start = true;
+            }
+            if (pa <= EA.y && pb <= EB.y) {
+                m.eae = pa; m.ebe = pb; end_idx = idx;
+            }
+        } else {
+            if (!have_start && pa >= EA.x && pb <= EB.y) {
+                m.eas = pa; m.ebe = pb; start_idx = idx; have_start = true;
+            }
+            if (pa <= EA.y && pb >= EB.x) {
+                m.eae = pa; m.ebs = pb; end_idx = idx;
+            }
+        }
+    }
+    m.active = a != b && !(start_idx >= end_idx);
+    m.type = HG_UNDEFINED;
+    if ((m.ebe - m.ebs) < P.aln_threshold || (m.eae - m.eas) < P.aln_threshold || !m.active) {
+        m.active = false;
+        m.type = HG_NOT_ACTIVE;
+    } else {
+        const int th = P.theta, th2 = P.theta2;
+        const int al = m.eas - EA.x, ar = EA.y - m.eae;
+        int bl = m.ebs - EB.x, br = EB.y - m.ebe;
+        if (m.comp) {
+            const int t = bl;
+            bl = br;
+            br = t;
+        }
+        if (max(al, ar) < th && min(bl, br) > th2)
+            m.type = HG_BCOVERA;
+        else if (max(bl, br) < th && min(al, ar) > th2)
+            m.type = HG_ACOVERB;
+        else if (min(al, ar) > th)
+            m.type = HG_INTERNAL;
+        else if (al <= th) {
+            if (br <= th && bl >= th)
+                m.type = HG_BACKWARD;
+            else if (br >= th && bl >= th)
+                m.type = HG_BACKWARD_INTERNAL;
+        } else if (ar <= th) {
+            if (bl <= th && br >= th)
+                m.type = HG_FORWARD;
+            else if (bl >= th && br >= th)
+                m.type = HG_FORWARD_INTERNAL;
+            else
+                m.type = HG_UNDEFINED;
+        }
+    }
+    m.weight = m.eae - m.eas + m.ebe - m.ebs;
+    m.length = m.ae - m.as + m.be - m.bs;
+    return m;
+}
+
+__device__ __forceinline__ int raw_length(const RecView& rv, int64_t k) {
+    // compare_overlap's key (LAInterface.cpp:4884); the B span is strand-invariant
+    return (rv.aepos[k] - rv.abpos[k]) + (rv.bepos[k] - rv.bbpos[k]);
+}
+
+// ------------------------------------------------------------------ emit (shared)
+
+__device__ void emit_pair(const RecView& rv, const ReadView& rd, const hg_layout_params& P,
+                          const int2* __restrict__ mask, const uint8_t* __restrict__ active,
+                          int mode, int a, int b, int64_t first, const int64_t top[2],
+                          uint8_t* __restrict__ rtype, const PairOut& po) {
+    int pair_slot = -1;
+    if (mode == 1) {
+        pair_slot = atomicAdd(&po.counters[4], 1);
+        if (pair_slot < po.pair_cap) {
+            po.pairs[pair_slot] = make_int4(a, b, (int)(first & 0x7fffffff), (int)(first >> 31));
+        } else {
+            atomicExch(&po.counters[3], 1);
+        }
+    }
+    for (int r = 0; r < 2; r++) {
+        if (top[r] < 0) break;
+        if (r == 1 && !P.use_two_matches) break;
+        const Match m = classify_record(rv, rd.rlen, mask, top[r], a, b, P);
+        if (mode == 0) {
+            rtype[top[r]] = (uint8_t)m.type;
+        } else {
+            const bool fwd = m.type == HG_FORWARD || m.type == HG_FORWARD_INTERNAL;
+            const bool bwd = m.type == HG_BACKWARD || m.type == HG_BACKWARD_INTERNAL;
+            if (m.type == HG_BCOVERA && active[b]) po.contained_flag[a] = 1;  // hinging.cpp:598
+            if (fwd || bwd) {
+                const int slot = atomicAdd(&po.counters[5], 1);
+                if (slot < po.cand_cap) {
+                    Cand c;
+                    c.a = a; c.b = b; c.type = m.type; c.comp = m.comp; c.weight = m.weight;
+                    c.length = m.length;
+                    c.eas = m.eas; c.eae = m.eae; c.ebs = m.ebs; c.ebe = m.ebe;
+                    c.as = m.as; c.ae = m.ae; c.bs = m.bs; c.be = m.be;
+                    c.rec = top[r];
+                    c.rank = r;
+                    c.pad = 0;
+                    po.cands[slot] = c;
+                } else {
+                    atomicExch(&po.counters[3], 1);
+                }
+            }
+        }
+    }
+}
+
+// One thread per record; the first record of every (A,B) run does the pair.
+// mode 0 (maximal): every pair of an active A; marks BCOVERA records.
+// mode 1 (layout): pairs whose A and B are both active; appends pair keys and
+// the classified top-two records to compact lists.
+__global__ void __launch_bounds__(256)
+k_classify_pairs(RecView rv, ReadView rd, hg_layout_params P, const int2* __restrict__ mask,
+                 const uint8_t* __restrict__ active, int mode, int sort_passes,
+                 uint8_t* __restrict__ rtype, PairOut po) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= rv.novl) return;
+    const int a = rv.aread[k], b = rv.bread[k];
+    if (k > 0 && rv.aread[k - 1] == a && rv.bread[k - 1] == b) return;  // not a pair leader
+    if (!active[a]) return;
+    if (mode == 1 && !(active[b] && P.keep_only_maximal)) return;
+    // run length
+    int64_t e = k + 1;
+    while (e < rv.novl && rv.aread[e] == a && rv.bread[e] == b) e++;
+    const int m = (int)(e - k);
+    int64_t top[2] = {k, -1};
+    if (m > 16) {
+        // std::sort is only stable up to 16 elements: leave it to the order-exact kernel
+        const int slot = atomicAdd(&po.counters[0], 1);
+        if (slot < po.big_cap) {
+            po.big_pairs[slot] = k;
+        } else {
+            atomicExch(&po.counters[3], 1);
+        }
+        return;
+    }
+    if (m > 1) {
+        // insertion sort by length, descending, is stable: best = earliest maximum,
+        // second = next in (length desc, file order)
+        int k1 = raw_length(rv, k), k2 = -2147483647 - 1;
+        int64_t i2 = -1;
+        for (int64_t i = k + 1; i < e; i++) {
+            const int key = raw_length(rv, i);
+            if (key > k1) {
+                k2 = k1; i2 = top[0];
+                k1 = key; top[0] = i;
+            } else if (i2 < 0 || key > k2) {
+                k2 = key; i2 = i;
+            }
+        }
+        top[1] = i2;
+    }
+    (void)sort_passes;
+    emit_pair(rv, rd, P, mask, active, mode, a, b, k, top, rtype, po);
+}
+
+// Pairs with more than 16 records: libstdc++'s introsort on (length, index),
+// applied as often as the reference applies it (twice in maximal.cpp:647-654 +
+// :791, once in hinging.cpp:534).
+__global__ void k_classify_big_pairs(RecView rv, ReadView rd, hg_layout_params P,
+                                     const int2* __restrict__ mask,
+                                     const uint8_t* __restrict__ active, int mode, int sort_passes,
+                                     uint8_t* __restrict__ rtype, PairOut po) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nbig = min(po.counters[0], po.big_cap);
+    if (t >= nbig) return;
+    const int64_t k = po.big_pairs[t];
+    const int a = rv.aread[k], b = rv.bread[k];
+    int64_t e = k + 1;
+    while (e < rv.novl && rv.aread[e] == a && rv.bread[e] == b) e++;
+    const int m = (int)(e - k);
+    const int off = atomicAdd(&po.counters[1], m);
+    if (off + m > po.sort_cap) {
+        atomicExch(&po.counters[3], 1);
+        return;
+    }
+    KeyIdx2* s = po.sort_scratch + off;
+    for (int i = 0; i < m; i++) {
+        s[i].key = raw_length(rv, k + i);
+        s[i].idx = i;
+    }
+    for (int p = 0; p < sort_passes; p++) std_sort_exact(s, m, KeyIdx2Greater());
+    int64_t top[2] = {k + s[0].idx, k + s[1].idx};
+    emit_pair(rv, rd, P, mask, active, mode, a, b, k, top, rtype, po);
+}
+
+// ------------------------------------------------------------------ containment
+
+// state: 0 unknown, 1 survives (maximal), 2 removed
+__global__ void k_contain_init(RecView rv, ReadView rd, const uint8_t* __restrict__ active0,
+                               const uint8_t* __restrict__ rtype, uint8_t* __restrict__ state) {
+    const int i = rd.r_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rd.r_hi) return;
+    if (!active0[i]) {
+        state[i] = 2;
+        return;
+    }
+    bool hi = false, lo = false;
+    for (int64_t k = rv.read_off[i]; k < rv.read_off[i + 1]; k++) {
+        if (rtype[k] != HG_BCOVERA) continue;
+        const int b = rv.bread[k];
+        if (!active0[b]) continue;
+        // B > A is still active when A is processed (maximal.cpp:809: reads[B]->active)
+        if (b > i) hi = true; else lo = true;
+    }
+    state[i] = hi ? 2 : (lo ? 0 : 1);
+}
+
+__global__ void k_contain_step(RecView rv, ReadView rd, const uint8_t* __restrict__ active0,
+                               const uint8_t* __restrict__ rtype, volatile uint8_t* state,
+                               int* __restrict__ remaining) {
+    const int i = rd.r_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rd.r_hi || state[i] != 0) return;
+    bool any_alive = false, any_unknown = false;
+    for (int64_t k = rv.read_off[i]; k < rv.read_off[i + 1]; k++) {
+        if (rtype[k] != HG_BCOVERA) continue;
+        const int b = rv.bread[k];
+        if (b >= i || !active0[b]) continue;
+        const uint8_t s = state[b];  // B < A: B's FINAL state decides (maximal.cpp:853-854)
+        any_alive = any_alive || s == 1;
+        any_unknown = any_unknown || s == 0;
+    }
+    if (any_alive)
+        state[i] = 2;
+    else if (!any_unknown)
+        state[i] = 1;
+    else
+        atomicAdd(remaining, 1);
+}
+
+// ------------------------------------------------------------------ K6: selection
+
+// hinging.cpp:1066-1071: std::sort of each read's candidate lists by weight, descending.
+__global__ void k_sort_candidates(SelectIO io) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= io.n_read || !io.active[i]) return;
+    const int4 r = io.ranges[i];
+    for (int half = 0; half < 2; half++) {
+        const int lo = half ? r.z : r.x, hi = half ? r.w : r.y;
+        const int n = hi - lo;
+        if (n <= 1) continue;
+        KeyIdx2* s = io.sort_scratch + lo;
+        for (int t = 0; t < n; t++) {
+            s[t].idx = io.order[lo + t];
+            s[t].key = io.cands[s[t].idx].weight;
+        }
+        std_sort_exact(s, n, KeyIdx2Greater());
+        for (int t = 0; t < n; t++) io.order[lo + t] = s[t].idx;
+    }
+}
+
+// LOverlap::GetMatchingPosition (LAInterface.cpp:4498-4546)
+__device__ int matching_position(const RecView& rv, const Cand& c, int pos_a) {
+    if (pos_a < c.as || pos_a > c.ae) return -1;
+    const int sign = 1 - 2 * c.comp;
+    int cur_a = c.as;
+    int cur_b = c.comp ? c.be : c.bs;
+    const int64_t toff = rv.trace_off[c.rec];
+    const int tlen = (int)((rv.trace_off[c.rec + 1] - toff) / rv.tbytes);
+    for (int j = 0; j < tlen / 2 - 1; j++) {
+        const int next_a = (cur_a / 100 + 1) * 100;
+        if (next_a >= pos_a) return cur_b + pos_a - cur_a;
+        cur_b += sign * trace_value(rv, toff, 2 * j + 1);
+        cur_a = next_a;
+    }
+    if (cur_a < pos_a) return cur_b + pos_a - cur_a;
+    return -2;
+}
+
+// Kill pass (hinging.cpp:1262-1321) and hinge graph (hinging.cpp:1365-1640),
+// one thread per active read that carries hinges.
+__global__ void k_hinge_graph(RecView rv, hg_layout_params P, SelectIO io) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= io.n_read || !io.active[i]) return;
+    const int64_t h0 = io.hv.off[i], h1 = io.hv.off[i + 1];
+    if (h0 == h1) return;
+    const int4 r = io.ranges[i];
+    // kill pass
+    for (int half = 0; half < 2; half++) {
+        const int lo = half ? r.z : r.x, hi = half ? r.w : r.y;
+        for (int t = lo; t < hi; t++) {
+            const Cand& m = io.cands[io.order[t]];
+            if (!io.active[m.b]) continue;
+            for (int64_t k = h0; k < h1; k++) {
+                const int pos = io.hv.pos[k], type = io.hv.type[k];
+                bool kill;
+                if (!half)
+                    kill = type == 1 &&
+                           ((m.eas < pos + P.kill_hinge_internal && m.type == HG_FORWARD_INTERNAL) ||
+                            (m.eas < pos - P.kill_hinge_overlap && m.type == HG_FORWARD));
+                else
+                    kill = type == -1 &&
+                           ((m.eae > pos - P.kill_hinge_internal && m.type == HG_BACKWARD_INTERNAL) ||
+                            (m.eae > pos + P.kill_hinge_overlap && m.type == HG_BACKWARD));
+                if (kill) io.hinge_alive[k] = 0;
+            }
+        }
+    }
+    // hinge graph
+    int seq = 0;
+    const int S = P.matching_hinge_slack;
+    for (int64_t k = h0; k < h1; k++) {
+        const int hpos = io.hv.pos[k], htype = io.hv.type[k];
+        for (int half = 0; half < 2; half++) {
+            const int lo = half ? r.z : r.x, hi = half ? r.w : r.y;
+            const int own_type = half ? -1 : 1;
+            for (int t = lo; t < hi; t++) {
+                const Cand& m = io.cands[io.order[t]];
+                if (!io.active[m.b]) continue;
+                const int pos_b = matching_position(rv, m, hpos);
+                const int req = m.comp ? -htype : htype;
+                const int rev = m.comp ? 1 : 0;
+                const int b = m.b;
+                for (int64_t l = io.hv.off[b]; l < io.hv.off[b + 1]; l++) {
+                    const int p2 = io.hv.pos[l];
+                    if (p2 < pos_b + S && p2 > pos_b - S && req == io.hv.type[l]) {
+                        const int slot = atomicAdd(&io.counters[0], 1);
+                        if (slot < io.graph_cap) {
+                            GraphRec g;
+                            g.owner = i; g.seq = seq; g.flag = 1; g.rev = rev;
+                            g.u = (int)k; g.v = (int)l;
+                            if (htype == own_type) {
+                                g.f[0] = i; g.f[1] = b; g.f[2] = hpos; g.f[3] = p2;
+                            } else {
+                                g.f[0] = b; g.f[1] = i; g.f[2] = p2; g.f[3] = hpos;
+                            }
+                            io.graph[slot] = g;
+                        } else {
+                            atomicExch(&io.counters[3], 1);
+                        }
+                        seq++;
+                    }
+                }
+                for (int64_t l = io.kv.off[b]; l < io.kv.off[b + 1]; l++) {
+                    const int p2 = io.kv.pos[l];
+                    if (p2 < pos_b + S && p2 > pos_b - S) {
+                        const bool tmatch = req == io.kv.type[l];
+                        if (tmatch) {
+                            const int slot = atomicAdd(&io.counters[0], 1);
+                            if (slot < io.graph_cap) {
+                                GraphRec g;
+                                g.owner = i; g.seq = seq; g.flag = 0; g.rev = rev; g.u = g.v = -1;
+                                if (htype == own_type) {
+                                    g.f[0] = i; g.f[1] = b; g.f[2] = hpos; g.f[3] = p2;
+                                } else {
+                                    g.f[0] = b; g.f[1] = i; g.f[2] = p2; g.f[3] = hpos;
+                                }
+                                io.graph[slot] = g;
+                            } else {
+                                atomicExch(&io.counters[3], 1);
+                            }
+                            seq++;
+                        }
+                        // forward: inside the type test (hinging.cpp:1472); backward: outside (:1616)
+                        const bool push = half ? m.type == HG_BACKWARD : (tmatch && m.type == HG_FORWARD);
+                        if (push) {
+                            const int slot = atomicAdd(&io.counters[1], 1);
+                            if (slot < io.nk_cap) {
+                                NkRec n;
+                                n.owner = i; n.seq = seq; n.pos = hpos; n.type = htype;
+                                io.nkout[slot] = n;
+                            } else {
+                                atomicExch(&io.counters[3], 1);
+                            }
+                            seq++;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// The best-overlap scoring loop (hinging.cpp:1911-2148): per active read, walk
+// the candidates in weight order; the first FORWARD not poisoned by a newly
+// killed hinge wins unless a FORWARD_INTERNAL that lands on an active hinge of B
+// is at most 2 * hinge_slack lighter; mirrored for the backward direction.
+__global__ void k_best_extension(hg_layout_params P, SelectIO io) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= io.n_read) return;
+    io.chosen[2 * i] = make_int2(-1, -1);
+    io.chosen[2 * i + 1] = make_int2(-1, -1);
+    if (!io.active[i]) return;
+    const int4 r = io.ranges[i];
+    const int64_t n0 = io.nk.off[i], n1 = io.nk.off[i + 1];
+    int seq = 0;
+    for (int half = 0; half < 2; half++) {
+        const int lo = half ? r.z : r.x, hi = half ? r.w : r.y;
+        const int plain = half ? HG_BACKWARD : HG_FORWARD;
+        const int internal = half ? HG_BACKWARD_INTERNAL : HG_FORWARD_INTERNAL;
+        int got = 0, got_internal = 0, chosen = -1, hinge_pos = -1, chosen_weight = 0;
+        for (int t = lo; t < hi; t++) {
+            const int ci = io.order[t];
+            const Cand& m = io.cands[ci];
+            if (!io.active[m.b]) continue;
+            if (m.type == plain && got == 0) {
+                bool poisoned = false;
+                for (int64_t k = n0; k < n1; k++) {
+                    const int kp = io.nk.pos[k], kt = io.nk.type[k];
+                    bool hit;
+                    if (!half)
+                        hit = (m.comp != 1 && kt == -1 && kp > m.ebe) || (m.comp == 1 && kt == 1 && kp < m.ebs);
+                    else
+                        hit = (m.comp != 1 && kt == 1 && kp < m.ebs) || (m.comp == 1 && kt == -1 && kp > m.ebe);
+                    if (hit) {
+                        const int slot = atomicAdd(&io.counters[2], 1);
+                        if (slot < io.skip_cap) {
+                            SkipRec s;
+                            s.owner = i; s.seq = seq; s.cand = ci;
+                            io.skips[slot] = s;
+                        } else {
+                            atomicExch(&io.counters[3], 1);
+                        }
+                        seq++;
+                        poisoned = true;
+                    }
+                }
+                if (!poisoned) {
+                    chosen = ci;
+                    chosen_weight = m.weight;
+                    hinge_pos = -1;
+                    got = 1;
+                }
+            } else if (m.type == internal && io.hv.off[m.b + 1] > io.hv.off[m.b] && got_internal == 0) {
+                int bpos, want;
+                if (!half) {
+                    bpos = m.comp == 1 ? m.be : m.bs;
+                    want = 1 - 2 * m.comp;
+                } else {
+                    bpos = m.comp == 1 ? m.bs : m.be;
+                    want = -1 + 2 * m.comp;
+                }
+                for (int64_t k = io.hv.off[m.b]; k < io.hv.off[m.b + 1]; k++) {
+                    const int hp = io.hv.pos[k];
+                    if (bpos > hp - P.hinge_tolerance && bpos < hp + P.hinge_tolerance &&
+                        io.hv.type[k] == want && io.hinge_alive[k]) {
+                        if (got == 0 || m.weight > chosen_weight - 2 * P.hinge_slack) {
+                            chosen = ci;
+                            chosen_weight = m.weight;
+                            got = 1;
+                            got_internal = 1;
+                            hinge_pos = hp;
+                        }
+                        break;
+                    }
+                }
+            }
+        }
+        io.chosen[2 * i + half] = make_int2(chosen, hinge_pos);
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+
+static inline int cdiv(int64_t a, int b) { return (int)((a + b - 1) / b); }
+
+void launch_classify(const RecView& rv, const ReadView& rd, const hg_layout_params& P,
+                     const int2* mask, const uint8_t* active, int mode, int sort_passes,
+                     uint8_t* rtype, const PairOut& po, cudaStream_t st) {
+    cudaMemsetAsync(po.counters, 0, sizeof(int) * 8, st);
+    k_classify_pairs<<<cdiv(rv.novl, 256), 256, 0, st>>>(rv, rd, P, mask, active, mode,
+                                                         sort_passes, rtype, po);
+    // the list length lives on the device; one thread per possible entry
+    k_classify_big_pairs<<<cdiv(po.big_cap, 128), 128, 0, st>>>(rv, rd, P, mask, active, mode,
+                                                                sort_passes, rtype, po);
+    g_launches += 2;
+}
+
+void launch_contain_init(const RecView& rv, const ReadView& rd, const uint8_t* active0,
+                         const uint8_t* rtype, uint8_t* state, cudaStream_t st) {
+    k_contain_init<<<cdiv(rd.r_hi - rd.r_lo, 256), 256, 0, st>>>(rv, rd, active0, rtype, state);
+    g_launches += 1;
+}
+
+void launch_contain_step(const RecView& rv, const ReadView& rd, const uint8_t* active0,
+                         const uint8_t* rtype, uint8_t* state, int* remaining, cudaStream_t st) {
+    cudaMemsetAsync(remaining, 0, sizeof(int), st);
+    k_contain_step<<<cdiv(rd.r_hi - rd.r_lo, 256), 256, 0, st>>>(rv, rd, active0, rtype, state,
+                                                                 remaining);
+    g_launches += 1;
+}
+
+void launch_sort_candidates(const SelectIO& io, cudaStream_t st) {
+    k_sort_candidates<<<cdiv(io.n_read, 128), 128, 0, st>>>(io);
+    g_launches += 1;
+}
+
+void launch_hinge_graph(const RecView& rv, const hg_layout_params& P, const SelectIO& io,
+                        cudaStream_t st) {
+    cudaMemsetAsync(io.counters, 0, sizeof(int) * 8, st);
+    k_hinge_graph<<<cdiv(io.n_read, 128), 128, 0, st>>>(rv, P, io);
+    g_launches += 1;
+}
+
+void launch_best_extension(const hg_layout_params& P, const SelectIO& io, cudaStream_t st) {
+    cudaMemsetAsync(io.counters + 2, 0, sizeof(int), st);
+    k_best_extension<<<cdiv(io.n_read, 128), 128, 0, st>>>(P, io);
+    g_launches += 1;
+}
+
+}  // namespace hg

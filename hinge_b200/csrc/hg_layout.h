@@ -1,0 +1,98 @@
+// Host-visible declarations of the maximal / layout kernels' launchers.
+#ifndef HG_LAYOUT_H
+#define HG_LAYOUT_H
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hg_params.h"
+
+namespace hg {
+
+struct RecView;
+struct ReadView;
+
+struct KeyIdx2 {
+    int key, idx;
+};
+struct KeyIdx2Greater {
+    __host__ __device__ bool operator()(const KeyIdx2& a, const KeyIdx2& b) const { return a.key > b.key; }
+};
+
+// One classified overlap between two maximal reads that extends A
+// (FORWARD / FORWARD_INTERNAL / BACKWARD / BACKWARD_INTERNAL).
+struct Cand {
+    int a, b, type, comp, weight, length;
+    int eas, eae, ebs, ebe;  // trimmed match
+    int as, ae, bs, be;      // raw match, B on its forward strand
+    int64_t rec;             // record index (trace, file order)
+    int rank, pad;           // 0 / 1: best or second-best of its pair
+};
+
+struct PairOut {
+    int* counters;          // [0] big pairs [1] sort scratch used [3] overflow [4] pairs [5] cands
+    int64_t* big_pairs;     // first record of pairs with > 16 records
+    int big_cap;
+    KeyIdx2* sort_scratch;
+    int sort_cap;
+    int4* pairs;            // layout: (a, b, first record lo31, hi)
+    int pair_cap;
+    Cand* cands;
+    int cand_cap;
+    uint8_t* contained_flag;  // layout: per read, "[contained] Should not happen"
+};
+
+void launch_classify(const RecView& rv, const ReadView& rd, const hg_layout_params& P,
+                     const int2* mask, const uint8_t* active, int mode, int sort_passes,
+                     uint8_t* rtype, const PairOut& po, cudaStream_t st);
+void launch_contain_init(const RecView& rv, const ReadView& rd, const uint8_t* active0,
+                         const uint8_t* rtype, uint8_t* state, cudaStream_t st);
+void launch_contain_step(const RecView& rv, const ReadView& rd, const uint8_t* active0,
+                         const uint8_t* rtype, uint8_t* state, int* remaining, cudaStream_t st);
+
+// ---- layout selection -------------------------------------------------------
+
+struct HingeView {           // CSR over reads, device
+    const int64_t* off;      // n_read + 1
+    const int* pos;
+    const int* type;
+};
+
+struct GraphRec {            // one .hgraph line (+ the union it implies)
+    int owner, seq;          // emitting read and order within it
+    int f[4];                // the four leading integers of the line
+    int flag, rev;           // 1 = hinge-hinge edge, 0 = hinge-killed hinge
+    int u, v;                // hinge node ids (flag == 1)
+};
+struct NkRec {               // new_killed_hinges_vec[owner].push_back(...)
+    int owner, seq, pos, type;
+};
+struct SkipRec {             // one .edges.skipped line
+    int owner, seq, cand;
+};
+
+struct SelectIO {
+    int n_read;
+    const uint8_t* active;   // reads
+    const Cand* cands;
+    const int4* ranges;      // per read: fwd [x,y), bwd [z,w) into order[]
+    int* order;              // candidate indices, sorted by weight per list
+    KeyIdx2* sort_scratch;   // one per candidate
+    HingeView hv, kv, nk;    // hinges, killed hinges, new killed hinges
+    uint8_t* hinge_alive;    // per hinge entry: kill pass result, later AND component size
+    int* counters;           // [0] graph recs [1] nk recs [2] skip recs [3] overflow
+    GraphRec* graph;
+    int graph_cap;
+    NkRec* nkout;
+    int nk_cap;
+    SkipRec* skips;
+    int skip_cap;
+    int2* chosen;            // per read x 2 (fwd, bwd): (candidate index or -1, hinge_pos)
+};
+
+void launch_sort_candidates(const SelectIO& io, cudaStream_t st);
+void launch_hinge_graph(const RecView& rv, const hg_layout_params& P, const SelectIO& io,
+                        cudaStream_t st);
+void launch_best_extension(const hg_layout_params& P, const SelectIO& io, cudaStream_t st);
+
+}  // namespace hg
+#endif
