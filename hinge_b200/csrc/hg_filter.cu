@@ -509,6 +509,249 @@ __device__ void mask_anno_read(const RecView& rv, const ReadView& rd, const hg_f
     __syncwarp();
 }
 
+// ---- K2 fast path --------------------------------------------------------------
+// Same results as mask_anno_read<uint32_t>, organised for instruction count: every
+// lane owns FOUR consecutive bins (one 128-bit shared-memory word), so a read of up
+// to 128 bins (5 kb) is one tile: one local scan + one warp scan, hardware warp
+// reductions (REDUX), and the repeat-annotation / hinge pre-test sweep shares a
+// single pass.  `self_records` tells whether the read has A == B records at all
+// (known from K1); without them the bread column is not even loaded.
+__device__ __forceinline__ uint4 lds128(const uint32_t* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void sts128(uint32_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+
+__device__ void mask_anno_read_fast(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
+                                    const int MIN_COV, const int read, uint32_t* hist, const int nbz,
+                                    const bool self_records, const MaskAnnoOut& out) {
+    typedef Packed<uint32_t> PK;
+    const int lane = lane_id();
+    constexpr int reso = kReso;
+    const int64_t o0 = rv.read_off[read], o1 = rv.read_off[read + 1];
+    const int ntile = (nbz + 127) >> 7;
+
+    for (int t = 0; t <= ntile; t++)  // one tile of slack: the sweep reads bin j + 1
+        if (t < ntile || lane == 0) sts128(hist + (t << 7) + (lane << 2), make_uint4(0, 0, 0, 0));
+    __syncwarp();
+
+    // ---- scatter (profileCoverage, LAInterface.cpp:4298-4320)
+    int m0 = -1, mc = -1;
+    const int C = P.cut_off;
+    for (int64_t k = o0 + lane; k < o1; k += 32) {
+        if (self_records && __ldg(rv.bread + k) == read) continue;  // filter.cpp:538-547
+        const int as = __ldg(rv.abpos + k), ae = __ldg(rv.aepos + k);
+        const int b_s0 = as / reso + 1, b_e0 = ae / reso + 1;  // 0 <= abpos < aepos (validated at ingest)
+        const int b_sc = cov_bin(as + C, reso), b_ec = cov_bin(ae - C, reso);
+        atomicAdd(&hist[b_s0], 1u);
+        atomicAdd(&hist[b_e0], 0u - 1u);
+        atomicAdd(&hist[b_sc], 1u << 16);
+        atomicAdd(&hist[b_ec], 0u - (1u << 16));
+        m0 = max(m0, b_e0);
+        mc = max(mc, max(b_sc, b_ec));
+    }
+    const int L0 = __reduce_max_sync(0xffffffffu, m0) + 1;
+    const int LC = __reduce_max_sync(0xffffffffu, mc) + 1;
+    __syncwarp();
+
+    // ---- pass 1: prefix sums in place + longest run of covered bins (filter.cpp:696-728)
+    uint32_t carry = 0;
+    int last_zero = 0;
+    unsigned best = 0;  // (gap << 16) | (0xffff - z): max gap, then smallest z
+    for (int t = 0; t < ntile; t++) {
+        uint32_t* hp = hist + (t << 7) + (lane << 2);
+        uint4 v = lds128(hp);
+        v.y += v.x;
+        v.z += v.y;
+        v.w += v.z;
+        const uint32_t incl = warp_incl_scan(v.w);
+        const uint32_t ex = incl - v.w + carry;
+        v.x += ex; v.y += ex; v.z += ex; v.w += ex;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+        sts128(hp, v);
+        const int j0 = (t << 7) + (lane << 2);
+        const bool z0 = j0 < LC && !(PK::hi(v.x) > MIN_COV);
+        const bool z1 = j0 + 1 < LC && !(PK::hi(v.y) > MIN_COV);
+        const bool z2 = j0 + 2 < LC && !(PK::hi(v.z) > MIN_COV);
+        const bool z3 = j0 + 3 < LC && !(PK::hi(v.w) > MIN_COV);
+        const int lz = z3 ? j0 + 3 : (z2 ? j0 + 2 : (z1 ? j0 + 1 : (z0 ? j0 : -1)));
+        const unsigned lanes = __ballot_sync(0xffffffffu, lz >= 0);
+        const unsigned below = lanes & ((1u << lane) - 1u);
+        const int src = below ? 31 - __clz(below) : 0;
+        const int lz_src = __shfl_sync(0xffffffffu, lz, src);
+        int p = below ? lz_src : last_zero;  // previous zero bin before this lane's four
+        if (lz >= 0) {
+#define HG_GAP(zf, j)                                                              \
+    if (zf) {                                                                      \
+        const int gap = (j) - p;                                                   \
+        if (gap >= 3) best = max(best, ((unsigned)gap << 16) | (unsigned)(0xffff - (j))); \
+        p = (j);                                                                   \
+    }
+            HG_GAP(z0, j0) HG_GAP(z1, j0 + 1) HG_GAP(z2, j0 + 2) HG_GAP(z3, j0 + 3)
+#undef HG_GAP
+        }
+        if (lanes) last_zero = __shfl_sync(0xffffffffu, lz, 31 - __clz(lanes));
+    }
+    best = __reduce_max_sync(0xffffffffu, best);
+    __syncwarp();
+    int maxstart = 0, maxend = 0, msc = 0, mec = 0;
+    if (best) {
+        const int gap = (int)(best >> 16), z = 0xffff - (int)(best & 0xffffu), p = z - gap;
+        msc = p + 1;
+        mec = z - 1;
+        maxstart = reso * (p + 1);
+        maxend = reso * (z - 1);
+    }
+
+    // ---- telomere / coverage-imbalance flag (filter.cpp:731-760)
+    uint8_t flags = 0;
+    if (P.delete_telomere) {
+        flags = out.rflags[read] & kFlagSelf;
+        int limit, div;
+        if (mec - msc + 1 > 20) {
+            limit = 10;
+            div = 10;
+        } else {
+            limit = (mec - msc) / 2;
+            div = limit;
+        }
+        int sc = 0, ec = 0;
+        for (int t = lane; t < limit; t += 32) {
+            sc += max(PK::hi(hist[msc + t]), MIN_COV);
+            ec += max(PK::hi(hist[mec - t]), MIN_COV);
+        }
+        sc = __reduce_add_sync(0xffffffffu, sc);
+        ec = __reduce_add_sync(0xffffffffu, ec);
+        if (div == 0) {
+            sc = 0;
+            ec = 0;
+        } else {
+            sc /= div;
+            ec /= div;
+        }
+        if (sc >= 10 * ec || ec >= 10 * sc) flags |= kFlagCov;
+    }
+
+    // ---- final mask (filter.cpp:777-788)
+    const int2 q = rd.qvmask[read];
+    int2 mk;
+    if (P.use_qv_mask && P.use_coverage_mask)
+        mk = make_int2(max(maxstart, q.x), min(maxend, q.y));
+    else if (P.use_coverage_mask && !P.use_qv_mask)
+        mk = make_int2(maxstart, maxend);
+    else
+        mk = q;
+
+    // ---- pass 2: hinge pre-test sums (filter.cpp:842-865), repeat annotation
+    // (filter.cpp:796-813), optional profile dump (filter.cpp:599-602)
+    const int NHR = P.no_hinge_region;
+    const int jn = max(L0 - 2, 0);
+    const int a_lo = mk.x + NHR, a_hi = mk.y - NHR;
+    const int MINT = P.min_repeat_annotation_threshold, MAXT = P.max_repeat_annotation_threshold;
+    const int RJ = min(MINT, MAXT);  // the threshold never drops below this
+    int cs = 0, ns = 0, ce = 0, ne = 0, cnt = 0;
+    int* dump = out.cov0 ? out.cov0 + out.cov0_off[read] : nullptr;
+    const int tiles0 = (L0 + 127) >> 7;
+    for (int t = 0; t < tiles0; t++) {
+        const int j0 = (t << 7) + (lane << 2);
+        const uint4 v = lds128(hist + j0);
+        uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
+        if (lane == 31) nx = hist[j0 + 4];
+        const int c[5] = {PK::lo(v.x), PK::lo(v.y), PK::lo(v.z), PK::lo(v.w), PK::lo(nx)};
+        int type[4];
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int j = j0 + i, pos = reso * j;
+            if (j < L0) {
+                if (pos >= mk.x && pos <= mk.x + NHR) {
+                    cs += c[i];
+                    ns++;
+                }
+                if (pos <= mk.y && pos >= mk.y - NHR) {
+                    ce += c[i];
+                    ne++;
+                }
+                if (dump) dump[j] = c[i];
+            }
+            type[i] = 0;
+            const int g = c[i + 1] - c[i];
+            // most bins are rejected without the division
+            if (j < jn && pos >= a_lo && pos <= a_hi && (g > RJ || g < -RJ)) {
+                const int thr = min(max((c[i] + MIN_COV) / P.coverage_fraction, MINT), MAXT);
+                type[i] = g > thr ? 1 : (g < -thr ? -1 : 0);
+            }
+            any = any || type[i] != 0;
+        }
+        const unsigned am = __ballot_sync(0xffffffffu, any);
+        if (am) {  // rare: compact (position, type) entries in bin order over the histogram words
+            const int mine = (type[0] != 0) + (type[1] != 0) + (type[2] != 0) + (type[3] != 0);
+            const int incl = warp_incl_scan(mine);
+            int slot = cnt + incl - mine;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (type[i] != 0) hist[slot++] = ((unsigned)(reso * (j0 + i)) << 2) | (unsigned)(type[i] + 1);
+            cnt += __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+        }
+    }
+    cs = __reduce_add_sync(0xffffffffu, cs);
+    ns = __reduce_add_sync(0xffffffffu, ns);
+    ce = __reduce_add_sync(0xffffffffu, ce);
+    ne = __reduce_add_sync(0xffffffffu, ne);
+    // float on purpose: 0/0 = NaN makes the '< 10' test false (filter.cpp:861-865)
+    const float avg_end = __fdiv_rn((float)ce, (float)ne);
+    const float avg_start = __fdiv_rn((float)cs, (float)ns);
+    const bool skip_hinges = fabsf(__fsub_rn(avg_end, avg_start)) < 10.0f;
+
+    // ---- merge pass (filter.cpp:817-829) + publication, as in the generic path
+    int kept = 0;
+    if (cnt > 0) {
+        if (lane == 0) {
+            const int GAP = P.repeat_annotation_gap_threshold;
+            unsigned cur = hist[0];
+            for (int k = 1; k < cnt; k++) {
+                const unsigned nxt = hist[k];
+                const int ct = (int)(cur & 3u) - 1, nt = (int)(nxt & 3u) - 1;
+                const int gap = (int)(nxt >> 2) - (int)(cur >> 2);
+                if (ct == 1 && nt == 1 && gap < GAP) {
+                    continue;
+                } else if (ct == -1 && nt == -1 && gap < GAP) {
+                    cur = nxt;
+                } else {
+                    hist[kept++] = cur;
+                    cur = nxt;
+                }
+            }
+            hist[kept++] = cur;
+        }
+        kept = __shfl_sync(0xffffffffu, kept, 0);
+    }
+    int off = 0;
+    if (kept > 0) {
+        if (lane == 0) {
+            off = atomicAdd(&out.counters[0], kept);
+            if (off + kept > out.anno_cap) {
+                atomicExch(&out.counters[2], 1);
+                off = -1;
+            }
+        }
+        off = __shfl_sync(0xffffffffu, off, 0);
+        __syncwarp();
+        if (off >= 0)
+            for (int k = lane; k < kept; k += 32) {
+                const unsigned w = hist[k];
+                out.anno_pool[off + k] = make_int2((int)(w >> 2), (int)(w & 3u) - 1);
+            }
+    }
+    if (lane == 0) {
+        out.mask[read] = mk;
+        out.cmask[read] = make_int2(msc, mec);
+        out.rflags[read] = flags | (skip_hinges ? kFlagSkipHinge : 0);
+        out.anno_ref[read] = make_int2(off, kept);
+        if (kept > 0 && !skip_hinges && off >= 0) out.work_list[atomicAdd(&out.counters[1], 1)] = read;
+    }
+    __syncwarp();
+}
+
 __device__ __forceinline__ int bins_needed(int rlen, const hg_filter_params& P) {
     return (rlen + max(P.cut_off, 0)) / kReso + 3;
 }
@@ -516,10 +759,10 @@ __device__ __forceinline__ int bins_needed(int rlen, const hg_filter_params& P) 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 k_mask_anno(RecView rv, ReadView rd, hg_filter_params P, const int* __restrict__ scal,
-            int r_begin, int r_end, int nb_cap, MaskAnnoOut out) {
-    extern __shared__ uint32_t sh[];  // WARPS x nb_cap packed histogram words
+            const int* __restrict__ self_cnt, int r_begin, int r_end, int nb_cap, MaskAnnoOut out) {
+    extern __shared__ __align__(16) uint32_t sh[];  // WARPS x (nb_cap + 128) packed histogram words
     const int warp = threadIdx.x >> 5;
-    uint32_t* hist = sh + (size_t)warp * nb_cap;
+    uint32_t* hist = sh + (size_t)warp * (nb_cap + 128);
     const int MIN_COV = scal[1];
     const int lo = max(rd.r_lo, r_begin), hi = min(rd.r_hi, r_end + 1);
     for (int read = lo + blockIdx.x * WARPS + warp; read < hi; read += gridDim.x * WARPS) {
@@ -529,7 +772,7 @@ k_mask_anno(RecView rv, ReadView rd, hg_filter_params P, const int* __restrict__
             if (lane_id() == 0) out.big_list[atomicAdd(&out.counters[3], 1)] = read;
             continue;
         }
-        mask_anno_read<uint32_t>(rv, rd, P, MIN_COV, read, hist, nbz, out);
+        mask_anno_read_fast(rv, rd, P, MIN_COV, read, hist, nbz, self_cnt[read] > 0, out);
     }
 }
 
@@ -860,10 +1103,10 @@ void launch_median(const ReadView& rd, const hg_filter_params& P, FilterScratch&
 
 int mask_anno_configure(FilterScratch& s, int nb_cap) {
     // shared memory per CTA = warps x nb_cap words; as many CTAs per SM as fit
-    nb_cap = (nb_cap + 31) & ~31;
-    const int max_words = (200 * 1024) / (4 * kMaskAnnoWarps);
+    nb_cap = (nb_cap + 127) & ~127;
+    const int max_words = ((200 * 1024) / (4 * kMaskAnnoWarps) - 128) & ~127;
     if (nb_cap > max_words) nb_cap = max_words;
-    const int smem = nb_cap * 4 * kMaskAnnoWarps;
+    const int smem = (nb_cap + 128) * 4 * kMaskAnnoWarps;
     cudaFuncSetAttribute(k_mask_anno<kMaskAnnoWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          smem);
     int per_sm = 0;
@@ -887,10 +1130,10 @@ void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_par
     cudaMemsetAsync(s.cmask, 0, sizeof(int2) * rd.n_read, st);
     cudaMemsetAsync(s.anno_ref, 0, sizeof(int2) * rd.n_read, st);
     cudaMemsetAsync(s.hinge_keep, 0, (size_t)s.anno_cap, st);
-    const int smem = s.nb_cap * 4 * kMaskAnnoWarps;
+    const int smem = (s.nb_cap + 128) * 4 * kMaskAnnoWarps;
     g_launches += 1 + (s.big_slot_words > 0);
     k_mask_anno<kMaskAnnoWarps><<<s.mask_anno_grid, kMaskAnnoWarps * 32, smem, st>>>(
-        rv, rd, P, s.scal, r_begin, r_end, s.nb_cap, out);
+        rv, rd, P, s.scal, s.self_cnt, r_begin, r_end, s.nb_cap, out);
     if (s.big_slot_words > 0)
         k_mask_anno_big<<<s.big_warps / 4, 128, 0, st>>>(rv, rd, P, s.scal, out, s.big_scratch,
                                                          s.big_slot_words);
