@@ -112,6 +112,7 @@ void hg_ctx_destroy(hg_ctx* c) {
     cudaFree(s.med_hist); cudaFree(s.scal); cudaFree(s.cmask); cudaFree(s.rflags);
     cudaFree(s.anno_ref); cudaFree(s.anno_pool); cudaFree(s.counters); cudaFree(s.work_list);
     cudaFree(s.big_list); cudaFree(s.big_scratch); cudaFree(s.hinge_keep); cudaFree(s.hinge_scratch);
+    cudaFree(s.item_log);
     cudaFree(c->d_cov0); cudaFree(c->d_cov0_off);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -129,6 +130,8 @@ int hg_set_option(hg_ctx* c, int option, int64_t value) {
         c->profile = value != 0;
         if (c->profile && !c->marks[0])
             for (int i = 0; i < hg_ctx::kMarks; i++) cudaEventCreate(&c->marks[i]);
+        if (c->profile && c->n_read > 0 && !c->fs.item_log)
+            HG_TRY(dev_alloc(c, &c->fs.item_log, c->n_read, "item log"));
         return HG_OK;
     }
     return set_err(c, HG_ERR_ARG, "unknown option");
@@ -289,7 +292,7 @@ int hg_set_overlaps(hg_ctx* c, int64_t novl, const int32_t* aread, const int32_t
     s.hinge_cap = (std::max(c->max_pileup, 32) + 3) & ~3;  // keeps every slot 16-byte aligned
     {
         const size_t slot = (size_t)s.hinge_cap * 40;
-        size_t warps = (size_t)c->num_sms * 16;
+        size_t warps = (size_t)c->num_sms * 48;  // the kernel is latency bound: many warps, few reads each
         const size_t budget = (size_t)768 << 20;
         if (warps * slot > budget) warps = std::max<size_t>(4, budget / slot);
         warps = std::max<size_t>(4, warps & ~(size_t)3);
@@ -420,6 +423,18 @@ int hg_filter_kernel_times(hg_ctx* c, float* ms, int n) {
 }
 
 int64_t hg_launch_count(void) { return hg::g_launches; }
+
+// Debug aid (HG_OPT_PROFILE set after hg_set_reads): per hinge-call work item
+// (read, cycles, largest support, pile-up size if the order-exact path ran).
+int hg_debug_item_log(hg_ctx* c, int32_t* out4, int64_t capacity, int64_t* n_items) {
+    if (!c || !c->fs.item_log || !n_items) return HG_ERR_ARG;
+    int cnt[8];
+    cudaMemcpy(cnt, c->fs.counters, sizeof cnt, cudaMemcpyDeviceToHost);
+    *n_items = cnt[1];
+    if (out4 && capacity >= cnt[1])
+        cudaMemcpy(out4, c->fs.item_log, sizeof(int4) * (size_t)cnt[1], cudaMemcpyDeviceToHost);
+    return HG_OK;
+}
 
 int hg_bind_buffer(hg_ctx* c, int which, void* dptr, int64_t bytes) {
     if (!c || !dptr || c->n_read <= 0) return HG_ERR_ARG;

@@ -519,25 +519,33 @@ __device__ void mask_anno_read(const RecView& rv, const ReadView& rd, const hg_f
 __device__ __forceinline__ uint4 lds128(const uint32_t* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void sts128(uint32_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
 
+template <bool DUMP>
 __device__ void mask_anno_read_fast(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
                                     const int MIN_COV, const int read, uint32_t* hist, const int nbz,
                                     const bool self_records, const MaskAnnoOut& out) {
-    typedef Packed<uint32_t> PK;
+    // After the scan the low half (cut-off-free coverage) is never negative, so the
+    // packed word decodes with one instruction per half.
+    auto LO = [](uint32_t v) { return (int)(v & 0xffffu); };
+    auto HI = [](uint32_t v) { return (int)v >> 16; };
     const int lane = lane_id();
     constexpr int reso = kReso;
-    const int64_t o0 = rv.read_off[read], o1 = rv.read_off[read + 1];
+    const int64_t o0 = rv.read_off[read];
+    const int n = (int)(rv.read_off[read + 1] - o0);
     const int ntile = (nbz + 127) >> 7;
 
-    for (int t = 0; t <= ntile; t++)  // one tile of slack: the sweep reads bin j + 1
-        if (t < ntile || lane == 0) sts128(hist + (t << 7) + (lane << 2), make_uint4(0, 0, 0, 0));
+    for (int t = 0; t < ntile; t++) sts128(hist + (t << 7) + (lane << 2), make_uint4(0, 0, 0, 0));
+    if (lane == 0) sts128(hist + (ntile << 7), make_uint4(0, 0, 0, 0));  // the sweep reads bin j + 1
     __syncwarp();
 
     // ---- scatter (profileCoverage, LAInterface.cpp:4298-4320)
-    int m0 = -1, mc = -1;
+    int m0 = -1;
     const int C = P.cut_off;
-    for (int64_t k = o0 + lane; k < o1; k += 32) {
-        if (self_records && __ldg(rv.bread + k) == read) continue;  // filter.cpp:538-547
-        const int as = __ldg(rv.abpos + k), ae = __ldg(rv.aepos + k);
+    const int* __restrict__ pa = rv.abpos + o0;
+    const int* __restrict__ pe = rv.aepos + o0;
+    const int* __restrict__ pb = rv.bread + o0;
+    for (int k = lane; k < n; k += 32) {
+        if (self_records && __ldg(pb + k) == read) continue;  // filter.cpp:538-547
+        const int as = __ldg(pa + k), ae = __ldg(pe + k);
         const int b_s0 = as / reso + 1, b_e0 = ae / reso + 1;  // 0 <= abpos < aepos (validated at ingest)
         const int b_sc = cov_bin(as + C, reso), b_ec = cov_bin(ae - C, reso);
         atomicAdd(&hist[b_s0], 1u);
@@ -545,13 +553,14 @@ __device__ void mask_anno_read_fast(const RecView& rv, const ReadView& rd, const
         atomicAdd(&hist[b_sc], 1u << 16);
         atomicAdd(&hist[b_ec], 0u - (1u << 16));
         m0 = max(m0, b_e0);
-        mc = max(mc, max(b_sc, b_ec));
     }
-    const int L0 = __reduce_max_sync(0xffffffffu, m0) + 1;
-    const int LC = __reduce_max_sync(0xffffffffu, mc) + 1;
+    const int L0 = __reduce_max_sync(0xffffffffu, m0) + 1;  // length of the cut-off-free profile
     __syncwarp();
 
-    // ---- pass 1: prefix sums in place + longest run of covered bins (filter.cpp:696-728)
+    // ---- pass 1: prefix sums in place + longest run of covered bins (filter.cpp:696-728).
+    // Bins past the end of the cut-off profile hold coverage 0; treating them as part of the
+    // profile changes nothing: with MIN_COV >= 0 the profile's own last bin is already a zero
+    // (all events consumed), with MIN_COV < 0 they are not zeros at all.
     uint32_t carry = 0;
     int last_zero = 0;
     unsigned best = 0;  // (gap << 16) | (0xffff - z): max gap, then smallest z
@@ -567,25 +576,20 @@ __device__ void mask_anno_read_fast(const RecView& rv, const ReadView& rd, const
         carry += __shfl_sync(0xffffffffu, incl, 31);
         sts128(hp, v);
         const int j0 = (t << 7) + (lane << 2);
-        const bool z0 = j0 < LC && !(PK::hi(v.x) > MIN_COV);
-        const bool z1 = j0 + 1 < LC && !(PK::hi(v.y) > MIN_COV);
-        const bool z2 = j0 + 2 < LC && !(PK::hi(v.z) > MIN_COV);
-        const bool z3 = j0 + 3 < LC && !(PK::hi(v.w) > MIN_COV);
-        const int lz = z3 ? j0 + 3 : (z2 ? j0 + 2 : (z1 ? j0 + 1 : (z0 ? j0 : -1)));
-        const unsigned lanes = __ballot_sync(0xffffffffu, lz >= 0);
+        const unsigned nib = (HI(v.x) > MIN_COV ? 0u : 1u) | (HI(v.y) > MIN_COV ? 0u : 2u) |
+                             (HI(v.z) > MIN_COV ? 0u : 4u) | (HI(v.w) > MIN_COV ? 0u : 8u);
+        const int lz = nib ? j0 + 31 - __clz(nib) : -1;  // last zero bin of this lane
+        const unsigned lanes = __ballot_sync(0xffffffffu, nib != 0);
         const unsigned below = lanes & ((1u << lane) - 1u);
-        const int src = below ? 31 - __clz(below) : 0;
-        const int lz_src = __shfl_sync(0xffffffffu, lz, src);
-        int p = below ? lz_src : last_zero;  // previous zero bin before this lane's four
-        if (lz >= 0) {
-#define HG_GAP(zf, j)                                                              \
-    if (zf) {                                                                      \
-        const int gap = (j) - p;                                                   \
-        if (gap >= 3) best = max(best, ((unsigned)gap << 16) | (unsigned)(0xffff - (j))); \
-        p = (j);                                                                   \
-    }
-            HG_GAP(z0, j0) HG_GAP(z1, j0 + 1) HG_GAP(z2, j0 + 2) HG_GAP(z3, j0 + 3)
-#undef HG_GAP
+        const int lz_src = __shfl_sync(0xffffffffu, lz, below ? 31 - __clz(below) : 0);
+        if (nib) {
+            // consecutive zeros inside one lane are at most 3 apart, so only two runs can score:
+            // the one ending at this lane's first zero, and the pattern 1001
+            const int p = below ? lz_src : last_zero;
+            const int fz = j0 + __ffs(nib) - 1;
+            const int gap = fz - p;
+            if (gap >= 3) best = max(best, ((unsigned)gap << 16) | (unsigned)(0xffff - fz));
+            if (nib == 9u) best = max(best, (3u << 16) | (unsigned)(0xffff - (j0 + 3)));
         }
         if (lanes) last_zero = __shfl_sync(0xffffffffu, lz, 31 - __clz(lanes));
     }
@@ -614,8 +618,8 @@ __device__ void mask_anno_read_fast(const RecView& rv, const ReadView& rd, const
         }
         int sc = 0, ec = 0;
         for (int t = lane; t < limit; t += 32) {
-            sc += max(PK::hi(hist[msc + t]), MIN_COV);
-            ec += max(PK::hi(hist[mec - t]), MIN_COV);
+            sc += max(HI(hist[msc + t]), MIN_COV);
+            ec += max(HI(hist[mec - t]), MIN_COV);
         }
         sc = __reduce_add_sync(0xffffffffu, sc);
         ec = __reduce_add_sync(0xffffffffu, ec);
@@ -639,42 +643,58 @@ __device__ void mask_anno_read_fast(const RecView& rv, const ReadView& rd, const
     else
         mk = q;
 
-    // ---- pass 2: hinge pre-test sums (filter.cpp:842-865), repeat annotation
-    // (filter.cpp:796-813), optional profile dump (filter.cpp:599-602)
+    // ---- hinge pre-test: mean coverage near both mask ends (filter.cpp:842-865)
     const int NHR = P.no_hinge_region;
-    const int jn = max(L0 - 2, 0);
-    const int a_lo = mk.x + NHR, a_hi = mk.y - NHR;
+    int cs = 0, ns = 0, ce = 0, ne = 0;
+    {
+        int jlo = mk.x <= 0 ? 0 : (mk.x + reso - 1) / reso;  // bins with mk.x <= 40 j <= mk.x + NHR
+        int jhi = mk.x + NHR < 0 ? -1 : min((mk.x + NHR) / reso, L0 - 1);
+        for (int j = jlo + lane; j <= jhi; j += 32) {
+            cs += LO(hist[j]);
+            ns++;
+        }
+        jlo = mk.y - NHR <= 0 ? 0 : (mk.y - NHR + reso - 1) / reso;  // mk.y - NHR <= 40 j <= mk.y
+        jhi = mk.y < 0 ? -1 : min(mk.y / reso, L0 - 1);
+        for (int j = jlo + lane; j <= jhi; j += 32) {
+            ce += LO(hist[j]);
+            ne++;
+        }
+        cs = __reduce_add_sync(0xffffffffu, cs);
+        ns = __reduce_add_sync(0xffffffffu, ns);
+        ce = __reduce_add_sync(0xffffffffu, ce);
+        ne = __reduce_add_sync(0xffffffffu, ne);
+    }
+    // float on purpose: 0/0 = NaN makes the '< 10' test false (filter.cpp:861-865)
+    const float avg_end = __fdiv_rn((float)ce, (float)ne);
+    const float avg_start = __fdiv_rn((float)cs, (float)ns);
+    const bool skip_hinges = fabsf(__fsub_rn(avg_end, avg_start)) < 10.0f;
+
+    // ---- pass 2: repeat annotation from the coverage gradient (filter.cpp:796-813),
+    // optional profile dump (filter.cpp:599-602)
     const int MINT = P.min_repeat_annotation_threshold, MAXT = P.max_repeat_annotation_threshold;
     const int RJ = min(MINT, MAXT);  // the threshold never drops below this
-    int cs = 0, ns = 0, ce = 0, ne = 0, cnt = 0;
-    int* dump = out.cov0 ? out.cov0 + out.cov0_off[read] : nullptr;
-    const int tiles0 = (L0 + 127) >> 7;
-    for (int t = 0; t < tiles0; t++) {
+    // bins j < L0 - 2 whose position lies in [mask.start + NHR, mask.end - NHR]
+    const int ja_lo = mk.x + NHR <= 0 ? 0 : (mk.x + NHR + reso - 1) / reso;
+    const int ja_hi = mk.y - NHR < 0 ? -1 : min((mk.y - NHR) / reso, L0 - 3);
+    int cnt = 0;
+    int* dump = DUMP ? out.cov0 + out.cov0_off[read] : nullptr;
+    const int t_lo = DUMP ? 0 : (ja_lo >> 7);
+    const int t_hi = DUMP ? ((L0 + 127) >> 7) - 1 : (ja_hi >> 7);
+    for (int t = t_lo; t <= t_hi; t++) {
         const int j0 = (t << 7) + (lane << 2);
         const uint4 v = lds128(hist + j0);
         uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
         if (lane == 31) nx = hist[j0 + 4];
-        const int c[5] = {PK::lo(v.x), PK::lo(v.y), PK::lo(v.z), PK::lo(v.w), PK::lo(nx)};
+        const int c[5] = {LO(v.x), LO(v.y), LO(v.z), LO(v.w), LO(nx)};
         int type[4];
         bool any = false;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const int j = j0 + i, pos = reso * j;
-            if (j < L0) {
-                if (pos >= mk.x && pos <= mk.x + NHR) {
-                    cs += c[i];
-                    ns++;
-                }
-                if (pos <= mk.y && pos >= mk.y - NHR) {
-                    ce += c[i];
-                    ne++;
-                }
-                if (dump) dump[j] = c[i];
-            }
+            const int j = j0 + i;
+            if (DUMP && j < L0) dump[j] = c[i];
             type[i] = 0;
             const int g = c[i + 1] - c[i];
-            // most bins are rejected without the division
-            if (j < jn && pos >= a_lo && pos <= a_hi && (g > RJ || g < -RJ)) {
+            if ((g > RJ || g < -RJ) && j >= ja_lo && j <= ja_hi) {  // rare: only now pay the division
                 const int thr = min(max((c[i] + MIN_COV) / P.coverage_fraction, MINT), MAXT);
                 type[i] = g > thr ? 1 : (g < -thr ? -1 : 0);
             }
@@ -693,14 +713,6 @@ __device__ void mask_anno_read_fast(const RecView& rv, const ReadView& rd, const
             __syncwarp();
         }
     }
-    cs = __reduce_add_sync(0xffffffffu, cs);
-    ns = __reduce_add_sync(0xffffffffu, ns);
-    ce = __reduce_add_sync(0xffffffffu, ce);
-    ne = __reduce_add_sync(0xffffffffu, ne);
-    // float on purpose: 0/0 = NaN makes the '< 10' test false (filter.cpp:861-865)
-    const float avg_end = __fdiv_rn((float)ce, (float)ne);
-    const float avg_start = __fdiv_rn((float)cs, (float)ns);
-    const bool skip_hinges = fabsf(__fsub_rn(avg_end, avg_start)) < 10.0f;
 
     // ---- merge pass (filter.cpp:817-829) + publication, as in the generic path
     int kept = 0;
@@ -756,7 +768,7 @@ __device__ __forceinline__ int bins_needed(int rlen, const hg_filter_params& P) 
     return (rlen + max(P.cut_off, 0)) / kReso + 3;
 }
 
-template <int WARPS>
+template <int WARPS, bool DUMP>
 __global__ void __launch_bounds__(WARPS * 32)
 k_mask_anno(RecView rv, ReadView rd, hg_filter_params P, const int* __restrict__ scal,
             const int* __restrict__ self_cnt, int r_begin, int r_end, int nb_cap, MaskAnnoOut out) {
@@ -772,7 +784,7 @@ k_mask_anno(RecView rv, ReadView rd, hg_filter_params P, const int* __restrict__
             if (lane_id() == 0) out.big_list[atomicAdd(&out.counters[3], 1)] = read;
             continue;
         }
-        mask_anno_read_fast(rv, rd, P, MIN_COV, read, hist, nbz, self_cnt[read] > 0, out);
+        mask_anno_read_fast<DUMP>(rv, rd, P, MIN_COV, read, hist, nbz, self_cnt[read] > 0, out);
     }
 }
 
@@ -795,7 +807,7 @@ k_mask_anno_big(RecView rv, ReadView rd, hg_filter_params P, const int* __restri
 
 // ------------------------------------------------------------------ K4
 
-struct KeyIdx {
+struct __align__(8) KeyIdx {
     int key, idx;
 };
 struct GreaterKey {
@@ -915,80 +927,127 @@ __device__ __forceinline__ int hinge_class(int2 e, bool out_hinge, int2 mk, int 
 // Scratch slot per warp (cap = deepest pile-up):
 //   int4 rec[cap] | KeyIdx ord[cap] | int2 ends[cap] | int2 sorted[cap]
 constexpr int kHingeSlotBytesPerRec = 16 + 8 + 8 + 8;
+constexpr int kHingeSmemEnds = 192;
+constexpr int kHingeSmemPile = 1024;
 
 __global__ void __launch_bounds__(128)
 k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict__ mask,
              const int2* __restrict__ anno_ref, const int2* __restrict__ anno_pool,
              int* __restrict__ counters, const int* __restrict__ work_list,
-             uint8_t* __restrict__ hinge_keep, uint8_t* scratch, int cap) {
+             uint8_t* __restrict__ hinge_keep, uint8_t* scratch, int cap, int4* __restrict__ item_log) {
     const int lane = lane_id();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     uint8_t* base = scratch + (size_t)warp * cap * kHingeSlotBytesPerRec;
     int4* rec = reinterpret_cast<int4*>(base);
-    KeyIdx* ord = reinterpret_cast<KeyIdx*>(base + (size_t)cap * 16);
+    KeyIdx* const ord_global = reinterpret_cast<KeyIdx*>(base + (size_t)cap * 16);
     int2* ends = reinterpret_cast<int2*>(base + (size_t)cap * 24);
     int2* sorted = reinterpret_cast<int2*>(base + (size_t)cap * 32);
     const int nwork = counters[1];
     const int THETA = P.theta, HTL = P.hinge_tolerance_length, HBL = P.hinge_bin_length;
+    // end lists of up to kHingeSmemEnds entries are sorted and walked in shared memory
+    __shared__ int2 sh_ends[4][kHingeSmemEnds], sh_sorted[4][kHingeSmemEnds];
+    __shared__ KeyIdx sh_ord[4][kHingeSmemPile];  // pile-up sort keys of the order-exact path
+    int2* const ends_s = sh_ends[threadIdx.x >> 5];
+    int2* const sorted_s = sh_sorted[threadIdx.x >> 5];
+    (void)nwarps;
 
-    for (int w = warp; w < nwork; w += nwarps) {
+    // reads are handed out one at a time: a read that needs the (sequential) order-exact
+    // path keeps its warp busy for a long time and must not delay a static share of others
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(&counters[5], 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= nwork) break;
+        const long long t_begin = item_log ? clock64() : 0;
+        int log_support = 0, log_exact = 0;
         const int read = work_list[w];
         const int64_t o0 = rv.read_off[read], o1 = rv.read_off[read + 1];
         const int2 mk = mask[read];
         const int2 ar = anno_ref[read];
         bool have_exact_order = false;
         int n_exact = 0;
+        KeyIdx* ord = ord_global;
         for (int j = 0; j < ar.y; j++) {
             const int2 an = anno_pool[ar.x + j];
             const int apos = an.x;
             const bool out_hinge = an.y == -1;
-            // ---- select in file order
+            // ---- select in file order, two steps: (1) the test on A's coordinates alone
+            // (two coalesced columns) keeps a minority of the pile-up; (2) only those pay for
+            // the B side (four more columns + gathers of rlen[B] and mask[B])
+            int* const near_idx = reinterpret_cast<int*>(ord_global);
+            int n_near = 0;
+            const int np = (int)(o1 - o0);
+#pragma unroll 2
+            for (int kb = 0; kb < np; kb += 32) {
+                const int k = kb + lane;
+                bool near = false;
+                if (k < np) {
+                    const int pos = out_hinge ? __ldg(rv.aepos + o0 + k) : __ldg(rv.abpos + o0 + k);
+                    near = pos > apos - HTL && pos < apos + HTL;
+                }
+                const unsigned nm = __ballot_sync(0xffffffffu, near);
+                if (near) near_idx[n_near + __popc(nm & ((1u << lane) - 1u))] = k;
+                n_near += __popc(nm);
+            }
+            __syncwarp();
             int support = 0;
-            for (int64_t kb = o0; kb < o1; kb += 32) {
-                const int64_t k = kb + lane;
+            for (int cb = 0; cb < n_near; cb += 32) {
+                const int c = cb + lane;
                 bool sel = false;
                 int2 e = make_int2(0, 0);
-                if (k < o1) {
-                    const PileRec r = load_pile_rec(rv, rd, mask, read, k);
+                if (c < n_near) {
+                    const PileRec r = load_pile_rec(rv, rd, mask, read, o0 + near_idx[c]);
                     sel = r.active && hinge_select(r, out_hinge, apos, THETA, HTL, &e);
                 }
                 const unsigned sm = __ballot_sync(0xffffffffu, sel);
-                if (sel) ends[support + __popc(sm & ((1u << lane) - 1u))] = e;
+                if (sel) {
+                    const int slot = support + __popc(sm & ((1u << lane) - 1u));
+                    ends[slot] = e;
+                    if (slot < kHingeSmemEnds) ends_s[slot] = e;
+                }
                 support += __popc(sm);
             }
             __syncwarp();
             uint8_t keep = 0;
             if (support >= P.hinge_min_support) {  // filter.cpp:910, 1005
+                const bool small = support <= kHingeSmemEnds;
+                const int2* const src = small ? ends_s : ends;
+                int2* const dst = small ? sorted_s : sorted;
                 // ---- stable rank sort by position (ascending for out-hinges, descending for
                 // in-hinges) and detection of position ties the walk could tell apart
                 bool danger = support > 1024;
                 if (!danger) {
+                    // descending order = ascending order of the negated position
+                    const int sgn = out_hinge ? 1 : -1;
                     for (int i = lane; i < support; i += 32) {
-                        const int2 me = ends[i];
+                        const int2 me = src[i];
+                        const int mx = sgn * me.x;
                         int rank = 0;
+#pragma unroll 4
                         for (int t = 0; t < support; t++) {
-                            const int x = ends[t].x;
-                            const bool before = out_hinge ? x < me.x : x > me.x;
-                            rank += (before || (x == me.x && t < i)) ? 1 : 0;
+                            const int x = sgn * src[t].x;
+                            rank += (x < mx || (x == mx && t < i)) ? 1 : 0;
                         }
-                        sorted[rank] = me;
+                        dst[rank] = me;
                     }
                     __syncwarp();
                     bool d = false;
                     for (int i = lane; i + 1 < support; i += 32) {
-                        const int2 a = sorted[i], b = sorted[i + 1];
+                        const int2 a = dst[i], b = dst[i + 1];
                         d = d || (a.x == b.x && hinge_class(a, out_hinge, mk, THETA, HBL) !=
                                                     hinge_class(b, out_hinge, mk, THETA, HBL));
                     }
                     danger = __any_sync(0xffffffffu, d);
                 }
                 if (!danger) {
-                    if (lane == 0) keep = hinge_walk(sorted, support, out_hinge, mk, P) ? 1 : 0;
+                    if (lane == 0) keep = hinge_walk(dst, support, out_hinge, mk, P) ? 1 : 0;
                 } else {
                     // ---- order-exact path.  Pile-up in file order, then std::sort by total
                     // length, descending (filter.cpp:565-567), once per read
                     if (!have_exact_order) {
+                        const bool ord_in_smem = o1 - o0 <= kHingeSmemPile;
+                        if (ord_in_smem) ord = sh_ord[threadIdx.x >> 5];
                         int n = 0;
                         for (int64_t kb = o0; kb < o1; kb += 32) {
                             const int64_t k = kb + lane;
@@ -1005,7 +1064,12 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
                             n += __popc(am);
                         }
                         __syncwarp();
-                        if (lane == 0) std_sort_exact(ord, n, GreaterKey());
+                        if (lane == 0) {
+                            if (ord_in_smem)  // separate call site: the sort runs on LDS/STS
+                                std_sort_exact(sh_ord[threadIdx.x >> 5], n, GreaterKey());
+                            else
+                                std_sort_exact(ord_global, n, GreaterKey());
+                        }
                         __syncwarp();
                         have_exact_order = true;
                         n_exact = n;
@@ -1022,23 +1086,32 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
                             sel = hinge_select(r, out_hinge, apos, THETA, HTL, &e);
                         }
                         const unsigned sm = __ballot_sync(0xffffffffu, sel);
-                        if (sel) ends[sup2 + __popc(sm & ((1u << lane) - 1u))] = e;
+                        if (sel) {
+                            const int slot = sup2 + __popc(sm & ((1u << lane) - 1u));
+                            ends[slot] = e;
+                            if (slot < kHingeSmemEnds) ends_s[slot] = e;
+                        }
                         sup2 += __popc(sm);
                     }
                     __syncwarp();
                     if (lane == 0) {
+                        int2* const ex = sup2 <= kHingeSmemEnds ? ends_s : ends;
                         if (out_hinge)
-                            std_sort_exact(ends, sup2, FirstAsc());  // filter.cpp:914
+                            std_sort_exact(ex, sup2, FirstAsc());  // filter.cpp:914
                         else
-                            std_sort_exact(ends, sup2, FirstDesc());  // filter.cpp:1010
-                        keep = hinge_walk(ends, sup2, out_hinge, mk, P) ? 1 : 0;
+                            std_sort_exact(ex, sup2, FirstDesc());  // filter.cpp:1010
+                        keep = hinge_walk(ex, sup2, out_hinge, mk, P) ? 1 : 0;
                         atomicAdd(&counters[4], 1);
                     }
                 }
             }
             if (lane == 0) hinge_keep[ar.x + j] = keep;
+            log_support = max(log_support, support);
             __syncwarp();
         }
+        log_exact = have_exact_order ? n_exact : 0;
+        if (item_log && lane == 0)
+            item_log[w] = make_int4(read, (int)(clock64() - t_begin), log_support, log_exact);
     }
 }
 
@@ -1107,10 +1180,12 @@ int mask_anno_configure(FilterScratch& s, int nb_cap) {
     const int max_words = ((200 * 1024) / (4 * kMaskAnnoWarps) - 128) & ~127;
     if (nb_cap > max_words) nb_cap = max_words;
     const int smem = (nb_cap + 128) * 4 * kMaskAnnoWarps;
-    cudaFuncSetAttribute(k_mask_anno<kMaskAnnoWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         smem);
+    cudaFuncSetAttribute(k_mask_anno<kMaskAnnoWarps, false>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_mask_anno<kMaskAnnoWarps, true>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mask_anno<kMaskAnnoWarps>,
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mask_anno<kMaskAnnoWarps, false>,
                                                   kMaskAnnoWarps * 32, smem);
     if (per_sm < 1) per_sm = 1;
     s.nb_cap = nb_cap;
@@ -1132,8 +1207,12 @@ void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_par
     cudaMemsetAsync(s.hinge_keep, 0, (size_t)s.anno_cap, st);
     const int smem = (s.nb_cap + 128) * 4 * kMaskAnnoWarps;
     g_launches += 1 + (s.big_slot_words > 0);
-    k_mask_anno<kMaskAnnoWarps><<<s.mask_anno_grid, kMaskAnnoWarps * 32, smem, st>>>(
-        rv, rd, P, s.scal, s.self_cnt, r_begin, r_end, s.nb_cap, out);
+    if (cov0)
+        k_mask_anno<kMaskAnnoWarps, true><<<s.mask_anno_grid, kMaskAnnoWarps * 32, smem, st>>>(
+            rv, rd, P, s.scal, s.self_cnt, r_begin, r_end, s.nb_cap, out);
+    else
+        k_mask_anno<kMaskAnnoWarps, false><<<s.mask_anno_grid, kMaskAnnoWarps * 32, smem, st>>>(
+            rv, rd, P, s.scal, s.self_cnt, r_begin, r_end, s.nb_cap, out);
     if (s.big_slot_words > 0)
         k_mask_anno_big<<<s.big_warps / 4, 128, 0, st>>>(rv, rd, P, s.scal, out, s.big_scratch,
                                                          s.big_slot_words);
@@ -1151,7 +1230,7 @@ void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_pa
     g_launches += 1;
     k_hinge_call<<<s.hinge_warps / 4, 128, 0, st>>>(rv, rd, P, s.mask, s.anno_ref, s.anno_pool,
                                                     s.counters, s.work_list, s.hinge_keep,
-                                                    s.hinge_scratch, s.hinge_cap);
+                                                    s.hinge_scratch, s.hinge_cap, s.item_log);
 }
 
 }  // namespace hg

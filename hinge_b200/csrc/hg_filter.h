@@ -43,6 +43,7 @@ struct FilterScratch {
     uint8_t* hinge_keep = nullptr;  // anno_cap
     uint8_t* hinge_scratch = nullptr;
     int hinge_cap = 0, hinge_warps = 0;
+    int4* item_log = nullptr;       // HG_OPT_PROFILE: (read, cycles, support, exact n) per work item
 };
 
 void launch_csr_validate(const RecView& rv, const ReadView& rd, int64_t* read_off, int* err,
