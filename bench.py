@@ -233,26 +233,19 @@ def main():
     params = api.FilterParams()
 
     # per-read arrays that cross shards live in torch tensors so NCCL can all-gather them in place
-    mean_cov = torch.full((world * chunk,), -1, dtype=torch.int32, device=dev)
-    mask = torch.zeros((world * chunk, 2), dtype=torch.int32, device=dev)
-    ctx.bind_buffer(api.HG_BUF_MEAN_COV, mean_cov)
-    ctx.bind_buffer(api.HG_BUF_MASK, mask)
+    from hinge_b200.sharding import ShardedArrays, run_filter_sharded
 
-    def exchange(t):
-        if world > 1:
-            dist.all_gather_into_tensor(t, t[rank * chunk:(rank + 1) * chunk].clone())
+    arrays = ShardedArrays(n_read, rank, world, dev)
+    assert (arrays.lo, arrays.hi) == (a_lo, a_hi)
+    ctx.bind_buffer(api.HG_BUF_MEAN_COV, arrays.mean_cov)
+    ctx.bind_buffer(api.HG_BUF_MASK, arrays.mask)
 
     def run_stage():
         """The sharded form of hg_filter: phase1 | all-gather means | phase2 | all-gather masks | phase3."""
-        for _ in range(8):
-            ctx.filter_phase1(params)
-            exchange(mean_cov)
-            ctx.filter_phase2()
-            exchange(mask)
-            rc, s = ctx.filter_phase3()
-            if rc != api.HG_RETRY_POOL:
-                return s
-            raise RuntimeError("annotation pool overflow in sharded mode (grow hg_set_overlaps' pool)")
+        rc, s = run_filter_sharded(ctx, params, arrays)
+        if rc == api.HG_RETRY_POOL:
+            raise RuntimeError("annotation pool overflow")
+        return s
 
     def barrier():
         if world > 1:

@@ -4,7 +4,7 @@
 
   dal_small    a real daligner-made fixture: DAZZ_DB `simulator 0.12 -c25. -r3`
                -> fasta2DB -> DBsplit -x500 -s400 -> daligner -> LAsort/LAmerge
-               -> DASqv -c25   (318 reads / 11 978 overlaps)
+               -> DASqv -c25   (278 reads after DBsplit trimming / 11 978 overlaps)
   synth_*      hinge_synth fixtures (tools/hg_synth.cpp), regenerated from the
                parameters in fixture.json at test time; only the reference's
                OUTPUTS are committed, plus the sha256 of the generated inputs.

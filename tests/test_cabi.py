@@ -53,7 +53,7 @@ def test_no_gpu_means_loud_failure_not_fallback(built, tmp_path):
     root, meta = ht.materialize("dal_small", str(tmp_path))
     r = ht.run_stage("product", "filter", str(tmp_path), root, "gpu", check=False)
     assert r.returncode == 1
-    assert "# Reads: 318" in r.stdout and "# Alignments: 11978" in r.stdout
+    assert "# Reads: 278" in r.stdout and "# Alignments: 11978" in r.stdout
     assert "no CPU fallback" in r.stdout
     assert not os.path.exists(os.path.join(str(tmp_path), "gpu.mas"))
 
