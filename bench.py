@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-downstream", action="store_true", help="skip the maximal/layout timing")
     return ap.parse_args()
 
 
@@ -186,6 +187,45 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+# ----------------------------------------------------------------------------- downstream stages
+
+
+def time_downstream(args, syn, ctx, api, filt, np, torch):
+    """hg_maximal and hg_layout on the same batch, fed with the filter's results (host buffers, traces
+    included): wall time of the C-ABI call and device time of its kernels.  Not part of `value`."""
+    t0 = time.perf_counter()
+    novl = syn.generate(want_trace=True, threads=host_threads())
+    cols = syn.cols()
+    trace_off, trace = syn.trace()
+    gen_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ctx.set_overlaps(novl, cols, trace_off=trace_off, trace=trace, tbytes=1, where=api.HG_MEM_HOST)
+    torch.cuda.synchronize()
+    load_s = time.perf_counter() - t0
+    lp = api.LayoutParams()
+    mask = filt["mask"]
+    out = {"overlaps": novl, "trace_bytes": int(trace_off[-1]), "generate_s": round(gen_s, 2), "h2d_s": round(load_s, 3)}
+    os.environ.setdefault("HINGE_B200_SKIP_CONTAINED_TXT", "1")
+    for rep in range(2):
+        t0 = time.perf_counter()
+        maximal, _, ms_dev = ctx.maximal(lp, mask)
+        out["maximal"] = {"wall_ms": 1e3 * (time.perf_counter() - t0), "device_ms": ms_dev,
+                          "maximal_reads": int(maximal.sum())}
+    n = len(mask)
+    off = filt["anno_off"]
+    keep = filt["hinge_keep"].astype(bool)
+    per_read = np.repeat(np.arange(n), np.diff(off))
+    hin_off = np.zeros(n + 1, np.int64)
+    np.cumsum(np.bincount(per_read[keep], minlength=n), out=hin_off[1:])
+    rep_csr = (off, filt["anno_pos"], filt["anno_type"])
+    hin_csr = (hin_off, filt["anno_pos"][keep], filt["anno_type"][keep])
+    for rep in range(2):
+        t0 = time.perf_counter()
+        edges, ms_dev = ctx.layout(lp, mask, maximal, rep_csr, hin_csr)
+        out["layout"] = {"wall_ms": 1e3 * (time.perf_counter() - t0), "device_ms": ms_dev, "edges": len(edges)}
+    return out
+
+
 # ----------------------------------------------------------------------------- our arm
 
 
@@ -315,9 +355,10 @@ def main():
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         kavg = {k: sum(v) / len(v) for k, v in ktimes.items()}
         owned = a_hi - a_lo
-        # algorithmic bytes of one launch: K2 reads bread/abpos/aepos (12 B per record)
-        # plus ~45 B per read of offsets, lengths, QV mask and results; K1 reads 16 B per record
-        kbytes = {"mask_anno": 12.0 * novl + 45.0 * owned, "cov_estimate": 16.0 * novl + 24.0 * owned}
+        # algorithmic bytes of one launch: K2 reads abpos/aepos (8 B per record; bread
+        # only for the few reads with self-overlaps) plus ~45 B per read of offsets, lengths, QV mask and
+        # results; K1 reads aread/bread/abpos/aepos (16 B per record)
+        kbytes = {"mask_anno": 8.0 * novl + 45.0 * owned, "cov_estimate": 16.0 * novl + 24.0 * owned}
         dom = max(("mask_anno", "cov_estimate"), key=lambda k: kavg[k])
         achieved = kbytes[dom] / (kavg[dom] * 1e-3) / 1e9
         traffic = None
@@ -346,6 +387,10 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             base, _ = time_reference_filter(args, 1, 0)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if world == 1 and not args.no_downstream:
+        # informational: the two stages downstream of the filter on the same batch (they need the trace)
+        line["downstream_stages"] = time_downstream(args, syn, ctx, api, res, np, torch)
+    if rank == 0:
         print(json.dumps(line))
     ctx.close()
     if world > 1:

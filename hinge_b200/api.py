@@ -145,10 +145,10 @@ class Context:
                     "hg_bind_buffer")
         self._bound = getattr(self, "_bound", []) + [tensor]
 
-    def maximal(self, params, mask=None):
+    def maximal(self, params, mask=None, want_contained_by=False):
         n = self.n_read
         mx = np.zeros(n, np.uint8)
-        by = np.zeros(n, np.int32)
+        by = np.zeros(n, np.int32) if want_contained_by else None
         ms = C.c_float()
         if mask is not None:
             mask = np.ascontiguousarray(mask, dtype=np.int32)

@@ -288,10 +288,10 @@ int hg_set_overlaps(hg_ctx* c, int64_t novl, const int32_t* aread, const int32_t
     // scratch that depends on the shape of the data
     FilterScratch& s = c->fs;
     if (s.anno_cap == 0) HG_TRY(alloc_anno_pool(c, 2 * (a_hi - a_lo) + (1 << 16)));
-    // K4: one slot of 40 B per pile-up record and warp
+    // K4: one slot of 48 B per pile-up record and warp
     s.hinge_cap = (std::max(c->max_pileup, 32) + 3) & ~3;  // keeps every slot 16-byte aligned
     {
-        const size_t slot = (size_t)s.hinge_cap * 40;
+        const size_t slot = (size_t)s.hinge_cap * 48;
         size_t warps = (size_t)c->num_sms * 48;  // the kernel is latency bound: many warps, few reads each
         const size_t budget = (size_t)768 << 20;
         if (warps * slot > budget) warps = std::max<size_t>(4, budget / slot);

@@ -925,8 +925,8 @@ __device__ __forceinline__ int hinge_class(int2 e, bool out_hinge, int2 mk, int 
 // the pile-up and on the end list.
 //
 // Scratch slot per warp (cap = deepest pile-up):
-//   int4 rec[cap] | KeyIdx ord[cap] | int2 ends[cap] | int2 sorted[cap]
-constexpr int kHingeSlotBytesPerRec = 16 + 8 + 8 + 8;
+//   int4 rec[cap] | KeyIdx ord[cap] | int2 ends[cap] | int2 sorted[cap] | int2 keys[cap]
+constexpr int kHingeSlotBytesPerRec = 16 + 8 + 8 + 8 + 8;
 constexpr int kHingeSmemEnds = 192;
 constexpr int kHingeSmemPile = 1024;
 
@@ -943,6 +943,7 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
     KeyIdx* const ord_global = reinterpret_cast<KeyIdx*>(base + (size_t)cap * 16);
     int2* ends = reinterpret_cast<int2*>(base + (size_t)cap * 24);
     int2* sorted = reinterpret_cast<int2*>(base + (size_t)cap * 32);
+    int2* keys = reinterpret_cast<int2*>(base + (size_t)cap * 40);  // (total length, selection index)
     const int nwork = counters[1];
     const int THETA = P.theta, HTL = P.hinge_tolerance_length, HBL = P.hinge_bin_length;
     // end lists of up to kHingeSmemEnds entries are sorted and walked in shared memory
@@ -996,14 +997,17 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
                 const int c = cb + lane;
                 bool sel = false;
                 int2 e = make_int2(0, 0);
+                int sel_key = 0;
                 if (c < n_near) {
                     const PileRec r = load_pile_rec(rv, rd, mask, read, o0 + near_idx[c]);
                     sel = r.active && hinge_select(r, out_hinge, apos, THETA, HTL, &e);
+                    sel_key = r.key;
                 }
                 const unsigned sm = __ballot_sync(0xffffffffu, sel);
                 if (sel) {
                     const int slot = support + __popc(sm & ((1u << lane) - 1u));
                     ends[slot] = e;
+                    keys[slot] = make_int2(sel_key, slot);
                     if (slot < kHingeSmemEnds) ends_s[slot] = e;
                 }
                 support += __popc(sm);
@@ -1042,8 +1046,36 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
                 }
                 if (!danger) {
                     if (lane == 0) keep = hinge_walk(dst, support, out_hinge, mk, P) ? 1 : 0;
-                } else {
-                    // ---- order-exact path.  Pile-up in file order, then std::sort by total
+                } else if (![&]() {
+                               // ---- order-exact path, cheap form.  The end list enters its std::sort in
+                               // pile-up order = total length, descending.  If the selected records have
+                               // pairwise different lengths that order is unique whatever the unstable
+                               // pile-up sort did to ties elsewhere: no pile-up sort needed at all.
+                               if (support > 1024) return false;
+                               bool tie = false;
+                               for (int i = lane; i < support; i += 32) {
+                                   const int2 me = keys[i];
+                                   int rank = 0;
+                                   for (int t = 0; t < support; t++) {
+                                       const int x = keys[t].x;
+                                       rank += (x > me.x || (x == me.x && t < i)) ? 1 : 0;
+                                       tie = tie || (x == me.x && t != i);
+                                   }
+                                   sorted[rank] = ends[me.y];
+                               }
+                               if (__any_sync(0xffffffffu, tie)) return false;
+                               __syncwarp();
+                               if (lane == 0) {
+                                   if (out_hinge)
+                                       std_sort_exact(sorted, support, FirstAsc());  // filter.cpp:914
+                                   else
+                                       std_sort_exact(sorted, support, FirstDesc());  // filter.cpp:1010
+                                   keep = hinge_walk(sorted, support, out_hinge, mk, P) ? 1 : 0;
+                                   atomicAdd(&counters[4], 1);
+                               }
+                               return true;
+                           }()) {
+                    // ---- order-exact path, full form.  Pile-up in file order, then std::sort by total
                     // length, descending (filter.cpp:565-567), once per read
                     if (!have_exact_order) {
                         const bool ord_in_smem = o1 - o0 <= kHingeSmemPile;

@@ -48,7 +48,11 @@ bool load_ini(const std::string& path, Params* p, std::string* err) {
             }
         std::string key = section + "=" + name;
         std::transform(key.begin(), key.end(), key.begin(), ::tolower);
-        kv[key] = value;
+        // lib/INIReader.cpp:74-81: a repeated key APPENDS "\n" + value, so numeric getters see the first one
+        if (kv.count(key) && !kv[key].empty())
+            kv[key] += "\n" + value;
+        else
+            kv[key] = value;
     }
     fclose(f);
     auto geti = [&](const char* k, int def) {

@@ -1,0 +1,115 @@
+"""Edge cases on hand-made inputs, product CLI vs oracle CLI, all output files:
+read pairs with more than 16 overlaps (std::sort stops being stable there), 16-bit
+traces (tspace > 125), reads without any overlap at both ends of the id range and
+in the middle, self-overlaps with the telomere switches on, no QV track, and INI
+variants that switch the masks."""
+import os
+
+import numpy as np
+import pytest
+
+import handmade as hm
+import hingetest as ht
+
+pytestmark = pytest.mark.gpu
+ALL = ht.FILTER_OUT + ht.MAXIMAL_OUT + ht.LAYOUT_OUT
+
+
+def _run_all(work, root, ini=ht.INI):
+    for stage in ("filter", "maximal", "layout"):
+        ht.run_stage("oracle", stage, work, root, "ora", ini=ini)
+        ht.run_stage("product", stage, work, root, "gpu", ini=ini)
+    ht.assert_same_files(work, "gpu", "ora", ALL)
+
+
+def _tiling(rng, n_read, rlen, genome, cov_step):
+    """Reads tiled along a line with dense genuine overlaps (both directions)."""
+    starts = np.sort(rng.integers(0, genome - max(rlen), n_read))
+    recs = []
+    for i in range(n_read):
+        for j in range(i + 1, n_read):
+            s, e = max(starts[i], starts[j]), min(starts[i] + rlen[i], starts[j] + rlen[j])
+            if e - s >= 1000:
+                recs += hm.both_directions(i, j, int(s - starts[i]), int(e - starts[i]), int(s - starts[j]),
+                                           int(e - starts[j]), 0, rlen)
+    return recs
+
+
+def test_many_overlaps_per_pair_and_ties(built, tmp_path):
+    rng = np.random.default_rng(1)
+    n = 60
+    rlen = [int(x) for x in rng.integers(6000, 12000, n)]
+    recs = _tiling(rng, n, rlen, 60000, 0)
+    # 40 extra overlaps for a few pairs, many with identical lengths (tandem-repeat like)
+    for (a, b) in [(3, 7), (10, 12), (20, 21)]:
+        for k in range(40):
+            ab = 100 * (k % 20) + 50
+            ln = 1500 + 100 * (k % 3)
+            recs += hm.both_directions(a, b, ab, ab + ln, 200 + 37 * k % 900, 200 + 37 * k % 900 + ln, 0, rlen)
+    hm.write_fixture(str(tmp_path), "H", rlen, recs, tspace=100, qv="good")
+    _run_all(str(tmp_path), "H")
+
+
+def test_sixteen_bit_traces(built, tmp_path):
+    rng = np.random.default_rng(2)
+    n = 50
+    rlen = [int(x) for x in rng.integers(7000, 15000, n)]
+    recs = _tiling(rng, n, rlen, 70000, 0)
+    for (a, b) in [(5, 30), (6, 31), (7, 32)]:  # a few complemented ones
+        recs += hm.both_directions(a, b, 500, 3500, 1000, 4000, 1, rlen)
+    hm.write_fixture(str(tmp_path), "W", rlen, recs, tspace=200, qv="good")
+    _run_all(str(tmp_path), "W")
+
+
+def test_reads_without_overlaps_and_self_overlaps(built, tmp_path):
+    rng = np.random.default_rng(3)
+    n = 70
+    rlen = [int(x) for x in rng.integers(11000, 16000, n)]
+    core = list(range(5, 60))  # reads 0-4 and 60-69 have no record at all, neither has 33
+    core.remove(33)
+    sub = [rlen[i] for i in core]
+    recs = []
+    for (i, j, ab, ae, bb, be, c) in _tiling(rng, len(core), sub, 90000, 0):
+        recs.append((core[i], core[j], ab, ae, bb, be, c))
+    for r in (8, 9, 40):  # heavy self-overlaps: > 4.5x the read length in total (filter.cpp:552-561)
+        for k in range(30):
+            recs.append((r, r, 100 + 10 * k, 100 + 10 * k + 9000, 300 + 5 * k, 300 + 5 * k + 9000, 0))
+    hm.write_fixture(str(tmp_path), "E", rlen, recs, tspace=100, qv=None)
+    ini = os.path.join(str(tmp_path), "telomere.ini")
+    with open(ini, "w") as f:
+        f.write(open(ht.INI).read() + "del_telomere = 1\ndel_telomeres = 1\nnum_events_telomere = 0\n")
+    _run_all(str(tmp_path), "E", ini=ini)
+    assert os.path.getsize(os.path.join(str(tmp_path), "ora.self.flag")) > 0, "fixture should flag self-overlapping reads"
+
+
+VARIANTS = [
+    {"use_qv": "false"},
+    {"coverage": "false"},
+    {"min_cov": "40", "ec": "90"},
+    {"theta": "100", "theta2": "50", "aln_threshold": "2500", "length_threshold": "4000",
+     "hinge_tolerance": "250", "matching_hinge_slack": "400", "min_connected_component_size": "2"},
+    {"no_hinge_region": "900", "hinge_min_support": "4", "hinge_unbridged": "3", "hinge_min_pileup": "4",
+     "hinge_tolerance_length": "150", "repeat_annotation_gap_threshold": "800",
+     "min_repeat_annotation_threshold": "6", "max_repeat_annotation_threshold": "9", "use_two_matches": "0"},
+]
+
+
+def write_ini(path, overrides):
+    filt = {"length_threshold": "1000;", "aln_threshold": "1000;", "min_cov": "5;", "cut_off": "300;",
+            "theta": "300;", "use_qv": "true;"}
+    layout = {"hinge_slack": "1000", "min_connected_component_size": "8"}
+    layout_keys = {"hinge_slack", "hinge_tolerance", "matching_hinge_slack", "min_connected_component_size",
+                   "use_two_matches", "kill_hinge_overlap", "kill_hinge_internal", "del_telomere", "del_telomeres"}
+    for k, v in overrides.items():
+        (layout if k in layout_keys else filt)[k] = v
+    with open(path, "w") as f:
+        f.write("[filter]\n" + "".join("%s = %s\n" % kv for kv in filt.items()))
+        f.write("\n[layout]\n" + "".join("%s = %s\n" % kv for kv in layout.items()))
+
+
+@pytest.mark.parametrize("overrides", VARIANTS)
+def test_ini_variants(built, tmp_path, overrides):
+    root, _ = ht.materialize("synth_small", str(tmp_path))
+    ini = os.path.join(str(tmp_path), "variant.ini")
+    write_ini(ini, overrides)
+    _run_all(str(tmp_path), root, ini=ini)

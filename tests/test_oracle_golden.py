@@ -3,6 +3,8 @@ must equal, byte for byte, what the unmodified reference binaries wrote for the
 committed fixtures (tests/golden, made by make_golden.py), and — where the
 reference binaries are available (oracle/_ref) — what they write for fresh
 synthetic inputs."""
+import os
+
 import pytest
 
 import hingetest as ht
@@ -32,3 +34,38 @@ def test_oracle_equals_reference_on_fresh_synthetic(built, tmp_path, args):
     for stage in ("filter", "maximal", "layout"):
         ht.run_stage("oracle", stage, str(tmp_path), "S", "ora")
     ht.assert_same_files(str(tmp_path), "ora", "S", ALL)
+
+
+@pytest.mark.skipif(not ht.have_reference(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_equals_reference_on_edge_cases(built, tmp_path):
+    """The hand-made edge-case fixtures and INI variants of tests/test_gpu_edge_cases.py, oracle vs the
+    unmodified reference binaries (this is what pins the oracle on those inputs)."""
+    import pathlib
+
+    import test_gpu_edge_cases as ec
+
+    def oracle_vs_reference(work, root, ini=ht.INI):
+        if not os.path.exists(os.path.join(work, "." + root + ".bps")):  # the reference loads the bases
+            import json
+
+            meta = json.load(open(os.path.join(ht.GOLDEN, "synth_small", "fixture.json")))
+            ht.synth(work, meta["synth_args"], root)
+        for stage in ("filter", "maximal", "layout"):
+            ht.run_stage("oracle", stage, work, root, "ora", ini=ini)
+            ht.run_stage("reference", stage, work, root, "ref", out="ref", ini=ini)
+        ht.assert_same_files(work, "ora", "ref", ALL)
+
+    saved = ec._run_all
+    ec._run_all = oracle_vs_reference
+    try:
+        for k, fn in enumerate((ec.test_many_overlaps_per_pair_and_ties, ec.test_sixteen_bit_traces,
+                                ec.test_reads_without_overlaps_and_self_overlaps)):
+            d = tmp_path / ("case%d" % k)
+            d.mkdir()
+            fn(True, pathlib.Path(d))
+        for k, ov in enumerate(ec.VARIANTS):
+            d = tmp_path / ("ini%d" % k)
+            d.mkdir()
+            ec.test_ini_variants(True, pathlib.Path(d), ov)
+    finally:
+        ec._run_all = saved
