@@ -288,10 +288,10 @@ int hg_set_overlaps(hg_ctx* c, int64_t novl, const int32_t* aread, const int32_t
     // scratch that depends on the shape of the data
     FilterScratch& s = c->fs;
     if (s.anno_cap == 0) HG_TRY(alloc_anno_pool(c, 2 * (a_hi - a_lo) + (1 << 16)));
-    // K4: one slot of 48 B per pile-up record and warp
+    // K4: one slot of 56 B per pile-up record and warp
     s.hinge_cap = (std::max(c->max_pileup, 32) + 3) & ~3;  // keeps every slot 16-byte aligned
     {
-        const size_t slot = (size_t)s.hinge_cap * 48;
+        const size_t slot = (size_t)s.hinge_cap * 56;
         size_t warps = (size_t)c->num_sms * 48;  // the kernel is latency bound: many warps, few reads each
         const size_t budget = (size_t)768 << 20;
         if (warps * slot > budget) warps = std::max<size_t>(4, budget / slot);
@@ -423,6 +423,39 @@ int hg_filter_kernel_times(hg_ctx* c, float* ms, int n) {
 }
 
 int64_t hg_launch_count(void) { return hg::g_launches; }
+
+// Test hooks for the order-exact sort: `count` arrays laid end to end (off has count+1 entries),
+// each element = (key, idx).  The device version runs warp_sort_exact, the host version the real
+// std::sort of this toolchain; tests/test_gpu_order_exact.py compares them element for element.
+int hg_debug_warp_sort(hg_ctx* c, int32_t* key_idx, const int32_t* off, int32_t count, int32_t descending) {
+    if (!c || !key_idx || !off || count <= 0) return HG_ERR_ARG;
+    cudaSetDevice(c->device);
+    const size_t total = (size_t)off[count];
+    int2* d = nullptr; int2* tmp = nullptr; int *g = nullptr, *l = nullptr, *doff = nullptr;
+    HG_TRY(dev_alloc(c, &d, total, "sort data")); HG_TRY(dev_alloc(c, &tmp, total, "sort tmp"));
+    HG_TRY(dev_alloc(c, &g, total, "sort g")); HG_TRY(dev_alloc(c, &l, total, "sort l"));
+    HG_TRY(dev_alloc(c, &doff, (size_t)count + 1, "sort off"));
+    cudaMemcpy(d, key_idx, 8 * total, cudaMemcpyHostToDevice);
+    cudaMemcpy(doff, off, 4 * ((size_t)count + 1), cudaMemcpyHostToDevice);
+    launch_debug_warp_sort(d, doff, count, descending, g, l, tmp, c->stream);
+    int rc = cuda_check(c, cudaStreamSynchronize(c->stream), "warp sort");
+    if (rc == HG_OK) cudaMemcpy(key_idx, d, 8 * total, cudaMemcpyDeviceToHost);
+    cudaFree(d); cudaFree(tmp); cudaFree(g); cudaFree(l); cudaFree(doff);
+    return rc;
+}
+
+int hg_debug_std_sort(int32_t* key_idx, const int32_t* off, int32_t count, int32_t descending) {
+    struct E { int key, idx; };
+    for (int w = 0; w < count; w++) {
+        E* b = reinterpret_cast<E*>(key_idx) + off[w];
+        E* e = reinterpret_cast<E*>(key_idx) + off[w + 1];
+        if (descending)
+            std::sort(b, e, [](const E& x, const E& y) { return x.key > y.key; });
+        else
+            std::sort(b, e, [](const E& x, const E& y) { return x.key < y.key; });
+    }
+    return HG_OK;
+}
 
 // Debug aid (HG_OPT_PROFILE set after hg_set_reads): per hinge-call work item
 // (read, cycles, largest support, pile-up size if the order-exact path ran).

@@ -915,6 +915,55 @@ __device__ __forceinline__ int hinge_class(int2 e, bool out_hinge, int2 mk, int 
     return e.y < THETA ? 2 : (e.y > THETA ? 3 : 0);
 }
 
+// The same walk, all 32 lanes (call with identical arguments).  Every quantity the
+// sequential loop carries is a prefix count over the sorted list, and a pile-up of more
+// than T reads inside one bin is just "entry id + T exists and lies within HBL", so each
+// lane evaluates the break conditions of its entries and the first entry that fires wins.
+__device__ bool hinge_walk_warp(const int2* ends, int support, bool out_hinge, int2 mk,
+                                const hg_filter_params& P) {
+    const int lane = lane_id();
+    const unsigned lt = (1u << lane) - 1u;
+    const int THETA = P.theta, HBL = P.hinge_bin_length, U = P.hinge_read_unbridged_threshold;
+    const int T = P.hinge_bin_pileup_threshold;
+    const int first0 = ends[0].x;
+    int considered = 0, to_end = 0;  // running totals before the current chunk
+    for (int base = 0; base < support; base += 32) {
+        const int id = base + lane;
+        int cls = 0, f = 0;
+        if (id < support) {
+            const int2 e = ends[id];
+            f = e.x;
+            cls = hinge_class(e, out_hinge, mk, THETA, HBL);
+        }
+        const unsigned m_cons = __ballot_sync(0xffffffffu, cls != 0);
+        const unsigned m_end = __ballot_sync(0xffffffffu, cls == 1);
+        const int cons_incl = considered + __popc(m_cons & lt) + (cls != 0 ? 1 : 0);
+        const int end_incl = to_end + __popc(m_end & lt) + (cls == 1 ? 1 : 0);
+        const int dist0 = out_hinge ? f - first0 : first0 - f;
+        bool fire_u = false, fire_b = false;
+        if (cls == 1 || cls == 2) {
+            fire_u = end_incl > U || (cons_incl > U && dist0 > HBL);
+        } else if (cls == 3) {
+            // pl = 1 + following entries closer than HBL; pl > T  <=>  entry id + T is that close
+            if (T <= 0) {
+                fire_b = true;
+            } else if (id + T < support) {
+                const int f2 = ends[id + T].x;
+                fire_b = (out_hinge ? f2 - f : f - f2) < HBL;
+            }
+        }
+        const unsigned m_fire = __ballot_sync(0xffffffffu, fire_u || fire_b);
+        if (m_fire) {
+            const int src = __ffs(m_fire) - 1;
+            const bool bridged = __shfl_sync(0xffffffffu, fire_b ? 1 : 0, src) != 0;
+            return !bridged && support > P.hinge_min_support;
+        }
+        considered += __popc(m_cons);
+        to_end += __popc(m_end);
+    }
+    return false;  // never left the initial `bridged = true`
+}
+
 // One warp per annotated read.  The reference feeds the walk with the selected
 // records in the order left by two unstable std::sorts (pile-up by length, then
 // the end list by position).  The walk only distinguishes entries by (position,
@@ -925,12 +974,12 @@ __device__ __forceinline__ int hinge_class(int2 e, bool out_hinge, int2 mk, int 
 // the pile-up and on the end list.
 //
 // Scratch slot per warp (cap = deepest pile-up):
-//   int4 rec[cap] | KeyIdx ord[cap] | int2 ends[cap] | int2 sorted[cap] | int2 keys[cap]
-constexpr int kHingeSlotBytesPerRec = 16 + 8 + 8 + 8 + 8;
+//   int4 rec[cap] | KeyIdx ord[cap] | int2 ends[cap] | int2 sorted[cap] | int2 keys[cap] | int gl[2 cap]
+constexpr int kHingeSlotBytesPerRec = 16 + 8 + 8 + 8 + 8 + 8;
 constexpr int kHingeSmemEnds = 192;
 constexpr int kHingeSmemPile = 1024;
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict__ mask,
              const int2* __restrict__ anno_ref, const int2* __restrict__ anno_pool,
              int* __restrict__ counters, const int* __restrict__ work_list,
@@ -944,11 +993,11 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
     int2* ends = reinterpret_cast<int2*>(base + (size_t)cap * 24);
     int2* sorted = reinterpret_cast<int2*>(base + (size_t)cap * 32);
     int2* keys = reinterpret_cast<int2*>(base + (size_t)cap * 40);  // (total length, selection index)
+    int* const gl = reinterpret_cast<int*>(base + (size_t)cap * 48);  // warp_sort_exact position lists
     const int nwork = counters[1];
     const int THETA = P.theta, HTL = P.hinge_tolerance_length, HBL = P.hinge_bin_length;
     // end lists of up to kHingeSmemEnds entries are sorted and walked in shared memory
     __shared__ int2 sh_ends[4][kHingeSmemEnds], sh_sorted[4][kHingeSmemEnds];
-    __shared__ KeyIdx sh_ord[4][kHingeSmemPile];  // pile-up sort keys of the order-exact path
     int2* const ends_s = sh_ends[threadIdx.x >> 5];
     int2* const sorted_s = sh_sorted[threadIdx.x >> 5];
     (void)nwarps;
@@ -976,20 +1025,24 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
             // ---- select in file order, two steps: (1) the test on A's coordinates alone
             // (two coalesced columns) keeps a minority of the pile-up; (2) only those pay for
             // the B side (four more columns + gathers of rlen[B] and mask[B])
-            int* const near_idx = reinterpret_cast<int*>(ord_global);
+            int* const near_idx = gl;  // free here: the position lists are only live inside a sort
             int n_near = 0;
             const int np = (int)(o1 - o0);
-#pragma unroll 2
-            for (int kb = 0; kb < np; kb += 32) {
-                const int k = kb + lane;
-                bool near = false;
-                if (k < np) {
-                    const int pos = out_hinge ? __ldg(rv.aepos + o0 + k) : __ldg(rv.abpos + o0 + k);
-                    near = pos > apos - HTL && pos < apos + HTL;
+            const int* __restrict__ pcol = (out_hinge ? rv.aepos : rv.abpos) + o0;
+            for (int kb = 0; kb < np; kb += 128) {  // four independent loads in flight per lane
+                int pos[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int k = kb + 32 * u + lane;
+                    pos[u] = k < np ? __ldg(pcol + k) : apos + HTL;
                 }
-                const unsigned nm = __ballot_sync(0xffffffffu, near);
-                if (near) near_idx[n_near + __popc(nm & ((1u << lane) - 1u))] = k;
-                n_near += __popc(nm);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool near = pos[u] > apos - HTL && pos[u] < apos + HTL;
+                    const unsigned nm = __ballot_sync(0xffffffffu, near);
+                    if (near) near_idx[n_near + __popc(nm & ((1u << lane) - 1u))] = kb + 32 * u + lane;
+                    n_near += __popc(nm);
+                }
             }
             __syncwarp();
             int support = 0;
@@ -1045,7 +1098,7 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
                     danger = __any_sync(0xffffffffu, d);
                 }
                 if (!danger) {
-                    if (lane == 0) keep = hinge_walk(dst, support, out_hinge, mk, P) ? 1 : 0;
+                    keep = hinge_walk_warp(dst, support, out_hinge, mk, P) ? 1 : 0;
                 } else if (![&]() {
                                // ---- order-exact path, cheap form.  The end list enters its std::sort in
                                // pile-up order = total length, descending.  If the selected records have
@@ -1065,21 +1118,17 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
                                }
                                if (__any_sync(0xffffffffu, tie)) return false;
                                __syncwarp();
-                               if (lane == 0) {
-                                   if (out_hinge)
-                                       std_sort_exact(sorted, support, FirstAsc());  // filter.cpp:914
-                                   else
-                                       std_sort_exact(sorted, support, FirstDesc());  // filter.cpp:1010
-                                   keep = hinge_walk(sorted, support, out_hinge, mk, P) ? 1 : 0;
-                                   atomicAdd(&counters[4], 1);
-                               }
+                               if (out_hinge)  // filter.cpp:914 / 1010, all lanes
+                                   warp_sort_exact(sorted, support, FirstAsc(), gl, gl + cap, keys);
+                               else
+                                   warp_sort_exact(sorted, support, FirstDesc(), gl, gl + cap, keys);
+                               keep = hinge_walk_warp(sorted, support, out_hinge, mk, P) ? 1 : 0;
+                               if (lane == 0) atomicAdd(&counters[4], 1);
                                return true;
                            }()) {
                     // ---- order-exact path, full form.  Pile-up in file order, then std::sort by total
                     // length, descending (filter.cpp:565-567), once per read
                     if (!have_exact_order) {
-                        const bool ord_in_smem = o1 - o0 <= kHingeSmemPile;
-                        if (ord_in_smem) ord = sh_ord[threadIdx.x >> 5];
                         int n = 0;
                         for (int64_t kb = o0; kb < o1; kb += 32) {
                             const int64_t k = kb + lane;
@@ -1096,12 +1145,8 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
                             n += __popc(am);
                         }
                         __syncwarp();
-                        if (lane == 0) {
-                            if (ord_in_smem)  // separate call site: the sort runs on LDS/STS
-                                std_sort_exact(sh_ord[threadIdx.x >> 5], n, GreaterKey());
-                            else
-                                std_sort_exact(ord_global, n, GreaterKey());
-                        }
+                        warp_sort_exact(ord_global, n, GreaterKey(), gl, gl + cap,
+                                        reinterpret_cast<KeyIdx*>(keys));
                         __syncwarp();
                         have_exact_order = true;
                         n_exact = n;
@@ -1126,15 +1171,13 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
                         sup2 += __popc(sm);
                     }
                     __syncwarp();
-                    if (lane == 0) {
-                        int2* const ex = sup2 <= kHingeSmemEnds ? ends_s : ends;
-                        if (out_hinge)
-                            std_sort_exact(ex, sup2, FirstAsc());  // filter.cpp:914
-                        else
-                            std_sort_exact(ex, sup2, FirstDesc());  // filter.cpp:1010
-                        keep = hinge_walk(ex, sup2, out_hinge, mk, P) ? 1 : 0;
-                        atomicAdd(&counters[4], 1);
-                    }
+                    int2* const ex = sup2 <= kHingeSmemEnds ? ends_s : ends;
+                    if (out_hinge)  // filter.cpp:914 / 1010, all lanes
+                        warp_sort_exact(ex, sup2, FirstAsc(), gl, gl + cap, keys);
+                    else
+                        warp_sort_exact(ex, sup2, FirstDesc(), gl, gl + cap, keys);
+                    keep = hinge_walk_warp(ex, sup2, out_hinge, mk, P) ? 1 : 0;
+                    if (lane == 0) atomicAdd(&counters[4], 1);
                 }
             }
             if (lane == 0) hinge_keep[ar.x + j] = keep;
@@ -1145,6 +1188,25 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
         if (item_log && lane == 0)
             item_log[w] = make_int4(read, (int)(clock64() - t_begin), log_support, log_exact);
     }
+}
+
+// Test hook: sorts `count` independent arrays of (key, idx) pairs with warp_sort_exact.
+__global__ void k_debug_warp_sort(KeyIdx* data, const int* off, int count, int descending, int* g, int* l,
+                                  KeyIdx* tmp) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= count) return;
+    const int o = off[w], n = off[w + 1] - o;
+    if (descending)
+        warp_sort_exact(data + o, n, GreaterKey(), g + o, l + o, tmp + o);
+    else
+        warp_sort_exact(data + o, n, [] __device__(const KeyIdx& a, const KeyIdx& b) { return a.key < b.key; },
+                        g + o, l + o, tmp + o);
+}
+
+void launch_debug_warp_sort(void* data, const int* off, int count, int descending, int* g, int* l, void* tmp,
+                            cudaStream_t st) {
+    k_debug_warp_sort<<<(count * 32 + 127) / 128, 128, 0, st>>>((KeyIdx*)data, off, count, descending, g, l,
+                                                                (KeyIdx*)tmp);
 }
 
 __global__ void k_max_pileup(const int64_t* __restrict__ read_off, int n_read, int* out_max) {

@@ -60,6 +60,8 @@ void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_par
                       cudaStream_t st);
 void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
                        FilterScratch& s, cudaStream_t st);
+void launch_debug_warp_sort(void* data, const int* off, int count, int descending, int* g, int* l, void* tmp,
+                            cudaStream_t st);
 void launch_max_pileup(const int64_t* read_off, int n_read, int* out_max, cudaStream_t st);
 
 }  // namespace hg

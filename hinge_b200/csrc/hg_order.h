@@ -177,5 +177,107 @@ HG_HD void std_sort_exact(T* a, int n, Less less) {
     }
 }
 
+
+#if defined(__CUDACC__)
+// ------------------------------------------------- std::sort, one warp, same result
+//
+// warp_sort_exact leaves a[0..n) in exactly the permutation std::sort would, but
+// spreads the work over the 32 lanes of the calling warp (all lanes must call it
+// with identical arguments):
+//   * Hoare partition: with G = positions (ascending) whose element is not less
+//     than the pivot and L = positions (descending) whose element is not greater,
+//     the sequential scan swaps G[i] <-> L[i] while G[i] < L[i] and returns
+//     min(G[m], L[m-1]) (elements between the two cursors are never touched, so
+//     the pairs can be read off the unpartitioned range).  Flags by ballot, pair
+//     count by a warp reduction, swaps in parallel.
+//   * the final insertion sort is a stable sort in which no element leaves its
+//     <= 16-element block (blocks are mutually ordered after the introsort loop):
+//     every lane ranks its elements inside a +-15 window.
+//   * median-of-3 and the heap-sort fallback (depth limit) stay on lane 0.
+// Scratch: idx_g / idx_l hold n ints each, tmp holds n elements.
+template <class T, class Less>
+__device__ void warp_sort_exact(T* a, int n, Less less, int* idx_g, int* idx_l, T* tmp) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    if (n <= 1) return;
+    int stack_first[64], stack_last[64], stack_depth[64];
+    int sp = 1, lg = 0;
+    for (unsigned v = (unsigned)n; v > 1; v >>= 1) lg++;
+    stack_first[0] = 0;
+    stack_last[0] = n;
+    stack_depth[0] = 2 * lg;
+    while (sp > 0) {
+        --sp;
+        int first = stack_first[sp], last = stack_last[sp], depth = stack_depth[sp];
+        while (last - first > 16) {
+            if (depth == 0) {
+                if (lane == 0) os_heap_sort(a, first, last, less);
+                __syncwarp();
+                break;
+            }
+            --depth;
+            if (lane == 0) {  // __move_median_to_first(first, first+1, mid, last-1)
+                const int mid = first + (last - first) / 2;
+                const int x = first + 1, y = mid, z = last - 1;
+                if (less(a[x], a[y])) {
+                    if (less(a[y], a[z])) os_swap(a, first, y);
+                    else if (less(a[x], a[z])) os_swap(a, first, z);
+                    else os_swap(a, first, x);
+                } else if (less(a[x], a[z])) {
+                    os_swap(a, first, x);
+                } else if (less(a[y], a[z])) {
+                    os_swap(a, first, z);
+                } else {
+                    os_swap(a, first, y);
+                }
+            }
+            __syncwarp();
+            const T pivot = a[first];
+            int ng = 0, nl = 0;
+            for (int base = first + 1; base < last; base += 32) {
+                const int p = base + lane;
+                bool ge = false, le = false;
+                if (p < last) {
+                    const T v = a[p];
+                    ge = !less(v, pivot);
+                    le = !less(pivot, v);
+                }
+                const unsigned mg = __ballot_sync(0xffffffffu, ge), ml = __ballot_sync(0xffffffffu, le);
+                if (ge) idx_g[ng + __popc(mg & lt)] = p;
+                if (le) idx_l[nl + __popc(ml & lt)] = p;
+                ng += __popc(mg);
+                nl += __popc(ml);
+            }
+            __syncwarp();
+            const int lim = ng < nl ? ng : nl;
+            int cnt = 0;
+            for (int i = lane; i < lim; i += 32) cnt += idx_g[i] < idx_l[nl - 1 - i] ? 1 : 0;
+            const int m = __reduce_add_sync(0xffffffffu, cnt);
+            for (int i = lane; i < m; i += 32) os_swap(a, idx_g[i], idx_l[nl - 1 - i]);
+            const int prev_hi = m > 0 ? idx_l[nl - m] : last;
+            const int cut = (m < ng && idx_g[m] < prev_hi) ? idx_g[m] : prev_hi;
+            __syncwarp();
+            stack_first[sp] = cut;
+            stack_last[sp] = last;
+            stack_depth[sp] = depth;
+            ++sp;
+            last = cut;
+        }
+    }
+    // __final_insertion_sort as a windowed stable rank
+    for (int p = lane; p < n; p += 32) {
+        const T v = a[p];
+        int np = p;
+        const int lo = p - 15 > 0 ? p - 15 : 0, hi = p + 15 < n - 1 ? p + 15 : n - 1;
+        for (int j = lo; j < p; j++) np -= less(v, a[j]) ? 1 : 0;
+        for (int j = p + 1; j <= hi; j++) np += less(a[j], v) ? 1 : 0;
+        tmp[np] = v;
+    }
+    __syncwarp();
+    for (int p = lane; p < n; p += 32) a[p] = tmp[p];
+    __syncwarp();
+}
+#endif
+
 }  // namespace hg
 #endif
