@@ -319,13 +319,11 @@ static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
     FilterScratch& s = c->fs;
     auto bins = [&](int rlen) { return (rlen + std::max(p->cut_off, 0)) / p->reso + 3; };
     mask_anno_configure(s, bins(c->rlen_q999));
-    if (bins(c->max_rlen) > s.nb_cap || c->max_pileup > 32000) {
-        s.big_slot_words = (bins(c->max_rlen) + 31) & ~31;
-        s.big_warps = 64;
-        HG_TRY(dev_alloc(c, &s.big_scratch, (size_t)s.big_warps * s.big_slot_words, "big-read scratch"));
-    } else {
-        s.big_slot_words = 0;
-    }
+    // the generic path is always armed: very long reads, very deep pile-ups, and reads with more
+    // raw annotations than the fast path keeps are rerouted to it at run time
+    s.big_slot_words = (bins(c->max_rlen) + 31) & ~31;
+    s.big_warps = 64;
+    HG_TRY(dev_alloc(c, &s.big_scratch, (size_t)s.big_warps * s.big_slot_words, "big-read scratch"));
     return HG_OK;
 }
 
