@@ -516,13 +516,14 @@ __device__ void mask_anno_read(const RecView& rv, const ReadView& rd, const hg_f
 // reductions (REDUX), and the repeat-annotation / hinge pre-test sweep shares a
 // single pass.  `self_records` tells whether the read has A == B records at all
 // (known from K1); without them the bread column is not even loaded.
+constexpr int kAnnSlack = 120;  // raw annotations a read may carry on the fast path
 __device__ __forceinline__ uint4 lds128(const uint32_t* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void sts128(uint32_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
 
 template <bool DUMP>
 __device__ void mask_anno_read_fast(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
-                                    const int MIN_COV, const int read, uint32_t* hist, const int nbz,
-                                    const bool self_records, const MaskAnnoOut& out) {
+                                    const int MIN_COV, const int read, uint32_t* hist, uint32_t* ann,
+                                    const int nbz, const bool self_records, const MaskAnnoOut& out) {
     // After the scan the low half (cut-off-free coverage) is never negative, so the
     // packed word decodes with one instruction per half.
     auto LO = [](uint32_t v) { return (int)(v & 0xffffu); };
@@ -643,34 +644,10 @@ __device__ void mask_anno_read_fast(const RecView& rv, const ReadView& rd, const
     else
         mk = q;
 
-    // ---- hinge pre-test: mean coverage near both mask ends (filter.cpp:842-865)
-    const int NHR = P.no_hinge_region;
-    int cs = 0, ns = 0, ce = 0, ne = 0;
-    {
-        int jlo = mk.x <= 0 ? 0 : (mk.x + reso - 1) / reso;  // bins with mk.x <= 40 j <= mk.x + NHR
-        int jhi = mk.x + NHR < 0 ? -1 : min((mk.x + NHR) / reso, L0 - 1);
-        for (int j = jlo + lane; j <= jhi; j += 32) {
-            cs += LO(hist[j]);
-            ns++;
-        }
-        jlo = mk.y - NHR <= 0 ? 0 : (mk.y - NHR + reso - 1) / reso;  // mk.y - NHR <= 40 j <= mk.y
-        jhi = mk.y < 0 ? -1 : min(mk.y / reso, L0 - 1);
-        for (int j = jlo + lane; j <= jhi; j += 32) {
-            ce += LO(hist[j]);
-            ne++;
-        }
-        cs = __reduce_add_sync(0xffffffffu, cs);
-        ns = __reduce_add_sync(0xffffffffu, ns);
-        ce = __reduce_add_sync(0xffffffffu, ce);
-        ne = __reduce_add_sync(0xffffffffu, ne);
-    }
-    // float on purpose: 0/0 = NaN makes the '< 10' test false (filter.cpp:861-865)
-    const float avg_end = __fdiv_rn((float)ce, (float)ne);
-    const float avg_start = __fdiv_rn((float)cs, (float)ns);
-    const bool skip_hinges = fabsf(__fsub_rn(avg_end, avg_start)) < 10.0f;
-
     // ---- pass 2: repeat annotation from the coverage gradient (filter.cpp:796-813),
-    // optional profile dump (filter.cpp:599-602)
+    // optional profile dump (filter.cpp:599-602).  Raw annotations are compacted, in bin
+    // order, into the slack words behind the histogram (`ann`).
+    const int NHR = P.no_hinge_region;
     const int MINT = P.min_repeat_annotation_threshold, MAXT = P.max_repeat_annotation_threshold;
     const int RJ = min(MINT, MAXT);  // the threshold never drops below this
     // bins j < L0 - 2 whose position lies in [mask.start + NHR, mask.end - NHR]
@@ -701,17 +678,50 @@ __device__ void mask_anno_read_fast(const RecView& rv, const ReadView& rd, const
             any = any || type[i] != 0;
         }
         const unsigned am = __ballot_sync(0xffffffffu, any);
-        if (am) {  // rare: compact (position, type) entries in bin order over the histogram words
+        if (am) {  // rare
             const int mine = (type[0] != 0) + (type[1] != 0) + (type[2] != 0) + (type[3] != 0);
             const int incl = warp_incl_scan(mine);
             int slot = cnt + incl - mine;
-            __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                if (type[i] != 0) hist[slot++] = ((unsigned)(reso * (j0 + i)) << 2) | (unsigned)(type[i] + 1);
+                if (type[i] != 0) {
+                    if (slot < kAnnSlack) ann[slot] = ((unsigned)(reso * (j0 + i)) << 2) | (unsigned)(type[i] + 1);
+                    slot++;
+                }
             cnt += __shfl_sync(0xffffffffu, incl, 31);
-            __syncwarp();
         }
+    }
+    if (cnt > kAnnSlack) {  // a read this noisy goes through the generic path instead
+        if (lane == 0) out.big_list[atomicAdd(&out.counters[3], 1)] = read;
+        return;
+    }
+    __syncwarp();
+
+    // ---- hinge pre-test: mean coverage near both mask ends (filter.cpp:842-865); its
+    // outcome only matters for reads that carry annotations
+    bool skip_hinges = false;
+    if (cnt > 0) {
+        int cs = 0, ns = 0, ce = 0, ne = 0;
+        int jlo = mk.x <= 0 ? 0 : (mk.x + reso - 1) / reso;  // bins with mk.x <= 40 j <= mk.x + NHR
+        int jhi = mk.x + NHR < 0 ? -1 : min((mk.x + NHR) / reso, L0 - 1);
+        for (int j = jlo + lane; j <= jhi; j += 32) {
+            cs += LO(hist[j]);
+            ns++;
+        }
+        jlo = mk.y - NHR <= 0 ? 0 : (mk.y - NHR + reso - 1) / reso;  // mk.y - NHR <= 40 j <= mk.y
+        jhi = mk.y < 0 ? -1 : min(mk.y / reso, L0 - 1);
+        for (int j = jlo + lane; j <= jhi; j += 32) {
+            ce += LO(hist[j]);
+            ne++;
+        }
+        cs = __reduce_add_sync(0xffffffffu, cs);
+        ns = __reduce_add_sync(0xffffffffu, ns);
+        ce = __reduce_add_sync(0xffffffffu, ce);
+        ne = __reduce_add_sync(0xffffffffu, ne);
+        // float on purpose: 0/0 = NaN makes the '< 10' test false (filter.cpp:861-865)
+        const float avg_end = __fdiv_rn((float)ce, (float)ne);
+        const float avg_start = __fdiv_rn((float)cs, (float)ns);
+        skip_hinges = fabsf(__fsub_rn(avg_end, avg_start)) < 10.0f;
     }
 
     // ---- merge pass (filter.cpp:817-829) + publication, as in the generic path
@@ -719,9 +729,9 @@ __device__ void mask_anno_read_fast(const RecView& rv, const ReadView& rd, const
     if (cnt > 0) {
         if (lane == 0) {
             const int GAP = P.repeat_annotation_gap_threshold;
-            unsigned cur = hist[0];
+            unsigned cur = ann[0];
             for (int k = 1; k < cnt; k++) {
-                const unsigned nxt = hist[k];
+                const unsigned nxt = ann[k];
                 const int ct = (int)(cur & 3u) - 1, nt = (int)(nxt & 3u) - 1;
                 const int gap = (int)(nxt >> 2) - (int)(cur >> 2);
                 if (ct == 1 && nt == 1 && gap < GAP) {
@@ -729,11 +739,11 @@ __device__ void mask_anno_read_fast(const RecView& rv, const ReadView& rd, const
                 } else if (ct == -1 && nt == -1 && gap < GAP) {
                     cur = nxt;
                 } else {
-                    hist[kept++] = cur;
+                    ann[kept++] = cur;
                     cur = nxt;
                 }
             }
-            hist[kept++] = cur;
+            ann[kept++] = cur;
         }
         kept = __shfl_sync(0xffffffffu, kept, 0);
     }
@@ -750,7 +760,7 @@ __device__ void mask_anno_read_fast(const RecView& rv, const ReadView& rd, const
         __syncwarp();
         if (off >= 0)
             for (int k = lane; k < kept; k += 32) {
-                const unsigned w = hist[k];
+                const unsigned w = ann[k];
                 out.anno_pool[off + k] = make_int2((int)(w >> 2), (int)(w & 3u) - 1);
             }
     }
@@ -784,7 +794,8 @@ k_mask_anno(RecView rv, ReadView rd, hg_filter_params P, const int* __restrict__
             if (lane_id() == 0) out.big_list[atomicAdd(&out.counters[3], 1)] = read;
             continue;
         }
-        mask_anno_read_fast<DUMP>(rv, rd, P, MIN_COV, read, hist, nbz, self_cnt[read] > 0, out);
+        mask_anno_read_fast<DUMP>(rv, rd, P, MIN_COV, read, hist, hist + nb_cap + 8, nbz, self_cnt[read] > 0,
+                                  out);
     }
 }
 
