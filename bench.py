@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--sample-mb", type=float, default=4.0, help="genome size of the CPU-baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--k2-variant", type=int, default=None, help="HG_OPT_K2_VARIANT (A/B aid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-downstream", action="store_true", help="skip the maximal/layout timing")
     return ap.parse_args()
@@ -269,6 +270,8 @@ def main():
     stream = torch.cuda.current_stream()
     ctx = api.Context(local, stream.cuda_stream)
     ctx.set_option(api.HG_OPT_PROFILE, 1)
+    if args.k2_variant is not None:
+        ctx.set_option(api.HG_OPT_K2_VARIANT, args.k2_variant)
     ctx.set_reads(syn.rlen, syn.qv_off, syn.qv, 100)
     params = api.FilterParams()
 

@@ -9,7 +9,7 @@ import numpy as np
 from ._lib import (EdgeC, FilterParamsC, FilterSummaryC, HingeError, LayoutParamsC, lib)
 
 HG_MEM_HOST, HG_MEM_DEVICE = 0, 1
-HG_OPT_KEEP_COVERAGE, HG_OPT_PROFILE = 1, 2
+HG_OPT_KEEP_COVERAGE, HG_OPT_PROFILE, HG_OPT_K2_VARIANT = 1, 2, 3
 HG_BUF_MEAN_COV, HG_BUF_MASK, HG_BUF_READ_FLAGS = 1, 2, 3
 HG_RETRY_POOL = 1
 

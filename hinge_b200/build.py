@@ -12,7 +12,7 @@ OUT = os.path.join(HERE, "_build")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--extended-lambda"]
-CU = ["hg_filter.cu", "hg_capi.cu", "hg_layout.cu", "hg_capi_layout.cu"]
+CU = ["hg_filter.cu", "hg_filter_flat.cu", "hg_capi.cu", "hg_layout.cu", "hg_capi_layout.cu"]
 CPP = ["hg_io.cpp", "hg_host.cpp", "hg_host_layout.cpp"]
 
 

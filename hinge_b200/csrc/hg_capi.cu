@@ -1,5 +1,6 @@
 // C ABI (include/hinge_b200.h): context, ingest, the filter stage.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -84,6 +85,9 @@ int hg_ctx_create(int device, void* stream, hg_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
     c->fs.num_sms = c->num_sms;
+    if (const char* v = getenv("HINGE_B200_K2_VARIANT")) {  // A/B aid; the variants give identical results
+        hg_set_option(c, HG_OPT_K2_VARIANT, atoi(v));
+    }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
     int rc = dev_alloc(c, &c->d_err, 4, "err flag");
@@ -112,7 +116,7 @@ void hg_ctx_destroy(hg_ctx* c) {
     cudaFree(s.med_hist); cudaFree(s.scal); cudaFree(s.cmask); cudaFree(s.rflags);
     cudaFree(s.anno_ref); cudaFree(s.anno_pool); cudaFree(s.counters); cudaFree(s.work_list);
     cudaFree(s.big_list); cudaFree(s.big_scratch); cudaFree(s.hinge_keep); cudaFree(s.hinge_scratch);
-    cudaFree(s.item_log);
+    cudaFree(s.item_log); cudaFree(s.flat_batch_first); cudaFree(s.flat_rbase);
     cudaFree(c->d_cov0); cudaFree(c->d_cov0_off);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -132,6 +136,17 @@ int hg_set_option(hg_ctx* c, int option, int64_t value) {
             for (int i = 0; i < hg_ctx::kMarks; i++) cudaEventCreate(&c->marks[i]);
         if (c->profile && c->n_read > 0 && !c->fs.item_log)
             HG_TRY(dev_alloc(c, &c->fs.item_log, c->n_read, "item log"));
+        return HG_OK;
+    }
+    if (option == HG_OPT_K2_VARIANT) {
+        if (value == kK2Flat || value == kK2WarpPerRead) {
+            c->fs.k2_variant = (int)value;
+        } else if (value > 100 && value <= 132) {  // tuning aid: flat form with a given scatter spread
+            c->fs.k2_variant = kK2Flat;
+            c->fs.flat_spread = (int)value - 100;
+        } else {
+            return set_err(c, HG_ERR_ARG, "HG_OPT_K2_VARIANT: 0 (flat) or 2 (warp per read)");
+        }
         return HG_OK;
     }
     return set_err(c, HG_ERR_ARG, "unknown option");
@@ -196,6 +211,7 @@ int hg_set_reads(hg_ctx* c, int32_t n_read, const int32_t* rlen, const int64_t* 
     c->a_hi = n_read;
     c->filter_done = false;
     c->shape_version++;
+    c->reads_version++;
     return cuda_check(c, cudaStreamSynchronize(st), "hg_set_reads");
 }
 
@@ -317,8 +333,28 @@ static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
     c->filter_params_set = true;
     c->configured_shape = c->shape_version;
     FilterScratch& s = c->fs;
-    auto bins = [&](int rlen) { return (rlen + std::max(p->cut_off, 0)) / p->reso + 3; };
+    auto bins = [&](int rlen) { return bins_needed(rlen, p->cut_off); };
     mask_anno_configure(s, bins(c->rlen_q999));
+    {
+        // flat K2: pack the reads that have records, [r_begin, r_end] within the owned range, into
+        // batches of kFlatBins histogram words; the plan only depends on read lengths and cut_off
+        const int lo = std::max(c->a_lo, c->r_begin), hi = std::min(c->a_hi, c->r_end + 1);
+        if (c->plan_reads_version != c->reads_version || c->plan_cut_off != p->cut_off ||
+            c->plan_lo != lo || c->plan_hi != hi) {
+            std::vector<int> first, rbase;
+            flat_plan(c->h_rlen.data(), lo, std::max(lo, hi), c->n_read, p->cut_off, &first, &rbase);
+            HG_TRY(dev_alloc(c, &s.flat_batch_first, first.size(), "flat K2 batches"));
+            HG_TRY(dev_alloc(c, &s.flat_rbase, rbase.size(), "flat K2 read offsets"));
+            HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_batch_first, first.data(), sizeof(int) * first.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
+            HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_rbase, rbase.data(), sizeof(int) * rbase.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
+            HG_TRY(cuda_check(c, cudaStreamSynchronize(c->stream), "flat K2 plan"));  // the vectors go away
+            s.flat_nbatch = hi > lo ? (int)first.size() - 1 : 0;
+            c->plan_reads_version = c->reads_version;
+            c->plan_cut_off = p->cut_off;
+            c->plan_lo = lo;
+            c->plan_hi = hi;
+        }
+    }
     // the generic path is always armed: very long reads, very deep pile-ups, and reads with more
     // raw annotations than the fast path keeps are rerouted to it at run time
     s.big_slot_words = (bins(c->max_rlen) + 31) & ~31;

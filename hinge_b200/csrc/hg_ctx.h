@@ -50,6 +50,7 @@ struct hg_ctx {
     hg_filter_params fp;
     bool filter_params_set = false, filter_done = false;
     int shape_version = 0, configured_shape = -1;
+    int reads_version = 0, plan_reads_version = -1, plan_cut_off = 0, plan_lo = 0, plan_hi = 0;  // flat K2 plan
     int keep_cov = 0;
     int* d_cov0 = nullptr;
     int64_t* d_cov0_off = nullptr;

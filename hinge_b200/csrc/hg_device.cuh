@@ -103,5 +103,28 @@ struct Packed<unsigned long long> {
     static __device__ __forceinline__ void add(W* p, W v) { atomicAdd(p, v); }
 };
 
+struct MaskAnnoOut {
+    int2* mask;        // .mas
+    int2* cmask;       // .cmas (bin coordinates)
+    uint8_t* rflags;   // kFlag*
+    int2* anno_ref;    // (offset into pool, count) per read
+    int2* anno_pool;   // (pos, type)
+    int anno_cap;
+    int* counters;     // [0] pool used  [1] work-list length  [2] overflow flag  [3] big-list length
+    int* work_list;    // reads that need hinge calling
+    int* big_list;     // reads whose profile does not fit the shared-memory path
+    int* cov0;         // optional dump of the cut-off-free profile (coverage.txt)
+    const int64_t* cov0_off;
+};
+
+// Histogram words one read needs: every event bin of both profiles (cut-off of either
+// sign) plus two trailing empty bins.
+__host__ __device__ __forceinline__ int bins_needed(int rlen, int cut_off) {
+    return (rlen + (cut_off < 0 ? -cut_off : cut_off)) / kReso + 3;
+}
+__device__ __forceinline__ int bins_needed(int rlen, const hg_filter_params& P) {
+    return bins_needed(rlen, P.cut_off);
+}
+
 }  // namespace hg
 #endif

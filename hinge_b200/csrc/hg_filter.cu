@@ -274,20 +274,6 @@ __global__ void k_median_radix_pick(int pass, unsigned int* __restrict__ dig, in
 
 // ------------------------------------------------------------------ K2
 
-struct MaskAnnoOut {
-    int2* mask;        // .mas
-    int2* cmask;       // .cmas (bin coordinates)
-    uint8_t* rflags;   // kFlag*
-    int2* anno_ref;    // (offset into pool, count) per read
-    int2* anno_pool;   // (pos, type)
-    int anno_cap;
-    int* counters;     // [0] pool used  [1] work-list length  [2] overflow flag  [3] big-list length
-    int* work_list;    // reads that need hinge calling
-    int* big_list;     // reads whose profile does not fit the shared-memory path
-    int* cov0;         // optional dump of the cut-off-free profile (coverage.txt)
-    const int64_t* cov0_off;
-};
-
 // One warp owns one read.  `hist` holds `nbz` packed words (shared memory on
 // the fast path, global scratch for very long reads / very deep pile-ups).
 template <typename W>
@@ -772,10 +758,6 @@ __device__ void mask_anno_read_fast(const RecView& rv, const ReadView& rd, const
         if (kept > 0 && !skip_hinges && off >= 0) out.work_list[atomicAdd(&out.counters[1], 1)] = read;
     }
     __syncwarp();
-}
-
-__device__ __forceinline__ int bins_needed(int rlen, const hg_filter_params& P) {
-    return (rlen + max(P.cut_off, 0)) / kReso + 3;
 }
 
 template <int WARPS, bool DUMP>
@@ -1310,14 +1292,19 @@ void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_par
     cudaMemsetAsync(s.cmask, 0, sizeof(int2) * rd.n_read, st);
     cudaMemsetAsync(s.anno_ref, 0, sizeof(int2) * rd.n_read, st);
     cudaMemsetAsync(s.hinge_keep, 0, (size_t)s.anno_cap, st);
-    const int smem = (s.nb_cap + 128) * 4 * kMaskAnnoWarps;
-    g_launches += 1 + (s.big_slot_words > 0);
-    if (cov0)
-        k_mask_anno<kMaskAnnoWarps, true><<<s.mask_anno_grid, kMaskAnnoWarps * 32, smem, st>>>(
-            rv, rd, P, s.scal, s.self_cnt, r_begin, r_end, s.nb_cap, out);
-    else
-        k_mask_anno<kMaskAnnoWarps, false><<<s.mask_anno_grid, kMaskAnnoWarps * 32, smem, st>>>(
-            rv, rd, P, s.scal, s.self_cnt, r_begin, r_end, s.nb_cap, out);
+    if (s.k2_variant != kK2WarpPerRead) {
+        launch_mask_anno_flat(rv, rd, P, s, out, st);
+    } else {
+        const int smem = (s.nb_cap + 128) * 4 * kMaskAnnoWarps;
+        g_launches += 1;
+        if (cov0)
+            k_mask_anno<kMaskAnnoWarps, true><<<s.mask_anno_grid, kMaskAnnoWarps * 32, smem, st>>>(
+                rv, rd, P, s.scal, s.self_cnt, r_begin, r_end, s.nb_cap, out);
+        else
+            k_mask_anno<kMaskAnnoWarps, false><<<s.mask_anno_grid, kMaskAnnoWarps * 32, smem, st>>>(
+                rv, rd, P, s.scal, s.self_cnt, r_begin, r_end, s.nb_cap, out);
+    }
+    g_launches += (s.big_slot_words > 0);
     if (s.big_slot_words > 0)
         k_mask_anno_big<<<s.big_warps / 4, 128, 0, st>>>(rv, rd, P, s.scal, out, s.big_scratch,
                                                          s.big_slot_words);

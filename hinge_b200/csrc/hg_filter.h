@@ -4,16 +4,23 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "hg_params.h"
 
 namespace hg {
 
 struct RecView;
 struct ReadView;
+struct MaskAnnoOut;
 
 enum : uint8_t { kFlagCov = 1, kFlagSelf = 2, kFlagSkipHinge = 4 };
 
-constexpr int kMaskAnnoWarps = 8;  // warps (= reads in flight) per CTA of K2
+constexpr int kMaskAnnoWarps = 8;  // warps (= reads in flight) per CTA of the warp-per-read K2
+constexpr int kFlatBins = 4096;    // histogram words (= coverage bins) per CTA of the flat K2
+
+// Which form of K2 runs (HG_OPT_K2_VARIANT; the results are identical)
+enum { kK2Flat = 0, kK2WarpPerRead = 2 };
 
 // Device buffers of one filter run (all sized at hg_set_reads / hg_set_overlaps).
 struct FilterScratch {
@@ -35,8 +42,13 @@ struct FilterScratch {
     int* counters = nullptr;   // 8
     int* work_list = nullptr;  // n_read
     int* big_list = nullptr;   // n_read
-    int nb_cap = 0;            // histogram words per warp on the shared-memory path
+    int nb_cap = 0;            // histogram words per warp on the warp-per-read path
     int mask_anno_grid = 0;
+    int k2_variant = kK2Flat;
+    int flat_spread = 8;              // flat K2: record windows per warp in the scatter (tuning aid)
+    int* flat_batch_first = nullptr;  // flat K2: first read of every batch (flat_nbatch + 1)
+    int* flat_rbase = nullptr;        // flat K2: per read, first histogram word inside its batch (-1: generic path)
+    int flat_nbatch = 0;
     unsigned long long* big_scratch = nullptr;
     int big_slot_words = 0, big_warps = 0;
     // K4
@@ -58,6 +70,11 @@ int mask_anno_configure(FilterScratch& s, int nb_cap);  // picks grid from occup
 void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
                       int r_begin, int r_end, FilterScratch& s, int* cov0, const int64_t* cov0_off,
                       cudaStream_t st);
+// flat K2 (hg_filter_flat.cu): host-side batch plan + launcher
+void flat_plan(const int* rlen, int lo, int hi, int n_read, int cut_off, std::vector<int>* batch_first,
+               std::vector<int>* rbase);
+void launch_mask_anno_flat(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
+                           FilterScratch& s, const MaskAnnoOut& out, cudaStream_t st);
 void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
                        FilterScratch& s, cudaStream_t st);
 void launch_debug_warp_sort(void* data, const int* off, int count, int descending, int* g, int* l, void* tmp,
