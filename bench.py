@@ -358,10 +358,12 @@ def main():
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         kavg = {k: sum(v) / len(v) for k, v in ktimes.items()}
         owned = a_hi - a_lo
-        # algorithmic bytes of one launch: K2 reads abpos/aepos (8 B per record; bread
-        # only for the few reads with self-overlaps) plus ~45 B per read of offsets, lengths, QV mask and
-        # results; K1 reads aread/bread/abpos/aepos (16 B per record)
-        kbytes = {"mask_anno": 8.0 * novl + 45.0 * owned, "cov_estimate": 16.0 * novl + 24.0 * owned}
+        # algorithmic bytes of one launch: the flat K2 reads aread/abpos/aepos (12 B
+        # per record; bread only for batches with self-overlaps; the warp-per-read form skips aread: 8 B)
+        # plus ~58 B per read of offsets, lengths, batch plan, QV mask and results; K1 reads
+        # aread/bread/abpos/aepos (16 B per record)
+        k2_rec_bytes = 8.0 if args.k2_variant == 2 else 12.0
+        kbytes = {"mask_anno": k2_rec_bytes * novl + 58.0 * owned, "cov_estimate": 16.0 * novl + 24.0 * owned}
         dom = max(("mask_anno", "cov_estimate"), key=lambda k: kavg[k])
         achieved = kbytes[dom] / (kavg[dom] * 1e-3) / 1e9
         traffic = None

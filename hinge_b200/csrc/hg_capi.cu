@@ -115,8 +115,8 @@ void hg_ctx_destroy(hg_ctx* c) {
         if (c->marks[i]) cudaEventDestroy(c->marks[i]);
     cudaFree(s.med_hist); cudaFree(s.scal); cudaFree(s.cmask); cudaFree(s.rflags);
     cudaFree(s.anno_ref); cudaFree(s.anno_pool); cudaFree(s.counters); cudaFree(s.work_list);
-    cudaFree(s.big_list); cudaFree(s.big_scratch); cudaFree(s.hinge_keep); cudaFree(s.hinge_scratch);
-    cudaFree(s.item_log); cudaFree(s.flat_batch_first); cudaFree(s.flat_rbase);
+    cudaFree(s.big_list); cudaFree(s.exact_list); cudaFree(s.big_scratch); cudaFree(s.hinge_keep); cudaFree(s.hinge_scratch);
+    cudaFree(s.item_log); cudaFree(s.flat_batch); cudaFree(s.flat_rbase); cudaFree(s.flat_read_batch); cudaFree(s.flat_batch_self);
     cudaFree(c->d_cov0); cudaFree(c->d_cov0_off);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -203,6 +203,7 @@ int hg_set_reads(hg_ctx* c, int32_t n_read, const int32_t* rlen, const int64_t* 
     HG_TRY(dev_alloc(c, &s.anno_ref, n_read, "anno_ref"));
     HG_TRY(dev_alloc(c, &s.work_list, n_read, "work_list"));
     HG_TRY(dev_alloc(c, &s.big_list, n_read, "big_list"));
+    HG_TRY(dev_alloc(c, &s.exact_list, n_read, "exact_list"));
     HG_TRY(dev_alloc(c, &c->d_read_off, (size_t)n_read + 1, "read_off"));
     cudaMemsetAsync(s.mean_cov, 0xff, sizeof(int) * n_read, st);
     cudaMemsetAsync(s.rflags, 0, n_read, st);
@@ -341,14 +342,18 @@ static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
         const int lo = std::max(c->a_lo, c->r_begin), hi = std::min(c->a_hi, c->r_end + 1);
         if (c->plan_reads_version != c->reads_version || c->plan_cut_off != p->cut_off ||
             c->plan_lo != lo || c->plan_hi != hi) {
-            std::vector<int> first, rbase;
-            flat_plan(c->h_rlen.data(), lo, std::max(lo, hi), c->n_read, p->cut_off, &first, &rbase);
-            HG_TRY(dev_alloc(c, &s.flat_batch_first, first.size(), "flat K2 batches"));
+            std::vector<int2> batch;
+            std::vector<int> rbase, read_batch;
+            flat_plan(c->h_rlen.data(), lo, std::max(lo, hi), c->n_read, p->cut_off, &batch, &rbase, &read_batch);
+            HG_TRY(dev_alloc(c, &s.flat_batch, batch.size(), "flat K2 batches"));
             HG_TRY(dev_alloc(c, &s.flat_rbase, rbase.size(), "flat K2 read offsets"));
-            HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_batch_first, first.data(), sizeof(int) * first.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
+            HG_TRY(dev_alloc(c, &s.flat_read_batch, read_batch.size(), "flat K2 read -> batch"));
+            HG_TRY(dev_alloc(c, &s.flat_batch_self, batch.size(), "flat K2 batch flags"));
+            HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_batch, batch.data(), sizeof(int2) * batch.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
             HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_rbase, rbase.data(), sizeof(int) * rbase.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
+            HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_read_batch, read_batch.data(), sizeof(int) * read_batch.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
             HG_TRY(cuda_check(c, cudaStreamSynchronize(c->stream), "flat K2 plan"));  // the vectors go away
-            s.flat_nbatch = hi > lo ? (int)first.size() - 1 : 0;
+            s.flat_nbatch = hi > lo ? (int)batch.size() - 1 : 0;
             c->plan_reads_version = c->reads_version;
             c->plan_cut_off = p->cut_off;
             c->plan_lo = lo;

@@ -161,7 +161,8 @@ __global__ void k_cov_finalize(RecView rv, ReadView rd, int r_begin, int r_end,
                                const unsigned long long* __restrict__ cov_sum,
                                const int* __restrict__ cov_maxbin,
                                const int* __restrict__ self_cnt, int* __restrict__ mean_cov,
-                               uint8_t* __restrict__ rflags) {
+                               uint8_t* __restrict__ rflags, const int* __restrict__ read_batch,
+                               int* __restrict__ batch_self) {
     const int i = rd.r_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rd.r_hi) return;
     const int len0 = cov_maxbin[i] + 1;
@@ -170,6 +171,7 @@ __global__ void k_cov_finalize(RecView rv, ReadView rd, int r_begin, int r_end,
     mean_cov[i] = (rl >= 5000 && i >= r_begin && i <= r_end) ? mean : -1;
     uint8_t f = 0;
     if (self_cnt[i] > 0) {
+        if (read_batch) batch_self[read_batch[i]] = 1;  // the flat K2 loads bread only for such batches
         float cov = 0.0f;
         for (int64_t k = rv.read_off[i]; k < rv.read_off[i + 1]; k++) {
             if (rv.bread[k] != i) continue;
@@ -970,19 +972,16 @@ __device__ bool hinge_walk_warp(const int2* ends, int support, bool out_hinge, i
 //   int4 rec[cap] | KeyIdx ord[cap] | int2 ends[cap] | int2 sorted[cap] | int2 keys[cap] | int gl[2 cap]
 constexpr int kHingeSlotBytesPerRec = 16 + 8 + 8 + 8 + 8 + 8;
 constexpr int kHingeSmemEnds = 192;
-constexpr int kHingeSmemPile = 1024;
 
 __global__ void __launch_bounds__(128, 8)
 k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict__ mask,
              const int2* __restrict__ anno_ref, const int2* __restrict__ anno_pool,
-             int* __restrict__ counters, const int* __restrict__ work_list,
+             int* __restrict__ counters, const int* __restrict__ work_list, int* __restrict__ exact_list,
              uint8_t* __restrict__ hinge_keep, uint8_t* scratch, int cap, int4* __restrict__ item_log) {
     const int lane = lane_id();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     uint8_t* base = scratch + (size_t)warp * cap * kHingeSlotBytesPerRec;
-    int4* rec = reinterpret_cast<int4*>(base);
-    KeyIdx* const ord_global = reinterpret_cast<KeyIdx*>(base + (size_t)cap * 16);
     int2* ends = reinterpret_cast<int2*>(base + (size_t)cap * 24);
     int2* sorted = reinterpret_cast<int2*>(base + (size_t)cap * 32);
     int2* keys = reinterpret_cast<int2*>(base + (size_t)cap * 40);  // (total length, selection index)
@@ -991,8 +990,10 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
     const int THETA = P.theta, HTL = P.hinge_tolerance_length, HBL = P.hinge_bin_length;
     // end lists of up to kHingeSmemEnds entries are sorted and walked in shared memory
     __shared__ int2 sh_ends[4][kHingeSmemEnds], sh_sorted[4][kHingeSmemEnds];
+    __shared__ __align__(16) int sh_keys[4][kHingeSmemEnds];
     int2* const ends_s = sh_ends[threadIdx.x >> 5];
     int2* const sorted_s = sh_sorted[threadIdx.x >> 5];
+    int* const keys_s = sh_keys[threadIdx.x >> 5];
     (void)nwarps;
 
     // reads are handed out one at a time: a read that needs the (sequential) order-exact
@@ -1008,9 +1009,7 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
         const int64_t o0 = rv.read_off[read], o1 = rv.read_off[read + 1];
         const int2 mk = mask[read];
         const int2 ar = anno_ref[read];
-        bool have_exact_order = false;
-        int n_exact = 0;
-        KeyIdx* ord = ord_global;
+        bool deferred = false;
         for (int j = 0; j < ar.y; j++) {
             const int2 an = anno_pool[ar.x + j];
             const int apos = an.x;
@@ -1070,6 +1069,23 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
                 if (!danger) {
                     // descending order = ascending order of the negated position
                     const int sgn = out_hinge ? 1 : -1;
+                    if (small && rd.rlen[read] < (1 << 22)) {
+                        // one distinct integer per entry, ordered like (position, index): the rank is a
+                        // count of smaller keys, four per 128-bit shared-memory load
+                        const int padded = (support + 3) & ~3;
+                        for (int i = lane; i < padded; i += 32)
+                            keys_s[i] = i < support ? sgn * ends_s[i].x * 256 + i : 0x7fffffff;
+                        __syncwarp();
+                        for (int i = lane; i < support; i += 32) {
+                            const int me = keys_s[i];
+                            int rank = 0;
+                            for (int t = 0; t < padded; t += 4) {
+                                const int4 k4 = *reinterpret_cast<const int4*>(keys_s + t);
+                                rank += (k4.x < me) + (k4.y < me) + (k4.z < me) + (k4.w < me);
+                            }
+                            sorted_s[rank] = ends_s[i];
+                        }
+                    } else
                     for (int i = lane; i < support; i += 32) {
                         const int2 me = src[i];
                         const int mx = sgn * me.x;
@@ -1119,67 +1135,112 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
                                if (lane == 0) atomicAdd(&counters[4], 1);
                                return true;
                            }()) {
-                    // ---- order-exact path, full form.  Pile-up in file order, then std::sort by total
-                    // length, descending (filter.cpp:565-567), once per read
-                    if (!have_exact_order) {
-                        int n = 0;
-                        for (int64_t kb = o0; kb < o1; kb += 32) {
-                            const int64_t k = kb + lane;
-                            PileRec r;
-                            r.active = false;
-                            if (k < o1) r = load_pile_rec(rv, rd, mask, read, k);
-                            const unsigned am = __ballot_sync(0xffffffffu, r.active);
-                            if (r.active) {
-                                const int s = n + __popc(am & ((1u << lane) - 1u));
-                                rec[s] = make_int4(r.as, r.ae, r.lo, r.ro);
-                                ord[s].key = r.key;
-                                ord[s].idx = s;
-                            }
-                            n += __popc(am);
-                        }
-                        __syncwarp();
-                        warp_sort_exact(ord_global, n, GreaterKey(), gl, gl + cap,
-                                        reinterpret_cast<KeyIdx*>(keys));
-                        __syncwarp();
-                        have_exact_order = true;
-                        n_exact = n;
-                    }
-                    int sup2 = 0;
-                    for (int kb = 0; kb < n_exact; kb += 32) {
-                        const int k = kb + lane;
-                        bool sel = false;
-                        int2 e = make_int2(0, 0);
-                        if (k < n_exact) {
-                            const int4 q = rec[ord[k].idx];
-                            PileRec r;
-                            r.as = q.x; r.ae = q.y; r.lo = q.z; r.ro = q.w; r.key = 0; r.active = true;
-                            sel = hinge_select(r, out_hinge, apos, THETA, HTL, &e);
-                        }
-                        const unsigned sm = __ballot_sync(0xffffffffu, sel);
-                        if (sel) {
-                            const int slot = sup2 + __popc(sm & ((1u << lane) - 1u));
-                            ends[slot] = e;
-                            if (slot < kHingeSmemEnds) ends_s[slot] = e;
-                        }
-                        sup2 += __popc(sm);
-                    }
-                    __syncwarp();
-                    int2* const ex = sup2 <= kHingeSmemEnds ? ends_s : ends;
-                    if (out_hinge)  // filter.cpp:914 / 1010, all lanes
-                        warp_sort_exact(ex, sup2, FirstAsc(), gl, gl + cap, keys);
-                    else
-                        warp_sort_exact(ex, sup2, FirstDesc(), gl, gl + cap, keys);
-                    keep = hinge_walk_warp(ex, sup2, out_hinge, mk, P) ? 1 : 0;
-                    if (lane == 0) atomicAdd(&counters[4], 1);
+                    // ---- order-exact path, full form: the whole pile-up has to go through std::sort.
+                    // That is a long, latency-bound job for one warp (~150 us when its scratch is in
+                    // global memory) and would set the duration of this kernel, so the read is handed
+                    // to k_hinge_exact, which redoes all its annotations out of shared memory.
+                    deferred = true;
                 }
             }
+            if (deferred) break;
             if (lane == 0) hinge_keep[ar.x + j] = keep;
             log_support = max(log_support, support);
             __syncwarp();
         }
-        log_exact = have_exact_order ? n_exact : 0;
+        if (deferred && lane == 0) exact_list[atomicAdd(&counters[6], 1)] = read;
+        log_exact = deferred ? 1 : 0;
         if (item_log && lane == 0)
             item_log[w] = make_int4(read, (int)(clock64() - t_begin), log_support, log_exact);
+    }
+}
+
+// Reads whose annotations need the reference's exact sort order (see k_hinge_call): one warp
+// per read, the reference's own sequence for every annotation of the read -- pile-up in file
+// order, std::sort by total length (filter.cpp:565-567), selection in that order, std::sort of the
+// end list by position (filter.cpp:914 / 1010), walk -- with libstdc++'s introsort restated in
+// hg_order.h.  The sort is a chain of short dependent steps, so its arrays live in shared memory
+// (48 B per pile-up record); deeper pile-ups than `scap` fall back to a global slot.
+constexpr int kHingeExactBytesPerRec = 16 + 8 + 8 + 8 + 8;
+
+__global__ void __launch_bounds__(32)
+k_hinge_exact(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict__ mask,
+              const int2* __restrict__ anno_ref, const int2* __restrict__ anno_pool,
+              int* __restrict__ counters, const int* __restrict__ exact_list,
+              uint8_t* __restrict__ hinge_keep, uint8_t* gscratch, int gcap, int scap) {
+    extern __shared__ __align__(16) uint8_t sm_exact[];
+    const int lane = lane_id();
+    const int nlist = counters[6];
+    const int THETA = P.theta, HTL = P.hinge_tolerance_length;
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(&counters[7], 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= nlist) break;
+        const int read = exact_list[w];
+        const int64_t o0 = rv.read_off[read], o1 = rv.read_off[read + 1];
+        const int np = (int)(o1 - o0);
+        const bool in_smem = np <= scap;
+        const int cap = in_smem ? scap : gcap;
+        uint8_t* base = in_smem ? sm_exact : gscratch + (size_t)blockIdx.x * gcap * kHingeSlotBytesPerRec;
+        int4* rec = reinterpret_cast<int4*>(base);
+        KeyIdx* ord = reinterpret_cast<KeyIdx*>(base + (size_t)cap * 16);
+        int2* ends = reinterpret_cast<int2*>(base + (size_t)cap * 24);
+        int2* tmp = reinterpret_cast<int2*>(base + (size_t)cap * 32);
+        int* gl = reinterpret_cast<int*>(base + (size_t)cap * 40);
+        const int2 mk = mask[read];
+        const int2 ar = anno_ref[read];
+
+        // pile-up in file order (A == B records are inactive, filter.cpp:538-547), then std::sort
+        int n = 0;
+        for (int kb = 0; kb < np; kb += 32) {
+            const int k = kb + lane;
+            PileRec r;
+            r.active = false;
+            if (k < np) r = load_pile_rec(rv, rd, mask, read, o0 + k);
+            const unsigned am = __ballot_sync(0xffffffffu, r.active);
+            if (r.active) {
+                const int s = n + __popc(am & ((1u << lane) - 1u));
+                rec[s] = make_int4(r.as, r.ae, r.lo, r.ro);
+                ord[s].key = r.key;
+                ord[s].idx = s;
+            }
+            n += __popc(am);
+        }
+        __syncwarp();
+        warp_sort_exact(ord, n, GreaterKey(), gl, gl + cap, reinterpret_cast<KeyIdx*>(tmp));
+        __syncwarp();
+
+        for (int j = 0; j < ar.y; j++) {
+            const int2 an = anno_pool[ar.x + j];
+            const bool out_hinge = an.y == -1;
+            int support = 0;
+            for (int kb = 0; kb < n; kb += 32) {
+                const int k = kb + lane;
+                bool sel = false;
+                int2 e = make_int2(0, 0);
+                if (k < n) {
+                    const int4 q = rec[ord[k].idx];
+                    PileRec r;
+                    r.as = q.x; r.ae = q.y; r.lo = q.z; r.ro = q.w; r.key = 0; r.active = true;
+                    sel = hinge_select(r, out_hinge, an.x, THETA, HTL, &e);
+                }
+                const unsigned sm = __ballot_sync(0xffffffffu, sel);
+                if (sel) ends[support + __popc(sm & ((1u << lane) - 1u))] = e;
+                support += __popc(sm);
+            }
+            __syncwarp();
+            uint8_t keep = 0;
+            if (support >= P.hinge_min_support) {  // filter.cpp:910, 1005
+                if (out_hinge)
+                    warp_sort_exact(ends, support, FirstAsc(), gl, gl + cap, tmp);
+                else
+                    warp_sort_exact(ends, support, FirstDesc(), gl, gl + cap, tmp);
+                keep = hinge_walk_warp(ends, support, out_hinge, mk, P) ? 1 : 0;
+                if (lane == 0) atomicAdd(&counters[4], 1);
+            }
+            if (lane == 0) hinge_keep[ar.x + j] = keep;
+            __syncwarp();
+        }
     }
 }
 
@@ -1231,6 +1292,7 @@ void launch_cov_estimate(const RecView& rv, const ReadView& rd, const hg_filter_
     cudaMemsetAsync(s.cov_sum, 0, sizeof(unsigned long long) * rd.n_read, st);
     cudaMemsetAsync(s.cov_maxbin, 0xff, sizeof(int) * rd.n_read, st);
     cudaMemsetAsync(s.self_cnt, 0, sizeof(int) * rd.n_read, st);
+    if (s.flat_batch_self) cudaMemsetAsync(s.flat_batch_self, 0, sizeof(int) * (s.flat_nbatch + 1), st);
     const bool aligned = (((uintptr_t)rv.aread | (uintptr_t)rv.bread | (uintptr_t)rv.abpos |
                            (uintptr_t)rv.aepos) & 15) == 0;
     if (rv.novl > 0) {
@@ -1246,7 +1308,8 @@ void launch_cov_estimate(const RecView& rv, const ReadView& rd, const hg_filter_
     if (owned > 0)
         k_cov_finalize<<<ceil_div64(owned, 256), 256, 0, st>>>(rv, rd, r_begin, r_end, s.cov_sum,
                                                                s.cov_maxbin, s.self_cnt,
-                                                               s.mean_cov, s.rflags);
+                                                               s.mean_cov, s.rflags, s.flat_read_batch,
+                                                               s.flat_batch_self);
 }
 
 void launch_median(const ReadView& rd, const hg_filter_params& P, FilterScratch& s,
@@ -1319,10 +1382,21 @@ void launch_max_pileup(const int64_t* read_off, int n_read, int* out_max, cudaSt
 void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
                        FilterScratch& s, cudaStream_t st) {
     if (s.hinge_cap <= 0) return;
-    g_launches += 1;
+    g_launches += 2;
     k_hinge_call<<<s.hinge_warps / 4, 128, 0, st>>>(rv, rd, P, s.mask, s.anno_ref, s.anno_pool,
-                                                    s.counters, s.work_list, s.hinge_keep,
+                                                    s.counters, s.work_list, s.exact_list, s.hinge_keep,
                                                     s.hinge_scratch, s.hinge_cap, s.item_log);
+    // the few reads that need the exact sort order: shared-memory scratch, one warp each
+    constexpr int scap = 1536;
+    const int smem = scap * kHingeExactBytesPerRec;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_hinge_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    const int grid = s.hinge_warps < 2 * s.num_sms ? s.hinge_warps : 2 * s.num_sms;
+    k_hinge_exact<<<grid, 32, smem, st>>>(rv, rd, P, s.mask, s.anno_ref, s.anno_pool, s.counters,
+                                          s.exact_list, s.hinge_keep, s.hinge_scratch, s.hinge_cap, scap);
 }
 
 }  // namespace hg

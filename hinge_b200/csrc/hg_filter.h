@@ -42,12 +42,15 @@ struct FilterScratch {
     int* counters = nullptr;   // 8
     int* work_list = nullptr;  // n_read
     int* big_list = nullptr;   // n_read
+    int* exact_list = nullptr; // n_read: reads whose hinge calls need the exact sort order
     int nb_cap = 0;            // histogram words per warp on the warp-per-read path
     int mask_anno_grid = 0;
     int k2_variant = kK2Flat;
     int flat_spread = 8;              // flat K2: record windows per warp in the scatter (tuning aid)
-    int* flat_batch_first = nullptr;  // flat K2: first read of every batch (flat_nbatch + 1)
+    int2* flat_batch = nullptr;       // flat K2: (first read, histogram words in use) per batch (flat_nbatch + 1)
     int* flat_rbase = nullptr;        // flat K2: per read, first histogram word inside its batch (-1: generic path)
+    int* flat_read_batch = nullptr;   // flat K2: per read, its batch
+    int* flat_batch_self = nullptr;   // flat K2: per batch, set by K1 when the batch holds A == B records
     int flat_nbatch = 0;
     unsigned long long* big_scratch = nullptr;
     int big_slot_words = 0, big_warps = 0;
@@ -71,8 +74,8 @@ void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_par
                       int r_begin, int r_end, FilterScratch& s, int* cov0, const int64_t* cov0_off,
                       cudaStream_t st);
 // flat K2 (hg_filter_flat.cu): host-side batch plan + launcher
-void flat_plan(const int* rlen, int lo, int hi, int n_read, int cut_off, std::vector<int>* batch_first,
-               std::vector<int>* rbase);
+void flat_plan(const int* rlen, int lo, int hi, int n_read, int cut_off, std::vector<int2>* batch,
+               std::vector<int>* rbase, std::vector<int>* read_batch);
 void launch_mask_anno_flat(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
                            FilterScratch& s, const MaskAnnoOut& out, cudaStream_t st);
 void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_params& P,

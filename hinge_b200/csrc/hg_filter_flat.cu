@@ -9,11 +9,12 @@
 // 65 % issue-active, 11 % of HBM).  Here the profiles of ~40 reads are laid end to end in
 // one shared-memory array and every phase runs flat over it with all lanes busy:
 //
-//   scatter   flat over the batch's records (int4 loads of aread/abpos/aepos): four packed
-//             +-1 events per record (low half: profile without cut-off, high half: with).
-//             Half of all records start in their read's first bin or end in its last one,
-//             so the lanes of a warp that hit those words are counted with a ballot and one
-//             lane adds the count: the shared-memory atomics stop serialising.
+//   scatter   flat over the batch's records (int4 loads of aread/abpos/aepos, the next
+//             step's loads in flight while this step's events go out): four packed +-1
+//             events per record (low half: profile without cut-off, high half: with).
+//             The lanes of a warp are spread over eight record windows (flat_group) so
+//             that the many records that start in their read's first bin or end in its
+//             last one do not all serialise on one shared-memory word.
 //   scan      ONE block-wide prefix sum over the concatenated array.  Every record adds
 //             +1 and -1 inside its own read's bins, so the running sum is back at zero at
 //             every read boundary: no segmentation needed.  The same pass leaves two bit
@@ -23,6 +24,10 @@
 //             (filter.cpp:696-728), mask, telomere flag, repeat annotations with the
 //             streaming form of the merge pass (filter.cpp:796-829), hinge pre-test
 //             (filter.cpp:842-865).
+//
+// The kernel is bound by the shared-memory data pipe (ncu: l1tex data-pipe wavefronts > 80 %
+// of peak): ~4 wavefronts per ATOMS on random bins is what the banks give, so the rest of the
+// design keeps every other shared-memory access conflict-free (sw) and the global loads wide.
 //
 // Reads longer than kFlatBins bins, pile-ups deeper than the 16-bit halves can count and
 // runs with MIN_COV < 0 go to the generic per-read kernel (k_mask_anno_big, hg_filter.cu).
@@ -44,50 +49,22 @@ __device__ __forceinline__ void sts128(uint32_t* p, uint4 v) { *reinterpret_cast
 __device__ __forceinline__ int f_lo(uint32_t v) { return (int)(v & 0xffffu); }   // after the scan: cov0 >= 0
 __device__ __forceinline__ int f_hi(uint32_t v) { return (int)v >> 16; }
 
-// The four events of one record (profileCoverage, LAInterface.cpp:4298-4320).
-//
-// AGG: about half of all records start in the first 40 bp of their A-read and about half end in
-// its last bin, so without care half the lanes of a warp add to the same shared-memory word and
-// the atomics serialise (ncu: ~9 wavefronts per ATOMS).  The lanes of a warp hold consecutive
-// records, i.e. the reads form contiguous lane segments: one ballot per hot bin restricted to the
-// lane's segment counts the records that hit it, the first of them adds the count, all other
-// records add their own +-1 in the same instruction.  (match.any does this for any bin but costs
-// ~120 cycles per warp on sm_100a: measured 2x slower than no aggregation at all.)
-// All 32 lanes call this; `valid` says whether the lane carries a record; `maxbin` is the last bin
-// of the read's cut-off-free profile (K1).
-template <bool AGG>
-__device__ __forceinline__ void scatter_record(uint32_t* hist, bool valid, int a, int base, int maxbin, int as,
-                                               int ae, int C, int lane, unsigned lt) {
+// Shared-memory layout of the histogram.  A thread of the scan owns 16 consecutive words and
+// moves them as four 128-bit vectors; with the identity layout the 8 lanes of a quarter warp
+// start 64 B apart and hit only two of the eight 16-byte bank groups (ncu: twice the ideal
+// wavefronts on every LDS.128 / STS.128).  Flipping word-index bits 2-3 with bits 5-6 keeps
+// every aligned 4-word group intact and makes those accesses conflict-free.
+__device__ __forceinline__ int sw(int j) { return j ^ ((j >> 3) & 12); }
+
+// The four events of one record (profileCoverage, LAInterface.cpp:4298-4320): low half of the
+// packed word = profile without cut-off, high half = with.
+__device__ __forceinline__ void scatter_record(uint32_t* hist, int base, int as, int ae, int C) {
     const int b_s0 = base + as / kReso + 1, b_e0 = base + ae / kReso + 1;  // 0 <= abpos < aepos (ingest check)
     const int b_sc = base + cov_bin(as + C, kReso), b_ec = base + cov_bin(ae - C, kReso);
-    if (!AGG) {
-        if (valid) {
-            atomicAdd(&hist[b_s0], 1u);
-            atomicAdd(&hist[b_e0], 0u - 1u);
-            atomicAdd(&hist[b_sc], 1u << 16);
-            atomicAdd(&hist[b_ec], 0u - (1u << 16));
-        }
-        return;
-    }
-    // lanes of my read: [s, e)
-    const int a_prev = __shfl_up_sync(0xffffffffu, a, 1);
-    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || a != a_prev);
-    const unsigned upto = (2u << lane) - 1u;  // lanes <= mine (all ones for lane 31)
-    const int s = 31 - __clz(heads & upto);
-    const unsigned above = heads & ~upto;
-    const unsigned seg = (above ? ((1u << (__ffs(above) - 1)) - 1u) : 0xffffffffu) & (0xffffffffu << s);
-    const bool hs = valid && b_s0 == base + 1, he = valid && b_e0 == base + maxbin;
-    const unsigned gs = __ballot_sync(0xffffffffu, hs) & seg, ge = __ballot_sync(0xffffffffu, he) & seg;
-    // records that share a bin of the cut-off-free profile fall in at most two ADJACENT bins of
-    // the other one (their positions differ by < 40): the bin's parity splits the group
-    const unsigned os = __ballot_sync(0xffffffffu, b_sc & 1), oe = __ballot_sync(0xffffffffu, b_ec & 1);
-    const unsigned gsc = gs & ((b_sc & 1) ? os : ~os), gec = ge & ((b_ec & 1) ? oe : ~oe);
-    if (valid) {
-        if (!hs || (gs & lt) == 0) atomicAdd(&hist[b_s0], hs ? (uint32_t)__popc(gs) : 1u);
-        if (!he || (ge & lt) == 0) atomicAdd(&hist[b_e0], 0u - (he ? (uint32_t)__popc(ge) : 1u));
-        if (!hs || (gsc & lt) == 0) atomicAdd(&hist[b_sc], (hs ? (uint32_t)__popc(gsc) : 1u) << 16);
-        if (!he || (gec & lt) == 0) atomicAdd(&hist[b_ec], 0u - ((he ? (uint32_t)__popc(gec) : 1u) << 16));
-    }
+    atomicAdd(&hist[sw(b_s0)], 1u);
+    atomicAdd(&hist[sw(b_e0)], 0u - 1u);
+    atomicAdd(&hist[sw(b_sc)], 1u << 16);
+    atomicAdd(&hist[sw(b_ec)], 0u - (1u << 16));
 }
 
 // Bit `i` of the map <=> entry i (maps are arrays of 32-bit words in shared memory).
@@ -101,10 +78,10 @@ __device__ __forceinline__ uint32_t map_word(const uint32_t* map, int w, int lo,
 }
 
 struct FlatParams {
-    const int* __restrict__ batch_first;  // nbatch + 1: first read of every batch
+    const int2* __restrict__ batch;       // nbatch + 1: (first read, histogram words in use) of every batch
     const int* __restrict__ rbase;        // per read: first word of its profile inside its batch, -1 = generic path
     const int* __restrict__ cov_maxbin;   // K1: last bin of the cut-off-free profile (-1 = empty pile-up)
-    const int* __restrict__ self_cnt;     // K1: records with A == B
+    const int* __restrict__ batch_self;   // K1: the batch holds records with A == B
     const int* __restrict__ scal;         // [1] = MIN_COV
 };
 
@@ -113,7 +90,7 @@ struct FlatParams {
 // start in the read's first bin (or end in its last) serialise on one shared-memory word.
 // Spreading the lanes over SPREAD windows 128 records apart (32 / SPREAD lanes, a 16 * 32 / SPREAD
 // byte run, per window) divides that multiplicity by SPREAD while every window still reads whole
-// sectors.
+// sectors.  Measured on B200 (K2 alone, ms): 1 -> 0.404, 4 -> 0.365, 8 -> 0.368, 16 -> 0.395, 32 -> 0.459.
 template <int SPREAD>
 __device__ __forceinline__ int flat_group(int tid) {
     if (SPREAD <= 1) return tid;
@@ -129,76 +106,70 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
     __shared__ __align__(16) uint16_t zmap16[kFlatMaps];  // bin has cut-off coverage <= MIN_COV
     __shared__ __align__(16) uint16_t cmap16[kFlatMaps];  // |cov0[j] - cov0[j-1]| above the smallest threshold
     __shared__ uint32_t wtot[2][kFlatThreads / 32];
-    __shared__ int sh_self;
     const uint32_t* zmap = reinterpret_cast<const uint32_t*>(zmap16);
     const uint32_t* cmap = reinterpret_cast<const uint32_t*>(cmap16);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    const int f0 = F.batch_first[blockIdx.x], f1 = F.batch_first[blockIdx.x + 1];
+    const int2 bt = F.batch[blockIdx.x];
+    const int f0 = bt.x, f1 = F.batch[blockIdx.x + 1].x;
     const int MIN_COV = F.scal[1];
     constexpr int reso = kReso;
-
-    // words in use: up to the end of the last read that is on the flat path
-    int nb = 0;
-    for (int r = f1 - 1; r >= f0; r--) {
-        const int b = F.rbase[r];
-        if (b >= 0) {
-            nb = b + bins_needed(rd.rlen[r], P);
-            break;
-        }
-    }
-    if (MIN_COV < 0) nb = 0;  // runs could cross read boundaries: everything goes the generic way
+    // MIN_COV < 0: runs could cross read boundaries, everything goes the generic way
+    const int nb = MIN_COV < 0 ? 0 : bt.y;
     const int npass = (nb + kFlatPass - 1) / kFlatPass;
+    const bool self_records = F.batch_self[blockIdx.x] != 0;  // otherwise the bread column is not even loaded
 
-    // ---- zero
-    if (tid == 0) sh_self = 0;
-    for (int j = tid * 4; j < npass * kFlatPass + 4 && j < kFlatWords; j += kFlatThreads * 4)
-        sts128(hist + j, make_uint4(0, 0, 0, 0));
-    __syncthreads();
-    for (int r = f0 + tid; r < f1; r += kFlatThreads)
-        if (F.self_cnt[r] > 0) sh_self = 1;
-    __syncthreads();
-    const bool self_records = sh_self != 0;  // without A == B records the bread column is not even loaded
-
-    // ---- scatter: flat over the batch's records, four records per thread and step
-    if (nb > 0) {
-        const int64_t k_begin = rv.read_off[f0], k_end = rv.read_off[f1];
-        const int64_t g0 = k_begin & ~(int64_t)3;
-        const int C = P.cut_off;
-        for (int64_t kb = g0; kb < k_end; kb += kFlatThreads * 4) {  // block-uniform trip count
-            const int64_t k = kb + flat_group<SPREAD>(tid) * 4;
+    // ---- the batch's records: four per thread and step
+    const int64_t k_begin = nb > 0 ? rv.read_off[f0] : 0, k_end = nb > 0 ? rv.read_off[f1] : 0;
+    const int64_t g0 = k_begin & ~(int64_t)3;
+    const int grp = flat_group<SPREAD>(tid) * 4;
+    int4 va = make_int4(-1, -1, -1, -1), vs = make_int4(0, 0, 0, 0), ve = vs, vb = make_int4(-2, -2, -2, -2);
+    auto load4 = [&](int64_t k) {
+        if (k >= k_begin && k + 4 <= k_end) {
+            va = __ldg(reinterpret_cast<const int4*>(rv.aread + k));
+            vs = __ldg(reinterpret_cast<const int4*>(rv.abpos + k));
+            ve = __ldg(reinterpret_cast<const int4*>(rv.aepos + k));
+            if (self_records) vb = __ldg(reinterpret_cast<const int4*>(rv.bread + k));
+        } else {  // ragged ends of the batch: records outside it get read id -1
             int a[4], s[4], e[4], b[4];
-            bool ok[4];
-            if (k >= k_begin && k + 4 <= k_end) {
-                const int4 va = __ldg(reinterpret_cast<const int4*>(rv.aread + k));
-                const int4 vs = __ldg(reinterpret_cast<const int4*>(rv.abpos + k));
-                const int4 ve = __ldg(reinterpret_cast<const int4*>(rv.aepos + k));
-                a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w;
-                s[0] = vs.x; s[1] = vs.y; s[2] = vs.z; s[3] = vs.w;
-                e[0] = ve.x; e[1] = ve.y; e[2] = ve.z; e[3] = ve.w;
-                ok[0] = ok[1] = ok[2] = ok[3] = true;
-                if (self_records) {
-                    const int4 vb = __ldg(reinterpret_cast<const int4*>(rv.bread + k));
-                    b[0] = vb.x; b[1] = vb.y; b[2] = vb.z; b[3] = vb.w;
-                }
-            } else {  // ragged ends of the batch
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int64_t ki = k + i;
-                    ok[i] = ki >= k_begin && ki < k_end;
-                    a[i] = ok[i] ? __ldg(rv.aread + ki) : f0;
-                    s[i] = ok[i] ? __ldg(rv.abpos + ki) : 0;
-                    e[i] = ok[i] ? __ldg(rv.aepos + ki) : 0;
-                    b[i] = (ok[i] && self_records) ? __ldg(rv.bread + ki) : -1;
-                }
-            }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int base = __ldg(F.rbase + a[i]);
-                bool valid = ok[i] && base >= 0;
+                const int64_t ki = k + i;
+                const bool in = ki >= k_begin && ki < k_end;
+                a[i] = in ? __ldg(rv.aread + ki) : -1;
+                s[i] = in ? __ldg(rv.abpos + ki) : 0;
+                e[i] = in ? __ldg(rv.aepos + ki) : 0;
+                b[i] = (in && self_records) ? __ldg(rv.bread + ki) : -2;
+            }
+            va = make_int4(a[0], a[1], a[2], a[3]);
+            vs = make_int4(s[0], s[1], s[2], s[3]);
+            ve = make_int4(e[0], e[1], e[2], e[3]);
+            vb = make_int4(b[0], b[1], b[2], b[3]);
+        }
+    };
+    if (g0 < k_end) load4(g0 + grp);  // in flight while the histogram is cleared
+
+    // ---- zero
+    for (int j = tid * 4; j < npass * kFlatPass + 16 && j < kFlatWords; j += kFlatThreads * 4)
+        sts128(hist + j, make_uint4(0, 0, 0, 0));
+    __syncthreads();
+
+    // ---- scatter: the next step's loads are issued before this step's events go out
+    {
+        const int C = P.cut_off;
+        for (int64_t kb = g0; kb < k_end; kb += kFlatThreads * 4) {
+            const int a[4] = {va.x, va.y, va.z, va.w}, s[4] = {vs.x, vs.y, vs.z, vs.w};
+            const int e[4] = {ve.x, ve.y, ve.z, ve.w}, b[4] = {vb.x, vb.y, vb.z, vb.w};
+            if (kb + kFlatThreads * 4 < k_end) load4(kb + kFlatThreads * 4 + grp);
+            // records are sorted by A-read: in most groups one lookup of the read's base serves all four
+            const int base0 = a[0] >= 0 ? __ldg(F.rbase + a[0]) : -1;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int base = base0;
+                if (a[i] != a[0]) base = a[i] >= 0 ? __ldg(F.rbase + a[i]) : -1;
+                bool valid = base >= 0;
                 if (self_records) valid = valid && b[i] != a[i];  // filter.cpp:538-547
-                scatter_record<false>(hist, valid, a[i], base, 0, s[i], e[i], C, lane, lt);
+                if (valid) scatter_record(hist, base, s[i], e[i], C);
             }
         }
     }
@@ -211,12 +182,13 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
     uint32_t carry = 0;
     for (int pass = 0; pass < npass; pass++) {
         const int j0 = pass * kFlatPass + tid * kFlatItems;
+        const int sx = sw(j0) ^ j0;  // the flipped bits: common to the whole 16-word chunk
         uint32_t v[kFlatItems];
         uint32_t cbits = 0;
         if (j0 < nb) {
 #pragma unroll
             for (int q = 0; q < kFlatItems / 4; q++) {
-                const uint4 x = lds128(hist + j0 + 4 * q);
+                const uint4 x = lds128(hist + ((j0 + 4 * q) ^ sx));
                 v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
             }
 #pragma unroll
@@ -249,7 +221,7 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
             }
 #pragma unroll
             for (int q = 0; q < kFlatItems / 4; q++)
-                sts128(hist + j0 + 4 * q, make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+                sts128(hist + ((j0 + 4 * q) ^ sx), make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
         }
         zmap16[pass * kFlatThreads + tid] = (uint16_t)zbits;
         cmap16[pass * kFlatThreads + tid] = (uint16_t)cbits;
@@ -268,7 +240,7 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
         }
         const int nbz = bins_needed(rd.rlen[read], P);
         const int L0 = F.cov_maxbin[read] + 1;  // length of the cut-off-free profile
-        const uint32_t* h = hist + base;
+        auto H = [&](int j) { return hist[sw(base + j)]; };  // packed coverage of the read's bin j
 
         // longest run of covered bins (filter.cpp:696-728): the run between two consecutive zeros
         // p < z scores 40 (z - p - 2); bin 0 acts as a zero; '>' keeps the earliest of the longest
@@ -313,8 +285,8 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
             }
             int sc = 0, ec = 0;
             for (int t = 0; t < limit; t++) {
-                sc += max(f_hi(h[msc + t]), MIN_COV);
-                ec += max(f_hi(h[mec - t]), MIN_COV);
+                sc += max(f_hi(H(msc + t)), MIN_COV);
+                ec += max(f_hi(H(mec - t)), MIN_COV);
             }
             if (div == 0) {
                 sc = 0;
@@ -356,8 +328,8 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
                         const int bit = __ffs(m) - 1;
                         m &= m - 1;
                         const int j = (w << 5) + bit - 1 - base;
-                        const int c0 = f_lo(h[j]);
-                        const int g = f_lo(h[j + 1]) - c0;
+                        const int c0 = f_lo(H(j));
+                        const int g = f_lo(H(j + 1)) - c0;
                         const int thr = min(max((c0 + MIN_COV) / P.coverage_fraction, MINT), MAXT);
                         const int type = g > thr ? 1 : (g < -thr ? -1 : 0);
                         if (type == 0) continue;
@@ -405,13 +377,13 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
             int jlo = mk.x <= 0 ? 0 : (mk.x + reso - 1) / reso;  // bins with mk.x <= 40 j <= mk.x + NHR
             int jhi = mk.x + NHR < 0 ? -1 : min((mk.x + NHR) / reso, L0 - 1);
             for (int j = jlo; j <= jhi; j++) {
-                cs += f_lo(h[j]);
+                cs += f_lo(H(j));
                 ns++;
             }
             jlo = mk.y - NHR <= 0 ? 0 : (mk.y - NHR + reso - 1) / reso;  // mk.y - NHR <= 40 j <= mk.y
             jhi = mk.y < 0 ? -1 : min(mk.y / reso, L0 - 1);
             for (int j = jlo; j <= jhi; j++) {
-                ce += f_lo(h[j]);
+                ce += f_lo(H(j));
                 ne++;
             }
             // float on purpose: 0/0 = NaN makes the '< 10' test false (filter.cpp:861-865)
@@ -434,35 +406,36 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
             if (base < 0 || rv.read_off[read + 1] - rv.read_off[read] > Packed<uint32_t>::kMaxCount) continue;
             const int L0 = F.cov_maxbin[read] + 1;
             int* dst = out.cov0 + out.cov0_off[read];
-            for (int j = lane; j < L0; j += 32) dst[j] = f_lo(hist[base + j]);
+            for (int j = lane; j < L0; j += 32) dst[j] = f_lo(hist[sw(base + j)]);
         }
     }
 }
 
 // Greedy packing of the reads [lo, hi) into batches of at most kFlatBins histogram words.
-void flat_plan(const int* rlen, int lo, int hi, int n_read, int cut_off, std::vector<int>* batch_first,
-               std::vector<int>* rbase) {
-    batch_first->clear();
+//   batch      (first read, words in use) per batch, closed by (hi, 0)
+//   rbase      per read: first word of its profile inside its batch; -1 = generic path
+//   read_batch per read: its batch (K1 flags the batches that hold A == B records)
+void flat_plan(const int* rlen, int lo, int hi, int n_read, int cut_off, std::vector<int2>* batch,
+               std::vector<int>* rbase, std::vector<int>* read_batch) {
+    batch->clear();
     rbase->assign((size_t)n_read, -1);
-    int used = kFlatBins + 1;  // forces the first read to open a batch
+    read_batch->assign((size_t)n_read, 0);
+    int used = 0;
     for (int r = lo; r < hi; r++) {
         const int nbz = bins_needed(rlen[r], cut_off);
-        if (nbz > kFlatBins) {  // generic path; still belongs to a batch, which reports it
-            if (batch_first->empty()) {
-                batch_first->push_back(r);
-                used = 0;
-            }
-            continue;
-        }
-        if (used + nbz > kFlatBins) {
-            batch_first->push_back(r);
+        const bool fits = nbz <= kFlatBins;  // otherwise generic path; still belongs to a batch, which reports it
+        if (batch->empty() || (fits && used + nbz > kFlatBins)) {
+            batch->push_back(make_int2(r, 0));
             used = 0;
         }
+        (*read_batch)[r] = (int)batch->size() - 1;
+        if (!fits) continue;
         (*rbase)[r] = used;
         used += nbz;
+        batch->back().y = used;
     }
-    if (batch_first->empty()) batch_first->push_back(lo);
-    batch_first->push_back(hi);
+    if (batch->empty()) batch->push_back(make_int2(lo, 0));
+    batch->push_back(make_int2(hi, 0));
 }
 
 template <int SPREAD>
@@ -477,10 +450,10 @@ static void launch_flat(int grid, bool dump, const RecView& rv, const ReadView& 
 void launch_mask_anno_flat(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
                            FilterScratch& s, const MaskAnnoOut& out, cudaStream_t st) {
     FlatParams F;
-    F.batch_first = s.flat_batch_first;
+    F.batch = s.flat_batch;
     F.rbase = s.flat_rbase;
     F.cov_maxbin = s.cov_maxbin;
-    F.self_cnt = s.self_cnt;
+    F.batch_self = s.flat_batch_self;
     F.scal = s.scal;
     const int grid = s.flat_nbatch;
     if (grid <= 0) return;
@@ -490,7 +463,6 @@ void launch_mask_anno_flat(const RecView& rv, const ReadView& rd, const hg_filte
         case 1: launch_flat<1>(grid, dump, rv, rd, P, F, out, st); break;
         case 4: launch_flat<4>(grid, dump, rv, rd, P, F, out, st); break;
         case 16: launch_flat<16>(grid, dump, rv, rd, P, F, out, st); break;
-        case 32: launch_flat<32>(grid, dump, rv, rd, P, F, out, st); break;
         default: launch_flat<8>(grid, dump, rv, rd, P, F, out, st); break;
     }
 }

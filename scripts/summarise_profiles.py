@@ -115,7 +115,7 @@ def main():
     # ---- ncu --set full captures
     traffic_path = os.path.join(PROF, "traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
-    alias = {"k_mask_anno": "mask_anno", "k_cov_accum": "cov_estimate", "k_hinge_call": "hinge_call",
+    alias = {"k_mask_anno_flat": "mask_anno", "k_cov_accum": "cov_estimate", "k_hinge_call": "hinge_call",
              "k_classify_pairs": "classify_pairs"}
     for f in sorted(os.listdir(OUT)):
         if not (f.startswith(src + "_k_") and f.endswith(".ncu-rep")):
