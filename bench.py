@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--sample-mb", type=float, default=4.0, help="genome size of the CPU-baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--seed", type=int, default=1234)
-    ap.add_argument("--k2-variant", type=int, default=None, help="HG_OPT_K2_VARIANT (A/B aid)")
+    ap.add_argument("--spread", type=int, default=None, help="HG_OPT_SCATTER_SPREAD (tuning aid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-downstream", action="store_true", help="skip the maximal/layout timing")
     return ap.parse_args()
@@ -270,8 +270,8 @@ def main():
     stream = torch.cuda.current_stream()
     ctx = api.Context(local, stream.cuda_stream)
     ctx.set_option(api.HG_OPT_PROFILE, 1)
-    if args.k2_variant is not None:
-        ctx.set_option(api.HG_OPT_K2_VARIANT, args.k2_variant)
+    if args.spread is not None:
+        ctx.set_option(api.HG_OPT_SCATTER_SPREAD, args.spread)
     ctx.set_reads(syn.rlen, syn.qv_off, syn.qv, 100)
     params = api.FilterParams()
 
@@ -357,14 +357,16 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         kavg = {k: sum(v) / len(v) for k, v in ktimes.items()}
+        # coverage bins of the owned reads (cut_off 300, filter.cpp:386: 40-bp bins)
+        summary_bins = int(((syn.rlen[a_lo:a_hi].astype(np.int64) + params.cut_off) // 40 + 3).sum())
         owned = a_hi - a_lo
-        # algorithmic bytes of one launch: the flat K2 reads aread/abpos/aepos (12 B
-        # per record; bread only for batches with self-overlaps; the warp-per-read form skips aread: 8 B)
-        # plus ~58 B per read of offsets, lengths, batch plan, QV mask and results; K1 reads
-        # aread/bread/abpos/aepos (16 B per record)
-        k2_rec_bytes = 8.0 if args.k2_variant == 2 else 12.0
-        kbytes = {"mask_anno": k2_rec_bytes * novl + 58.0 * owned, "cov_estimate": 16.0 * novl + 24.0 * owned}
-        dom = max(("mask_anno", "cov_estimate"), key=lambda k: kavg[k])
+        # algorithmic bytes of one launch.  K1 (profile build) reads aread / abpos /
+        # aepos (12 B per record; bread only in batches with self-overlaps), ~30 B per read of offsets,
+        # lengths and plan, and writes the scanned profiles (4 B per coverage bin) and 9 B per read;
+        # K2 (mask + annotation) reads the profiles back plus ~60 B per read of inputs and results.
+        bins = float(summary_bins)
+        kbytes = {"profile": 12.0 * novl + 4.0 * bins + 39.0 * owned, "mask_anno": 4.0 * bins + 60.0 * owned}
+        dom = max(kbytes, key=lambda k: kavg[k])
         achieved = kbytes[dom] / (kavg[dom] * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")

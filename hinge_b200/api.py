@@ -9,7 +9,7 @@ import numpy as np
 from ._lib import (EdgeC, FilterParamsC, FilterSummaryC, HingeError, LayoutParamsC, lib)
 
 HG_MEM_HOST, HG_MEM_DEVICE = 0, 1
-HG_OPT_KEEP_COVERAGE, HG_OPT_PROFILE, HG_OPT_K2_VARIANT = 1, 2, 3
+HG_OPT_KEEP_COVERAGE, HG_OPT_PROFILE, HG_OPT_SCATTER_SPREAD = 1, 2, 3
 HG_BUF_MEAN_COV, HG_BUF_MASK, HG_BUF_READ_FLAGS = 1, 2, 3
 HG_RETRY_POOL = 1
 
@@ -133,7 +133,7 @@ class Context:
     def filter_kernel_times(self):
         ms = (C.c_float * 4)()
         self._check(lib.hg_filter_kernel_times(self._h, ms, 4), "hg_filter_kernel_times")
-        return {"cov_estimate": ms[0], "median": ms[1], "mask_anno": ms[2], "hinge_call": ms[3]}
+        return {"profile": ms[0], "median": ms[1], "mask_anno": ms[2], "hinge_call": ms[3]}
 
     def device_buffer(self, which):
         p, b = C.c_void_p(), C.c_int64()

@@ -85,15 +85,14 @@ int hg_ctx_create(int device, void* stream, hg_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
     c->fs.num_sms = c->num_sms;
-    if (const char* v = getenv("HINGE_B200_K2_VARIANT")) {  // A/B aid; the variants give identical results
-        hg_set_option(c, HG_OPT_K2_VARIANT, atoi(v));
-    }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
     int rc = dev_alloc(c, &c->d_err, 4, "err flag");
     if (rc == HG_OK) rc = dev_alloc(c, &c->fs.scal, 8, "scalars");
-    if (rc == HG_OK) rc = dev_alloc(c, &c->fs.counters, 8, "counters");
-    if (rc == HG_OK) rc = dev_alloc(c, &c->fs.med_hist, 4097 + 4096, "median histogram");
+    if (rc == HG_OK) rc = dev_alloc(c, &c->fs.counters, 16, "counters");
+    if (rc == HG_OK) c->fs.counters1 = c->fs.counters + 8;
+    if (rc == HG_OK) rc = dev_alloc(c, &c->fs.med_hist, 4098, "median histogram");
+    if (rc == HG_OK) rc = cuda_check(c, cudaMemset(c->fs.med_hist, 0, sizeof(unsigned int) * 4098), "median histogram");
     if (rc != HG_OK) {
         hg_ctx_destroy(c);
         return rc;
@@ -108,7 +107,7 @@ void hg_ctx_destroy(hg_ctx* c) {
     free_overlaps(c);
     cudaFree(c->d_rlen); cudaFree(c->d_qvmask); cudaFree(c->d_read_off); cudaFree(c->d_err);
     FilterScratch& s = c->fs;
-    cudaFree(s.cov_sum); cudaFree(s.cov_maxbin); cudaFree(s.self_cnt);
+    cudaFree(s.cov_maxbin); cudaFree(s.self_cnt); cudaFree(s.flat_prof);
     if (!c->ext_mean_cov) cudaFree(s.mean_cov);
     if (!c->ext_mask) cudaFree(s.mask);
     for (int i = 0; i < hg_ctx::kMarks; i++)
@@ -116,7 +115,7 @@ void hg_ctx_destroy(hg_ctx* c) {
     cudaFree(s.med_hist); cudaFree(s.scal); cudaFree(s.cmask); cudaFree(s.rflags);
     cudaFree(s.anno_ref); cudaFree(s.anno_pool); cudaFree(s.counters); cudaFree(s.work_list);
     cudaFree(s.big_list); cudaFree(s.exact_list); cudaFree(s.big_scratch); cudaFree(s.hinge_keep); cudaFree(s.hinge_scratch);
-    cudaFree(s.item_log); cudaFree(s.flat_batch); cudaFree(s.flat_rbase); cudaFree(s.flat_read_batch); cudaFree(s.flat_batch_self);
+    cudaFree(s.item_log); cudaFree(s.flat_batch); cudaFree(s.flat_rbase);
     cudaFree(c->d_cov0); cudaFree(c->d_cov0_off);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -138,15 +137,10 @@ int hg_set_option(hg_ctx* c, int option, int64_t value) {
             HG_TRY(dev_alloc(c, &c->fs.item_log, c->n_read, "item log"));
         return HG_OK;
     }
-    if (option == HG_OPT_K2_VARIANT) {
-        if (value == kK2Flat || value == kK2WarpPerRead) {
-            c->fs.k2_variant = (int)value;
-        } else if (value > 100 && value <= 132) {  // tuning aid: flat form with a given scatter spread
-            c->fs.k2_variant = kK2Flat;
-            c->fs.flat_spread = (int)value - 100;
-        } else {
-            return set_err(c, HG_ERR_ARG, "HG_OPT_K2_VARIANT: 0 (flat) or 2 (warp per read)");
-        }
+    if (option == HG_OPT_SCATTER_SPREAD) {
+        if (value != 1 && value != 4 && value != 8 && value != 16)
+            return set_err(c, HG_ERR_ARG, "HG_OPT_SCATTER_SPREAD: 1, 4, 8 or 16");
+        c->fs.flat_spread = (int)value;
         return HG_OK;
     }
     return set_err(c, HG_ERR_ARG, "unknown option");
@@ -191,7 +185,6 @@ int hg_set_reads(hg_ctx* c, int32_t n_read, const int32_t* rlen, const int64_t* 
     }
     // per-read buffers
     FilterScratch& s = c->fs;
-    HG_TRY(dev_alloc(c, &s.cov_sum, n_read, "cov_sum"));
     HG_TRY(dev_alloc(c, &s.cov_maxbin, n_read, "cov_maxbin"));
     HG_TRY(dev_alloc(c, &s.self_cnt, n_read, "self_cnt"));
     if (c->ext_mean_cov) { s.mean_cov = nullptr; c->ext_mean_cov = false; }
@@ -291,7 +284,7 @@ int hg_set_overlaps(hg_ctx* c, int64_t novl, const int32_t* aread, const int32_t
     c->r_end = last_a;
     // CSR + validation + deepest pile-up
     cudaMemsetAsync(c->d_err, 0, sizeof(int) * 4, st);
-    launch_csr_validate(c->rec_view(), c->read_view(), c->d_read_off, c->d_err, st);
+    launch_csr_validate(c->rec_view(), c->read_view(), c->d_read_off, c->fs.self_cnt, c->d_err, st);
     launch_max_pileup(c->d_read_off, c->n_read, c->d_err + 1, st);
     int h[2] = {0, 0};
     HG_TRY(cuda_check(c, cudaMemcpyAsync(h, c->d_err, 8, cudaMemcpyDeviceToHost, st), "D2H"));
@@ -335,7 +328,6 @@ static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
     c->configured_shape = c->shape_version;
     FilterScratch& s = c->fs;
     auto bins = [&](int rlen) { return bins_needed(rlen, p->cut_off); };
-    mask_anno_configure(s, bins(c->rlen_q999));
     {
         // flat K2: pack the reads that have records, [r_begin, r_end] within the owned range, into
         // batches of kFlatBins histogram words; the plan only depends on read lengths and cut_off
@@ -343,17 +335,22 @@ static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
         if (c->plan_reads_version != c->reads_version || c->plan_cut_off != p->cut_off ||
             c->plan_lo != lo || c->plan_hi != hi) {
             std::vector<int2> batch;
-            std::vector<int> rbase, read_batch;
-            flat_plan(c->h_rlen.data(), lo, std::max(lo, hi), c->n_read, p->cut_off, &batch, &rbase, &read_batch);
-            HG_TRY(dev_alloc(c, &s.flat_batch, batch.size(), "flat K2 batches"));
-            HG_TRY(dev_alloc(c, &s.flat_rbase, rbase.size(), "flat K2 read offsets"));
-            HG_TRY(dev_alloc(c, &s.flat_read_batch, read_batch.size(), "flat K2 read -> batch"));
-            HG_TRY(dev_alloc(c, &s.flat_batch_self, batch.size(), "flat K2 batch flags"));
+            std::vector<int> rbase;
+            flat_plan(c->h_rlen.data(), lo, std::max(lo, hi), c->n_read, p->cut_off, &batch, &rbase);
+            s.flat_nbatch = hi > lo ? (int)batch.size() - 1 : 0;
+            HG_TRY(dev_alloc(c, &s.flat_batch, batch.size(), "flat batches"));
+            HG_TRY(dev_alloc(c, &s.flat_rbase, rbase.size(), "flat read offsets"));
+            HG_TRY(dev_alloc(c, &s.flat_prof, (size_t)std::max(s.flat_nbatch, 1) * kFlatBins, "coverage profiles"));
             HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_batch, batch.data(), sizeof(int2) * batch.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
             HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_rbase, rbase.data(), sizeof(int) * rbase.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
-            HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_read_batch, read_batch.data(), sizeof(int) * read_batch.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
-            HG_TRY(cuda_check(c, cudaStreamSynchronize(c->stream), "flat K2 plan"));  // the vectors go away
-            s.flat_nbatch = hi > lo ? (int)batch.size() - 1 : 0;
+            // per-read results of the reads outside the planned range: "no pile-up"
+            cudaMemsetAsync(s.cov_maxbin, 0xff, sizeof(int) * c->n_read, c->stream);
+            cudaMemsetAsync(s.mean_cov, 0xff, sizeof(int) * c->n_read, c->stream);
+            cudaMemsetAsync(s.rflags, 0, c->n_read, c->stream);
+            cudaMemsetAsync(s.mask, 0, sizeof(int2) * c->n_read, c->stream);
+            cudaMemsetAsync(s.cmask, 0, sizeof(int2) * c->n_read, c->stream);
+            cudaMemsetAsync(s.anno_ref, 0, sizeof(int2) * c->n_read, c->stream);
+            HG_TRY(cuda_check(c, cudaStreamSynchronize(c->stream), "flat plan"));  // the vectors go away
             c->plan_reads_version = c->reads_version;
             c->plan_cut_off = p->cut_off;
             c->plan_lo = lo;
@@ -374,7 +371,7 @@ int hg_filter_phase1(hg_ctx* c, const hg_filter_params* p) {
     HG_TRY(configure_filter(c, p));
     cudaEventRecord(c->ev0, c->stream);
     c->mark(0);
-    launch_cov_estimate(c->rec_view(), c->read_view(), c->fp, c->r_begin, c->r_end, c->fs, c->stream);
+    launch_profile(c->rec_view(), c->read_view(), c->fp, c->r_begin, c->r_end, c->fs, c->stream);
     c->mark(1);
     return cuda_check(c, cudaGetLastError(), "filter phase 1");
 }
@@ -453,7 +450,7 @@ int hg_filter(hg_ctx* c, const hg_filter_params* p, hg_filter_summary* out) {
     return set_err(c, HG_ERR_NOMEM, "annotation pool kept overflowing");
 }
 
-// ms[0..3] = coverage estimate (K1), median, mask + annotation (K2), hinge calls (K4)
+// ms[0..3] = coverage profiles (K1), median, mask + annotation (K2), hinge calls (K4)
 int hg_filter_kernel_times(hg_ctx* c, float* ms, int n) {
     if (!c || !c->profile || !c->filter_done) return set_err(c, HG_ERR_ARG, "profiling is off");
     const int pairs[4][2] = {{0, 1}, {2, 3}, {3, 4}, {5, 6}};
@@ -514,12 +511,16 @@ int hg_bind_buffer(hg_ctx* c, int which, void* dptr, int64_t bytes) {
         if (!c->ext_mean_cov) cudaFree(c->fs.mean_cov);
         c->fs.mean_cov = (int*)dptr;
         c->ext_mean_cov = true;
+        c->plan_reads_version = -1;  // the next run clears the entries outside its read range
+        c->filter_params_set = false;
         return HG_OK;
     }
     if (which == HG_BUF_MASK && bytes >= 8ll * c->n_read) {
         if (!c->ext_mask) cudaFree(c->fs.mask);
         c->fs.mask = (int2*)dptr;
         c->ext_mask = true;
+        c->plan_reads_version = -1;
+        c->filter_params_set = false;
         return HG_OK;
     }
     return set_err(c, HG_ERR_ARG, "hg_bind_buffer: unknown buffer or too small");

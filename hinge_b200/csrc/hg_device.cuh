@@ -109,6 +109,7 @@ struct MaskAnnoOut {
     uint8_t* rflags;   // kFlag*
     int2* anno_ref;    // (offset into pool, count) per read
     int2* anno_pool;   // (pos, type)
+    uint8_t* hinge_keep;  // per pooled annotation: is a hinge (cleared here, set by K4)
     int anno_cap;
     int* counters;     // [0] pool used  [1] work-list length  [2] overflow flag  [3] big-list length
     int* work_list;    // reads that need hinge calling

@@ -23,7 +23,7 @@ int64_t g_launches = 0;
 
 // ------------------------------------------------------------------ K0
 
-__global__ void k_csr_validate(RecView rv, ReadView rd, int64_t* read_off, int* err) {
+__global__ void k_csr_validate(RecView rv, ReadView rd, int64_t* read_off, int* self_cnt, int* err) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k > rv.novl) return;
     const int prev = k == 0 ? rd.r_lo - 1 : rv.aread[k - 1];
@@ -39,6 +39,7 @@ __global__ void k_csr_validate(RecView rv, ReadView rd, int64_t* read_off, int* 
             atomicExch(err, 1);
             return;
         }
+        if (a == b) atomicAdd(&self_cnt[a], 1);  // inactive in every stage (filter.cpp:538-547); rare
     }
     // every read in (prev, cur] starts at record k
     for (int r = max(prev + 1, rd.r_lo); r <= cur; r++) read_off[r] = k;
@@ -74,123 +75,20 @@ __global__ void k_qv_mask(int n_read, const int64_t* __restrict__ qv_off,
     out[i] = make_int2(bs * tspace, be * tspace);
 }
 
-// ------------------------------------------------------------------ K1
+// ------------------------------------------------------------------ median
+// (K1, the profile build, and the flat K2 live in hg_filter_flat.cu)
 
-// The mean of read i's profile needs no histogram:
-//   sum_j cov[j] = sum_records (bin(aepos) - bin(abpos)),  length = max bin(aepos) + 1
-// so the coverage estimate is one flat, coalesced pass over (aread, bread, abpos,
-// aepos): 16 B per record, int4 loads, warp segmented reduction by A-read, one
-// atomic per (warp, read).
-template <int VEC>
+// Median by counting: per-read means are small integers, so a 4096-bin histogram resolves the
+// rank exactly (filter.cpp:660 median_id = size / 2); means >= 4095 (coverage in the thousands)
+// take the generic three-digit radix select below.  The block that finishes last picks the
+// median and clears the histogram for the next run: one launch, no host round trip.
+// scal: [0] cov_est  [1] MIN_COV  [2] radix prefix  [3] radix rank  [4] need radix pass
 __global__ void __launch_bounds__(256)
-k_cov_accum(RecView rv, unsigned long long* __restrict__ cov_sum,
-            int* __restrict__ cov_maxbin, int* __restrict__ self_cnt) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t k0 = t * VEC;
-    int a[VEC], b[VEC], s[VEC], e[VEC];
-    bool vec_loaded = false;
-    if constexpr (VEC == 4) {
-        if (k0 + 4 <= rv.novl) {
-            const int4 va = __ldg(reinterpret_cast<const int4*>(rv.aread + k0));
-            const int4 vb = __ldg(reinterpret_cast<const int4*>(rv.bread + k0));
-            const int4 vs = __ldg(reinterpret_cast<const int4*>(rv.abpos + k0));
-            const int4 ve = __ldg(reinterpret_cast<const int4*>(rv.aepos + k0));
-            a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w;
-            b[0] = vb.x; b[1] = vb.y; b[2] = vb.z; b[3] = vb.w;
-            s[0] = vs.x; s[1] = vs.y; s[2] = vs.z; s[3] = vs.w;
-            e[0] = ve.x; e[1] = ve.y; e[2] = ve.z; e[3] = ve.w;
-            vec_loaded = true;
-        }
-    }
-    if (!vec_loaded) {
-#pragma unroll
-        for (int i = 0; i < VEC; i++) {
-            const int64_t k = k0 + i;
-            const bool in = k < rv.novl;
-            a[i] = in ? rv.aread[k] : -2;
-            b[i] = in ? rv.bread[k] : -1;
-            s[i] = in ? rv.abpos[k] : 0;
-            e[i] = in ? rv.aepos[k] : 0;
-        }
-    }
-    int key = -2, mx = -1;
-    unsigned acc = 0;  // per-warp partial: <= 128 records x bins, far below 2^32
-#pragma unroll
-    for (int i = 0; i < VEC; i++) {
-        if (a[i] != key) {
-            if (key >= 0) {  // a read ended inside this thread's records
-                if (acc) atomicAdd(&cov_sum[key], (unsigned long long)acc);
-                if (mx >= 0) atomicMax(&cov_maxbin[key], mx);
-            }
-            key = a[i];
-            acc = 0;
-            mx = -1;
-        }
-        if (a[i] >= 0) {
-            if (a[i] != b[i]) {
-                const int be = cov_bin(e[i], kReso);
-                acc += (unsigned)(be - cov_bin(s[i], kReso));
-                mx = max(mx, be);
-            } else {
-                atomicAdd(&self_cnt[a[i]], 1);
-            }
-        }
-    }
-    // warp segmented reduction of the tails (keys are non-decreasing across lanes)
-    const int lane = lane_id();
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int okey = __shfl_up_sync(0xffffffffu, key, d);
-        const unsigned oacc = __shfl_up_sync(0xffffffffu, acc, d);
-        const int omx = __shfl_up_sync(0xffffffffu, mx, d);
-        if (lane >= d && okey == key) {
-            acc += oacc;
-            mx = max(mx, omx);
-        }
-    }
-    const int nkey = __shfl_down_sync(0xffffffffu, key, 1);
-    if (key >= 0 && (lane == 31 || nkey != key)) {
-        if (acc) atomicAdd(&cov_sum[key], (unsigned long long)acc);
-        if (mx >= 0) atomicMax(&cov_maxbin[key], mx);
-    }
-}
-
-// filter.cpp:642-656 (mean over reads >= 5000 bp inside [r_begin, r_end]) and
-// filter.cpp:552-561 (self-match reads; float accumulation in record order).
-__global__ void k_cov_finalize(RecView rv, ReadView rd, int r_begin, int r_end,
-                               const unsigned long long* __restrict__ cov_sum,
-                               const int* __restrict__ cov_maxbin,
-                               const int* __restrict__ self_cnt, int* __restrict__ mean_cov,
-                               uint8_t* __restrict__ rflags, const int* __restrict__ read_batch,
-                               int* __restrict__ batch_self) {
-    const int i = rd.r_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rd.r_hi) return;
-    const int len0 = cov_maxbin[i] + 1;
-    const int mean = (int)((long long)cov_sum[i] / (long long)max(1, len0));
-    const int rl = rd.rlen[i];
-    mean_cov[i] = (rl >= 5000 && i >= r_begin && i <= r_end) ? mean : -1;
-    uint8_t f = 0;
-    if (self_cnt[i] > 0) {
-        if (read_batch) batch_self[read_batch[i]] = 1;  // the flat K2 loads bread only for such batches
-        float cov = 0.0f;
-        for (int64_t k = rv.read_off[i]; k < rv.read_off[i + 1]; k++) {
-            if (rv.bread[k] != i) continue;
-            cov = __fadd_rn(cov, (float)(rv.aepos[k] - rv.abpos[k]));
-            // B span is strand-invariant: (blen-bbpos) - (blen-bepos) = bepos - bbpos
-            cov = __fadd_rn(cov, (float)(rv.bepos[k] - rv.bbpos[k]));
-        }
-        cov = __fdiv_rn(cov, (float)rl);
-        if ((double)cov > 4.5 && rl > 10000) f |= kFlagSelf;
-    }
-    rflags[i] = f;
-}
-
-// Median by counting: per-read means are small integers, so a 4096-bin
-// shared-memory histogram resolves the rank exactly; means >= 4095 (coverage
-// in the thousands) take the generic three-digit radix select below.
-__global__ void k_median_hist(const int* __restrict__ mean_cov, int n_read,
-                              unsigned int* __restrict__ hist /*4096 + 1*/) {
+k_median_hist(const int* __restrict__ mean_cov, int n_read, unsigned int* __restrict__ hist /*4096 + 2*/,
+              int est_cov, int min_cov, int* __restrict__ scal) {
     __shared__ unsigned int sh[4096];
+    __shared__ unsigned int wsum[8];
+    __shared__ int is_last;
     for (int i = threadIdx.x; i < 4096; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     unsigned int valid = 0;
@@ -206,68 +104,96 @@ __global__ void k_median_hist(const int* __restrict__ mean_cov, int n_read,
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
     valid = (unsigned int)warp_sum((int)valid);
     if (lane_id() == 0 && valid) atomicAdd(&hist[4096], valid);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&hist[4097], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // ---- the pick: thread t owns bins [16 t, 16 t + 16)
+    const int t = threadIdx.x;
+    unsigned int loc[16], tot = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        loc[i] = __ldcg(&hist[16 * t + i]);
+        tot += loc[i];
+    }
+    const unsigned int m = __ldcg(&hist[4096]);
+    const unsigned int incl = warp_incl_scan(tot);
+    if (lane_id() == 31) wsum[t >> 5] = incl;
+    __syncthreads();
+    unsigned int before = incl - tot;
+    for (int w = 0; w < (t >> 5); w++) before += wsum[w];
+    const unsigned int rank = m / 2;
+    if (m == 0) {
+        if (t == 0) {
+            const int cov_est = est_cov != 0 ? est_cov : 0;  // filter.cpp:671
+            scal[0] = cov_est;
+            scal[1] = max(min_cov, cov_est / 3);
+            scal[2] = 0;
+            scal[4] = 0;
+        }
+    } else if (before <= rank && rank < before + tot) {  // exactly one thread
+        unsigned int run = before;
+        int v = 16 * t;
+        for (int i = 0; i < 16; i++, v++) {
+            if (run + loc[i] > rank) break;
+            run += loc[i];
+        }
+        const int need = v >= 4095;  // inside the overflow bin: resolve with the radix passes
+        scal[2] = 0;
+        scal[3] = (int)(rank - run);
+        scal[4] = need;
+        if (!need) {
+            const int cov_est = est_cov != 0 ? est_cov : v;  // filter.cpp:671
+            scal[0] = cov_est;
+            scal[1] = max(min_cov, cov_est / 3);  // filter.cpp:677-678
+        }
+    }
+    __syncthreads();
+    for (int i = t; i < 4098; i += blockDim.x) hist[i] = 0;
 }
 
-// scal: [0] cov_est  [1] MIN_COV  [2] radix prefix  [3] radix rank  [4] need radix pass
-__global__ void k_median_pick(const unsigned int* __restrict__ hist, int est_cov, int min_cov,
-                              int* __restrict__ scal) {
-    // single thread: 4096 adds, negligible next to the launch itself
-    if (threadIdx.x || blockIdx.x) return;
-    const unsigned int m = hist[4096];
-    unsigned int rank = m / 2, run = 0;  // filter.cpp:660 median_id = size / 2
-    int cov_est = 0, need = 0;
-    if (m > 0) {
-        int v = 0;
-        for (; v < 4096; v++) {
-            if (run + hist[v] > rank) break;
-            run += hist[v];
-        }
-        if (v >= 4095) {  // inside the overflow bin: resolve with the radix passes
-            need = 1;
-            scal[3] = (int)(rank - run);
-        }
-        cov_est = v;
-    }
-    scal[2] = 0;
-    scal[4] = need;
-    if (!need) {
-        if (est_cov != 0) cov_est = est_cov;  // filter.cpp:671
-        scal[0] = cov_est;
-        scal[1] = max(min_cov, cov_est / 3);  // filter.cpp:677-678
-    }
-}
-
-// Generic fallback, three passes (digits 12/10/10 bits of v - 4095, high to low).
-__global__ void k_median_radix(const int* __restrict__ mean_cov, int n_read, int pass,
-                               unsigned int* __restrict__ dig /*4096*/, int* __restrict__ scal) {
+// Generic fallback, one CTA, three passes (digits 12/10/10 bits of v - 4095, high to low).
+// Only does anything when the median lies in the overflow bin.
+__global__ void __launch_bounds__(1024)
+k_median_radix(const int* __restrict__ mean_cov, int n_read, int est_cov, int min_cov,
+               int* __restrict__ scal) {
     if (!scal[4]) return;
-    const int shift = pass == 0 ? 20 : (pass == 1 ? 10 : 0);
-    const int bits = pass == 0 ? 12 : 10;
-    const unsigned int prefix = (unsigned int)scal[2];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_read; i += gridDim.x * blockDim.x) {
-        const int v = mean_cov[i];
-        if (v < 4095) continue;
-        const unsigned int u = (unsigned int)(v - 4095);
-        const unsigned int hi = pass == 0 ? 0u : (u >> (shift + bits));
-        if (hi != prefix) continue;
-        atomicAdd(&dig[(u >> shift) & ((1u << bits) - 1u)], 1u);
+    __shared__ unsigned int dig[4096];
+    __shared__ unsigned int s_prefix, s_rank;
+    if (threadIdx.x == 0) {
+        s_prefix = 0;
+        s_rank = (unsigned int)scal[3];
     }
-}
-__global__ void k_median_radix_pick(int pass, unsigned int* __restrict__ dig, int est_cov,
-                                    int min_cov, int* __restrict__ scal) {
-    if (threadIdx.x || blockIdx.x || !scal[4]) return;
-    const int bits = pass == 0 ? 12 : 10;
-    unsigned int rank = (unsigned int)scal[3], run = 0;
-    unsigned int d = 0;
-    for (; d < (1u << bits); d++) {
-        if (run + dig[d] > rank) break;
-        run += dig[d];
+    for (int pass = 0; pass < 3; pass++) {
+        const int shift = pass == 0 ? 20 : (pass == 1 ? 10 : 0);
+        const int bits = pass == 0 ? 12 : 10;
+        for (int i = threadIdx.x; i < 4096; i += blockDim.x) dig[i] = 0;
+        __syncthreads();
+        const unsigned int prefix = s_prefix;
+        for (int i = threadIdx.x; i < n_read; i += blockDim.x) {
+            const int v = mean_cov[i];
+            if (v < 4095) continue;
+            const unsigned int u = (unsigned int)(v - 4095);
+            const unsigned int hi = pass == 0 ? 0u : (u >> (shift + bits));
+            if (hi != prefix) continue;
+            atomicAdd(&dig[(u >> shift) & ((1u << bits) - 1u)], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int rank = s_rank, run = 0, d = 0;
+            for (; d < (1u << bits); d++) {
+                if (run + dig[d] > rank) break;
+                run += dig[d];
+            }
+            s_rank = rank - run;
+            s_prefix = (prefix << bits) | d;
+        }
+        __syncthreads();
     }
-    scal[3] = (int)(rank - run);
-    scal[2] = (int)(((unsigned int)scal[2] << bits) | d);
-    for (unsigned int i = 0; i < 4096; i++) dig[i] = 0;
-    if (pass == 2) {
-        int cov_est = (int)((unsigned int)scal[2] + 4095u);
+    if (threadIdx.x == 0) {
+        int cov_est = (int)(s_prefix + 4095u);
         if (est_cov != 0) cov_est = est_cov;
         scal[0] = cov_est;
         scal[1] = max(min_cov, cov_est / 3);
@@ -486,6 +412,7 @@ __device__ void mask_anno_read(const RecView& rv, const ReadView& rd, const hg_f
         for (int k = lane; k < kept; k += 32) {
             const unsigned w = (unsigned)hist[k];
             out.anno_pool[off + k] = make_int2((int)(w >> 2), (int)(w & 3u) - 1);
+            out.hinge_keep[off + k] = 0;
         }
     if (lane == 0) {
         out.mask[read] = mk;
@@ -497,293 +424,7 @@ __device__ void mask_anno_read(const RecView& rv, const ReadView& rd, const hg_f
     __syncwarp();
 }
 
-// ---- K2 fast path --------------------------------------------------------------
-// Same results as mask_anno_read<uint32_t>, organised for instruction count: every
-// lane owns FOUR consecutive bins (one 128-bit shared-memory word), so a read of up
-// to 128 bins (5 kb) is one tile: one local scan + one warp scan, hardware warp
-// reductions (REDUX), and the repeat-annotation / hinge pre-test sweep shares a
-// single pass.  `self_records` tells whether the read has A == B records at all
-// (known from K1); without them the bread column is not even loaded.
-constexpr int kAnnSlack = 120;  // raw annotations a read may carry on the fast path
-__device__ __forceinline__ uint4 lds128(const uint32_t* p) { return *reinterpret_cast<const uint4*>(p); }
-__device__ __forceinline__ void sts128(uint32_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
-
-template <bool DUMP>
-__device__ void mask_anno_read_fast(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
-                                    const int MIN_COV, const int read, uint32_t* hist, uint32_t* ann,
-                                    const int nbz, const bool self_records, const MaskAnnoOut& out) {
-    // After the scan the low half (cut-off-free coverage) is never negative, so the
-    // packed word decodes with one instruction per half.
-    auto LO = [](uint32_t v) { return (int)(v & 0xffffu); };
-    auto HI = [](uint32_t v) { return (int)v >> 16; };
-    const int lane = lane_id();
-    constexpr int reso = kReso;
-    const int64_t o0 = rv.read_off[read];
-    const int n = (int)(rv.read_off[read + 1] - o0);
-    const int ntile = (nbz + 127) >> 7;
-
-    for (int t = 0; t < ntile; t++) sts128(hist + (t << 7) + (lane << 2), make_uint4(0, 0, 0, 0));
-    if (lane == 0) sts128(hist + (ntile << 7), make_uint4(0, 0, 0, 0));  // the sweep reads bin j + 1
-    __syncwarp();
-
-    // ---- scatter (profileCoverage, LAInterface.cpp:4298-4320)
-    int m0 = -1;
-    const int C = P.cut_off;
-    const int* __restrict__ pa = rv.abpos + o0;
-    const int* __restrict__ pe = rv.aepos + o0;
-    const int* __restrict__ pb = rv.bread + o0;
-    for (int k = lane; k < n; k += 32) {
-        if (self_records && __ldg(pb + k) == read) continue;  // filter.cpp:538-547
-        const int as = __ldg(pa + k), ae = __ldg(pe + k);
-        const int b_s0 = as / reso + 1, b_e0 = ae / reso + 1;  // 0 <= abpos < aepos (validated at ingest)
-        const int b_sc = cov_bin(as + C, reso), b_ec = cov_bin(ae - C, reso);
-        atomicAdd(&hist[b_s0], 1u);
-        atomicAdd(&hist[b_e0], 0u - 1u);
-        atomicAdd(&hist[b_sc], 1u << 16);
-        atomicAdd(&hist[b_ec], 0u - (1u << 16));
-        m0 = max(m0, b_e0);
-    }
-    const int L0 = __reduce_max_sync(0xffffffffu, m0) + 1;  // length of the cut-off-free profile
-    __syncwarp();
-
-    // ---- pass 1: prefix sums in place + longest run of covered bins (filter.cpp:696-728).
-    // Bins past the end of the cut-off profile hold coverage 0; treating them as part of the
-    // profile changes nothing: with MIN_COV >= 0 the profile's own last bin is already a zero
-    // (all events consumed), with MIN_COV < 0 they are not zeros at all.
-    uint32_t carry = 0;
-    int last_zero = 0;
-    unsigned best = 0;  // (gap << 16) | (0xffff - z): max gap, then smallest z
-    for (int t = 0; t < ntile; t++) {
-        uint32_t* hp = hist + (t << 7) + (lane << 2);
-        uint4 v = lds128(hp);
-        v.y += v.x;
-        v.z += v.y;
-        v.w += v.z;
-        const uint32_t incl = warp_incl_scan(v.w);
-        const uint32_t ex = incl - v.w + carry;
-        v.x += ex; v.y += ex; v.z += ex; v.w += ex;
-        carry += __shfl_sync(0xffffffffu, incl, 31);
-        sts128(hp, v);
-        const int j0 = (t << 7) + (lane << 2);
-        const unsigned nib = (HI(v.x) > MIN_COV ? 0u : 1u) | (HI(v.y) > MIN_COV ? 0u : 2u) |
-                             (HI(v.z) > MIN_COV ? 0u : 4u) | (HI(v.w) > MIN_COV ? 0u : 8u);
-        const int lz = nib ? j0 + 31 - __clz(nib) : -1;  // last zero bin of this lane
-        const unsigned lanes = __ballot_sync(0xffffffffu, nib != 0);
-        const unsigned below = lanes & ((1u << lane) - 1u);
-        const int lz_src = __shfl_sync(0xffffffffu, lz, below ? 31 - __clz(below) : 0);
-        if (nib) {
-            // consecutive zeros inside one lane are at most 3 apart, so only two runs can score:
-            // the one ending at this lane's first zero, and the pattern 1001
-            const int p = below ? lz_src : last_zero;
-            const int fz = j0 + __ffs(nib) - 1;
-            const int gap = fz - p;
-            if (gap >= 3) best = max(best, ((unsigned)gap << 16) | (unsigned)(0xffff - fz));
-            if (nib == 9u) best = max(best, (3u << 16) | (unsigned)(0xffff - (j0 + 3)));
-        }
-        if (lanes) last_zero = __shfl_sync(0xffffffffu, lz, 31 - __clz(lanes));
-    }
-    best = __reduce_max_sync(0xffffffffu, best);
-    __syncwarp();
-    int maxstart = 0, maxend = 0, msc = 0, mec = 0;
-    if (best) {
-        const int gap = (int)(best >> 16), z = 0xffff - (int)(best & 0xffffu), p = z - gap;
-        msc = p + 1;
-        mec = z - 1;
-        maxstart = reso * (p + 1);
-        maxend = reso * (z - 1);
-    }
-
-    // ---- telomere / coverage-imbalance flag (filter.cpp:731-760)
-    uint8_t flags = 0;
-    if (P.delete_telomere) {
-        flags = out.rflags[read] & kFlagSelf;
-        int limit, div;
-        if (mec - msc + 1 > 20) {
-            limit = 10;
-            div = 10;
-        } else {
-            limit = (mec - msc) / 2;
-            div = limit;
-        }
-        int sc = 0, ec = 0;
-        for (int t = lane; t < limit; t += 32) {
-            sc += max(HI(hist[msc + t]), MIN_COV);
-            ec += max(HI(hist[mec - t]), MIN_COV);
-        }
-        sc = __reduce_add_sync(0xffffffffu, sc);
-        ec = __reduce_add_sync(0xffffffffu, ec);
-        if (div == 0) {
-            sc = 0;
-            ec = 0;
-        } else {
-            sc /= div;
-            ec /= div;
-        }
-        if (sc >= 10 * ec || ec >= 10 * sc) flags |= kFlagCov;
-    }
-
-    // ---- final mask (filter.cpp:777-788)
-    const int2 q = rd.qvmask[read];
-    int2 mk;
-    if (P.use_qv_mask && P.use_coverage_mask)
-        mk = make_int2(max(maxstart, q.x), min(maxend, q.y));
-    else if (P.use_coverage_mask && !P.use_qv_mask)
-        mk = make_int2(maxstart, maxend);
-    else
-        mk = q;
-
-    // ---- pass 2: repeat annotation from the coverage gradient (filter.cpp:796-813),
-    // optional profile dump (filter.cpp:599-602).  Raw annotations are compacted, in bin
-    // order, into the slack words behind the histogram (`ann`).
-    const int NHR = P.no_hinge_region;
-    const int MINT = P.min_repeat_annotation_threshold, MAXT = P.max_repeat_annotation_threshold;
-    const int RJ = min(MINT, MAXT);  // the threshold never drops below this
-    // bins j < L0 - 2 whose position lies in [mask.start + NHR, mask.end - NHR]
-    const int ja_lo = mk.x + NHR <= 0 ? 0 : (mk.x + NHR + reso - 1) / reso;
-    const int ja_hi = mk.y - NHR < 0 ? -1 : min((mk.y - NHR) / reso, L0 - 3);
-    int cnt = 0;
-    int* dump = DUMP ? out.cov0 + out.cov0_off[read] : nullptr;
-    const int t_lo = DUMP ? 0 : (ja_lo >> 7);
-    const int t_hi = DUMP ? ((L0 + 127) >> 7) - 1 : (ja_hi >> 7);
-    for (int t = t_lo; t <= t_hi; t++) {
-        const int j0 = (t << 7) + (lane << 2);
-        const uint4 v = lds128(hist + j0);
-        uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
-        if (lane == 31) nx = hist[j0 + 4];
-        const int c[5] = {LO(v.x), LO(v.y), LO(v.z), LO(v.w), LO(nx)};
-        int type[4];
-        bool any = false;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int j = j0 + i;
-            if (DUMP && j < L0) dump[j] = c[i];
-            type[i] = 0;
-            const int g = c[i + 1] - c[i];
-            if ((g > RJ || g < -RJ) && j >= ja_lo && j <= ja_hi) {  // rare: only now pay the division
-                const int thr = min(max((c[i] + MIN_COV) / P.coverage_fraction, MINT), MAXT);
-                type[i] = g > thr ? 1 : (g < -thr ? -1 : 0);
-            }
-            any = any || type[i] != 0;
-        }
-        const unsigned am = __ballot_sync(0xffffffffu, any);
-        if (am) {  // rare
-            const int mine = (type[0] != 0) + (type[1] != 0) + (type[2] != 0) + (type[3] != 0);
-            const int incl = warp_incl_scan(mine);
-            int slot = cnt + incl - mine;
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (type[i] != 0) {
-                    if (slot < kAnnSlack) ann[slot] = ((unsigned)(reso * (j0 + i)) << 2) | (unsigned)(type[i] + 1);
-                    slot++;
-                }
-            cnt += __shfl_sync(0xffffffffu, incl, 31);
-        }
-    }
-    if (cnt > kAnnSlack) {  // a read this noisy goes through the generic path instead
-        if (lane == 0) out.big_list[atomicAdd(&out.counters[3], 1)] = read;
-        return;
-    }
-    __syncwarp();
-
-    // ---- hinge pre-test: mean coverage near both mask ends (filter.cpp:842-865); its
-    // outcome only matters for reads that carry annotations
-    bool skip_hinges = false;
-    if (cnt > 0) {
-        int cs = 0, ns = 0, ce = 0, ne = 0;
-        int jlo = mk.x <= 0 ? 0 : (mk.x + reso - 1) / reso;  // bins with mk.x <= 40 j <= mk.x + NHR
-        int jhi = mk.x + NHR < 0 ? -1 : min((mk.x + NHR) / reso, L0 - 1);
-        for (int j = jlo + lane; j <= jhi; j += 32) {
-            cs += LO(hist[j]);
-            ns++;
-        }
-        jlo = mk.y - NHR <= 0 ? 0 : (mk.y - NHR + reso - 1) / reso;  // mk.y - NHR <= 40 j <= mk.y
-        jhi = mk.y < 0 ? -1 : min(mk.y / reso, L0 - 1);
-        for (int j = jlo + lane; j <= jhi; j += 32) {
-            ce += LO(hist[j]);
-            ne++;
-        }
-        cs = __reduce_add_sync(0xffffffffu, cs);
-        ns = __reduce_add_sync(0xffffffffu, ns);
-        ce = __reduce_add_sync(0xffffffffu, ce);
-        ne = __reduce_add_sync(0xffffffffu, ne);
-        // float on purpose: 0/0 = NaN makes the '< 10' test false (filter.cpp:861-865)
-        const float avg_end = __fdiv_rn((float)ce, (float)ne);
-        const float avg_start = __fdiv_rn((float)cs, (float)ns);
-        skip_hinges = fabsf(__fsub_rn(avg_end, avg_start)) < 10.0f;
-    }
-
-    // ---- merge pass (filter.cpp:817-829) + publication, as in the generic path
-    int kept = 0;
-    if (cnt > 0) {
-        if (lane == 0) {
-            const int GAP = P.repeat_annotation_gap_threshold;
-            unsigned cur = ann[0];
-            for (int k = 1; k < cnt; k++) {
-                const unsigned nxt = ann[k];
-                const int ct = (int)(cur & 3u) - 1, nt = (int)(nxt & 3u) - 1;
-                const int gap = (int)(nxt >> 2) - (int)(cur >> 2);
-                if (ct == 1 && nt == 1 && gap < GAP) {
-                    continue;
-                } else if (ct == -1 && nt == -1 && gap < GAP) {
-                    cur = nxt;
-                } else {
-                    ann[kept++] = cur;
-                    cur = nxt;
-                }
-            }
-            ann[kept++] = cur;
-        }
-        kept = __shfl_sync(0xffffffffu, kept, 0);
-    }
-    int off = 0;
-    if (kept > 0) {
-        if (lane == 0) {
-            off = atomicAdd(&out.counters[0], kept);
-            if (off + kept > out.anno_cap) {
-                atomicExch(&out.counters[2], 1);
-                off = -1;
-            }
-        }
-        off = __shfl_sync(0xffffffffu, off, 0);
-        __syncwarp();
-        if (off >= 0)
-            for (int k = lane; k < kept; k += 32) {
-                const unsigned w = ann[k];
-                out.anno_pool[off + k] = make_int2((int)(w >> 2), (int)(w & 3u) - 1);
-            }
-    }
-    if (lane == 0) {
-        out.mask[read] = mk;
-        out.cmask[read] = make_int2(msc, mec);
-        out.rflags[read] = flags | (skip_hinges ? kFlagSkipHinge : 0);
-        out.anno_ref[read] = make_int2(off, kept);
-        if (kept > 0 && !skip_hinges && off >= 0) out.work_list[atomicAdd(&out.counters[1], 1)] = read;
-    }
-    __syncwarp();
-}
-
-template <int WARPS, bool DUMP>
-__global__ void __launch_bounds__(WARPS * 32)
-k_mask_anno(RecView rv, ReadView rd, hg_filter_params P, const int* __restrict__ scal,
-            const int* __restrict__ self_cnt, int r_begin, int r_end, int nb_cap, MaskAnnoOut out) {
-    extern __shared__ __align__(16) uint32_t sh[];  // WARPS x (nb_cap + 128) packed histogram words
-    const int warp = threadIdx.x >> 5;
-    uint32_t* hist = sh + (size_t)warp * (nb_cap + 128);
-    const int MIN_COV = scal[1];
-    const int lo = max(rd.r_lo, r_begin), hi = min(rd.r_hi, r_end + 1);
-    for (int read = lo + blockIdx.x * WARPS + warp; read < hi; read += gridDim.x * WARPS) {
-        const int nbz = bins_needed(rd.rlen[read], P);
-        const int64_t n = rv.read_off[read + 1] - rv.read_off[read];
-        if (nbz > nb_cap || n > Packed<uint32_t>::kMaxCount) {
-            if (lane_id() == 0) out.big_list[atomicAdd(&out.counters[3], 1)] = read;
-            continue;
-        }
-        mask_anno_read_fast<DUMP>(rv, rd, P, MIN_COV, read, hist, hist + nb_cap + 8, nbz, self_cnt[read] > 0,
-                                  out);
-    }
-}
-
-// Slow path for reads longer than nb_cap bins or deeper than 32000 records:
+// Generic path for reads longer than kFlatBins bins or deeper than 32000 records:
 // 64-bit packed words in a global scratch slot per warp.
 __global__ void __launch_bounds__(128)
 k_mask_anno_big(RecView rv, ReadView rd, hg_filter_params P, const int* __restrict__ scal,
@@ -1275,9 +916,10 @@ __global__ void k_max_pileup(const int64_t* __restrict__ read_off, int n_read, i
 
 static inline int ceil_div64(int64_t a, int b) { return (int)((a + b - 1) / b); }
 
-void launch_csr_validate(const RecView& rv, const ReadView& rd, int64_t* read_off, int* err,
+void launch_csr_validate(const RecView& rv, const ReadView& rd, int64_t* read_off, int* self_cnt, int* err,
                          cudaStream_t st) {
-    k_csr_validate<<<ceil_div64(rv.novl + 1, 256), 256, 0, st>>>(rv, rd, read_off, err);
+    cudaMemsetAsync(self_cnt, 0, sizeof(int) * rd.n_read, st);
+    k_csr_validate<<<ceil_div64(rv.novl + 1, 256), 256, 0, st>>>(rv, rd, read_off, self_cnt, err);
     g_launches += 1;
 }
 
@@ -1287,60 +929,12 @@ void launch_qv_mask(int n_read, const int64_t* qv_off, const uint8_t* qv, int ts
     g_launches += 1;
 }
 
-void launch_cov_estimate(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
-                         int r_begin, int r_end, FilterScratch& s, cudaStream_t st) {
-    cudaMemsetAsync(s.cov_sum, 0, sizeof(unsigned long long) * rd.n_read, st);
-    cudaMemsetAsync(s.cov_maxbin, 0xff, sizeof(int) * rd.n_read, st);
-    cudaMemsetAsync(s.self_cnt, 0, sizeof(int) * rd.n_read, st);
-    if (s.flat_batch_self) cudaMemsetAsync(s.flat_batch_self, 0, sizeof(int) * (s.flat_nbatch + 1), st);
-    const bool aligned = (((uintptr_t)rv.aread | (uintptr_t)rv.bread | (uintptr_t)rv.abpos |
-                           (uintptr_t)rv.aepos) & 15) == 0;
-    if (rv.novl > 0) {
-        if (aligned)
-            k_cov_accum<4><<<ceil_div64((rv.novl + 3) / 4, 256), 256, 0, st>>>(
-                rv, s.cov_sum, s.cov_maxbin, s.self_cnt);
-        else
-            k_cov_accum<1><<<ceil_div64(rv.novl, 256), 256, 0, st>>>(rv, s.cov_sum,
-                                                                      s.cov_maxbin, s.self_cnt);
-    }
-    g_launches += (rv.novl > 0) + 1;
-    const int owned = rd.r_hi - rd.r_lo;
-    if (owned > 0)
-        k_cov_finalize<<<ceil_div64(owned, 256), 256, 0, st>>>(rv, rd, r_begin, r_end, s.cov_sum,
-                                                               s.cov_maxbin, s.self_cnt,
-                                                               s.mean_cov, s.rflags, s.flat_read_batch,
-                                                               s.flat_batch_self);
-}
-
 void launch_median(const ReadView& rd, const hg_filter_params& P, FilterScratch& s,
                    cudaStream_t st) {
-    cudaMemsetAsync(s.med_hist, 0, sizeof(unsigned int) * (4097 + 4096), st);
-    g_launches += 8;
-    k_median_hist<<<148 * 2, 256, 0, st>>>(s.mean_cov, rd.n_read, s.med_hist);
-    k_median_pick<<<1, 32, 0, st>>>(s.med_hist, P.est_cov, P.min_cov, s.scal);
-    for (int pass = 0; pass < 3; pass++) {  // no-ops unless the median is >= 4095
-        k_median_radix<<<148, 256, 0, st>>>(s.mean_cov, rd.n_read, pass, s.med_hist + 4097, s.scal);
-        k_median_radix_pick<<<1, 32, 0, st>>>(pass, s.med_hist + 4097, P.est_cov, P.min_cov, s.scal);
-    }
-}
-
-int mask_anno_configure(FilterScratch& s, int nb_cap) {
-    // shared memory per CTA = warps x nb_cap words; as many CTAs per SM as fit
-    nb_cap = (nb_cap + 127) & ~127;
-    const int max_words = ((200 * 1024) / (4 * kMaskAnnoWarps) - 128) & ~127;
-    if (nb_cap > max_words) nb_cap = max_words;
-    const int smem = (nb_cap + 128) * 4 * kMaskAnnoWarps;
-    cudaFuncSetAttribute(k_mask_anno<kMaskAnnoWarps, false>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_mask_anno<kMaskAnnoWarps, true>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mask_anno<kMaskAnnoWarps, false>,
-                                                  kMaskAnnoWarps * 32, smem);
-    if (per_sm < 1) per_sm = 1;
-    s.nb_cap = nb_cap;
-    s.mask_anno_grid = s.num_sms * per_sm;
-    return per_sm;
+    // med_hist is zero on entry (cleared at allocation and by every run's last block)
+    g_launches += 2;
+    k_median_hist<<<148 * 2, 256, 0, st>>>(s.mean_cov, rd.n_read, s.med_hist, P.est_cov, P.min_cov, s.scal);
+    k_median_radix<<<1, 1024, 0, st>>>(s.mean_cov, rd.n_read, P.est_cov, P.min_cov, s.scal);
 }
 
 void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
@@ -1348,25 +942,11 @@ void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_par
                       cudaStream_t st) {
     MaskAnnoOut out;
     out.mask = s.mask; out.cmask = s.cmask; out.rflags = s.rflags; out.anno_ref = s.anno_ref;
-    out.anno_pool = s.anno_pool; out.anno_cap = s.anno_cap; out.counters = s.counters;
+    out.anno_pool = s.anno_pool; out.hinge_keep = s.hinge_keep; out.anno_cap = s.anno_cap; out.counters = s.counters;
     out.work_list = s.work_list; out.big_list = s.big_list; out.cov0 = cov0; out.cov0_off = cov0_off;
-    cudaMemsetAsync(s.counters, 0, sizeof(int) * 8, st);
-    cudaMemsetAsync(s.mask, 0, sizeof(int2) * rd.n_read, st);
-    cudaMemsetAsync(s.cmask, 0, sizeof(int2) * rd.n_read, st);
-    cudaMemsetAsync(s.anno_ref, 0, sizeof(int2) * rd.n_read, st);
-    cudaMemsetAsync(s.hinge_keep, 0, (size_t)s.anno_cap, st);
-    if (s.k2_variant != kK2WarpPerRead) {
-        launch_mask_anno_flat(rv, rd, P, s, out, st);
-    } else {
-        const int smem = (s.nb_cap + 128) * 4 * kMaskAnnoWarps;
-        g_launches += 1;
-        if (cov0)
-            k_mask_anno<kMaskAnnoWarps, true><<<s.mask_anno_grid, kMaskAnnoWarps * 32, smem, st>>>(
-                rv, rd, P, s.scal, s.self_cnt, r_begin, r_end, s.nb_cap, out);
-        else
-            k_mask_anno<kMaskAnnoWarps, false><<<s.mask_anno_grid, kMaskAnnoWarps * 32, smem, st>>>(
-                rv, rd, P, s.scal, s.self_cnt, r_begin, r_end, s.nb_cap, out);
-    }
+    // no clearing here: every read of the planned range gets its results written (flat or generic
+    // path), the rest was cleared when the plan was made; the counters are zeroed by launch_profile
+    launch_mask_anno_flat(rv, rd, P, r_begin, r_end, s, out, st);
     g_launches += (s.big_slot_words > 0);
     if (s.big_slot_words > 0)
         k_mask_anno_big<<<s.big_warps / 4, 128, 0, st>>>(rv, rd, P, s.scal, out, s.big_scratch,

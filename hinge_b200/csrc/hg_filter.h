@@ -16,19 +16,17 @@ struct MaskAnnoOut;
 
 enum : uint8_t { kFlagCov = 1, kFlagSelf = 2, kFlagSkipHinge = 4 };
 
-constexpr int kMaskAnnoWarps = 8;  // warps (= reads in flight) per CTA of the warp-per-read K2
-constexpr int kFlatBins = 4096;    // histogram words (= coverage bins) per CTA of the flat K2
-
-// Which form of K2 runs (HG_OPT_K2_VARIANT; the results are identical)
-enum { kK2Flat = 0, kK2WarpPerRead = 2 };
+constexpr int kFlatBins = 4096;     // histogram words (= coverage bins) per CTA of the flat kernels
+constexpr int kFlatMaxReads = 512;  // reads per batch
 
 // Device buffers of one filter run (all sized at hg_set_reads / hg_set_overlaps).
 struct FilterScratch {
     int num_sms = 148;
-    // K1
-    unsigned long long* cov_sum = nullptr;  // n_read
-    int* cov_maxbin = nullptr;              // n_read
-    int* self_cnt = nullptr;                // n_read
+    // ingest
+    int* self_cnt = nullptr;                // n_read: records with A == B
+    // K1 (profile build)
+    int* cov_maxbin = nullptr;              // n_read: last bin of the cut-off-free profile
+    int* counters1 = nullptr;               // 8: [0] reads handed to the per-read fallback
     int* mean_cov = nullptr;                // n_read, -1 = not part of the estimate
     unsigned int* med_hist = nullptr;       // 4097 + 4096
     int* scal = nullptr;                    // 8: cov_est, MIN_COV, radix state
@@ -43,15 +41,11 @@ struct FilterScratch {
     int* work_list = nullptr;  // n_read
     int* big_list = nullptr;   // n_read
     int* exact_list = nullptr; // n_read: reads whose hinge calls need the exact sort order
-    int nb_cap = 0;            // histogram words per warp on the warp-per-read path
-    int mask_anno_grid = 0;
-    int k2_variant = kK2Flat;
-    int flat_spread = 8;              // flat K2: record windows per warp in the scatter (tuning aid)
-    int2* flat_batch = nullptr;       // flat K2: (first read, histogram words in use) per batch (flat_nbatch + 1)
-    int* flat_rbase = nullptr;        // flat K2: per read, first histogram word inside its batch (-1: generic path)
-    int* flat_read_batch = nullptr;   // flat K2: per read, its batch
-    int* flat_batch_self = nullptr;   // flat K2: per batch, set by K1 when the batch holds A == B records
+    int2* flat_batch = nullptr;       // (first read, histogram words in use) per batch (flat_nbatch + 1)
+    int* flat_rbase = nullptr;        // per read, first histogram word inside its batch (-1: fallback path)
+    uint32_t* flat_prof = nullptr;    // scanned packed profiles, kFlatBins words per batch (K1 -> K2)
     int flat_nbatch = 0;
+    int flat_spread = 8;              // record windows per warp in the scatter (tuning aid)
     unsigned long long* big_scratch = nullptr;
     int big_slot_words = 0, big_warps = 0;
     // K4
@@ -61,23 +55,22 @@ struct FilterScratch {
     int4* item_log = nullptr;       // HG_OPT_PROFILE: (read, cycles, support, exact n) per work item
 };
 
-void launch_csr_validate(const RecView& rv, const ReadView& rd, int64_t* read_off, int* err,
+void launch_csr_validate(const RecView& rv, const ReadView& rd, int64_t* read_off, int* self_cnt, int* err,
                          cudaStream_t st);
 void launch_qv_mask(int n_read, const int64_t* qv_off, const uint8_t* qv, int tspace, int2* out,
                     cudaStream_t st);
-void launch_cov_estimate(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
-                         int r_begin, int r_end, FilterScratch& s, cudaStream_t st);
 void launch_median(const ReadView& rd, const hg_filter_params& P, FilterScratch& s,
                    cudaStream_t st);
-int mask_anno_configure(FilterScratch& s, int nb_cap);  // picks grid from occupancy
 void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
                       int r_begin, int r_end, FilterScratch& s, int* cov0, const int64_t* cov0_off,
                       cudaStream_t st);
-// flat K2 (hg_filter_flat.cu): host-side batch plan + launcher
+// flat kernels (hg_filter_flat.cu): host-side batch plan + launchers of the two phases
 void flat_plan(const int* rlen, int lo, int hi, int n_read, int cut_off, std::vector<int2>* batch,
-               std::vector<int>* rbase, std::vector<int>* read_batch);
-void launch_mask_anno_flat(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
-                           FilterScratch& s, const MaskAnnoOut& out, cudaStream_t st);
+               std::vector<int>* rbase);
+void launch_profile(const RecView& rv, const ReadView& rd, const hg_filter_params& P, int r_begin,
+                    int r_end, FilterScratch& s, cudaStream_t st);
+void launch_mask_anno_flat(const RecView& rv, const ReadView& rd, const hg_filter_params& P, int r_begin,
+                           int r_end, FilterScratch& s, const MaskAnnoOut& out, cudaStream_t st);
 void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
                        FilterScratch& s, cudaStream_t st);
 void launch_debug_warp_sort(void* data, const int* off, int count, int descending, int* g, int* l, void* tmp,

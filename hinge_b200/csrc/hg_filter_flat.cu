@@ -1,36 +1,43 @@
-// K2, flat form: coverage mask + repeat annotation + hinge pre-test of the
-// `hinge filter` stage (/root/reference/src/filter/filter.cpp:696-865,
-// /root/reference/src/lib/LAInterface.cpp:4298-4320) for a BATCH of consecutive
-// A-reads per CTA instead of one read per warp.
+// The pile-up scan of `hinge filter` (/root/reference/src/filter/filter.cpp:588-865,
+// /root/reference/src/lib/LAInterface.cpp:4298-4320) in flat form: a BATCH of consecutive
+// A-reads per CTA instead of one read per warp, and the records read from HBM ONCE.
 //
-// Why this shape.  A PacBio-like read has ~90 coverage bins and ~90 pile-up records:
-// far too little work for a warp, so a warp-per-read kernel spends its time in per-read
-// fixed overhead executed by 32 mostly idle lanes (ncu: 606 warp instructions per read,
-// 65 % issue-active, 11 % of HBM).  Here the profiles of ~40 reads are laid end to end in
-// one shared-memory array and every phase runs flat over it with all lanes busy:
+// Why this shape.  A PacBio-like read has ~90 coverage bins and ~90 pile-up records: far too
+// little work for a warp, so a warp-per-read kernel spends its time in per-read fixed
+// overhead executed by 32 mostly idle lanes (first cut of this round, ncu: 606 warp
+// instructions per read, 65 % issue-active, 11 % of HBM).  Here the profiles of ~40 reads are
+// laid end to end in one shared-memory array and every phase runs flat over it with all lanes
+// busy.  The stage has one global dependency -- MIN_COV, from the median of the per-read mean
+// coverage (filter.cpp:642-678) -- so it is split there:
 //
-//   scatter   flat over the batch's records (int4 loads of aread/abpos/aepos, the next
-//             step's loads in flight while this step's events go out): four packed +-1
-//             events per record (low half: profile without cut-off, high half: with).
-//             The lanes of a warp are spread over eight record windows (flat_group) so
-//             that the many records that start in their read's first bin or end in its
-//             last one do not all serialise on one shared-memory word.
-//   scan      ONE block-wide prefix sum over the concatenated array.  Every record adds
-//             +1 and -1 inside its own read's bins, so the running sum is back at zero at
-//             every read boundary: no segmentation needed.  The same pass leaves two bit
-//             maps: bins whose cut-off coverage is <= MIN_COV ("zeros") and bins where the
-//             coverage jumps by more than the smallest annotation threshold.
-//   per read  one thread per read walks its slice of the two bit maps: longest covered run
-//             (filter.cpp:696-728), mask, telomere flag, repeat annotations with the
-//             streaming form of the merge pass (filter.cpp:796-829), hinge pre-test
-//             (filter.cpp:842-865).
+//   K1 k_profile_flat    (before the median) builds both coverage profiles of every read:
+//     scatter   flat over the batch's records (int4 loads of aread/abpos/aepos, the next
+//               step's loads in flight while this step's events go out): four packed +-1
+//               events per record (low half: profile without cut-off, high half: with).
+//               The lanes of a warp are spread over eight record windows (flat_group) so
+//               that the many records that start in their read's first bin or end in its
+//               last one do not all serialise on one shared-memory word.
+//     scan      ONE block-wide prefix sum over the concatenated array.  Every record adds
+//               +1 and -1 inside its own read's bins, so the running sum is back at zero at
+//               every read boundary: no segmentation needed.  The scanned words go to HBM
+//               (4 B per bin, about 4 B per record) for K2.
+//     per read  profile length and mean coverage (filter.cpp:642-656), self-overlap flag.
+//   K2 k_mask_anno_flat  (after the median) streams the stored profiles: bit maps of bins whose
+//     cut-off coverage is <= MIN_COV ("zeros") and of bins where the coverage jumps by more
+//     than the smallest annotation threshold, then one thread per read walks its slice of the
+//     maps: longest covered run (filter.cpp:696-728), mask, telomere flag, repeat annotations
+//     with the streaming form of the merge pass (filter.cpp:796-829), hinge pre-test
+//     (filter.cpp:842-865).
 //
-// The kernel is bound by the shared-memory data pipe (ncu: l1tex data-pipe wavefronts > 80 %
-// of peak): ~4 wavefronts per ATOMS on random bins is what the banks give, so the rest of the
-// design keeps every other shared-memory access conflict-free (sw) and the global loads wide.
+// K1 is bound by the shared-memory data pipe (ncu: l1tex data-pipe wavefronts > 70 % of peak,
+// ~4 wavefronts per ATOMS on random bins is what the banks give), so everything else in it is
+// kept conflict-free (sw) and the global accesses wide.  Tried and measured on B200, K2 of the
+// previous form alone: match.any aggregation of equal bins 0.84 ms, ballot aggregation of the
+// hot bins 0.54 ms, none 0.40 ms, + lane spreading 0.365 ms, + swizzle and prefetch 0.34 ms.
 //
-// Reads longer than kFlatBins bins, pile-ups deeper than the 16-bit halves can count and
-// runs with MIN_COV < 0 go to the generic per-read kernel (k_mask_anno_big, hg_filter.cu).
+// Reads longer than kFlatBins bins and pile-ups deeper than the 16-bit halves can count go
+// to per-read fallbacks (k_cov_big here, k_mask_anno_big in hg_filter.cu); so does everything
+// when MIN_COV < 0 (covered runs could then cross read boundaries).
 #include "hg_device.cuh"
 #include "hg_filter.h"
 
@@ -41,7 +48,7 @@ extern int64_t g_launches;
 constexpr int kFlatThreads = 256;
 constexpr int kFlatItems = 16;                           // bins per thread and scan pass
 constexpr int kFlatPass = kFlatThreads * kFlatItems;     // bins per scan pass
-constexpr int kFlatWords = kFlatBins + 32;               // histogram words per CTA (+ slack for the j + 1 reads)
+constexpr int kFlatWords = kFlatBins + 32;               // histogram words per CTA (+ slack)
 constexpr int kFlatMaps = (kFlatBins + kFlatPass - 1) / kFlatPass * kFlatThreads;  // 16-bit map entries
 
 __device__ __forceinline__ uint4 lds128(const uint32_t* p) { return *reinterpret_cast<const uint4*>(p); }
@@ -56,17 +63,6 @@ __device__ __forceinline__ int f_hi(uint32_t v) { return (int)v >> 16; }
 // every aligned 4-word group intact and makes those accesses conflict-free.
 __device__ __forceinline__ int sw(int j) { return j ^ ((j >> 3) & 12); }
 
-// The four events of one record (profileCoverage, LAInterface.cpp:4298-4320): low half of the
-// packed word = profile without cut-off, high half = with.
-__device__ __forceinline__ void scatter_record(uint32_t* hist, int base, int as, int ae, int C) {
-    const int b_s0 = base + as / kReso + 1, b_e0 = base + ae / kReso + 1;  // 0 <= abpos < aepos (ingest check)
-    const int b_sc = base + cov_bin(as + C, kReso), b_ec = base + cov_bin(ae - C, kReso);
-    atomicAdd(&hist[sw(b_s0)], 1u);
-    atomicAdd(&hist[sw(b_e0)], 0u - 1u);
-    atomicAdd(&hist[sw(b_sc)], 1u << 16);
-    atomicAdd(&hist[sw(b_ec)], 0u - (1u << 16));
-}
-
 // Bit `i` of the map <=> entry i (maps are arrays of 32-bit words in shared memory).
 __device__ __forceinline__ uint32_t map_word(const uint32_t* map, int w, int lo, int hi) {
     // word w restricted to entries in [lo, hi)
@@ -78,11 +74,17 @@ __device__ __forceinline__ uint32_t map_word(const uint32_t* map, int w, int lo,
 }
 
 struct FlatParams {
-    const int2* __restrict__ batch;       // nbatch + 1: (first read, histogram words in use) of every batch
-    const int* __restrict__ rbase;        // per read: first word of its profile inside its batch, -1 = generic path
-    const int* __restrict__ cov_maxbin;   // K1: last bin of the cut-off-free profile (-1 = empty pile-up)
-    const int* __restrict__ batch_self;   // K1: the batch holds records with A == B
-    const int* __restrict__ scal;         // [1] = MIN_COV
+    const int2* __restrict__ batch;      // nbatch + 1: (first read, histogram words in use) of every batch
+    const int* __restrict__ rbase;       // per read: first word of its profile inside its batch, -1 = fallback
+    const int* __restrict__ self_cnt;    // ingest: records with A == B per read
+    uint32_t* __restrict__ prof;         // scanned packed profiles, kFlatBins words per batch
+    int* __restrict__ cov_maxbin;        // last bin of the cut-off-free profile (-1 = empty pile-up)
+    int* __restrict__ mean_cov;          // per-read mean coverage, -1 = not part of the estimate
+    uint8_t* __restrict__ rflags;
+    int* __restrict__ counters1;         // [0] length of big_list (phase 1)
+    int* __restrict__ big_list;
+    const int* __restrict__ scal;        // [1] = MIN_COV (K2 only)
+    int r_begin, r_end;                  // first / last A-read with records
 };
 
 // Which 4-record group of a 1024-record tile a thread takes.  With the identity map the 32
@@ -90,7 +92,7 @@ struct FlatParams {
 // start in the read's first bin (or end in its last) serialise on one shared-memory word.
 // Spreading the lanes over SPREAD windows 128 records apart (32 / SPREAD lanes, a 16 * 32 / SPREAD
 // byte run, per window) divides that multiplicity by SPREAD while every window still reads whole
-// sectors.  Measured on B200 (K2 alone, ms): 1 -> 0.404, 4 -> 0.365, 8 -> 0.368, 16 -> 0.395, 32 -> 0.459.
+// sectors.  Measured (ms): 1 -> 0.404, 4 -> 0.365, 8 -> 0.368, 16 -> 0.395, 32 -> 0.459.
 template <int SPREAD>
 __device__ __forceinline__ int flat_group(int tid) {
     if (SPREAD <= 1) return tid;
@@ -99,39 +101,59 @@ __device__ __forceinline__ int flat_group(int tid) {
     return (lane % L) + L * warp + (kFlatThreads / SPREAD) * (lane / L);
 }
 
-template <int SPREAD, bool DUMP>
+// filter.cpp:642-656 (mean over reads >= 5000 bp that have a pile-up) and filter.cpp:552-561
+// (self-match reads; float accumulation in record order), shared by K1 and its fallback.
+__device__ __forceinline__ void finalize_read(const RecView& rv, const ReadView& rd, const FlatParams& F, int read,
+                                              long long sum, int maxbin) {
+    const int len0 = maxbin + 1;
+    const int mean = (int)(sum / (long long)max(1, len0));
+    const int rl = rd.rlen[read];
+    F.cov_maxbin[read] = maxbin;
+    F.mean_cov[read] = (rl >= 5000 && read >= F.r_begin && read <= F.r_end) ? mean : -1;
+    uint8_t f = 0;
+    if (F.self_cnt[read] > 0) {
+        float cov = 0.0f;
+        for (int64_t k = rv.read_off[read]; k < rv.read_off[read + 1]; k++) {
+            if (rv.bread[k] != read) continue;
+            cov = __fadd_rn(cov, (float)(rv.aepos[k] - rv.abpos[k]));
+            // B span is strand-invariant: (blen-bbpos) - (blen-bepos) = bepos - bbpos
+            cov = __fadd_rn(cov, (float)(rv.bepos[k] - rv.bbpos[k]));
+        }
+        cov = __fdiv_rn(cov, (float)rl);
+        if ((double)cov > 4.5 && rl > 10000) f |= kFlagSelf;
+    }
+    F.rflags[read] = f;
+}
+
+// ------------------------------------------------------------------ K1
+
+template <int SPREAD>
 __global__ void __launch_bounds__(kFlatThreads)
-k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, MaskAnnoOut out) {
+k_profile_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
     __shared__ __align__(16) uint32_t hist[kFlatWords];
-    __shared__ __align__(16) uint16_t zmap16[kFlatMaps];  // bin has cut-off coverage <= MIN_COV
-    __shared__ __align__(16) uint16_t cmap16[kFlatMaps];  // |cov0[j] - cov0[j-1]| above the smallest threshold
     __shared__ uint32_t wtot[2][kFlatThreads / 32];
-    const uint32_t* zmap = reinterpret_cast<const uint32_t*>(zmap16);
-    const uint32_t* cmap = reinterpret_cast<const uint32_t*>(cmap16);
+    // per read of the batch: sum_records (bin(aepos) - bin(abpos)) = sum_j cov0[j], max bin(aepos) =
+    // profile length - 1, and the same maximum without the A == B records for the reads that have some
+    __shared__ int sh_sum[kFlatMaxReads], sh_max[kFlatMaxReads], sh_max2[kFlatMaxReads];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int2 bt = F.batch[blockIdx.x];
     const int f0 = bt.x, f1 = F.batch[blockIdx.x + 1].x;
-    const int MIN_COV = F.scal[1];
-    constexpr int reso = kReso;
-    // MIN_COV < 0: runs could cross read boundaries, everything goes the generic way
-    const int nb = MIN_COV < 0 ? 0 : bt.y;
+    const int nb = bt.y;
     const int npass = (nb + kFlatPass - 1) / kFlatPass;
-    const bool self_records = F.batch_self[blockIdx.x] != 0;  // otherwise the bread column is not even loaded
 
     // ---- the batch's records: four per thread and step
     const int64_t k_begin = nb > 0 ? rv.read_off[f0] : 0, k_end = nb > 0 ? rv.read_off[f1] : 0;
     const int64_t g0 = k_begin & ~(int64_t)3;
     const int grp = flat_group<SPREAD>(tid) * 4;
-    int4 va = make_int4(-1, -1, -1, -1), vs = make_int4(0, 0, 0, 0), ve = vs, vb = make_int4(-2, -2, -2, -2);
+    int4 va = make_int4(-1, -1, -1, -1), vs = make_int4(0, 0, 0, 0), ve = vs;
     auto load4 = [&](int64_t k) {
         if (k >= k_begin && k + 4 <= k_end) {
             va = __ldg(reinterpret_cast<const int4*>(rv.aread + k));
             vs = __ldg(reinterpret_cast<const int4*>(rv.abpos + k));
             ve = __ldg(reinterpret_cast<const int4*>(rv.aepos + k));
-            if (self_records) vb = __ldg(reinterpret_cast<const int4*>(rv.bread + k));
         } else {  // ragged ends of the batch: records outside it get read id -1
-            int a[4], s[4], e[4], b[4];
+            int a[4], s[4], e[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int64_t ki = k + i;
@@ -139,12 +161,10 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
                 a[i] = in ? __ldg(rv.aread + ki) : -1;
                 s[i] = in ? __ldg(rv.abpos + ki) : 0;
                 e[i] = in ? __ldg(rv.aepos + ki) : 0;
-                b[i] = (in && self_records) ? __ldg(rv.bread + ki) : -2;
             }
             va = make_int4(a[0], a[1], a[2], a[3]);
             vs = make_int4(s[0], s[1], s[2], s[3]);
             ve = make_int4(e[0], e[1], e[2], e[3]);
-            vb = make_int4(b[0], b[1], b[2], b[3]);
         }
     };
     if (g0 < k_end) load4(g0 + grp);  // in flight while the histogram is cleared
@@ -152,49 +172,90 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
     // ---- zero
     for (int j = tid * 4; j < npass * kFlatPass + 16 && j < kFlatWords; j += kFlatThreads * 4)
         sts128(hist + j, make_uint4(0, 0, 0, 0));
-    __syncthreads();
-
-    // ---- scatter: the next step's loads are issued before this step's events go out
-    {
-        const int C = P.cut_off;
-        for (int64_t kb = g0; kb < k_end; kb += kFlatThreads * 4) {
-            const int a[4] = {va.x, va.y, va.z, va.w}, s[4] = {vs.x, vs.y, vs.z, vs.w};
-            const int e[4] = {ve.x, ve.y, ve.z, ve.w}, b[4] = {vb.x, vb.y, vb.z, vb.w};
-            if (kb + kFlatThreads * 4 < k_end) load4(kb + kFlatThreads * 4 + grp);
-            // records are sorted by A-read: in most groups one lookup of the read's base serves all four
-            const int base0 = a[0] >= 0 ? __ldg(F.rbase + a[0]) : -1;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                int base = base0;
-                if (a[i] != a[0]) base = a[i] >= 0 ? __ldg(F.rbase + a[i]) : -1;
-                bool valid = base >= 0;
-                if (self_records) valid = valid && b[i] != a[i];  // filter.cpp:538-547
-                if (valid) scatter_record(hist, base, s[i], e[i], C);
-            }
-        }
+    for (int r = tid; r < f1 - f0; r += kFlatThreads) {
+        sh_sum[r] = 0;
+        sh_max[r] = -1;
     }
     __syncthreads();
 
-    // ---- one prefix sum over the whole batch + the two bit maps.  zero <=> high half <= MIN_COV
-    // <=> the word, as a signed integer, is below (MIN_COV + 1) << 16 (the low half is >= 0).
-    const int zthr = (MIN_COV + 1 > 32767 ? 32767 : MIN_COV + 1) << 16;
-    const int RJ = min(P.min_repeat_annotation_threshold, P.max_repeat_annotation_threshold);
+    // ---- scatter (profileCoverage, LAInterface.cpp:4298-4320): the next step's loads are
+    // issued before this step's events go out.  Every record is scattered, A == B ones included
+    // (telling them apart would need the bread column): they are taken out again below.
+    const int C = P.cut_off;
+    for (int64_t kb = g0; kb < k_end; kb += kFlatThreads * 4) {
+        const int a[4] = {va.x, va.y, va.z, va.w}, s[4] = {vs.x, vs.y, vs.z, vs.w};
+        const int e[4] = {ve.x, ve.y, ve.z, ve.w};
+        if (kb + kFlatThreads * 4 < k_end) load4(kb + kFlatThreads * 4 + grp);
+        // records are sorted by A-read: in most groups one lookup of the read's base serves all four
+        const int base0 = a[0] >= 0 ? __ldg(F.rbase + a[0]) : -1;
+        int cur = -1, acc = 0, mx = -1;  // run of records of one read inside this group
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int base = base0;
+            if (a[i] != a[0]) base = a[i] >= 0 ? __ldg(F.rbase + a[i]) : -1;
+            if (base < 0) continue;
+            // 0 <= abpos < aepos (ingest check)
+            const int q_s = s[i] / kReso + 1, q_e = e[i] / kReso + 1;
+            const int b_sc = base + cov_bin(s[i] + C, kReso), b_ec = base + cov_bin(e[i] - C, kReso);
+            atomicAdd(&hist[sw(base + q_s)], 1u);
+            atomicAdd(&hist[sw(base + q_e)], 0u - 1u);
+            atomicAdd(&hist[sw(b_sc)], 1u << 16);
+            atomicAdd(&hist[sw(b_ec)], 0u - (1u << 16));
+            if (a[i] != cur) {
+                if (cur >= 0) {
+                    atomicAdd(&sh_sum[cur - f0], acc);
+                    atomicMax(&sh_max[cur - f0], mx);
+                }
+                cur = a[i];
+                acc = 0;
+                mx = -1;
+            }
+            acc += q_e - q_s;
+            mx = max(mx, q_e);
+        }
+        if (cur >= 0) {
+            atomicAdd(&sh_sum[cur - f0], acc);
+            atomicMax(&sh_max[cur - f0], mx);
+        }
+    }
+    // A == B records are inactive (filter.cpp:538-547) and rare; their per-read count comes from
+    // the ingest.  One thread per such read removes their events again (atomic adds commute, so
+    // this needs no barrier) and recomputes the maximum without them.
+    for (int r = tid; r < f1 - f0; r += kFlatThreads) {
+        const int read = f0 + r;
+        const int base = F.rbase[read];
+        if (F.self_cnt[read] <= 0 || base < 0) continue;
+        int mx = -1, acc = 0;
+        for (int64_t k = rv.read_off[read]; k < rv.read_off[read + 1]; k++) {
+            const int as = rv.abpos[k], ae = rv.aepos[k];
+            const int q_s = as / kReso + 1, q_e = ae / kReso + 1;
+            if (rv.bread[k] != read) {
+                mx = max(mx, q_e);
+                continue;
+            }
+            atomicAdd(&hist[sw(base + q_s)], 0u - 1u);
+            atomicAdd(&hist[sw(base + q_e)], 1u);
+            atomicAdd(&hist[sw(base + cov_bin(as + C, kReso))], 0u - (1u << 16));
+            atomicAdd(&hist[sw(base + cov_bin(ae - C, kReso))], 1u << 16);
+            acc += q_e - q_s;
+        }
+        atomicAdd(&sh_sum[r], -acc);
+        sh_max2[r] = mx;
+    }
+    __syncthreads();
+
+    // ---- one prefix sum over the whole batch; the scanned words also go to HBM for K2
+    uint32_t* const pw = F.prof + (size_t)blockIdx.x * kFlatBins;
     uint32_t carry = 0;
     for (int pass = 0; pass < npass; pass++) {
         const int j0 = pass * kFlatPass + tid * kFlatItems;
         const int sx = sw(j0) ^ j0;  // the flipped bits: common to the whole 16-word chunk
         uint32_t v[kFlatItems];
-        uint32_t cbits = 0;
         if (j0 < nb) {
 #pragma unroll
             for (int q = 0; q < kFlatItems / 4; q++) {
                 const uint4 x = lds128(hist + ((j0 + 4 * q) ^ sx));
                 v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-            }
-#pragma unroll
-            for (int i = 0; i < kFlatItems; i++) {
-                const int g = (int)(int16_t)(v[i] & 0xffffu);  // cov0[j0 + i] - cov0[j0 + i - 1]
-                cbits |= (g > RJ || g < -RJ) ? (1u << i) : 0u;
             }
 #pragma unroll
             for (int i = 1; i < kFlatItems; i++) v[i] += v[i - 1];
@@ -212,16 +273,105 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
             if (w < warp) pre += t;
             carry += t;
         }
-        uint32_t zbits = 0;
+        if (j0 < nb) {
+#pragma unroll
+            for (int i = 0; i < kFlatItems; i++) v[i] += pre;
+#pragma unroll
+            for (int q = 0; q < kFlatItems / 4; q++) {
+                const uint4 x = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                sts128(hist + ((j0 + 4 * q) ^ sx), x);
+                *reinterpret_cast<uint4*>(pw + j0 + 4 * q) = x;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- per read: length and mean of the cut-off-free profile (filter.cpp:642-656)
+    for (int read = f0 + tid; read < f1; read += kFlatThreads) {
+        const int base = F.rbase[read];
+        const int64_t nrec = rv.read_off[read + 1] - rv.read_off[read];
+        if (base < 0 || nrec > Packed<uint32_t>::kMaxCount) {
+            F.big_list[atomicAdd(&F.counters1[0], 1)] = read;
+            continue;
+        }
+        finalize_read(rv, rd, F, read, sh_sum[read - f0],
+                      F.self_cnt[read] > 0 ? sh_max2[read - f0] : sh_max[read - f0]);
+    }
+}
+
+// Fallback of K1 for the reads the flat path cannot take: one warp per read, the same sums
+// straight from the records:  sum_j cov[j] = sum_records (bin(aepos) - bin(abpos)),
+// length = max bin(aepos) + 1.
+__global__ void __launch_bounds__(128)
+k_cov_big(RecView rv, ReadView rd, FlatParams F) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nbig = F.counters1[0];
+    for (int w = warp; w < nbig; w += nwarps) {
+        const int read = F.big_list[w];
+        long long sum = 0;
+        int mx = -1;
+        for (int64_t k = rv.read_off[read] + lane_id(); k < rv.read_off[read + 1]; k += 32) {
+            if (rv.bread[k] == read) continue;
+            const int be = cov_bin(rv.aepos[k], kReso);
+            sum += be - cov_bin(rv.abpos[k], kReso);
+            mx = max(mx, be);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        mx = warp_max(mx);
+        if (lane_id() == 0) finalize_read(rv, rd, F, read, sum, mx);
+    }
+}
+
+// ------------------------------------------------------------------ K2
+
+template <bool DUMP>
+__global__ void __launch_bounds__(kFlatThreads, 8)
+k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, MaskAnnoOut out) {
+    __shared__ __align__(16) uint16_t zmap16[kFlatMaps];  // bin has cut-off coverage <= MIN_COV
+    __shared__ __align__(16) uint16_t cmap16[kFlatMaps];  // |cov0[j] - cov0[j-1]| above the smallest threshold
+    const uint32_t* zmap = reinterpret_cast<const uint32_t*>(zmap16);
+    const uint32_t* cmap = reinterpret_cast<const uint32_t*>(cmap16);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int2 bt = F.batch[blockIdx.x];
+    const int f0 = bt.x, f1 = F.batch[blockIdx.x + 1].x;
+    const int MIN_COV = F.scal[1];
+    constexpr int reso = kReso;
+    // MIN_COV < 0: runs could cross read boundaries, everything goes the generic way
+    const int nb = MIN_COV < 0 ? 0 : bt.y;
+    const int npass = (nb + kFlatPass - 1) / kFlatPass;
+    const uint32_t* __restrict__ const pw = F.prof + (size_t)blockIdx.x * kFlatBins;
+
+    // ---- the two bit maps, flat over the batch's bins.  zero <=> high half <= MIN_COV <=> the
+    // word, as a signed integer, is below (MIN_COV + 1) << 16 (the low half is >= 0).
+    const int zthr = (MIN_COV + 1 > 32767 ? 32767 : MIN_COV + 1) << 16;
+    const int RJ = min(P.min_repeat_annotation_threshold, P.max_repeat_annotation_threshold);
+    for (int pass = 0; pass < npass; pass++) {
+        const int j0 = pass * kFlatPass + tid * kFlatItems;
+        uint32_t zbits = 0, cbits = 0;
+        uint32_t v[kFlatItems];
+        if (j0 < nb) {
+#pragma unroll
+            for (int q = 0; q < kFlatItems / 4; q++) {
+                const uint4 x = __ldg(reinterpret_cast<const uint4*>(pw + j0 + 4 * q));
+                v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kFlatItems; i++) v[i] = 0;
+        }
+        // the word before this thread's chunk (chunks of one warp are contiguous)
+        uint32_t prev = __shfl_up_sync(0xffffffffu, v[kFlatItems - 1], 1);
+        if (lane == 0) prev = (j0 > 0 && j0 < nb) ? __ldg(pw + j0 - 1) : 0u;
         if (j0 < nb) {
 #pragma unroll
             for (int i = 0; i < kFlatItems; i++) {
-                v[i] += pre;
                 zbits |= ((int)v[i] < zthr) ? (1u << i) : 0u;
+                const int g = f_lo(v[i]) - f_lo(i ? v[i - 1] : prev);  // cov0[j0 + i] - cov0[j0 + i - 1]
+                cbits |= (g > RJ || g < -RJ) ? (1u << i) : 0u;
             }
-#pragma unroll
-            for (int q = 0; q < kFlatItems / 4; q++)
-                sts128(hist + ((j0 + 4 * q) ^ sx), make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
         }
         zmap16[pass * kFlatThreads + tid] = (uint16_t)zbits;
         cmap16[pass * kFlatThreads + tid] = (uint16_t)cbits;
@@ -240,7 +390,7 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
         }
         const int nbz = bins_needed(rd.rlen[read], P);
         const int L0 = F.cov_maxbin[read] + 1;  // length of the cut-off-free profile
-        auto H = [&](int j) { return hist[sw(base + j)]; };  // packed coverage of the read's bin j
+        auto H = [&](int j) { return __ldg(pw + base + j); };  // packed coverage of the read's bin j (L1 hit)
 
         // longest run of covered bins (filter.cpp:696-728): the run between two consecutive zeros
         // p < z scores 40 (z - p - 2); bin 0 acts as a zero; '>' keeps the earliest of the longest
@@ -346,7 +496,10 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
                         } else if (ct == -1 && type == -1 && gap < GAP) {
                             cur = nxt;  // -1,-1 close together: the earlier one goes
                         } else {
-                            if (wr) out.anno_pool[off + n] = make_int2((int)(cur >> 2), (int)(cur & 3u) - 1);
+                            if (wr) {
+                                out.anno_pool[off + n] = make_int2((int)(cur >> 2), (int)(cur & 3u) - 1);
+                                out.hinge_keep[off + n] = 0;
+                            }
                             n++;
                             cur = nxt;
                         }
@@ -354,7 +507,10 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
                 }
             }
             if (have) {
-                if (wr) out.anno_pool[off + n] = make_int2((int)(cur >> 2), (int)(cur & 3u) - 1);
+                if (wr) {
+                    out.anno_pool[off + n] = make_int2((int)(cur >> 2), (int)(cur & 3u) - 1);
+                    out.hinge_keep[off + n] = 0;
+                }
                 n++;
             }
             if (wr == 0) {
@@ -406,29 +562,29 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
             if (base < 0 || rv.read_off[read + 1] - rv.read_off[read] > Packed<uint32_t>::kMaxCount) continue;
             const int L0 = F.cov_maxbin[read] + 1;
             int* dst = out.cov0 + out.cov0_off[read];
-            for (int j = lane; j < L0; j += 32) dst[j] = f_lo(hist[sw(base + j)]);
+            for (int j = lane; j < L0; j += 32) dst[j] = f_lo(__ldg(pw + base + j));
         }
     }
 }
 
-// Greedy packing of the reads [lo, hi) into batches of at most kFlatBins histogram words.
-//   batch      (first read, words in use) per batch, closed by (hi, 0)
-//   rbase      per read: first word of its profile inside its batch; -1 = generic path
-//   read_batch per read: its batch (K1 flags the batches that hold A == B records)
+// ------------------------------------------------------------------ host side
+
+// Greedy packing of the reads [lo, hi) into batches of at most kFlatBins histogram words and
+// kFlatMaxReads reads.
+//   batch  (first read, words in use) per batch, closed by (hi, 0)
+//   rbase  per read: first word of its profile inside its batch; -1 = fallback path
 void flat_plan(const int* rlen, int lo, int hi, int n_read, int cut_off, std::vector<int2>* batch,
-               std::vector<int>* rbase, std::vector<int>* read_batch) {
+               std::vector<int>* rbase) {
     batch->clear();
     rbase->assign((size_t)n_read, -1);
-    read_batch->assign((size_t)n_read, 0);
     int used = 0;
     for (int r = lo; r < hi; r++) {
         const int nbz = bins_needed(rlen[r], cut_off);
-        const bool fits = nbz <= kFlatBins;  // otherwise generic path; still belongs to a batch, which reports it
-        if (batch->empty() || (fits && used + nbz > kFlatBins)) {
+        const bool fits = nbz <= kFlatBins;  // otherwise fallback; still belongs to a batch, which reports it
+        if (batch->empty() || (fits && used + nbz > kFlatBins) || r - batch->back().x >= kFlatMaxReads) {
             batch->push_back(make_int2(r, 0));
             used = 0;
         }
-        (*read_batch)[r] = (int)batch->size() - 1;
         if (!fits) continue;
         (*rbase)[r] = used;
         used += nbz;
@@ -438,33 +594,54 @@ void flat_plan(const int* rlen, int lo, int hi, int n_read, int cut_off, std::ve
     batch->push_back(make_int2(hi, 0));
 }
 
-template <int SPREAD>
-static void launch_flat(int grid, bool dump, const RecView& rv, const ReadView& rd, const hg_filter_params& P,
-                        const FlatParams& F, const MaskAnnoOut& out, cudaStream_t st) {
-    if (dump)
-        k_mask_anno_flat<SPREAD, true><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F, out);
-    else
-        k_mask_anno_flat<SPREAD, false><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F, out);
-}
-
-void launch_mask_anno_flat(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
-                           FilterScratch& s, const MaskAnnoOut& out, cudaStream_t st) {
+static FlatParams flat_params(const FilterScratch& s, int r_begin, int r_end) {
     FlatParams F;
     F.batch = s.flat_batch;
     F.rbase = s.flat_rbase;
+    F.self_cnt = s.self_cnt;
+    F.prof = s.flat_prof;
     F.cov_maxbin = s.cov_maxbin;
-    F.batch_self = s.flat_batch_self;
+    F.mean_cov = s.mean_cov;
+    F.rflags = s.rflags;
+    F.counters1 = s.counters1;
+    F.big_list = s.big_list;
     F.scal = s.scal;
+    F.r_begin = r_begin;
+    F.r_end = r_end;
+    return F;
+}
+
+// Phase 1 of the stage: both coverage profiles of every owned read, their lengths and means.
+void launch_profile(const RecView& rv, const ReadView& rd, const hg_filter_params& P, int r_begin,
+                    int r_end, FilterScratch& s, cudaStream_t st) {
+    const FlatParams F = flat_params(s, r_begin, r_end);
+    // the counters of both phases; per-read results of reads outside the planned range were
+    // cleared when the plan was made (hg_capi.cu)
+    cudaMemsetAsync(s.counters, 0, sizeof(int) * 16, st);
+    const int grid = s.flat_nbatch;
+    if (grid <= 0) return;
+    g_launches += 2;
+    switch (s.flat_spread) {
+        case 1: k_profile_flat<1><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;
+        case 4: k_profile_flat<4><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;
+        case 16: k_profile_flat<16><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;
+        default: k_profile_flat<8><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;
+    }
+    k_cov_big<<<16, 128, 0, st>>>(rv, rd, F);
+}
+
+// Phase 2 after the median: masks, annotations, hinge work list (the generic fallback kernel
+// for the reads it reports is launched by launch_mask_anno, hg_filter.cu).
+void launch_mask_anno_flat(const RecView& rv, const ReadView& rd, const hg_filter_params& P, int r_begin,
+                           int r_end, FilterScratch& s, const MaskAnnoOut& out, cudaStream_t st) {
+    const FlatParams F = flat_params(s, r_begin, r_end);
     const int grid = s.flat_nbatch;
     if (grid <= 0) return;
     g_launches += 1;
-    const bool dump = out.cov0 != nullptr;
-    switch (s.flat_spread) {
-        case 1: launch_flat<1>(grid, dump, rv, rd, P, F, out, st); break;
-        case 4: launch_flat<4>(grid, dump, rv, rd, P, F, out, st); break;
-        case 16: launch_flat<16>(grid, dump, rv, rd, P, F, out, st); break;
-        default: launch_flat<8>(grid, dump, rv, rd, P, F, out, st); break;
-    }
+    if (out.cov0)
+        k_mask_anno_flat<true><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F, out);
+    else
+        k_mask_anno_flat<false><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F, out);
 }
 
 }  // namespace hg

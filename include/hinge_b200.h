@@ -43,8 +43,7 @@ enum { HG_MEM_HOST = 0, HG_MEM_DEVICE = 1 };
 enum hg_option {
     HG_OPT_KEEP_COVERAGE = 1, /* keep the 40-bp coverage profiles (.coverage.txt) */
     HG_OPT_PROFILE = 2,       /* record CUDA events between the kernels of a stage */
-    HG_OPT_K2_VARIANT = 3     /* form of the mask/annotation kernel: 0 flat batches of reads per CTA
-                                 (default), 2 one warp per read; identical results */
+    HG_OPT_SCATTER_SPREAD = 3 /* tuning aid: record windows per warp in the profile scatter (1, 4, 8, 16) */
 };
 
 enum hg_buffer { /* per-read device arrays a sharded run exchanges between phases */

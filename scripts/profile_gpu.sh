@@ -35,7 +35,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "launch list exit $?"
 
 echo "== ncu --set full (hot kernels, steady-state launches)"
-for K in k_mask_anno_flat k_cov_accum k_hinge_call k_hinge_exact; do
+for K in k_profile_flat k_mask_anno_flat k_hinge_call k_hinge_exact; do
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^$K\$" -s 3 -c 1 -f \
         -o $OUT/${TAG}_$K $BENCH_SHORT > $OUT/${TAG}_ncu_$K.log 2>&1
     echo "ncu $K exit $?"

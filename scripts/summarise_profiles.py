@@ -91,9 +91,9 @@ def main():
         rows = [r for r in csv.reader(open(lp)) if len(r) > 14 and r[0].isdigit()]
         names = [short_name(r[4]) if "hg::" in r[4] else "torch:" + r[4][:48] for r in rows]
         ns = [float(r[14].replace(",", "")) for r in rows]
-        # one step = from a k_cov_accum launch to the next; the second one is a warm, device-resident step
+        # one step = from a k_profile_flat launch to the next; the second one is a warm, device-resident step
         # (later ones belong to the end-to-end arm, which re-ingests: k_csr_validate, k_max_pileup)
-        starts = [i for i, n in enumerate(names) if n == "k_cov_accum"]
+        starts = [i for i, n in enumerate(names) if n == "k_profile_flat"]
         lines = ["# ncu launch list (%s): per-kernel device time of ONE steady-state filter step" % dst, "",
                  "`ncu --metrics gpu__time_duration.sum --clock-control none` serialises launches and runs them with a",
                  "cold cache, so only the SHARES are comparable with the CUDA-event times in the bench line.", ""]
@@ -115,7 +115,7 @@ def main():
     # ---- ncu --set full captures
     traffic_path = os.path.join(PROF, "traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
-    alias = {"k_mask_anno_flat": "mask_anno", "k_cov_accum": "cov_estimate", "k_hinge_call": "hinge_call",
+    alias = {"k_mask_anno_flat": "mask_anno", "k_profile_flat": "profile", "k_hinge_call": "hinge_call",
              "k_classify_pairs": "classify_pairs"}
     for f in sorted(os.listdir(OUT)):
         if not (f.startswith(src + "_k_") and f.endswith(".ncu-rep")):

@@ -113,3 +113,47 @@ def test_ini_variants(built, tmp_path, overrides):
     ini = os.path.join(str(tmp_path), "variant.ini")
     write_ini(ini, overrides)
     _run_all(str(tmp_path), root, ini=ini)
+
+
+def _run_filter(work, root, ini=ht.INI):
+    ht.run_stage("oracle", "filter", work, root, "ora", ini=ini)
+    ht.run_stage("product", "filter", work, root, "gpu", ini=ini)
+    ht.assert_same_files(work, "gpu", "ora", ht.FILTER_OUT)
+
+
+def test_very_deep_pileups_take_the_fallbacks(built, tmp_path):
+    """Pile-ups deeper than the 16-bit histogram halves can count (> 32000 records: per-read
+    fallback kernels of both phases) and a median coverage >= 4095 (radix select)."""
+    rlen = [6000, 6100, 6200, 6300]
+    recs = []
+    for a in range(4):
+        for b in range(4):
+            if a == b:
+                continue
+            for k in range(11000):
+                ab, ae = (k * 7) % 200, rlen[a] - (k * 11) % 300
+                bb, be = (k * 5) % 150, rlen[b] - (k * 13) % 250
+                recs.append((a, b, ab, ae, bb, be, k & 1))
+    hm.write_fixture(str(tmp_path), "D", rlen, recs, tspace=100, qv="good")
+    _run_filter(str(tmp_path), "D")
+    cov = open(os.path.join(str(tmp_path), "ora.coverage.txt")).readline().split()
+    assert max(int(x.split(",")[1]) for x in cov[2:]) > 32000
+
+
+def test_long_read_and_overlaps_inside_one_bin(built, tmp_path):
+    """A read with more coverage bins than a batch holds (per-read fallback by length) and records
+    that start and end inside one 40-bp bin, including one that alone sets a profile's length."""
+    rng = np.random.default_rng(5)
+    n = 40
+    rlen = [int(x) for x in rng.integers(7000, 12000, n)] + [200000]
+    recs = _tiling(rng, n, rlen[:n], 60000, 0)
+    long_id = n
+    for i in range(0, n, 2):  # the long read overlaps every other read somewhere along its length
+        ln = min(rlen[i], 6000)
+        at = 4000 * i + 123
+        recs += hm.both_directions(long_id, i, at, at + ln, 0, ln, i % 4 == 0, rlen)
+    for r in (3, 4, 5):  # 17-bp records inside one bin; for read 5 beyond every other record's end
+        pos = 40 * 100 + 3 if r != 5 else 40 * (rlen[5] // 40 - 1) + 2
+        recs.append((r, 20, pos, pos + 17, 1000, 1017, 0))
+    hm.write_fixture(str(tmp_path), "L", rlen, recs, tspace=100, qv="good")
+    _run_filter(str(tmp_path), "L")
