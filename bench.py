@@ -89,7 +89,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -236,6 +236,11 @@ def main():
         run_reference_arm(args)
         return
 
+    # the contract is ONE JSON line on stdout: libraries that chat there (NCCL prints its version at
+    # the first communicator) are sent to stderr until the line is ready
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -312,10 +317,14 @@ def main():
     # ---- arm 1: records resident in HBM
     cols_dev = {k: torch.from_numpy(cols_np[k]).to(dev) for k in names}
     ctx.set_overlaps(novl, cols_dev, where=api.HG_MEM_DEVICE, a_lo=a_lo, a_hi=a_hi)
+    # the timed region lasts milliseconds: the sampler starts ahead of the warm-up so that nvidia-smi is
+    # already reporting while the same kernels run
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        time.sleep(0.3)
     for _ in range(max(3, args.warmup)):
         summary = run_stage()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = api.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ktimes = {}
@@ -397,8 +406,11 @@ def main():
     if world == 1 and not args.no_downstream:
         # informational: the two stages downstream of the filter on the same batch (they need the trace)
         line["downstream_stages"] = time_downstream(args, syn, ctx, api, res, np, torch)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
