@@ -285,8 +285,7 @@ def main():
 
     arrays = ShardedArrays(n_read, rank, world, dev)
     assert (arrays.lo, arrays.hi) == (a_lo, a_hi)
-    ctx.bind_buffer(api.HG_BUF_MEAN_COV, arrays.mean_cov)
-    ctx.bind_buffer(api.HG_BUF_MASK, arrays.mask)
+    arrays.bind(ctx)
 
     def run_stage():
         """The sharded form of hg_filter: phase1 | all-gather means | phase2 | all-gather masks | phase3."""

@@ -112,7 +112,8 @@ void hg_ctx_destroy(hg_ctx* c) {
     if (!c->ext_mask) cudaFree(s.mask);
     for (int i = 0; i < hg_ctx::kMarks; i++)
         if (c->marks[i]) cudaEventDestroy(c->marks[i]);
-    cudaFree(s.med_hist); cudaFree(s.scal); cudaFree(s.cmask); cudaFree(s.rflags);
+    if (!c->ext_med_hist) cudaFree(s.med_hist);
+    cudaFree(s.scal); cudaFree(s.cmask); cudaFree(s.rflags);
     cudaFree(s.anno_ref); cudaFree(s.anno_pool); cudaFree(s.counters); cudaFree(s.work_list);
     cudaFree(s.big_list); cudaFree(s.exact_list); cudaFree(s.big_scratch); cudaFree(s.hinge_keep); cudaFree(s.hinge_scratch);
     cudaFree(s.item_log); cudaFree(s.flat_batch); cudaFree(s.flat_rbase);
@@ -372,6 +373,8 @@ int hg_filter_phase1(hg_ctx* c, const hg_filter_params* p) {
     cudaEventRecord(c->ev0, c->stream);
     c->mark(0);
     launch_profile(c->rec_view(), c->read_view(), c->fp, c->r_begin, c->r_end, c->fs, c->stream);
+    // sharded: the rank's part of the coverage histogram, summed across ranks by the caller
+    if (c->ext_med_hist) launch_median(c->read_view(), c->fp, c->fs, 1, c->stream);
     c->mark(1);
     return cuda_check(c, cudaGetLastError(), "filter phase 1");
 }
@@ -398,7 +401,7 @@ int hg_filter_phase2(hg_ctx* c) {
         cov0 = c->d_cov0;
     }
     c->mark(2);
-    launch_median(c->read_view(), c->fp, s, st);
+    launch_median(c->read_view(), c->fp, s, c->ext_med_hist ? 2 : 0, st);
     c->mark(3);
     launch_mask_anno(c->rec_view(), c->read_view(), c->fp, c->r_begin, c->r_end, s, cov0,
                      c->d_cov0_off, st);
@@ -419,6 +422,9 @@ int hg_filter_phase3(hg_ctx* c, hg_filter_summary* out) {
     HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, s.counters, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
     HG_TRY(cuda_check(c, cudaMemcpyAsync(scal, s.scal, sizeof scal, cudaMemcpyDeviceToHost, st), "D2H"));
     HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "filter"));
+    if (scal[5])
+        return set_err(c, HG_ERR_INPUT, "median coverage >= 4095: not supported with a shared coverage histogram "
+                                        "(HG_BUF_MEDIAN_HIST); all-gather HG_BUF_MEAN_COV instead");
     if (cnt[2]) return HG_RETRY_POOL;  // annotation pool overflow: hg_filter grows it and reruns
     c->filter_done = true;
     if (out) {
@@ -514,6 +520,12 @@ int hg_bind_buffer(hg_ctx* c, int which, void* dptr, int64_t bytes) {
         c->plan_reads_version = -1;  // the next run clears the entries outside its read range
         c->filter_params_set = false;
         return HG_OK;
+    }
+    if (which == HG_BUF_MEDIAN_HIST && bytes >= 4ll * 4098) {
+        if (!c->ext_med_hist) cudaFree(c->fs.med_hist);
+        c->fs.med_hist = (unsigned int*)dptr;
+        c->ext_med_hist = true;
+        return cuda_check(c, cudaMemset(dptr, 0, 4 * 4098), "median histogram");
     }
     if (which == HG_BUF_MASK && bytes >= 8ll * c->n_read) {
         if (!c->ext_mask) cudaFree(c->fs.mask);

@@ -63,7 +63,7 @@ struct hg_ctx {
     void mark(int i) {
         if (profile) cudaEventRecord(marks[i], stream);
     }
-    bool ext_mean_cov = false, ext_mask = false;  // bound to caller-owned memory
+    bool ext_mean_cov = false, ext_mask = false, ext_med_hist = false;  // bound to caller-owned memory
 
     hg::LayoutResult* layout = nullptr;  // result of the last hg_layout
 

@@ -83,16 +83,23 @@ __global__ void k_qv_mask(int n_read, const int64_t* __restrict__ qv_off,
 // take the generic three-digit radix select below.  The block that finishes last picks the
 // median and clears the histogram for the next run: one launch, no host round trip.
 // scal: [0] cov_est  [1] MIN_COV  [2] radix prefix  [3] radix rank  [4] need radix pass
+//
+// Sharded runs (hg_bind_buffer(HG_BUF_MEDIAN_HIST)): the accumulation covers the rank's own reads
+// (pick = 0), the histograms are summed across ranks (16 KB instead of the per-read means), and
+// k_median_pick finishes on every rank; the radix fallback would need all the means, so a
+// median in the overflow bin is reported as an error there (scal[5]).
+__device__ void median_pick_block(unsigned int* __restrict__ hist, int est_cov, int min_cov,
+                                  int* __restrict__ scal, bool allow_radix);
+
 __global__ void __launch_bounds__(256)
-k_median_hist(const int* __restrict__ mean_cov, int n_read, unsigned int* __restrict__ hist /*4096 + 2*/,
-              int est_cov, int min_cov, int* __restrict__ scal) {
+k_median_hist(const int* __restrict__ mean_cov, int r_lo, int r_hi, unsigned int* __restrict__ hist /*4096 + 2*/,
+              int est_cov, int min_cov, int* __restrict__ scal, int pick) {
     __shared__ unsigned int sh[4096];
-    __shared__ unsigned int wsum[8];
     __shared__ int is_last;
     for (int i = threadIdx.x; i < 4096; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     unsigned int valid = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_read; i += gridDim.x * blockDim.x) {
+    for (int i = r_lo + blockIdx.x * blockDim.x + threadIdx.x; i < r_hi; i += gridDim.x * blockDim.x) {
         const int v = mean_cov[i];
         if (v >= 0) {
             atomicAdd(&sh[min(v, 4095)], 1u);
@@ -104,13 +111,25 @@ k_median_hist(const int* __restrict__ mean_cov, int n_read, unsigned int* __rest
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
     valid = (unsigned int)warp_sum((int)valid);
     if (lane_id() == 0 && valid) atomicAdd(&hist[4096], valid);
+    if (!pick) return;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = atomicAdd(&hist[4097], 1u) == gridDim.x - 1;
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // ---- the pick: thread t owns bins [16 t, 16 t + 16)
+    median_pick_block(hist, est_cov, min_cov, scal, true);
+}
+
+__global__ void __launch_bounds__(256)
+k_median_pick(unsigned int* __restrict__ hist, int est_cov, int min_cov, int* __restrict__ scal) {
+    median_pick_block(hist, est_cov, min_cov, scal, false);
+}
+
+// One CTA of 256 threads: thread t owns bins [16 t, 16 t + 16); clears the histogram afterwards.
+__device__ void median_pick_block(unsigned int* __restrict__ hist, int est_cov, int min_cov,
+                                  int* __restrict__ scal, bool allow_radix) {
+    __shared__ unsigned int wsum[8];
     const int t = threadIdx.x;
     unsigned int loc[16], tot = 0;
 #pragma unroll
@@ -132,6 +151,7 @@ k_median_hist(const int* __restrict__ mean_cov, int n_read, unsigned int* __rest
             scal[1] = max(min_cov, cov_est / 3);
             scal[2] = 0;
             scal[4] = 0;
+            scal[5] = 0;
         }
     } else if (before <= rank && rank < before + tot) {  // exactly one thread
         unsigned int run = before;
@@ -143,8 +163,9 @@ k_median_hist(const int* __restrict__ mean_cov, int n_read, unsigned int* __rest
         const int need = v >= 4095;  // inside the overflow bin: resolve with the radix passes
         scal[2] = 0;
         scal[3] = (int)(rank - run);
-        scal[4] = need;
-        if (!need) {
+        scal[4] = need && allow_radix;
+        scal[5] = need && !allow_radix;
+        if (!need || !allow_radix) {
             const int cov_est = est_cov != 0 ? est_cov : v;  // filter.cpp:671
             scal[0] = cov_est;
             scal[1] = max(min_cov, cov_est / 3);  // filter.cpp:677-678
@@ -929,12 +950,21 @@ void launch_qv_mask(int n_read, const int64_t* qv_off, const uint8_t* qv, int ts
     g_launches += 1;
 }
 
-void launch_median(const ReadView& rd, const hg_filter_params& P, FilterScratch& s,
+// mode 0: accumulate + pick + radix fallback in one go (single context)
+// mode 1: accumulate the owned reads only (sharded, before the all-reduce of the histogram)
+// mode 2: pick from the summed histogram (sharded, after it)
+void launch_median(const ReadView& rd, const hg_filter_params& P, FilterScratch& s, int mode,
                    cudaStream_t st) {
-    // med_hist is zero on entry (cleared at allocation and by every run's last block)
-    g_launches += 2;
-    k_median_hist<<<148 * 2, 256, 0, st>>>(s.mean_cov, rd.n_read, s.med_hist, P.est_cov, P.min_cov, s.scal);
-    k_median_radix<<<1, 1024, 0, st>>>(s.mean_cov, rd.n_read, P.est_cov, P.min_cov, s.scal);
+    // med_hist is zero on entry (cleared at allocation / binding and by every run's pick)
+    if (mode == 2) {
+        g_launches += 1;
+        k_median_pick<<<1, 256, 0, st>>>(s.med_hist, P.est_cov, P.min_cov, s.scal);
+        return;
+    }
+    g_launches += mode == 0 ? 2 : 1;
+    k_median_hist<<<148 * 2, 256, 0, st>>>(s.mean_cov, mode == 0 ? 0 : rd.r_lo, mode == 0 ? rd.n_read : rd.r_hi,
+                                           s.med_hist, P.est_cov, P.min_cov, s.scal, mode == 0);
+    if (mode == 0) k_median_radix<<<1, 1024, 0, st>>>(s.mean_cov, rd.n_read, P.est_cov, P.min_cov, s.scal);
 }
 
 void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_params& P,

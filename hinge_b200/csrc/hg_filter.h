@@ -59,7 +59,7 @@ void launch_csr_validate(const RecView& rv, const ReadView& rd, int64_t* read_of
                          cudaStream_t st);
 void launch_qv_mask(int n_read, const int64_t* qv_off, const uint8_t* qv, int tspace, int2* out,
                     cudaStream_t st);
-void launch_median(const ReadView& rd, const hg_filter_params& P, FilterScratch& s,
+void launch_median(const ReadView& rd, const hg_filter_params& P, FilterScratch& s, int mode,
                    cudaStream_t st);
 void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
                       int r_begin, int r_end, FilterScratch& s, int* cov0, const int64_t* cov0_off,

@@ -5,7 +5,8 @@ Overlap records of one A-read are contiguous in a LAsort-ed .las
 shard by A-read id.  Two per-read arrays cross shards inside `hinge filter`:
 
   * the per-read mean coverage, whose global median sets MIN_COV
-    (filter.cpp:642-678)                                    -> all-gather, 4 B/read
+    (filter.cpp:642-678).  The median is found by counting, so the ranks only sum
+    their 4096-bin histograms of it                         -> all-reduce, 16 KB
   * the mask of every B read a pile-up touches
     (filter.cpp:884-889)                                    -> all-gather, 8 B/read
 
@@ -37,6 +38,15 @@ class ShardedArrays:
         self.lo, self.hi = self.ranges[rank]
         self.mean_cov = torch.full((world * self.chunk,), -1, dtype=torch.int32, device=device)
         self.mask = torch.zeros((world * self.chunk, 2), dtype=torch.int32, device=device)
+        self.hist = torch.zeros((4098,), dtype=torch.int32, device=device)  # HG_BUF_MEDIAN_HIST
+
+    def bind(self, ctx):
+        """Makes the context compute straight into the exchanged arrays."""
+        from . import api
+
+        ctx.bind_buffer(api.HG_BUF_MASK, self.mask)
+        if self.world > 1:
+            ctx.bind_buffer(api.HG_BUF_MEDIAN_HIST, self.hist)
 
     def exchange(self, t):
         """All-gather the rank's own slice of `t` into every rank's copy of `t`."""
@@ -49,7 +59,8 @@ class ShardedArrays:
 def run_filter_sharded(ctx, params, arrays):
     """hg_filter split at its two global dependencies (include/hinge_b200.h)."""
     ctx.filter_phase1(params)
-    arrays.exchange(arrays.mean_cov)
+    if arrays.world > 1:
+        dist.all_reduce(arrays.hist)  # the context was bound to arrays.hist (HG_BUF_MEDIAN_HIST)
     ctx.filter_phase2()
     arrays.exchange(arrays.mask)
     return ctx.filter_phase3()

@@ -49,7 +49,10 @@ enum hg_option {
 enum hg_buffer { /* per-read device arrays a sharded run exchanges between phases */
     HG_BUF_MEAN_COV = 1,  /* int32[n_read], -1 = not part of the estimate      */
     HG_BUF_MASK = 2,      /* int32[n_read][2], the .mas intervals               */
-    HG_BUF_READ_FLAGS = 3 /* uint8[n_read]                                       */
+    HG_BUF_READ_FLAGS = 3,/* uint8[n_read]                                       */
+    HG_BUF_MEDIAN_HIST = 4 /* uint32[4098]: histogram of the per-read mean coverage; when bound,
+                              phase 1 adds the rank's own reads and the caller sums it across
+                              ranks (all-reduce) instead of all-gathering HG_BUF_MEAN_COV */
 };
 
 /* ---- context ---------------------------------------------------------- */
@@ -120,7 +123,7 @@ int hg_filter(hg_ctx* ctx, const hg_filter_params* params, hg_filter_summary* ou
 /* The same stage split at its two global dependencies, for contexts that own
  * a slice of the reads: exchange (all-gather) the named device array between
  * the calls.  hg_filter == phase1; phase2; phase3 on one context. */
-int hg_filter_phase1(hg_ctx* ctx, const hg_filter_params* params); /* -> HG_BUF_MEAN_COV */
+int hg_filter_phase1(hg_ctx* ctx, const hg_filter_params* params); /* -> HG_BUF_MEAN_COV / HG_BUF_MEDIAN_HIST */
 int hg_filter_phase2(hg_ctx* ctx);                                 /* -> HG_BUF_MASK     */
 int hg_filter_phase3(hg_ctx* ctx, hg_filter_summary* out);         /* hinge calls        */
 

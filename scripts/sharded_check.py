@@ -25,8 +25,7 @@ novl = syn.generate(arrays.lo, arrays.hi, want_trace=False, threads=4)
 cols = {k: v.copy() for k, v in syn.cols().items()}
 ctx = api.Context(local, torch.cuda.current_stream().cuda_stream)
 ctx.set_reads(syn.rlen, syn.qv_off, syn.qv, 100)
-ctx.bind_buffer(api.HG_BUF_MEAN_COV, arrays.mean_cov)
-ctx.bind_buffer(api.HG_BUF_MASK, arrays.mask)
+arrays.bind(ctx)
 ctx.set_overlaps(novl, cols, a_lo=arrays.lo, a_hi=arrays.hi)
 rc, summ = run_filter_sharded(ctx, api.FilterParams(), arrays)
 assert rc == 0
