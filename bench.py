@@ -131,7 +131,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------- reference arm
 
 
-def time_reference_filter(args, steps, warmup):
+def time_reference_filter(args, steps, warmup, with_cli=False):
     """Times the reference's own `Reads_filter` (1 thread: the reference has no parallel region) on a bounded
     sample of the workload.  Falls back to the oracle port when oracle/_ref is absent."""
     import hgsynth
@@ -158,6 +158,27 @@ def time_reference_filter(args, steps, warmup):
             subprocess.run(cmd, cwd=work, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
+        cli = None
+        if with_cli:
+            # the same files through the product's own `hinge filter` (process start, CUDA context, .las
+            # parse, H2D, kernels, D2H, all output files): the drop-in, file-to-file comparison
+            exe = os.path.join(ROOT, "hinge_b200", "_build", "hinge")
+            mine = [exe, "filter", "--db", "S", "--las", "S.las", "-x", "gpu", "--config", ini]
+            env = dict(os.environ, HINGE_B200_TIMING="1")
+            best, phases = None, ""
+            for _ in range(2):
+                t0 = time.perf_counter()
+                r = subprocess.run(mine, cwd=work, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE,
+                                   text=True, env=env)
+                dt = time.perf_counter() - t0
+                if best is None or dt < best:
+                    best, phases = dt, r.stderr
+            same = all(open(os.path.join(work, "gpu." + e), "rb").read() == open(os.path.join(work, "ref." + e), "rb").read()
+                       for e in ("mas", "cmas", "repeat.txt", "hinges.txt", "coverage.txt"))
+            cli = {"seconds": best, "overlaps_per_s": novl / best, "reference_seconds": sum(times) / len(times),
+                   "outputs_identical_to_reference": same,
+                   "phases_ms": {ln.split("]")[1].rsplit(None, 2)[0].strip(): float(ln.split()[-2])
+                                 for ln in phases.splitlines() if "timing]" in ln}}
     finally:
         shutil.rmtree(work, ignore_errors=True)
     sec = sum(times) / len(times)
@@ -166,6 +187,7 @@ def time_reference_filter(args, steps, warmup):
         "sample": "%s on a %g Mb / %gx sample of the workload (%d reads, %d overlaps, .las on page cache -> "
                   "output files), single thread (the reference has no parallel region), %d host cores available"
                   % (os.path.basename(ref), args.sample_mb, args.cov, n_read, novl, os.cpu_count() or 0),
+        "cli": cli,
     }, novl
 
 
@@ -400,8 +422,10 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            base, _ = time_reference_filter(args, 1, 0)
+            base, _ = time_reference_filter(args, 1, 0, with_cli=True)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            # informational: the same sample, file to file, through the product's `hinge filter` executable
+            line["cli_filter"] = base["cli"]
     if world == 1 and not args.no_downstream:
         # informational: the two stages downstream of the filter on the same batch (they need the trace)
         line["downstream_stages"] = time_downstream(args, syn, ctx, api, res, np, torch)

@@ -6,8 +6,11 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <time.h>
 
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hinge_b200.h"
@@ -81,6 +84,21 @@ bool parse_args(int argc, char** argv, bool layout, Args* a, std::string* err) {
     return true;
 }
 
+// HINGE_B200_TIMING=1: wall time of the phases of a stage driver on stderr
+struct PhaseTimer {
+    bool on = getenv("HINGE_B200_TIMING") != nullptr;
+    struct timespec t0;
+    PhaseTimer() { clock_gettime(CLOCK_MONOTONIC, &t0); }
+    void lap(const char* what) {
+        if (!on) return;
+        struct timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        fprintf(stderr, "[hinge_b200 timing] %-28s %8.1f ms\n", what,
+                1e3 * (double)(t1.tv_sec - t0.tv_sec) + 1e-6 * (double)(t1.tv_nsec - t0.tv_nsec));
+        t0 = t1;
+    }
+};
+
 static void say(const char* fmt, const std::string& s = std::string()) {
     printf("[hinge_b200] ");
     printf(fmt, s.c_str());
@@ -116,10 +134,47 @@ int check_inputs(const Args& a, std::string* las_name) {
     return 0;
 }
 
+// Creating the CUDA context takes about half a second: it runs beside the reading of the inputs.
+namespace {
+struct EarlyContext {
+    std::thread worker;
+    hg_ctx* ctx = nullptr;
+    int rc = HG_OK;
+    bool started = false;
+    void start() {
+        started = true;
+        worker = std::thread([this]() { rc = hg_ctx_create(0, nullptr, &ctx); });
+    }
+    int take(hg_ctx** out) {
+        if (!started) return hg_ctx_create(0, nullptr, out);
+        if (worker.joinable()) worker.join();
+        started = false;
+        *out = ctx;
+        ctx = nullptr;
+        return rc;
+    }
+    void drop() {
+        hg_ctx* c = nullptr;
+        if (started && take(&c) == HG_OK) hg_ctx_destroy(c);
+    }
+} g_early;
+}  // namespace
+
+static int load_inputs_inner(const Args& a, bool want_trace, Ini* ini, ReadDB* db, LasFile* las);
+
 int load_inputs(const Args& a, bool want_trace, Ini* ini, ReadDB* db, LasFile* las) {
     std::string las_name;
     int rc = check_inputs(a, &las_name);
     if (rc) return rc;
+    g_early.start();
+    rc = load_inputs_inner(a, want_trace, ini, db, las);
+    if (rc) g_early.drop();
+    return rc;
+}
+
+static int load_inputs_inner(const Args& a, bool want_trace, Ini* ini, ReadDB* db, LasFile* las) {
+    std::string las_name;
+    check_inputs(a, &las_name);
     if (db->open(a.db) != 0) {  // LAInterface::openDB exits 1
         fprintf(stderr, "%s\n", db->error.c_str());
         return 1;
@@ -142,19 +197,23 @@ int load_inputs(const Args& a, bool want_trace, Ini* ini, ReadDB* db, LasFile* l
 }
 
 int open_context(const ReadDB& db, const LasFile& las, bool with_trace, hg_ctx** ctx) {
-    int rc = hg_ctx_create(0, nullptr, ctx);
+    PhaseTimer timer;
+    int rc = g_early.take(ctx);
+    timer.lap("  wait for CUDA context");
     if (rc != HG_OK) {
         fprintf(stderr, "hinge_b200: cannot create a CUDA context (status %d)\n", rc);
         return rc;
     }
     rc = hg_set_reads(*ctx, db.n_read, db.rlen.data(), db.has_qv ? db.qv_off.data() : nullptr,
                       db.has_qv ? db.qv.data() : nullptr, las.tspace);
+    timer.lap("  hg_set_reads");
     if (rc == HG_OK)
         rc = hg_set_overlaps(*ctx, las.novl, las.aread.data(), las.bread.data(), las.abpos.data(),
                              las.aepos.data(), las.bbpos.data(), las.bepos.data(), las.diffs.data(),
                              las.flags.data(), with_trace ? las.trace_off.data() : nullptr,
                              with_trace ? las.trace.data() : nullptr, las.tbytes, HG_MEM_HOST, 0,
                              db.n_read);
+    timer.lap("  hg_set_overlaps");
     if (rc != HG_OK) fprintf(stderr, "hinge_b200: %s\n", hg_last_error(*ctx));
     return rc;
 }
@@ -181,11 +240,13 @@ extern "C" int hg_main_filter(int argc, char** argv) {
         return 1;
     }
     say("Reads filtering");
+    PhaseTimer timer;
     Ini ini;
     ReadDB db;
     LasFile las;
     int rc = load_inputs(a, false, &ini, &db, &las);
     if (rc) return rc;
+    timer.lap("read db + ini + las");
     hg_filter_params fp;
     load_filter_params(ini, db.has_qv, &fp);
 
@@ -194,6 +255,7 @@ extern "C" int hg_main_filter(int argc, char** argv) {
         hg_ctx_destroy(ctx);
         return 1;
     }
+    timer.lap("context + H2D + CSR");
     const bool want_cov = getenv("HINGE_B200_SKIP_COVERAGE_TXT") == nullptr;
     hg_set_option(ctx, HG_OPT_KEEP_COVERAGE, want_cov);
     hg_filter_summary sum;
@@ -204,6 +266,7 @@ extern "C" int hg_main_filter(int argc, char** argv) {
         return 1;
     }
     say("Estimated median coverage: %s", std::to_string(sum.cov_est));
+    timer.lap("hg_filter");
 
     const int n = db.n_read;
     std::vector<int32_t> mask(2 * (size_t)n), cmask(2 * (size_t)n);
@@ -228,6 +291,7 @@ extern "C" int hg_main_filter(int argc, char** argv) {
         return 1;
     }
     hg_ctx_destroy(ctx);
+    timer.lap("fetch results + destroy");
 
     const std::string& x = a.prefix;
     {  // filter.cpp:449-457 opens all of these, some stay empty
@@ -238,19 +302,52 @@ extern "C" int hg_main_filter(int argc, char** argv) {
         TextOut frep(x + ".repeat.txt"), fhg(x + ".hinges.txt");
         TextOut fcf(x + ".cov.flag"), fsf(x + ".self.flag");
         int64_t hinges = 0;
-        for (int i = sum.r_begin; i <= sum.r_end; i++) {
-            if (want_cov) {  // filter.cpp:599-602
-                fcov.put_str("read ");
-                fcov.put_int(i);
-                fcov.put_char(' ');
-                for (int64_t k = cov_off[i]; k < cov_off[i + 1]; k++) {
-                    fcov.put_int((long)(k - cov_off[i]) * fp.reso);
-                    fcov.put_char(',');
-                    fcov.put_int(cov[k]);
-                    fcov.put_char(' ');
-                }
-                fcov.put_char('\n');
+        if (want_cov) {
+            // .coverage.txt (filter.cpp:599-602) is ~11 bytes per 40-bp bin of every read, by far the
+            // largest output: formatted by all cores, a block of reads at a time, written in order
+            int workers = (int)std::thread::hardware_concurrency();
+            if (const char* v = getenv("HINGE_B200_IO_THREADS")) workers = atoi(v);
+            workers = std::max(1, std::min(workers, 32));
+            const int block = 4096 * workers;
+            std::vector<std::vector<char>> bufs((size_t)workers);
+            auto put_int = [](std::vector<char>& b, long v) {
+                char tmp[24];
+                int n = 0;
+                unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
+                do {
+                    tmp[n++] = (char)('0' + u % 10);
+                    u /= 10;
+                } while (u);
+                if (v < 0) b.push_back('-');
+                while (n) b.push_back(tmp[--n]);
+            };
+            for (int b0 = sum.r_begin; b0 <= sum.r_end; b0 += block) {
+                const int b1 = std::min(sum.r_end + 1, b0 + block);
+                std::vector<std::thread> pool;
+                for (int w = 0; w < workers; w++)
+                    pool.emplace_back([&, w]() {
+                        std::vector<char>& out = bufs[w];
+                        out.clear();
+                        const int per = (b1 - b0 + workers - 1) / workers;
+                        for (int i = b0 + w * per; i < std::min(b1, b0 + (w + 1) * per); i++) {
+                            const char* head = "read ";
+                            out.insert(out.end(), head, head + 5);
+                            put_int(out, i);
+                            out.push_back(' ');
+                            for (int64_t k = cov_off[i]; k < cov_off[i + 1]; k++) {
+                                put_int(out, (long)(k - cov_off[i]) * fp.reso);
+                                out.push_back(',');
+                                put_int(out, cov[k]);
+                                out.push_back(' ');
+                            }
+                            out.push_back('\n');
+                        }
+                    });
+                for (auto& th : pool) th.join();
+                for (int w = 0; w < workers; w++) fcov.put_bytes(bufs[w].data(), bufs[w].size());
             }
+        }
+        for (int i = sum.r_begin; i <= sum.r_end; i++) {
             fcmask.put_int(i); fcmask.put_char(' '); fcmask.put_int(cmask[2 * i]); fcmask.put_char(' ');
             fcmask.put_int(cmask[2 * i + 1]); fcmask.put_char('\n');
             fmask.put_int(i); fmask.put_char(' '); fmask.put_int(mask[2 * i]); fmask.put_char(' ');
@@ -277,5 +374,6 @@ extern "C" int hg_main_filter(int argc, char** argv) {
         say("Number of hinges before filtering: %s", std::to_string(sum.n_annotations));
         say("Number of hinges: %s", std::to_string(hinges));
     }
+    timer.lap("write output files");
     return 0;
 }

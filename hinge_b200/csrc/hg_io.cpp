@@ -8,9 +8,11 @@
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <thread>
 
 namespace hg {
 
@@ -165,6 +167,93 @@ int ReadDB::open(const std::string& db_name) {
     return 0;
 }
 
+// A .las is a chain: record i + 1 starts where the trace of record i ends, so finding the
+// records is a pointer chase over the file.  The ingest runs the chase on T chunks at once:
+// every worker but the first guesses where a record starts inside its chunk (the first offset
+// from which kSyncChain records in a row look sane: lengths, coordinates and A-read order, and
+// the trace length daligner writes for them, align.c:3124-3148), walks to the end of its chunk
+// and the walks are then CHECKED to join up exactly -- worker t must end on worker t + 1's
+// guess.  If any joint is off (a file that breaks the heuristics), the whole thing is redone
+// by one sequential walk, so the result never depends on the guess.
+namespace {
+
+const size_t kRec = 40;  // tlen diffs abpos bbpos aepos bepos flags aread bread pad (align.h:126-132,332-337)
+const int kSyncChain = 8;
+
+struct RecHead {
+    int32_t tlen, diffs, abpos, bbpos, aepos, bepos, flags, aread, bread;
+};
+
+inline bool plausible(const RecHead& r, int tspace) {
+    if (r.tlen < 0 || (r.tlen & 1) || r.diffs < 0 || r.abpos < 0 || r.aepos <= r.abpos || r.bbpos < 0 ||
+        r.bepos < r.bbpos || r.aread < 0 || r.bread < 0 || (r.flags & ~0xff))
+        return false;
+    return r.tlen == 2 * ((r.aepos - 1) / tspace - r.abpos / tspace + 1);
+}
+
+// First offset >= from (and < limit) where a chain of plausible records starts; fsize if none.
+size_t find_sync(const uint8_t* base, size_t fsize, size_t from, size_t limit, int tspace, int tbytes) {
+    // record offsets are multiples of 2 * tbytes: 12-byte header, 40-byte records, even trace lengths
+    const size_t step = 2 * (size_t)tbytes;
+    for (size_t p = (from + step - 1) / step * step; p < limit && p + kRec <= fsize; p += step) {
+        size_t q = p;
+        int prev_a = -1, k = 0;
+        for (; k < kSyncChain; k++) {
+            if (q == fsize) break;  // chain runs into the end of the file: fine
+            if (q + kRec > fsize) {
+                k = -1;
+                break;
+            }
+            RecHead r;
+            memcpy(&r, base + q, sizeof r);
+            if (!plausible(r, tspace) || r.aread < prev_a) {
+                k = -1;
+                break;
+            }
+            prev_a = r.aread;
+            q += kRec + (size_t)r.tlen * tbytes;
+            if (q > fsize) {
+                k = -1;
+                break;
+            }
+        }
+        if (k >= 0) return p;
+    }
+    return fsize;
+}
+
+struct Walk {
+    size_t begin = 0, end = 0;       // byte range actually walked: [begin, end)
+    std::vector<uint64_t> rec_off;   // start of every record found
+    int64_t trace_bytes = 0;
+    bool ok = true;
+};
+
+// Walks the records from `begin` until the first record start >= stop.
+void walk_records(const uint8_t* base, size_t fsize, size_t begin, size_t stop, int tbytes, Walk* w) {
+    w->begin = begin;
+    size_t p = begin;
+    while (p < stop) {
+        if (p + kRec > fsize) {
+            w->ok = false;
+            break;
+        }
+        int32_t tlen;
+        memcpy(&tlen, base + p, 4);
+        const size_t tb = (size_t)tlen * (size_t)tbytes;
+        if (tlen < 0 || p + kRec + tb > fsize) {
+            w->ok = false;
+            break;
+        }
+        w->rec_off.push_back(p);
+        w->trace_bytes += (int64_t)tb;
+        p += kRec + tb;
+    }
+    w->end = p;
+}
+
+}  // namespace
+
 int LasFile::open(const std::string& las_name, bool want_trace) {
     int fd = ::open(las_name.c_str(), O_RDONLY);
     if (fd < 0) {
@@ -178,56 +267,164 @@ int LasFile::open(const std::string& las_name, bool want_trace) {
         return -1;
     }
     const size_t fsize = (size_t)st.st_size;
-    const uint8_t* base = (const uint8_t*)mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0);
+    const uint8_t* base = (const uint8_t*)mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
     ::close(fd);
     if (base == MAP_FAILED) {
         error = "mmap failed for " + las_name;
         return -1;
     }
-    madvise((void*)base, fsize, MADV_SEQUENTIAL);
     memcpy(&novl, base, 8);
     memcpy(&tspace, base + 8, 4);
     tbytes = tspace <= 125 ? 1 : 2;
+    auto fail = [&](const std::string& msg) {
+        munmap((void*)base, fsize);
+        error = msg;
+        return -1;
+    };
+    if (novl < 0 || tspace <= 0) return fail("bad .las header in " + las_name);
+    const bool timing = getenv("HINGE_B200_TIMING") != nullptr;
+    struct timespec ts0;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        struct timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        fprintf(stderr, "[hinge_b200 timing]   las: %-22s %8.1f ms\n", what,
+                1e3 * (double)(t1.tv_sec - ts0.tv_sec) + 1e-6 * (double)(t1.tv_nsec - ts0.tv_nsec));
+        ts0 = t1;
+    };
 
+    // ---- the record walk, chunked when the file is big enough to pay for threads
+    int T = (int)std::thread::hardware_concurrency();
+    if (const char* v = getenv("HINGE_B200_IO_THREADS")) T = atoi(v);
+    T = std::max(1, std::min(T, 32));
+    size_t min_bytes = (size_t)8 << 20;  // below this the threads cost more than the walk
+    if (const char* v = getenv("HINGE_B200_IO_MIN_BYTES")) min_bytes = (size_t)atoll(v);
+    if (fsize < min_bytes) T = 1;
+    std::vector<Walk> walks((size_t)T);
+    bool joined = false;
+    if (T > 1) {
+        std::vector<size_t> start((size_t)T + 1, fsize);
+        start[0] = 12;
+        std::vector<std::thread> pool;
+        for (int t = 1; t < T; t++)
+            pool.emplace_back([&, t]() {
+                const size_t lo = 12 + (fsize - 12) / T * t, hi = 12 + (fsize - 12) / T * (t + 1);
+                start[t] = find_sync(base, fsize, lo, hi, tspace, tbytes);
+            });
+        for (auto& th : pool) th.join();
+        pool.clear();
+        // chunks without a sync point are absorbed by their left neighbour
+        std::vector<size_t> stop((size_t)T, fsize);
+        for (int t = T - 1; t >= 0; t--) {
+            size_t s = fsize;
+            for (int u = t + 1; u < T; u++)
+                if (start[u] < fsize) {
+                    s = start[u];
+                    break;
+                }
+            stop[t] = s;
+        }
+        for (int t = 0; t < T; t++)
+            pool.emplace_back([&, t]() {
+                if (t > 0 && start[t] >= fsize) return;  // nothing of its own
+                walk_records(base, fsize, start[t], stop[t], tbytes, &walks[t]);
+            });
+        for (auto& th : pool) th.join();
+        joined = true;
+        int64_t total = 0;
+        for (int t = 0; t < T && joined; t++) {
+            if (t > 0 && start[t] >= fsize) continue;
+            const Walk& w = walks[t];
+            joined = w.ok && w.end == stop[t];  // lands exactly on the neighbour's first record
+            total += (int64_t)w.rec_off.size();
+        }
+        joined = joined && total == novl;
+    }
+    if (!joined) {  // one chase from the header (small files, or a guess that did not hold)
+        T = 1;
+        walks.assign(1, Walk());
+        walks[0].rec_off.reserve((size_t)novl);
+        walk_records(base, fsize, 12, fsize, tbytes, &walks[0]);
+        // a well-formed file holds exactly novl records; trailing bytes are ignored like the reference does
+        if (!walks[0].ok && (int64_t)walks[0].rec_off.size() < novl) return fail("truncated .las " + las_name);
+        if ((int64_t)walks[0].rec_off.size() < novl) return fail("truncated .las " + las_name);
+        walks[0].rec_off.resize((size_t)novl);
+    }
+    threads_used = T;
+    lap(T > 1 ? "record walk (chunked)" : "record walk (one chase)");
+
+    // ---- gather into the struct of arrays, every walk's records in parallel
     const size_t n = (size_t)novl;
     aread.resize(n); bread.resize(n); abpos.resize(n); aepos.resize(n);
     bbpos.resize(n); bepos.resize(n); diffs.resize(n); flags.resize(n);
-    trace_off.assign(n + 1, 0);
-    // record = 40 B: tlen diffs abpos bbpos aepos bepos flags aread bread pad
-    // (align.h:126-132,332-337 minus the leading trace pointer, align.c:3042-3049)
-    size_t p = 12;
-    int64_t tpos = 0;
-    for (size_t i = 0; i < n; i++) {
-        if (p + 40 > fsize) {
-            munmap((void*)base, fsize);
-            error = "truncated .las " + las_name;
-            return -1;
+    trace_off.resize(n + 1);
+    std::vector<size_t> first((size_t)walks.size() + 1, 0);
+    std::vector<int64_t> tfirst((size_t)walks.size() + 1, 0);
+    for (size_t t = 0; t < walks.size(); t++) {
+        first[t + 1] = first[t] + walks[t].rec_off.size();
+        int64_t tb = 0;
+        if (walks.size() == 1) {  // the sequential walk may have counted records past novl
+            for (size_t i = 0; i < walks[0].rec_off.size(); i++) {
+                int32_t tlen;
+                memcpy(&tlen, base + walks[0].rec_off[i], 4);
+                tb += (int64_t)tlen * tbytes;
+            }
+        } else {
+            tb = walks[t].trace_bytes;
         }
-        int32_t rec[9];
-        memcpy(rec, base + p, 36);
-        diffs[i] = rec[1]; abpos[i] = rec[2]; bbpos[i] = rec[3]; aepos[i] = rec[4];
-        bepos[i] = rec[5]; flags[i] = rec[6]; aread[i] = rec[7]; bread[i] = rec[8];
-        size_t tb = (size_t)rec[0] * (size_t)tbytes;
-        p += 40;
-        if (rec[0] < 0 || p + tb > fsize) {
-            munmap((void*)base, fsize);
-            error = "truncated .las " + las_name;
-            return -1;
-        }
-        tpos += (int64_t)tb;
-        trace_off[i + 1] = tpos;
-        p += tb;
+        tfirst[t + 1] = tfirst[t] + tb;
     }
-    if (want_trace) {
-        trace.resize((size_t)tpos);
-        p = 12;
-        for (size_t i = 0; i < n; i++) {
-            size_t tb = (size_t)(trace_off[i + 1] - trace_off[i]);
-            memcpy(trace.data() + trace_off[i], base + p + 40, tb);
-            p += 40 + tb;
+    const int64_t trace_total = tfirst[walks.size()];
+    if (want_trace) trace.resize((size_t)trace_total);
+    {
+        // split every walk's records over a few workers so that T = 1 still fills in parallel
+        int workers = (int)std::thread::hardware_concurrency();
+        if (const char* v = getenv("HINGE_B200_IO_THREADS")) workers = atoi(v);
+        workers = std::max(1, std::min(workers, 32));
+        if (n < (1u << 16)) workers = 1;
+        std::vector<std::thread> pool;
+        auto fill = [&](size_t wi, size_t lo, size_t hi, int64_t tpos) {
+            const Walk& w = walks[wi];
+            for (size_t i = lo; i < hi; i++) {
+                const uint8_t* r = base + w.rec_off[i];
+                int32_t rec[9];
+                memcpy(rec, r, 36);
+                const size_t g = first[wi] + i;
+                diffs[g] = rec[1]; abpos[g] = rec[2]; bbpos[g] = rec[3]; aepos[g] = rec[4];
+                bepos[g] = rec[5]; flags[g] = rec[6]; aread[g] = rec[7]; bread[g] = rec[8];
+                trace_off[g] = tpos;
+                const size_t tb = (size_t)rec[0] * (size_t)tbytes;
+                if (want_trace) memcpy(trace.data() + tpos, r + kRec, tb);
+                tpos += (int64_t)tb;
+            }
+        };
+        if (walks.size() > 1 || workers == 1) {
+            for (size_t wi = 0; wi < walks.size(); wi++)
+                pool.emplace_back(fill, wi, (size_t)0, walks[wi].rec_off.size(), tfirst[wi]);
+        } else {
+            // one walk, many workers: slice it; every slice needs its trace offset first
+            const Walk& w = walks[0];
+            const size_t per = (n + workers - 1) / workers;
+            std::vector<int64_t> tpos((size_t)workers + 1, 0);
+            for (int k = 0; k < workers; k++) {
+                int64_t tb = 0;
+                for (size_t i = std::min(n, per * k); i < std::min(n, per * (k + 1)); i++) {
+                    int32_t tlen;
+                    memcpy(&tlen, base + w.rec_off[i], 4);
+                    tb += (int64_t)tlen * tbytes;
+                }
+                tpos[k + 1] = tpos[k] + tb;
+            }
+            for (int k = 0; k < workers; k++)
+                pool.emplace_back(fill, (size_t)0, std::min(n, per * k), std::min(n, per * (k + 1)), tpos[k]);
         }
+        for (auto& th : pool) th.join();
     }
+    trace_off[n] = trace_total;
+    lap("gather to columns");
     munmap((void*)base, fsize);
+    lap("munmap");
     return 0;
 }
 
@@ -405,6 +602,11 @@ void TextOut::close() {
 void TextOut::put_char(char c) {
     if (len_ + 1 > buf_.size()) flush();
     buf_[len_++] = c;
+}
+
+void TextOut::put_bytes(const char* s, size_t n) {
+    flush();
+    if (fp_ && n) fwrite(s, 1, n, (FILE*)fp_);
 }
 
 void TextOut::put_str(const char* s) {

@@ -7,6 +7,7 @@
 #ifndef HG_IO_H
 #define HG_IO_H
 #include <stdint.h>
+#include <stdlib.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -30,15 +31,40 @@ struct ReadDB {
     int open(const std::string& db_name);
 };
 
+// Column buffer without value-initialisation (a std::vector would zero 28 B per record first,
+// single-threaded, before the ingest overwrites them).
+template <class T>
+struct RawColumn {
+    T* p = nullptr;
+    size_t n = 0;
+    RawColumn() {}
+    RawColumn(const RawColumn&) = delete;
+    RawColumn& operator=(const RawColumn&) = delete;
+    ~RawColumn() { free(p); }
+    void resize(size_t count) {  // contents undefined
+        free(p);
+        p = static_cast<T*>(malloc((count ? count : 1) * sizeof(T)));
+        n = count;
+    }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    size_t size() const { return n; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+    const T& front() const { return p[0]; }
+    const T& back() const { return p[n - 1]; }
+};
+
 // A whole .las file as a struct of arrays (the layout the kernels consume).
 struct LasFile {
     int64_t novl = 0;
     int32_t tspace = 0;
     int32_t tbytes = 1;  // 1 if tspace <= 125 (align.h:58 TRACE_XOVR), else 2
-    std::vector<int32_t> aread, bread, abpos, aepos, bbpos, bepos, diffs, flags;
-    std::vector<int64_t> trace_off;  // novl + 1 byte offsets into trace
-    std::vector<uint8_t> trace;      // raw trace bytes, (diff, bdelta) pairs
+    RawColumn<int32_t> aread, bread, abpos, aepos, bbpos, bepos, diffs, flags;
+    RawColumn<int64_t> trace_off;  // novl + 1 byte offsets into trace
+    RawColumn<uint8_t> trace;      // raw trace bytes, (diff, bdelta) pairs
     std::string error;
+    int threads_used = 1;          // how the record walk went: > 1 = chunked, verified
 
     // Mirrors LAInterface::openAlignmentFile + getOverlap(0, n_read)
     // (/root/reference/src/lib/LAInterface.cpp:595-621,1519-1634).
@@ -77,6 +103,7 @@ public:
     void put_int(long v);
     void put_char(char c);
     void put_str(const char* s);
+    void put_bytes(const char* s, size_t n);  // flushes, then writes straight through
     void close();
 
 private:
