@@ -88,6 +88,10 @@ VARIANTS = [
     {"min_cov": "40", "ec": "90"},
     {"theta": "100", "theta2": "50", "aln_threshold": "2500", "length_threshold": "4000",
      "hinge_tolerance": "250", "matching_hinge_slack": "400", "min_connected_component_size": "2"},
+    {"cut_off": "0"},
+    {"cut_off": "-1", "min_cov": "2"},
+    {"cut_off": "130"},
+    {"ec": "-30", "min_cov": "-5"},  # MIN_COV < 0: covered runs are not closed by read ends any more
     {"no_hinge_region": "900", "hinge_min_support": "4", "hinge_unbridged": "3", "hinge_min_pileup": "4",
      "hinge_tolerance_length": "150", "repeat_annotation_gap_threshold": "800",
      "min_repeat_annotation_threshold": "6", "max_repeat_annotation_threshold": "9", "use_two_matches": "0"},
@@ -157,3 +161,22 @@ def test_long_read_and_overlaps_inside_one_bin(built, tmp_path):
         recs.append((r, 20, pos, pos + 17, 1000, 1017, 0))
     hm.write_fixture(str(tmp_path), "L", rlen, recs, tspace=100, qv="good")
     _run_filter(str(tmp_path), "L")
+
+
+def test_many_tiny_reads_per_batch(built, tmp_path):
+    """Hundreds of very short reads: batches of the flat kernels close on the read-count limit,
+    not on the bin limit; no read reaches the 5000 bp the coverage estimate wants."""
+    rng = np.random.default_rng(8)
+    n = 1500
+    rlen = [int(x) for x in rng.integers(60, 140, n)]
+    recs = []
+    for i in range(n - 1):
+        for d in (1, 2, 3):
+            j = i + d
+            if j < n:
+                ln = min(rlen[i], rlen[j]) - int(rng.integers(5, 20))
+                recs += hm.both_directions(i, j, rlen[i] - ln, rlen[i], 0, ln, 0, rlen)
+    hm.write_fixture(str(tmp_path), "T", rlen, recs, tspace=100, qv=None)
+    ini = os.path.join(str(tmp_path), "tiny.ini")
+    write_ini(ini, {"cut_off": "0", "length_threshold": "50", "aln_threshold": "30", "theta": "10"})
+    _run_filter(str(tmp_path), "T", ini=ini)
