@@ -114,7 +114,7 @@ void hg_ctx_destroy(hg_ctx* c) {
         if (c->marks[i]) cudaEventDestroy(c->marks[i]);
     if (!c->ext_med_hist) cudaFree(s.med_hist);
     cudaFree(s.scal); cudaFree(s.cmask); cudaFree(s.rflags);
-    cudaFree(s.anno_ref); cudaFree(s.anno_pool); cudaFree(s.counters); cudaFree(s.work_list);
+    cudaFree(s.anno_ref); cudaFree(s.anno_pool); cudaFree(s.counters); cudaFree(s.work_items);
     cudaFree(s.big_list); cudaFree(s.exact_list); cudaFree(s.big_scratch); cudaFree(s.hinge_keep); cudaFree(s.hinge_scratch);
     cudaFree(s.item_log); cudaFree(s.flat_batch); cudaFree(s.flat_rbase);
     cudaFree(c->d_cov0); cudaFree(c->d_cov0_off);
@@ -195,7 +195,7 @@ int hg_set_reads(hg_ctx* c, int32_t n_read, const int32_t* rlen, const int64_t* 
     HG_TRY(dev_alloc(c, &s.cmask, n_read, "cmask"));
     HG_TRY(dev_alloc(c, &s.rflags, n_read, "rflags"));
     HG_TRY(dev_alloc(c, &s.anno_ref, n_read, "anno_ref"));
-    HG_TRY(dev_alloc(c, &s.work_list, n_read, "work_list"));
+    HG_TRY(dev_alloc(c, &s.work_items, 3 * (size_t)n_read, "work items"));
     HG_TRY(dev_alloc(c, &s.big_list, n_read, "big_list"));
     HG_TRY(dev_alloc(c, &s.exact_list, n_read, "exact_list"));
     HG_TRY(dev_alloc(c, &c->d_read_off, (size_t)n_read + 1, "read_off"));

@@ -112,11 +112,25 @@ struct MaskAnnoOut {
     uint8_t* hinge_keep;  // per pooled annotation: is a hinge (cleared here, set by K4)
     int anno_cap;
     int* counters;     // [0] pool used  [1] work-list length  [2] overflow flag  [3] big-list length
-    int* work_list;    // reads that need hinge calling
+    int4* work_items;  // reads that need hinge calling: 3 x int4 each, see push_work_item
     int* big_list;     // reads whose profile does not fit the shared-memory path
     int* cov0;         // optional dump of the cut-off-free profile (coverage.txt)
     const int64_t* cov0_off;
 };
+
+// K4 is a chain of dependent loads per read; everything it needs to get going travels in the
+// work item itself (one 48-byte read instead of read id -> offsets / mask / annotation ref ->
+// annotations): (read, pile-up size, first record lo, hi) (mask.x, mask.y, first annotation,
+// annotations) (pos0, type0, pos1, type1: the first two annotations, most reads have no more)
+__device__ __forceinline__ void push_work_item(const MaskAnnoOut& out, int read, int64_t o0, int np, int2 mk,
+                                               int off, int kept) {
+    const int slot = atomicAdd(&out.counters[1], 1);
+    const int2 a0 = out.anno_pool[off], a1 = kept > 1 ? out.anno_pool[off + 1] : make_int2(0, 0);
+    int4* it = out.work_items + 3 * (size_t)slot;
+    it[0] = make_int4(read, np, (int)(o0 & 0xffffffffll), (int)(o0 >> 32));
+    it[1] = make_int4(mk.x, mk.y, off, kept);
+    it[2] = make_int4(a0.x, a0.y, a1.x, a1.y);
+}
 
 // Histogram words one read needs: every event bin of both profiles (cut-off of either
 // sign) plus two trailing empty bins.

@@ -435,12 +435,14 @@ __device__ void mask_anno_read(const RecView& rv, const ReadView& rd, const hg_f
             out.anno_pool[off + k] = make_int2((int)(w >> 2), (int)(w & 3u) - 1);
             out.hinge_keep[off + k] = 0;
         }
+    __syncwarp();  // lane 0 reads the first two annotations back for the work item
     if (lane == 0) {
         out.mask[read] = mk;
         out.cmask[read] = make_int2(msc, mec);
         out.rflags[read] = flags | (skip_hinges ? kFlagSkipHinge : 0);
         out.anno_ref[read] = make_int2(off, kept);
-        if (kept > 0 && !skip_hinges && off >= 0) out.work_list[atomicAdd(&out.counters[1], 1)] = read;
+        if (kept > 0 && !skip_hinges && off >= 0)
+            push_work_item(out, read, o0, (int)min((int64_t)0x7fffffff, o1 - o0), mk, off, kept);
     }
     __syncwarp();
 }
@@ -638,7 +640,7 @@ constexpr int kHingeSmemEnds = 192;
 __global__ void __launch_bounds__(128, 8)
 k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict__ mask,
              const int2* __restrict__ anno_ref, const int2* __restrict__ anno_pool,
-             int* __restrict__ counters, const int* __restrict__ work_list, int* __restrict__ exact_list,
+             int* __restrict__ counters, const int4* __restrict__ work_items, int* __restrict__ exact_list,
              uint8_t* __restrict__ hinge_keep, uint8_t* scratch, int cap, int4* __restrict__ item_log) {
     const int lane = lane_id();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -667,13 +669,16 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
         if (w >= nwork) break;
         const long long t_begin = item_log ? clock64() : 0;
         int log_support = 0, log_exact = 0;
-        const int read = work_list[w];
-        const int64_t o0 = rv.read_off[read], o1 = rv.read_off[read + 1];
-        const int2 mk = mask[read];
-        const int2 ar = anno_ref[read];
+        const int4 it0 = __ldg(work_items + 3 * (size_t)w), it1 = __ldg(work_items + 3 * (size_t)w + 1);
+        const int4 it2 = __ldg(work_items + 3 * (size_t)w + 2);
+        const int read = it0.x;
+        const int64_t o0 = (int64_t)(((unsigned long long)(unsigned)it0.w << 32) | (unsigned)it0.z);
+        const int64_t o1 = o0 + it0.y;
+        const int2 mk = make_int2(it1.x, it1.y);
+        const int2 ar = make_int2(it1.z, it1.w);
         bool deferred = false;
         for (int j = 0; j < ar.y; j++) {
-            const int2 an = anno_pool[ar.x + j];
+            const int2 an = j == 0 ? make_int2(it2.x, it2.y) : (j == 1 ? make_int2(it2.z, it2.w) : anno_pool[ar.x + j]);
             const int apos = an.x;
             const bool out_hinge = an.y == -1;
             // ---- select in file order, two steps: (1) the test on A's coordinates alone
@@ -973,7 +978,7 @@ void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_par
     MaskAnnoOut out;
     out.mask = s.mask; out.cmask = s.cmask; out.rflags = s.rflags; out.anno_ref = s.anno_ref;
     out.anno_pool = s.anno_pool; out.hinge_keep = s.hinge_keep; out.anno_cap = s.anno_cap; out.counters = s.counters;
-    out.work_list = s.work_list; out.big_list = s.big_list; out.cov0 = cov0; out.cov0_off = cov0_off;
+    out.work_items = s.work_items; out.big_list = s.big_list; out.cov0 = cov0; out.cov0_off = cov0_off;
     // no clearing here: every read of the planned range gets its results written (flat or generic
     // path), the rest was cleared when the plan was made; the counters are zeroed by launch_profile
     launch_mask_anno_flat(rv, rd, P, r_begin, r_end, s, out, st);
@@ -994,7 +999,7 @@ void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_pa
     if (s.hinge_cap <= 0) return;
     g_launches += 2;
     k_hinge_call<<<s.hinge_warps / 4, 128, 0, st>>>(rv, rd, P, s.mask, s.anno_ref, s.anno_pool,
-                                                    s.counters, s.work_list, s.exact_list, s.hinge_keep,
+                                                    s.counters, s.work_items, s.exact_list, s.hinge_keep,
                                                     s.hinge_scratch, s.hinge_cap, s.item_log);
     // the few reads that need the exact sort order: shared-memory scratch, one warp each
     constexpr int scap = 1536;

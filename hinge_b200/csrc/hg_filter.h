@@ -38,7 +38,7 @@ struct FilterScratch {
     int2* anno_pool = nullptr;
     int anno_cap = 0;
     int* counters = nullptr;   // 8
-    int* work_list = nullptr;  // n_read
+    int4* work_items = nullptr;  // 3 x n_read: K4 work items (push_work_item)
     int* big_list = nullptr;   // n_read
     int* exact_list = nullptr; // n_read: reads whose hinge calls need the exact sort order
     int2* flat_batch = nullptr;       // (first read, histogram words in use) per batch (flat_nbatch + 1)

@@ -552,7 +552,8 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
         out.cmask[read] = make_int2(msc, mec);
         out.rflags[read] = flags | (skip_hinges ? kFlagSkipHinge : 0);
         out.anno_ref[read] = make_int2(off, kept);
-        if (kept > 0 && !skip_hinges && off >= 0) out.work_list[atomicAdd(&out.counters[1], 1)] = read;
+        if (kept > 0 && !skip_hinges && off >= 0)
+            push_work_item(out, read, rv.read_off[read], (int)nrec, mk, off, kept);
     }
 
     // ---- optional dump of the cut-off-free profiles for .coverage.txt (filter.cpp:599-602)
