@@ -10,7 +10,7 @@ from ._lib import (EdgeC, FilterParamsC, FilterSummaryC, HingeError, LayoutParam
 
 HG_MEM_HOST, HG_MEM_DEVICE = 0, 1
 HG_OPT_KEEP_COVERAGE, HG_OPT_PROFILE, HG_OPT_SCATTER_SPREAD = 1, 2, 3
-HG_BUF_MEAN_COV, HG_BUF_MASK, HG_BUF_READ_FLAGS, HG_BUF_MEDIAN_HIST = 1, 2, 3, 4
+HG_BUF_MEAN_COV, HG_BUF_MASK, HG_BUF_READ_FLAGS, HG_BUF_MEDIAN_HIST, HG_BUF_MASK_PACKED = 1, 2, 3, 4, 5
 HG_RETRY_POOL = 1
 
 

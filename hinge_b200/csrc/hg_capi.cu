@@ -527,6 +527,20 @@ int hg_bind_buffer(hg_ctx* c, int which, void* dptr, int64_t bytes) {
         c->ext_med_hist = true;
         return cuda_check(c, cudaMemset(dptr, 0, 4 * 4098), "median histogram");
     }
+    if (which == HG_BUF_MASK_PACKED && bytes >= 4ll * c->n_read) {
+        // every mask bound is a multiple of gcd(40, tspace): coverage bins and QV tiles
+        int g = kReso, t = c->tspace > 0 ? c->tspace : kReso;
+        while (t) {
+            const int r = g % t;
+            g = t;
+            t = r;
+        }
+        if (c->max_rlen / g >= 65536)
+            return set_err(c, HG_ERR_ARG, "HG_BUF_MASK_PACKED: reads too long for 16-bit mask bounds; bind HG_BUF_MASK");
+        c->fs.mask_pk = (uint32_t*)dptr;
+        c->fs.mask_g = g;
+        return cuda_check(c, cudaMemset(dptr, 0, 4ull * c->n_read), "packed masks");
+    }
     if (which == HG_BUF_MASK && bytes >= 8ll * c->n_read) {
         if (!c->ext_mask) cudaFree(c->fs.mask);
         c->fs.mask = (int2*)dptr;

@@ -103,8 +103,25 @@ struct Packed<unsigned long long> {
     static __device__ __forceinline__ void add(W* p, W v) { atomicAdd(p, v); }
 };
 
+// The masks of all reads as K4 sees them.  Sharded runs exchange them between phase 2 and
+// phase 3; every mask bound is a multiple of g = gcd(40, tspace) (40-bp coverage bins, tspace-bp
+// QV tiles), so when the longest read has fewer than 65536 such units both bounds travel in
+// one 32-bit word (4 B per read on the wire instead of 8).
+struct MaskView {
+    const int2* full;
+    const uint32_t* packed;  // nullptr = use `full`
+    int g;
+    __device__ __forceinline__ int2 get(int b) const {
+        if (!packed) return full[b];
+        const uint32_t w = __ldg(packed + b);
+        return make_int2((int)(w & 0xffffu) * g, (int)(w >> 16) * g);
+    }
+};
+
 struct MaskAnnoOut {
     int2* mask;        // .mas
+    uint32_t* mask_pk; // optional packed copy (MaskView), unit mask_g
+    int mask_g;
     int2* cmask;       // .cmas (bin coordinates)
     uint8_t* rflags;   // kFlag*
     int2* anno_ref;    // (offset into pool, count) per read
@@ -117,6 +134,11 @@ struct MaskAnnoOut {
     int* cov0;         // optional dump of the cut-off-free profile (coverage.txt)
     const int64_t* cov0_off;
 };
+
+__device__ __forceinline__ void store_mask(const MaskAnnoOut& out, int read, int2 mk) {
+    out.mask[read] = mk;
+    if (out.mask_pk) out.mask_pk[read] = (uint32_t)(mk.x / out.mask_g) | ((uint32_t)(mk.y / out.mask_g) << 16);
+}
 
 // K4 is a chain of dependent loads per read; everything it needs to get going travels in the
 // work item itself (one 48-byte read instead of read id -> offsets / mask / annotation ref ->

@@ -437,7 +437,7 @@ __device__ void mask_anno_read(const RecView& rv, const ReadView& rd, const hg_f
         }
     __syncwarp();  // lane 0 reads the first two annotations back for the work item
     if (lane == 0) {
-        out.mask[read] = mk;
+        store_mask(out, read, mk);
         out.cmask[read] = make_int2(msc, mec);
         out.rflags[read] = flags | (skip_hinges ? kFlagSkipHinge : 0);
         out.anno_ref[read] = make_int2(off, kept);
@@ -487,7 +487,7 @@ struct PileRec {
     bool active;
 };
 __device__ __forceinline__ PileRec load_pile_rec(const RecView& rv, const ReadView& rd,
-                                                 const int2* __restrict__ mask, int read, int64_t k) {
+                                                 const MaskView& mask, int read, int64_t k) {
     PileRec r;
     const int b = __ldg(rv.bread + k);
     r.active = b != read;  // A == B records are inactive (filter.cpp:538-547)
@@ -501,7 +501,7 @@ __device__ __forceinline__ PileRec load_pile_rec(const RecView& rv, const ReadVi
         be = bl - bs;
         bs = t;
     }
-    const int2 mb = mask[b];
+    const int2 mb = mask.get(b);
     const int r0 = max(mb.y - be, 0), l0 = max(bs - mb.x, 0);
     r.ro = comp ? l0 : r0;
     r.lo = comp ? r0 : l0;
@@ -638,7 +638,7 @@ constexpr int kHingeSlotBytesPerRec = 16 + 8 + 8 + 8 + 8 + 8;
 constexpr int kHingeSmemEnds = 192;
 
 __global__ void __launch_bounds__(128, 8)
-k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict__ mask,
+k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
              const int2* __restrict__ anno_ref, const int2* __restrict__ anno_pool,
              int* __restrict__ counters, const int4* __restrict__ work_items, int* __restrict__ exact_list,
              uint8_t* __restrict__ hinge_keep, uint8_t* scratch, int cap, int4* __restrict__ item_log) {
@@ -830,7 +830,7 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict
 constexpr int kHingeExactBytesPerRec = 16 + 8 + 8 + 8 + 8;
 
 __global__ void __launch_bounds__(32)
-k_hinge_exact(RecView rv, ReadView rd, hg_filter_params P, const int2* __restrict__ mask,
+k_hinge_exact(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
               const int2* __restrict__ anno_ref, const int2* __restrict__ anno_pool,
               int* __restrict__ counters, const int* __restrict__ exact_list,
               uint8_t* __restrict__ hinge_keep, uint8_t* gscratch, int gcap, int scap) {
@@ -854,7 +854,7 @@ k_hinge_exact(RecView rv, ReadView rd, hg_filter_params P, const int2* __restric
         int2* ends = reinterpret_cast<int2*>(base + (size_t)cap * 24);
         int2* tmp = reinterpret_cast<int2*>(base + (size_t)cap * 32);
         int* gl = reinterpret_cast<int*>(base + (size_t)cap * 40);
-        const int2 mk = mask[read];
+        const int2 mk = mask.full[read];  // the read's own mask: always in the local array
         const int2 ar = anno_ref[read];
 
         // pile-up in file order (A == B records are inactive, filter.cpp:538-547), then std::sort
@@ -976,7 +976,7 @@ void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_par
                       int r_begin, int r_end, FilterScratch& s, int* cov0, const int64_t* cov0_off,
                       cudaStream_t st) {
     MaskAnnoOut out;
-    out.mask = s.mask; out.cmask = s.cmask; out.rflags = s.rflags; out.anno_ref = s.anno_ref;
+    out.mask = s.mask; out.mask_pk = s.mask_pk; out.mask_g = s.mask_g; out.cmask = s.cmask; out.rflags = s.rflags; out.anno_ref = s.anno_ref;
     out.anno_pool = s.anno_pool; out.hinge_keep = s.hinge_keep; out.anno_cap = s.anno_cap; out.counters = s.counters;
     out.work_items = s.work_items; out.big_list = s.big_list; out.cov0 = cov0; out.cov0_off = cov0_off;
     // no clearing here: every read of the planned range gets its results written (flat or generic
@@ -998,7 +998,11 @@ void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_pa
                        FilterScratch& s, cudaStream_t st) {
     if (s.hinge_cap <= 0) return;
     g_launches += 2;
-    k_hinge_call<<<s.hinge_warps / 4, 128, 0, st>>>(rv, rd, P, s.mask, s.anno_ref, s.anno_pool,
+    MaskView mv;
+    mv.full = s.mask;
+    mv.packed = s.mask_pk;
+    mv.g = s.mask_g;
+    k_hinge_call<<<s.hinge_warps / 4, 128, 0, st>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool,
                                                     s.counters, s.work_items, s.exact_list, s.hinge_keep,
                                                     s.hinge_scratch, s.hinge_cap, s.item_log);
     // the few reads that need the exact sort order: shared-memory scratch, one warp each
@@ -1010,7 +1014,7 @@ void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_pa
         attr_set = true;
     }
     const int grid = s.hinge_warps < 2 * s.num_sms ? s.hinge_warps : 2 * s.num_sms;
-    k_hinge_exact<<<grid, 32, smem, st>>>(rv, rd, P, s.mask, s.anno_ref, s.anno_pool, s.counters,
+    k_hinge_exact<<<grid, 32, smem, st>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters,
                                           s.exact_list, s.hinge_keep, s.hinge_scratch, s.hinge_cap, scap);
 }
 

@@ -32,6 +32,8 @@ struct FilterScratch {
     int* scal = nullptr;                    // 8: cov_est, MIN_COV, radix state
     // K2
     int2* mask = nullptr;      // n_read
+    uint32_t* mask_pk = nullptr;  // n_read, caller-owned (HG_BUF_MASK_PACKED): both bounds in units of mask_g
+    int mask_g = 1;
     int2* cmask = nullptr;     // n_read
     uint8_t* rflags = nullptr; // n_read
     int2* anno_ref = nullptr;  // n_read

@@ -548,7 +548,7 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
             skip_hinges = fabsf(__fsub_rn(avg_end, avg_start)) < 10.0f;
         }
 
-        out.mask[read] = mk;
+        store_mask(out, read, mk);
         out.cmask[read] = make_int2(msc, mec);
         out.rflags[read] = flags | (skip_hinges ? kFlagSkipHinge : 0);
         out.anno_ref[read] = make_int2(off, kept);

@@ -8,7 +8,9 @@ shard by A-read id.  Two per-read arrays cross shards inside `hinge filter`:
     (filter.cpp:642-678).  The median is found by counting, so the ranks only sum
     their 4096-bin histograms of it                         -> all-reduce, 16 KB
   * the mask of every B read a pile-up touches
-    (filter.cpp:884-889)                                    -> all-gather, 8 B/read
+    (filter.cpp:884-889)                                    -> all-gather, 4 B/read
+    (both bounds are multiples of gcd(40, tspace) and travel as 16-bit units; 8 B/read
+    when a read is too long for that)
 
 Both live in padded torch tensors bound into the context (hg_bind_buffer), so
 `torch.distributed.all_gather_into_tensor` moves them over NCCL/NVLink in place.
@@ -39,14 +41,22 @@ class ShardedArrays:
         self.mean_cov = torch.full((world * self.chunk,), -1, dtype=torch.int32, device=device)
         self.mask = torch.zeros((world * self.chunk, 2), dtype=torch.int32, device=device)
         self.hist = torch.zeros((4098,), dtype=torch.int32, device=device)  # HG_BUF_MEDIAN_HIST
+        self.mask_pk = torch.zeros((world * self.chunk,), dtype=torch.int32, device=device)
+        self.packed = False
 
     def bind(self, ctx):
         """Makes the context compute straight into the exchanged arrays."""
         from . import api
 
-        ctx.bind_buffer(api.HG_BUF_MASK, self.mask)
         if self.world > 1:
             ctx.bind_buffer(api.HG_BUF_MEDIAN_HIST, self.hist)
+            try:
+                ctx.bind_buffer(api.HG_BUF_MASK_PACKED, self.mask_pk)
+                self.packed = True
+            except Exception:  # a read too long for 16-bit bounds: exchange the full masks
+                self.packed = False
+        if not self.packed:
+            ctx.bind_buffer(api.HG_BUF_MASK, self.mask)
 
     def exchange(self, t):
         """All-gather the rank's own slice of `t` into every rank's copy of `t`."""
@@ -62,5 +72,5 @@ def run_filter_sharded(ctx, params, arrays):
     if arrays.world > 1:
         dist.all_reduce(arrays.hist)  # the context was bound to arrays.hist (HG_BUF_MEDIAN_HIST)
     ctx.filter_phase2()
-    arrays.exchange(arrays.mask)
+    arrays.exchange(arrays.mask_pk if arrays.packed else arrays.mask)
     return ctx.filter_phase3()

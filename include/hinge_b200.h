@@ -50,6 +50,10 @@ enum hg_buffer { /* per-read device arrays a sharded run exchanges between phase
     HG_BUF_MEAN_COV = 1,  /* int32[n_read], -1 = not part of the estimate      */
     HG_BUF_MASK = 2,      /* int32[n_read][2], the .mas intervals               */
     HG_BUF_READ_FLAGS = 3,/* uint8[n_read]                                       */
+    HG_BUF_MASK_PACKED = 5, /* uint32[n_read]: both mask bounds in units of gcd(40, tspace), 16 bits each; when
+                              bound, phase 2 fills it next to the masks and phase 3 looks B-reads up in it, so a
+                              sharded run all-gathers 4 B per read instead of HG_BUF_MASK's 8 (refused with
+                              HG_ERR_ARG when a read is too long for 16 bits: bind HG_BUF_MASK then) */
     HG_BUF_MEDIAN_HIST = 4 /* uint32[4098]: histogram of the per-read mean coverage; when bound,
                               phase 1 adds the rank's own reads and the caller sums it across
                               ranks (all-reduce) instead of all-gathering HG_BUF_MEAN_COV */

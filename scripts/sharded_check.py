@@ -41,7 +41,14 @@ if rank == 0:
     ref.set_overlaps(novl_all, {k: v.copy() for k, v in syn.cols().items()})
     s1 = ref.filter(api.FilterParams())
     want = ref.filter_fetch(int(s1.n_annotations))
-    got_mask = arrays.mask[:syn.n_read].cpu().numpy()
+    if arrays.packed:  # both bounds in units of gcd(40, tspace), 16 bits each
+        import math
+
+        pk = arrays.mask_pk[:syn.n_read].cpu().numpy().view(np.uint32)
+        g = math.gcd(40, 100)
+        got_mask = np.stack([(pk & 0xffff).astype(np.int32) * g, (pk >> 16).astype(np.int32) * g], axis=1)
+    else:
+        got_mask = arrays.mask[:syn.n_read].cpu().numpy()
     ok &= bool(np.array_equal(got_mask, want["mask"]))
     for p in parts:
         lo, hi = p["lo"], p["hi"]
