@@ -4,7 +4,7 @@
   python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU stage)
 
-A *step* is one pass of the `hinge filter` stage (coverage estimate, masks,
+A *step* is one pass of the `hinge filter` stage (coverage profiles + estimate, masks,
 repeat annotation, hinge calls) over one batch of synthetic overlap records:
 
   value     overlaps/s with the struct-of-arrays already resident in HBM,
@@ -16,11 +16,14 @@ repeat annotation, hinge calls) over one batch of synthetic overlap records:
             against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline  the unmodified reference `Reads_filter` (oracle/_ref) timed on
             a bounded sample of the same workload on this box's host cores
+  cli_filter    (informational) the product's own `hinge filter` executable on
+            that same sample, file to file, with its phase breakdown
 
 Workload = BASELINE.json configs[2]: synthetic 50 Mb genome, 50x, reads
 N(3500,1500) >= 1000 bp, ~52 M overlaps per GPU (weak scaling: the genome grows
-with the number of GPUs; reads shard by A-read id; per-read coverage means and
-masks are all-gathered over NCCL between the phases of the stage).
+with the number of GPUs; reads shard by A-read id; a 16 KB coverage histogram is
+all-reduced and the masks, 4 B per read, are all-gathered over NCCL between the
+phases of the stage).
 """
 import argparse
 import ctypes
@@ -276,6 +279,12 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         sys.exit("bench.py: no CUDA device; the product path has no CPU fallback")
+    # CPU baseline + the file-to-file run of the product's own executable on the same sample: first,
+    # while this process holds no CUDA context yet (a second context on a busy GPU takes seconds to
+    # create and would be charged to the executable)
+    base = None
+    if world == 1 and not args.no_cpu_baseline:
+        base, _ = time_reference_filter(args, 1, 0, with_cli=True)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -421,8 +430,7 @@ def main():
                     "ms_per_step": 1e3 * e2e_s},
             "gpu_launches": int(launches), "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            base, _ = time_reference_filter(args, 1, 0, with_cli=True)
+        if base is not None:
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
             # informational: the same sample, file to file, through the product's `hinge filter` executable
             line["cli_filter"] = base["cli"]
