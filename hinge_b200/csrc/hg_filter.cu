@@ -12,6 +12,7 @@
 //   K4 hinge_call      one warp per annotated read: order-exact pile-up sort and
 //                      bridged / unbridged walk                (filter.cpp:867-1066)
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "hg_device.cuh"
 #include "hg_filter.h"
@@ -821,7 +822,7 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
     }
 }
 
-// Reads whose annotations need the reference's exact sort order (see k_hinge_call): one warp
+// Reads whose annotations need the reference's exact sort order (see k_hinge_call): one CTA
 // per read, the reference's own sequence for every annotation of the read -- pile-up in file
 // order, std::sort by total length (filter.cpp:565-567), selection in that order, std::sort of the
 // end list by position (filter.cpp:914 / 1010), walk -- with libstdc++'s introsort restated in
@@ -829,19 +830,23 @@ k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
 // (48 B per pile-up record); deeper pile-ups than `scap` fall back to a global slot.
 constexpr int kHingeExactBytesPerRec = 16 + 8 + 8 + 8 + 8;
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 k_hinge_exact(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
               const int2* __restrict__ anno_ref, const int2* __restrict__ anno_pool,
               int* __restrict__ counters, const int* __restrict__ exact_list,
               uint8_t* __restrict__ hinge_keep, uint8_t* gscratch, int gcap, int scap) {
     extern __shared__ __align__(16) uint8_t sm_exact[];
-    const int lane = lane_id();
+    __shared__ CtaSortState sort_state;
+    __shared__ int sh_w, sh_n;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
     const int nlist = counters[6];
     const int THETA = P.theta, HTL = P.hinge_tolerance_length;
     for (;;) {
-        int w = 0;
-        if (lane == 0) w = atomicAdd(&counters[7], 1);
-        w = __shfl_sync(0xffffffffu, w, 0);
+        if (threadIdx.x == 0) sh_w = atomicAdd(&counters[7], 1);
+        __syncthreads();
+        const int w = sh_w;
+        __syncthreads();
         if (w >= nlist) break;
         const int read = exact_list[w];
         const int64_t o0 = rv.read_off[read], o1 = rv.read_off[read + 1];
@@ -857,56 +862,80 @@ k_hinge_exact(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
         const int2 mk = mask.full[read];  // the read's own mask: always in the local array
         const int2 ar = anno_ref[read];
 
-        // pile-up in file order (A == B records are inactive, filter.cpp:538-547), then std::sort
-        int n = 0;
-        for (int kb = 0; kb < np; kb += 32) {
-            const int k = kb + lane;
-            PileRec r;
-            r.active = false;
-            if (k < np) r = load_pile_rec(rv, rd, mask, read, o0 + k);
-            const unsigned am = __ballot_sync(0xffffffffu, r.active);
-            if (r.active) {
-                const int s = n + __popc(am & ((1u << lane) - 1u));
-                rec[s] = make_int4(r.as, r.ae, r.lo, r.ro);
-                ord[s].key = r.key;
-                ord[s].idx = s;
-            }
-            n += __popc(am);
+        // pile-up in file order: all threads fetch (records, then the gathers of rlen[B] and mask[B]),
+        // one warp squeezes out the inactive A == B records (filter.cpp:538-547) in place
+        for (int k = threadIdx.x; k < np; k += blockDim.x) {
+            const PileRec r = load_pile_rec(rv, rd, mask, read, o0 + k);
+            rec[k] = make_int4(r.as, r.ae, r.lo, r.ro);
+            ord[k].key = r.key;
+            ord[k].idx = r.active ? 1 : 0;
         }
-        __syncwarp();
-        warp_sort_exact(ord, n, GreaterKey(), gl, gl + cap, reinterpret_cast<KeyIdx*>(tmp));
-        __syncwarp();
+        __syncthreads();
+        if (warp == 0) {
+            int n = 0;
+            for (int kb = 0; kb < np; kb += 32) {
+                const int k = kb + lane;
+                int4 q = make_int4(0, 0, 0, 0);
+                int key = 0;
+                bool active = false;
+                if (k < np) {
+                    q = rec[k];
+                    key = ord[k].key;
+                    active = ord[k].idx != 0;
+                }
+                const unsigned am = __ballot_sync(0xffffffffu, active);
+                if (active) {
+                    const int s = n + __popc(am & lt);
+                    rec[s] = q;
+                    ord[s].key = key;
+                    ord[s].idx = s;
+                }
+                n += __popc(am);
+                __syncwarp();
+            }
+            if (lane == 0) sh_n = n;
+        }
+        __syncthreads();
+        const int n = sh_n;
+        // std::sort by total length (filter.cpp:565-567), the warps on different sub-ranges
+        cta_sort_exact(ord, n, GreaterKey(), gl, gl + cap, reinterpret_cast<KeyIdx*>(tmp), &sort_state);
 
         for (int j = 0; j < ar.y; j++) {
             const int2 an = anno_pool[ar.x + j];
             const bool out_hinge = an.y == -1;
-            int support = 0;
-            for (int kb = 0; kb < n; kb += 32) {
-                const int k = kb + lane;
-                bool sel = false;
-                int2 e = make_int2(0, 0);
-                if (k < n) {
-                    const int4 q = rec[ord[k].idx];
-                    PileRec r;
-                    r.as = q.x; r.ae = q.y; r.lo = q.z; r.ro = q.w; r.key = 0; r.active = true;
-                    sel = hinge_select(r, out_hinge, an.x, THETA, HTL, &e);
+            if (warp == 0) {  // selection in pile-up order
+                int support = 0;
+                for (int kb = 0; kb < n; kb += 32) {
+                    const int k = kb + lane;
+                    bool sel = false;
+                    int2 e = make_int2(0, 0);
+                    if (k < n) {
+                        const int4 q = rec[ord[k].idx];
+                        PileRec r;
+                        r.as = q.x; r.ae = q.y; r.lo = q.z; r.ro = q.w; r.key = 0; r.active = true;
+                        sel = hinge_select(r, out_hinge, an.x, THETA, HTL, &e);
+                    }
+                    const unsigned sm = __ballot_sync(0xffffffffu, sel);
+                    if (sel) ends[support + __popc(sm & lt)] = e;
+                    support += __popc(sm);
                 }
-                const unsigned sm = __ballot_sync(0xffffffffu, sel);
-                if (sel) ends[support + __popc(sm & ((1u << lane) - 1u))] = e;
-                support += __popc(sm);
+                if (lane == 0) sh_n = support;
             }
-            __syncwarp();
+            __syncthreads();
+            const int support = sh_n;
             uint8_t keep = 0;
-            if (support >= P.hinge_min_support) {  // filter.cpp:910, 1005
-                if (out_hinge)
-                    warp_sort_exact(ends, support, FirstAsc(), gl, gl + cap, tmp);
+            if (support >= P.hinge_min_support) {  // filter.cpp:910, 1005 (uniform over the CTA)
+                if (out_hinge)  // filter.cpp:914 / 1010
+                    cta_sort_exact(ends, support, FirstAsc(), gl, gl + cap, tmp, &sort_state);
                 else
-                    warp_sort_exact(ends, support, FirstDesc(), gl, gl + cap, tmp);
-                keep = hinge_walk_warp(ends, support, out_hinge, mk, P) ? 1 : 0;
-                if (lane == 0) atomicAdd(&counters[4], 1);
+                    cta_sort_exact(ends, support, FirstDesc(), gl, gl + cap, tmp, &sort_state);
+                if (warp == 0) {
+                    keep = hinge_walk_warp(ends, support, out_hinge, mk, P) ? 1 : 0;
+                    if (lane == 0) atomicAdd(&counters[4], 1);
+                }
             }
-            if (lane == 0) hinge_keep[ar.x + j] = keep;
-            __syncwarp();
+            if (threadIdx.x == 0) hinge_keep[ar.x + j] = keep;
+            __syncthreads();
         }
     }
 }
@@ -924,8 +953,26 @@ __global__ void k_debug_warp_sort(KeyIdx* data, const int* off, int count, int d
                         g + o, l + o, tmp + o);
 }
 
+// The same test for cta_sort_exact: one CTA of 128 threads per array.
+__global__ void __launch_bounds__(128)
+k_debug_cta_sort(KeyIdx* data, const int* off, int count, int descending, int* g, int* l, KeyIdx* tmp) {
+    __shared__ CtaSortState st;
+    const int w = blockIdx.x;
+    if (w >= count) return;
+    const int o = off[w], n = off[w + 1] - o;
+    if (descending)
+        cta_sort_exact(data + o, n, GreaterKey(), g + o, l + o, tmp + o, &st);
+    else
+        cta_sort_exact(data + o, n, [] __device__(const KeyIdx& a, const KeyIdx& b) { return a.key < b.key; },
+                       g + o, l + o, tmp + o, &st);
+}
+
 void launch_debug_warp_sort(void* data, const int* off, int count, int descending, int* g, int* l, void* tmp,
                             cudaStream_t st) {
+    if (getenv("HINGE_B200_DEBUG_SORT_CTA")) {
+        k_debug_cta_sort<<<count, 128, 0, st>>>((KeyIdx*)data, off, count, descending, g, l, (KeyIdx*)tmp);
+        return;
+    }
     k_debug_warp_sort<<<(count * 32 + 127) / 128, 128, 0, st>>>((KeyIdx*)data, off, count, descending, g, l,
                                                                 (KeyIdx*)tmp);
 }
@@ -1014,7 +1061,7 @@ void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_pa
         attr_set = true;
     }
     const int grid = s.hinge_warps < 2 * s.num_sms ? s.hinge_warps : 2 * s.num_sms;
-    k_hinge_exact<<<grid, 32, smem, st>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters,
+    k_hinge_exact<<<grid, 128, smem, st>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters,
                                           s.exact_list, s.hinge_keep, s.hinge_scratch, s.hinge_cap, scap);
 }
 

@@ -277,6 +277,153 @@ __device__ void warp_sort_exact(T* a, int n, Less less, int* idx_g, int* idx_l, 
     for (int p = lane; p < n; p += 32) a[p] = tmp[p];
     __syncwarp();
 }
+
+// ------------------------------------------------- std::sort, one CTA, same result
+//
+// The introsort loop is a tree: after a partition the two parts are independent (disjoint
+// ranges commute, see std_sort_exact), so the warps of a CTA work on different sub-ranges at the
+// same time and the critical path shrinks from the ~n/8 partition steps of one warp to the
+// depth of the tree.  Ranges wait in a small shared-memory stack guarded by a spin lock that
+// only lane 0 of a warp ever touches.  All threads of the CTA call this with identical
+// arguments; idx_g / idx_l hold n ints each (a range uses its own [first, last) slice), tmp n
+// elements.
+struct CtaSortState {
+    int first[160], last[160], depth[160];
+    int top, busy, lock;
+};
+
+template <class T, class Less>
+__device__ void cta_sort_exact(T* a, int n, Less less, int* idx_g, int* idx_l, T* tmp, CtaSortState* st) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    if (n <= 1) return;  // uniform
+    if (threadIdx.x == 0) {
+        int lg = 0;
+        for (unsigned v = (unsigned)n; v > 1; v >>= 1) lg++;
+        st->first[0] = 0;
+        st->last[0] = n;
+        st->depth[0] = 2 * lg;
+        st->top = 1;
+        st->busy = 0;
+        st->lock = 0;
+    }
+    __syncthreads();
+    auto lock = [&]() {
+        while (atomicCAS(&st->lock, 0, 1) != 0) {
+        }
+        __threadfence_block();
+    };
+    auto unlock = [&]() {
+        __threadfence_block();
+        atomicExch(&st->lock, 0);
+    };
+    for (;;) {
+        int first = 0, last = 0, depth = 0, state = 0;  // state: 1 = got a range, 2 = all done
+        if (lane == 0) {
+            lock();
+            if (st->top > 0) {
+                const int s = --st->top;
+                first = st->first[s];
+                last = st->last[s];
+                depth = st->depth[s];
+                st->busy++;
+                state = 1;
+            } else if (st->busy == 0) {
+                state = 2;
+            }
+            unlock();
+        }
+        state = __shfl_sync(0xffffffffu, state, 0);
+        if (state == 2) break;
+        if (state == 0) {
+            __nanosleep(200);
+            continue;
+        }
+        first = __shfl_sync(0xffffffffu, first, 0);
+        last = __shfl_sync(0xffffffffu, last, 0);
+        depth = __shfl_sync(0xffffffffu, depth, 0);
+        while (last - first > 16) {
+            if (depth == 0) {
+                if (lane == 0) os_heap_sort(a, first, last, less);
+                __syncwarp();
+                break;
+            }
+            --depth;
+            if (lane == 0) {  // __move_median_to_first(first, first+1, mid, last-1)
+                const int mid = first + (last - first) / 2;
+                const int x = first + 1, y = mid, z = last - 1;
+                if (less(a[x], a[y])) {
+                    if (less(a[y], a[z])) os_swap(a, first, y);
+                    else if (less(a[x], a[z])) os_swap(a, first, z);
+                    else os_swap(a, first, x);
+                } else if (less(a[x], a[z])) {
+                    os_swap(a, first, x);
+                } else if (less(a[y], a[z])) {
+                    os_swap(a, first, z);
+                } else {
+                    os_swap(a, first, y);
+                }
+            }
+            __syncwarp();
+            const T pivot = a[first];
+            int* const pg = idx_g + first;  // at most last - first - 1 entries each
+            int* const pl = idx_l + first;
+            int ng = 0, nl = 0;
+            for (int base = first + 1; base < last; base += 32) {
+                const int p = base + lane;
+                bool ge = false, le = false;
+                if (p < last) {
+                    const T v = a[p];
+                    ge = !less(v, pivot);
+                    le = !less(pivot, v);
+                }
+                const unsigned mg = __ballot_sync(0xffffffffu, ge), ml = __ballot_sync(0xffffffffu, le);
+                if (ge) pg[ng + __popc(mg & lt)] = p;
+                if (le) pl[nl + __popc(ml & lt)] = p;
+                ng += __popc(mg);
+                nl += __popc(ml);
+            }
+            __syncwarp();
+            const int lim = ng < nl ? ng : nl;
+            int cnt = 0;
+            for (int i = lane; i < lim; i += 32) cnt += pg[i] < pl[nl - 1 - i] ? 1 : 0;
+            const int m = __reduce_add_sync(0xffffffffu, cnt);
+            for (int i = lane; i < m; i += 32) os_swap(a, pg[i], pl[nl - 1 - i]);
+            const int prev_hi = m > 0 ? pl[nl - m] : last;
+            const int cut = (m < ng && pg[m] < prev_hi) ? pg[m] : prev_hi;
+            __syncwarp();
+            if (last - cut > 16) {  // right part: for whoever is free (parts of <= 16 need nothing here)
+                if (lane == 0) {
+                    lock();
+                    const int s = st->top++;
+                    st->first[s] = cut;
+                    st->last[s] = last;
+                    st->depth[s] = depth;
+                    unlock();
+                }
+            }
+            last = cut;
+        }
+        if (lane == 0) {
+            lock();
+            st->busy--;
+            unlock();
+        }
+    }
+    __syncthreads();
+    // __final_insertion_sort as a windowed stable rank (see warp_sort_exact), all threads
+    for (int p = threadIdx.x; p < n; p += blockDim.x) {
+        const T v = a[p];
+        int np = p;
+        const int lo = p - 15 > 0 ? p - 15 : 0, hi = p + 15 < n - 1 ? p + 15 : n - 1;
+        for (int j = lo; j < p; j++) np -= less(v, a[j]) ? 1 : 0;
+        for (int j = p + 1; j <= hi; j++) np += less(a[j], v) ? 1 : 0;
+        tmp[np] = v;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < n; p += blockDim.x) a[p] = tmp[p];
+    __syncthreads();
+}
 #endif
 
 }  // namespace hg

@@ -2,6 +2,7 @@
 hinge call's order-exact path, against the real std::sort: element for element on tie-heavy arrays,
 sorted / reversed inputs and median-of-3 killer sequences (heap-sort fallback)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -46,13 +47,18 @@ def test_warp_sort_matches_std_sort(built):
     for w in range(len(arrays)):
         data[off[w]:off[w + 1], 1] = np.arange(off[w + 1] - off[w])
     ctx = Context(0)
-    for desc in (0, 1):
+    for cta, desc in ((0, 0), (0, 1), (1, 0), (1, 1)):  # one warp per array / one CTA per array
+        if cta:
+            os.environ["HINGE_B200_DEBUG_SORT_CTA"] = "1"
+        else:
+            os.environ.pop("HINGE_B200_DEBUG_SORT_CTA", None)
         want, got = data.copy(), data.copy()
         assert lib.hg_debug_std_sort(want.ctypes.data, off.ctypes.data, len(arrays), desc) == 0
         assert lib.hg_debug_warp_sort(ctx._h, got.ctypes.data, off.ctypes.data, len(arrays), desc) == 0
         bad = np.nonzero((want != got).any(axis=1))[0]
         if len(bad):
             w = int(np.searchsorted(off, bad[0], side="right") - 1)
-            raise AssertionError("array %d (n=%d, descending=%d) differs from std::sort at element %d"
-                                 % (w, off[w + 1] - off[w], desc, bad[0] - off[w]))
+            raise AssertionError("array %d (n=%d, descending=%d, cta=%d) differs from std::sort at element %d"
+                                 % (w, off[w + 1] - off[w], desc, cta, bad[0] - off[w]))
+    os.environ.pop("HINGE_B200_DEBUG_SORT_CTA", None)
     ctx.close()
