@@ -1,16 +1,16 @@
 // Kernels of the `hinge filter` stage (sm_100a, integer / index work, no tensor
 // cores).  Reference behaviour: /root/reference/src/filter/filter.cpp:529-1098.
 //
-//   K0 csr_validate    .las order + invariants, CSR offsets by A-read
+//   K0 csr_validate    .las order + invariants, CSR offsets by A-read, A == B records per read
 //   K0 qv_mask         longest good-QV run per read          (filter.cpp:340-369)
-//   K1 cov_accum       flat streaming pass: per-read sum / length of the
-//                      coverage profile without building it  (filter.cpp:588-656)
-//   K1 median_*        median of the per-read means -> MIN_COV (filter.cpp:660-678)
-//   K2 mask_anno       one warp per A-read: packed coverage histogram in shared
-//                      memory + warp scan -> coverage mask, repeat annotation,
-//                      hinge pre-test                          (filter.cpp:696-865)
-//   K4 hinge_call      one warp per annotated read: order-exact pile-up sort and
-//                      bridged / unbridged walk                (filter.cpp:867-1066)
+//   K1 / K2            coverage profiles, masks, annotation: hg_filter_flat.cu; here only
+//                      the generic per-read path for reads those kernels cannot take
+//                      (mask_anno_read, k_mask_anno_big)       (filter.cpp:588-865)
+//      median_*        median of the per-read means -> MIN_COV (filter.cpp:660-678)
+//   K4 hinge_call      one warp per annotated read: selection, rank sort, tie
+//                      detection, bridged / unbridged walk     (filter.cpp:867-1066)
+//      hinge_exact     one CTA per read whose result depends on the reference's
+//                      unstable sort order: introsort restated (hg_order.h)
 #include <stdio.h>
 #include <stdlib.h>
 

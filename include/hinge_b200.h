@@ -121,14 +121,16 @@ typedef struct hg_filter_summary {
 } hg_filter_summary;
 
 /* One call = the whole stage on the device, no host round trip in between:
- * coverage estimate -> masks -> repeat annotation -> hinge calls. */
+ * coverage profiles + estimate -> masks -> repeat annotation -> hinge calls. */
 int hg_filter(hg_ctx* ctx, const hg_filter_params* params, hg_filter_summary* out);
 
 /* The same stage split at its two global dependencies, for contexts that own
- * a slice of the reads: exchange (all-gather) the named device array between
- * the calls.  hg_filter == phase1; phase2; phase3 on one context. */
-int hg_filter_phase1(hg_ctx* ctx, const hg_filter_params* params); /* -> HG_BUF_MEAN_COV / HG_BUF_MEDIAN_HIST */
-int hg_filter_phase2(hg_ctx* ctx);                                 /* -> HG_BUF_MASK     */
+ * a slice of the reads: exchange the named device array between the calls
+ * (all-reduce HG_BUF_MEDIAN_HIST -- or all-gather HG_BUF_MEAN_COV --, then
+ * all-gather HG_BUF_MASK_PACKED -- or HG_BUF_MASK).  hg_filter == phase1; phase2;
+ * phase3 on one context. */
+int hg_filter_phase1(hg_ctx* ctx, const hg_filter_params* params); /* -> HG_BUF_MEDIAN_HIST / HG_BUF_MEAN_COV */
+int hg_filter_phase2(hg_ctx* ctx);                                 /* -> HG_BUF_MASK_PACKED / HG_BUF_MASK   */
 int hg_filter_phase3(hg_ctx* ctx, hg_filter_summary* out);         /* hinge calls        */
 
 /* Results of the last filter run, copied to caller-owned host arrays (any may
