@@ -38,11 +38,21 @@ def _worker(rank, world, port, n_read, q):
     arr.mean_cov[arr.lo:arr.hi] = ids * 3 + 1
     arr.mask[arr.lo:arr.hi, 0] = ids
     arr.mask[arr.lo:arr.hi, 1] = ids + 1000
+    # the two exchanges run_filter_sharded makes: histogram of the owned reads' mean coverage summed
+    # over the ranks, masks gathered as one packed word per read
+    arr.hist[:4096] += torch.bincount((ids % 4096).to(torch.int64), minlength=4096).to(torch.int32)
+    arr.hist[4096] += len(ids)
+    arr.mask_pk[arr.lo:arr.hi] = (ids // 20) | ((ids // 20 + 7) << 16)
     arr.exchange(arr.mean_cov)
     arr.exchange(arr.mask)
+    arr.exchange(arr.mask_pk)
+    dist.all_reduce(arr.hist)
     full = torch.arange(n_read, dtype=torch.int32)
+    want_hist = torch.bincount((full % 4096).to(torch.int64), minlength=4096).to(torch.int32)
     ok = bool(torch.equal(arr.mean_cov[:n_read], full * 3 + 1) and torch.equal(arr.mask[:n_read, 0], full)
-              and torch.equal(arr.mask[:n_read, 1], full + 1000))
+              and torch.equal(arr.mask[:n_read, 1], full + 1000)
+              and torch.equal(arr.mask_pk[:n_read], (full // 20) | ((full // 20 + 7) << 16))
+              and torch.equal(arr.hist[:4096], want_hist) and int(arr.hist[4096]) == n_read)
     q.put((rank, ok))
     dist.destroy_process_group()
 
