@@ -342,6 +342,9 @@ __device__ void cta_sort_exact(T* a, int n, Less less, int* idx_g, int* idx_l, T
         first = __shfl_sync(0xffffffffu, first, 0);
         last = __shfl_sync(0xffffffffu, last, 0);
         depth = __shfl_sync(0xffffffffu, depth, 0);
+        // the range was written by another warp before it pushed it: lane 0's lock acquire + fence
+        // orders those writes before lane 0, this orders them before the other 31 lanes
+        __syncwarp();
         while (last - first > 16) {
             if (depth == 0) {
                 if (lane == 0) os_heap_sort(a, first, last, less);
