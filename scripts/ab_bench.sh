@@ -1,5 +1,5 @@
 # Parity tests + bench (optionally for several scatter spreads) + ncu captures.  Run under gpurun.
-#   bash scripts/ab_k2.sh <tag> "<spread> ..." "<kernel> ..."
+#   bash scripts/ab_bench.sh <tag> "<spread> ..." "<kernel> ..."
 mkdir -p gpurun_out
 TAG=${1:-ab}
 SPREADS=${2:-"8"}
