@@ -486,6 +486,23 @@ int hg_debug_warp_sort(hg_ctx* c, int32_t* key_idx, const int32_t* off, int32_t 
     return rc;
 }
 
+// Test hook (no GPU needed): the host-side batch plan of the flat filter kernels.
+// batch_out gets (first read, histogram words in use) pairs, closed by (hi, 0); returns the number
+// of batches, or -1 when capacity (in pairs) is too small.
+int hg_debug_flat_plan(const int32_t* rlen, int32_t n_read, int32_t lo, int32_t hi, int32_t cut_off,
+                       int32_t* batch_out, int32_t capacity, int32_t* rbase_out) {
+    std::vector<int2> batch;
+    std::vector<int> rbase;
+    flat_plan(rlen, lo, hi, n_read, cut_off, &batch, &rbase);
+    if ((int)batch.size() > capacity) return -1;
+    for (size_t i = 0; i < batch.size(); i++) {
+        batch_out[2 * i] = batch[i].x;
+        batch_out[2 * i + 1] = batch[i].y;
+    }
+    memcpy(rbase_out, rbase.data(), sizeof(int) * (size_t)n_read);
+    return (int)batch.size() - 1;
+}
+
 int hg_debug_std_sort(int32_t* key_idx, const int32_t* off, int32_t count, int32_t descending) {
     struct E { int key, idx; };
     for (int w = 0; w < count; w++) {
