@@ -69,3 +69,83 @@ def test_all_gather_assembles_the_global_arrays(n_read):
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, True), (1, True)]
+
+
+class _FakeContext:
+    """Stands in for hinge_b200.api.Context on the CPU: computes into the bound tensors what the
+    phases of the real context leave there, and records the order of the calls."""
+
+    def __init__(self, arrays, refuse_packed):
+        self.arrays, self.refuse_packed, self.calls, self.bound = arrays, refuse_packed, [], {}
+
+    def bind_buffer(self, which, tensor):
+        from hinge_b200 import api
+
+        if which == api.HG_BUF_MASK_PACKED and self.refuse_packed:
+            raise RuntimeError("reads too long for 16-bit mask bounds")
+        self.bound[which] = tensor
+
+    def filter_phase1(self, params):
+        from hinge_b200 import api
+
+        a = self.arrays
+        self.calls.append("phase1")
+        self.bound[api.HG_BUF_MEDIAN_HIST][7] += a.hi - a.lo  # every owned read has mean coverage 7
+
+    def filter_phase2(self):
+        from hinge_b200 import api
+
+        a = self.arrays
+        self.calls.append("phase2")
+        self.hist_seen = int(self.bound[api.HG_BUF_MEDIAN_HIST][7])
+        ids = torch.arange(a.lo, a.hi, dtype=torch.int32)
+        if api.HG_BUF_MASK_PACKED in self.bound:
+            self.bound[api.HG_BUF_MASK_PACKED][a.lo:a.hi] = ids | ((ids + 5) << 16)
+        else:
+            self.bound[api.HG_BUF_MASK][a.lo:a.hi, 0] = ids
+            self.bound[api.HG_BUF_MASK][a.lo:a.hi, 1] = ids + 5
+
+    def filter_phase3(self):
+        from hinge_b200 import api
+
+        self.calls.append("phase3")
+        if api.HG_BUF_MASK_PACKED in self.bound:
+            m = self.bound[api.HG_BUF_MASK_PACKED]
+            self.masks_seen = torch.stack([m & 0xffff, m >> 16], dim=1)
+        else:
+            self.masks_seen = self.bound[api.HG_BUF_MASK].clone()
+        return 0, None
+
+
+def _flow_worker(rank, world, port, n_read, refuse_packed, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hinge_b200.sharding import ShardedArrays, run_filter_sharded
+
+    arr = ShardedArrays(n_read, rank, world, torch.device("cpu"))
+    ctx = _FakeContext(arr, refuse_packed)
+    arr.bind(ctx)
+    rc, _ = run_filter_sharded(ctx, None, arr)
+    full = torch.arange(n_read, dtype=torch.int32)
+    ok = (rc == 0 and ctx.calls == ["phase1", "phase2", "phase3"]
+          and ctx.hist_seen == n_read  # phase 2 saw the histogram of ALL ranks
+          and arr.packed == (not refuse_packed)
+          and bool(torch.equal(ctx.masks_seen[:n_read, 0], full))  # phase 3 saw the masks of ALL reads
+          and bool(torch.equal(ctx.masks_seen[:n_read, 1], full + 5)))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("refuse_packed", [False, True])
+def test_sharded_filter_flow_exchanges_between_the_phases(refuse_packed):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 11 + int(refuse_packed)
+    procs = [ctx.Process(target=_flow_worker, args=(r, 2, port, 1001, refuse_packed, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)]
