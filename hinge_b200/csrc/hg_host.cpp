@@ -84,21 +84,6 @@ bool parse_args(int argc, char** argv, bool layout, Args* a, std::string* err) {
     return true;
 }
 
-// HINGE_B200_TIMING=1: wall time of the phases of a stage driver on stderr
-struct PhaseTimer {
-    bool on = getenv("HINGE_B200_TIMING") != nullptr;
-    struct timespec t0;
-    PhaseTimer() { clock_gettime(CLOCK_MONOTONIC, &t0); }
-    void lap(const char* what) {
-        if (!on) return;
-        struct timespec t1;
-        clock_gettime(CLOCK_MONOTONIC, &t1);
-        fprintf(stderr, "[hinge_b200 timing] %-28s %8.1f ms\n", what,
-                1e3 * (double)(t1.tv_sec - t0.tv_sec) + 1e-6 * (double)(t1.tv_nsec - t0.tv_nsec));
-        t0 = t1;
-    }
-};
-
 static void say(const char* fmt, const std::string& s = std::string()) {
     printf("[hinge_b200] ");
     printf(fmt, s.c_str());

@@ -1,6 +1,10 @@
 // Shared pieces of the file-level stage drivers (hg_host*.cpp).
 #ifndef HG_HOST_H
 #define HG_HOST_H
+#include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
+
 #include <string>
 
 #include "../../include/hinge_b200.h"
@@ -13,6 +17,21 @@ namespace hg {
 struct Args {
     std::string db, las, paf, config, fasta, prefix = "out", restrictreads, log = "log", out;
     bool mlas = false, debug = false;
+};
+
+// HINGE_B200_TIMING=1: wall time of the phases of a stage driver on stderr
+struct PhaseTimer {
+    bool on = getenv("HINGE_B200_TIMING") != nullptr;
+    struct timespec t0;
+    PhaseTimer() { clock_gettime(CLOCK_MONOTONIC, &t0); }
+    void lap(const char* what) {
+        if (!on) return;
+        struct timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        fprintf(stderr, "[hinge_b200 timing] %-28s %8.1f ms\n", what,
+                1e3 * (double)(t1.tv_sec - t0.tv_sec) + 1e-6 * (double)(t1.tv_nsec - t0.tv_nsec));
+        t0 = t1;
+    }
 };
 
 bool parse_args(int argc, char** argv, bool layout, Args* a, std::string* err);

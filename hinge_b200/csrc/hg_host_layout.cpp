@@ -134,6 +134,7 @@ extern "C" int hg_main_maximal(int argc, char** argv) {
         fprintf(stderr, "%s\n", err.c_str());
         return 1;
     }
+    PhaseTimer timer;
     Ini ini;
     ReadDB db;
     LasFile las;
@@ -147,11 +148,13 @@ extern "C" int hg_main_maximal(int argc, char** argv) {
         fprintf(stderr, "hinge maximal: cannot read %s.mas (run hinge filter first)\n", a.prefix.c_str());
         return 1;
     }
+    timer.lap("read db + ini + las + mas");
     hg_ctx* ctx = nullptr;
     if (open_context(db, las, true, &ctx) != HG_OK) {
         hg_ctx_destroy(ctx);
         return 1;
     }
+    timer.lap("context + H2D + CSR");
     std::vector<uint8_t> maximal(n);
     std::vector<int32_t> by(n, -1);
     const bool want_contained = getenv("HINGE_B200_SKIP_CONTAINED_TXT") == nullptr;
@@ -162,6 +165,7 @@ extern "C" int hg_main_maximal(int argc, char** argv) {
         hg_ctx_destroy(ctx);
         return 1;
     }
+    timer.lap("hg_maximal");
     hg_ctx_destroy(ctx);
     const int r_begin = las.aread.front(), r_end = las.aread.back();
     touch(a.prefix + ".homologous.txt");  // maximal.cpp:515-517 reopens (truncates) these
@@ -182,6 +186,7 @@ extern "C" int hg_main_maximal(int argc, char** argv) {
         }
     }
     printf("[hinge_b200] removed contained reads, active reads: %d (%.3f ms on device)\n", kept, ms);
+    timer.lap("destroy + write output files");
     return 0;
 }
 
@@ -194,6 +199,7 @@ extern "C" int hg_main_layout(int argc, char** argv) {
         return 1;
     }
     printf("[hinge_b200] Hinging layout\n");
+    PhaseTimer timer;
     Ini ini;
     ReadDB db;
     LasFile las;
@@ -216,12 +222,14 @@ extern "C" int hg_main_layout(int argc, char** argv) {
     read_pairs_file(x + ".hinges.txt", n, &hin_off, &hin_pos, &hin_type);
     // pointers must be valid even for empty lists
     rep_pos.push_back(0); rep_type.push_back(0); hin_pos.push_back(0); hin_type.push_back(0);
+    timer.lap("read inputs");
 
     hg_ctx* ctx = nullptr;
     if (open_context(db, las, true, &ctx) != HG_OK) {
         hg_ctx_destroy(ctx);
         return 1;
     }
+    timer.lap("context + H2D + CSR");
     float ms = 0;
     rc = hg_layout(ctx, &lp, mask.data(), maximal.data(), rep_off.data(), rep_pos.data(), rep_type.data(),
                    hin_off.data(), hin_pos.data(), hin_type.data(), &ms);
@@ -231,6 +239,7 @@ extern "C" int hg_main_layout(int argc, char** argv) {
         return 1;
     }
     const LayoutResult& R = *layout_result(ctx);
+    timer.lap("hg_layout");
 
     {  // files that only depend on the inputs and the hinge bookkeeping
         TextOut garbage(x + ".garbage.txt");  // hinging.cpp:954-960
@@ -341,5 +350,6 @@ extern "C" int hg_main_layout(int argc, char** argv) {
         printf("[hinge_b200] %lld edges, %.3f ms on device\n", (long long)n_edges, ms);
     }
     hg_ctx_destroy(ctx);
+    timer.lap("write output files + destroy");
     return 0;
 }
