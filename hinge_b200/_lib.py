@@ -62,6 +62,11 @@ PROTOTYPES = {
     "hg_launch_count": (i64, []),
     "hg_set_reads": (C.c_int, [vp, i32, vp, vp, vp, i32]),
     "hg_set_overlaps": (C.c_int, [vp, i64] + [vp] * 8 + [vp, vp, i32, i32, i32, i32]),
+    "hg_set_global_range": (C.c_int, [vp, i32, i32]),
+    "hg_peer_export": (C.c_int, [vp, i32, i32, vp]),
+    "hg_peer_connect": (C.c_int, [vp, vp]),
+    "hg_peer_connect_local": (C.c_int, [C.POINTER(vp), i32]),
+    "hg_peer_masks": (C.c_int, [vp, vp]),
     "hg_filter": (C.c_int, [vp, C.POINTER(FilterParamsC), C.POINTER(FilterSummaryC)]),
     "hg_filter_phase1": (C.c_int, [vp, C.POINTER(FilterParamsC)]),
     "hg_filter_phase2": (C.c_int, [vp]),

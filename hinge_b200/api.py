@@ -9,9 +9,10 @@ import numpy as np
 from ._lib import (EdgeC, FilterParamsC, FilterSummaryC, HingeError, LayoutParamsC, lib)
 
 HG_MEM_HOST, HG_MEM_DEVICE = 0, 1
-HG_OPT_KEEP_COVERAGE, HG_OPT_PROFILE, HG_OPT_SCATTER_SPREAD = 1, 2, 3
+HG_OPT_KEEP_COVERAGE, HG_OPT_PROFILE, HG_OPT_SCATTER_SPREAD, HG_OPT_PROFILE_KERNEL = 1, 2, 3, 4
 HG_BUF_MEAN_COV, HG_BUF_MASK, HG_BUF_READ_FLAGS, HG_BUF_MEDIAN_HIST, HG_BUF_MASK_PACKED = 1, 2, 3, 4, 5
 HG_RETRY_POOL = 1
+HG_PEER_HANDLE_BYTES = 64
 
 
 def FilterParams(**kw):
@@ -82,6 +83,7 @@ class Context:
     def set_reads(self, rlen, qv_off=None, qv=None, tspace=100):
         rlen = np.ascontiguousarray(rlen, dtype=np.int32)
         self.n_read = len(rlen)
+        self.tspace = int(tspace)
         if qv_off is not None:
             qv_off = np.ascontiguousarray(qv_off, dtype=np.int64)
             qv = np.ascontiguousarray(qv, dtype=np.uint8)
@@ -98,6 +100,25 @@ class Context:
                                  _ptr(trace_off), _ptr(trace), int(tbytes), int(where), int(a_lo), int(a_hi))
         self._check(rc, "hg_set_overlaps")
         self._keep = (cols, trace_off, trace)  # adopted device memory must outlive the context's use
+
+    def set_global_range(self, first_aread, last_aread):
+        self._check(lib.hg_set_global_range(self._h, int(first_aread), int(last_aread)), "hg_set_global_range")
+
+    def peer_export(self, rank, world):
+        """Allocates this rank's exchange block; returns its CUDA IPC handle (bytes)."""
+        buf = C.create_string_buffer(HG_PEER_HANDLE_BYTES)
+        self._check(lib.hg_peer_export(self._h, int(rank), int(world), buf), "hg_peer_export")
+        return buf.raw
+
+    def peer_connect(self, handles):
+        """handles: the concatenated handles of all ranks, in rank order."""
+        buf = C.create_string_buffer(bytes(handles), len(handles))
+        self._check(lib.hg_peer_connect(self._h, buf), "hg_peer_connect")
+
+    def peer_masks(self):
+        out = np.zeros((self.n_read, 2), np.int32)
+        self._check(lib.hg_peer_masks(self._h, _ptr(out)), "hg_peer_masks")
+        return out
 
     def filter(self, params):
         s = FilterSummaryC()

@@ -101,9 +101,27 @@ int hg_ctx_create(int device, void* stream, hg_ctx** out) {
     return HG_OK;
 }
 
+static void peer_teardown(hg_ctx* c) {
+    for (int r = 0; r < kMaxPeers; r++) {
+        if (c->peer_ipc[r] && c->peer.base[r]) cudaIpcCloseMemHandle(c->peer.base[r]);
+        c->peer_ipc[r] = false;
+        c->peer.base[r] = nullptr;
+    }
+    if (c->peer_block) {
+        if (c->fs.mask_pk == reinterpret_cast<uint32_t*>(c->peer_block + kPeerFlagBytes + kPeerHistBytes))
+            c->fs.mask_pk = nullptr;
+        cudaFree(c->peer_block);
+    }
+    c->peer_block = nullptr;
+    c->peer.world = 0;
+    c->peer_connected = false;
+}
+
 void hg_ctx_destroy(hg_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    peer_teardown(c);
     free_overlaps(c);
     cudaFree(c->d_rlen); cudaFree(c->d_qvmask); cudaFree(c->d_read_off); cudaFree(c->d_err);
     FilterScratch& s = c->fs;
@@ -144,6 +162,11 @@ int hg_set_option(hg_ctx* c, int option, int64_t value) {
         c->fs.flat_spread = (int)value;
         return HG_OK;
     }
+    if (option == HG_OPT_PROFILE_KERNEL) {
+        if (value != 0 && value != 1) return set_err(c, HG_ERR_ARG, "HG_OPT_PROFILE_KERNEL: 0 or 1");
+        c->fs.flat_kernel = (int)value;
+        return HG_OK;
+    }
     return set_err(c, HG_ERR_ARG, "unknown option");
 }
 
@@ -152,6 +175,8 @@ int hg_set_reads(hg_ctx* c, int32_t n_read, const int32_t* rlen, const int64_t* 
     if (!c || n_read <= 0 || !rlen) return set_err(c, HG_ERR_ARG, "hg_set_reads: bad arguments");
     cudaSetDevice(c->device);
     cudaStream_t st = c->stream;
+    if (c->peer_block) peer_teardown(c);  // sized by n_read
+    c->g_begin = c->g_end = -1;
     c->n_read = n_read;
     c->tspace = tspace;
     c->h_rlen.assign(rlen, rlen + n_read);
@@ -283,6 +308,13 @@ int hg_set_overlaps(hg_ctx* c, int64_t novl, const int32_t* aread, const int32_t
     }
     c->r_begin = first_a;
     c->r_end = last_a;
+    // a global range set earlier (hg_set_global_range) stays in force while the records fit in it
+    if (c->g_begin >= 0 && first_a >= c->g_begin && last_a <= c->g_end) {
+        c->r_begin = c->g_begin;
+        c->r_end = c->g_end;
+    } else {
+        c->g_begin = c->g_end = -1;
+    }
     // CSR + validation + deepest pile-up
     cudaMemsetAsync(c->d_err, 0, sizeof(int) * 4, st);
     launch_csr_validate(c->rec_view(), c->read_view(), c->d_read_off, c->fs.self_cnt, c->d_err, st);
@@ -332,7 +364,7 @@ static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
     {
         // flat K2: pack the reads that have records, [r_begin, r_end] within the owned range, into
         // batches of kFlatBins histogram words; the plan only depends on read lengths and cut_off
-        const int lo = std::max(c->a_lo, c->r_begin), hi = std::min(c->a_hi, c->r_end + 1);
+        const int lo = std::max(c->a_lo, c->r_begin), hi = std::min(c->a_hi, c->r_end + 1);  // r_begin / r_end: global when set
         if (c->plan_reads_version != c->reads_version || c->plan_cut_off != p->cut_off ||
             c->plan_lo != lo || c->plan_hi != hi) {
             std::vector<int2> batch;
@@ -370,11 +402,21 @@ int hg_filter_phase1(hg_ctx* c, const hg_filter_params* p) {
     if (!c || !p || c->novl <= 0) return set_err(c, HG_ERR_ARG, "hg_filter: no overlaps loaded");
     cudaSetDevice(c->device);
     HG_TRY(configure_filter(c, p));
+    if (c->peer.world > 1 && !c->peer_connected)
+        return set_err(c, HG_ERR_ARG, "hg_peer_export without hg_peer_connect");
     cudaEventRecord(c->ev0, c->stream);
     c->mark(0);
     launch_profile(c->rec_view(), c->read_view(), c->fp, c->r_begin, c->r_end, c->fs, c->stream);
-    // sharded: the rank's part of the coverage histogram, summed across ranks by the caller
-    if (c->ext_med_hist) launch_median(c->read_view(), c->fp, c->fs, 1, c->stream);
+    if (c->peer.world > 1) {
+        // sharded, peer exchange: the rank's part of the coverage histogram goes straight into every
+        // rank's exchange block
+        c->peer.epoch++;
+        launch_median(c->read_view(), c->fp, c->fs, 1, c->stream);
+        launch_peer_hist_push(c->fs, c->peer, c->stream);
+    } else if (c->ext_med_hist) {
+        // sharded, NCCL exchange: the rank's part, summed across ranks by the caller
+        launch_median(c->read_view(), c->fp, c->fs, 1, c->stream);
+    }
     c->mark(1);
     return cuda_check(c, cudaGetLastError(), "filter phase 1");
 }
@@ -401,10 +443,14 @@ int hg_filter_phase2(hg_ctx* c) {
         cov0 = c->d_cov0;
     }
     c->mark(2);
-    launch_median(c->read_view(), c->fp, s, c->ext_med_hist ? 2 : 0, st);
+    if (c->peer.world > 1)
+        launch_peer_median_pick(c->fp, s, c->peer, st);  // waits for the parts of all ranks
+    else
+        launch_median(c->read_view(), c->fp, s, c->ext_med_hist ? 2 : 0, st);
     c->mark(3);
     launch_mask_anno(c->rec_view(), c->read_view(), c->fp, c->r_begin, c->r_end, s, cov0,
-                     c->d_cov0_off, st);
+                     c->d_cov0_off, c->peer, st);
+    if (c->peer.world > 1) launch_peer_signal_masks(s, c->peer, st);
     c->mark(4);
     return cuda_check(c, cudaGetLastError(), "filter phase 2");
 }
@@ -415,17 +461,25 @@ int hg_filter_phase3(hg_ctx* c, hg_filter_summary* out) {
     cudaStream_t st = c->stream;
     FilterScratch& s = c->fs;
     c->mark(5);
-    launch_hinge_call(c->rec_view(), c->read_view(), c->fp, s, st);
+    launch_hinge_call(c->rec_view(), c->read_view(), c->fp, s, c->peer, st);
     c->mark(6);
     cudaEventRecord(c->ev1, st);
-    int cnt[8], scal[8];
+    HG_TRY(cuda_check(c, cudaGetLastError(), "filter phase 3"));
+    int cnt[16], scal[8];
     HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, s.counters, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
     HG_TRY(cuda_check(c, cudaMemcpyAsync(scal, s.scal, sizeof scal, cudaMemcpyDeviceToHost, st), "D2H"));
     HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "filter"));
+    if (cnt[15])
+        return set_err(c, HG_ERR_CUDA, "peer exchange timed out: a rank did not reach the same hg_filter call");
     if (scal[5])
         return set_err(c, HG_ERR_INPUT, "median coverage >= 4095: not supported with a shared coverage histogram "
-                                        "(HG_BUF_MEDIAN_HIST); all-gather HG_BUF_MEAN_COV instead");
-    if (cnt[2]) return HG_RETRY_POOL;  // annotation pool overflow: hg_filter grows it and reruns
+                                        "(HG_BUF_MEDIAN_HIST / peer exchange); all-gather HG_BUF_MEAN_COV instead");
+    if (cnt[2]) {
+        // annotation pool overflow (here, or on another rank of a peer-connected run): grow it if it
+        // was ours and tell the caller to rerun the three phases
+        if (cnt[0] > s.anno_cap) HG_TRY(alloc_anno_pool(c, std::max(cnt[0] + (1 << 16), s.anno_cap * 2)));
+        return HG_RETRY_POOL;
+    }
     c->filter_done = true;
     if (out) {
         out->r_begin = c->r_begin;
@@ -447,11 +501,7 @@ int hg_filter(hg_ctx* c, const hg_filter_params* p, hg_filter_summary* out) {
         HG_TRY(hg_filter_phase1(c, p));
         HG_TRY(hg_filter_phase2(c));
         const int rc = hg_filter_phase3(c, out);
-        if (rc != HG_RETRY_POOL) return rc;
-        // the annotation pool was too small for this data: grow and run again
-        int used = 0;
-        cudaMemcpy(&used, c->fs.counters, sizeof(int), cudaMemcpyDeviceToHost);
-        HG_TRY(alloc_anno_pool(c, std::max(used + (1 << 16), c->fs.anno_cap * 2)));
+        if (rc != HG_RETRY_POOL) return rc;  // else: the pool has been grown, run again
     }
     return set_err(c, HG_ERR_NOMEM, "annotation pool kept overflowing");
 }
@@ -577,6 +627,117 @@ int hg_device_buffer(hg_ctx* c, int which, void** dptr, int64_t* bytes) {
         case HG_BUF_READ_FLAGS: *dptr = c->fs.rflags; *bytes = c->n_read; return HG_OK;
         default: return set_err(c, HG_ERR_ARG, "unknown buffer");
     }
+}
+
+int hg_set_global_range(hg_ctx* c, int32_t first_aread, int32_t last_aread) {
+    if (!c || c->novl <= 0) return set_err(c, HG_ERR_ARG, "hg_set_global_range: call hg_set_overlaps first");
+    if (first_aread < 0 || last_aread >= c->n_read || first_aread > last_aread)
+        return set_err(c, HG_ERR_ARG, "hg_set_global_range: range does not contain this context's records");
+    c->g_begin = first_aread;
+    c->g_end = last_aread;
+    c->r_begin = first_aread;
+    c->r_end = last_aread;
+    c->shape_version++;
+    return HG_OK;
+}
+
+// ---- peer exchange ---------------------------------------------------------------------
+
+static int peer_alloc_block(hg_ctx* c, int rank, int world) {
+    if (c->n_read <= 0) return set_err(c, HG_ERR_ARG, "hg_peer_export: call hg_set_reads first");
+    if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world)
+        return set_err(c, HG_ERR_ARG, "hg_peer_export: 2 <= world <= 16, 0 <= rank < world");
+    if (c->ext_med_hist || (c->fs.mask_pk && !c->peer_block))
+        return set_err(c, HG_ERR_ARG, "hg_peer_export: context already bound to NCCL-exchanged buffers");
+    int g = kReso, t = c->tspace > 0 ? c->tspace : kReso;
+    while (t) {
+        const int r = g % t;
+        g = t;
+        t = r;
+    }
+    if (c->max_rlen / g >= 65536)
+        return set_err(c, HG_ERR_ARG, "peer exchange: reads too long for 16-bit mask bounds; use the NCCL exchange with HG_BUF_MASK");
+    cudaSetDevice(c->device);
+    peer_teardown(c);
+    c->peer_block_bytes = kPeerFlagBytes + kPeerHistBytes + sizeof(uint32_t) * (size_t)c->n_read;
+    HG_TRY(cuda_check(c, cudaMalloc((void**)&c->peer_block, c->peer_block_bytes), "exchange block"));
+    HG_TRY(cuda_check(c, cudaMemset(c->peer_block, 0, c->peer_block_bytes), "exchange block"));
+    HG_TRY(cuda_check(c, cudaDeviceSynchronize(), "exchange block"));
+    c->peer.rank = rank;
+    c->peer.world = world;
+    c->peer.epoch = 0;
+    c->peer.base[rank] = c->peer_block;
+    c->fs.mask_pk = c->peer.mask_pk(rank);
+    c->fs.mask_g = g;
+    c->peer_connected = false;
+    return HG_OK;
+}
+
+int hg_peer_export(hg_ctx* c, int32_t rank, int32_t world, void* handle_out) {
+    if (!c || !handle_out) return HG_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) <= HG_PEER_HANDLE_BYTES, "handle size");
+    HG_TRY(peer_alloc_block(c, rank, world));
+    cudaIpcMemHandle_t h;
+    HG_TRY(cuda_check(c, cudaIpcGetMemHandle(&h, c->peer_block), "cudaIpcGetMemHandle"));
+    memset(handle_out, 0, HG_PEER_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof h);
+    return HG_OK;
+}
+
+int hg_peer_connect(hg_ctx* c, const void* handles) {
+    if (!c || !handles || c->peer.world < 2 || !c->peer_block)
+        return set_err(c, HG_ERR_ARG, "hg_peer_connect: call hg_peer_export first");
+    cudaSetDevice(c->device);
+    for (int r = 0; r < c->peer.world; r++) {
+        if (r == c->peer.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const uint8_t*)handles + (size_t)r * HG_PEER_HANDLE_BYTES, sizeof h);
+        void* p = nullptr;
+        HG_TRY(cuda_check(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle"));
+        c->peer.base[r] = (uint8_t*)p;
+        c->peer_ipc[r] = true;
+    }
+    c->peer_connected = true;
+    return HG_OK;
+}
+
+int hg_peer_connect_local(hg_ctx** ctxs, int32_t world) {
+    if (!ctxs || world < 2 || world > kMaxPeers) return HG_ERR_ARG;
+    for (int r = 0; r < world; r++) {
+        if (!ctxs[r]) return HG_ERR_ARG;
+        HG_TRY(peer_alloc_block(ctxs[r], r, world));
+    }
+    for (int r = 0; r < world; r++) {
+        hg_ctx* c = ctxs[r];
+        cudaSetDevice(c->device);
+        for (int q = 0; q < world; q++) {
+            if (q == r) continue;
+            if (ctxs[q]->device != c->device) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, c->device, ctxs[q]->device);
+                if (!can) return set_err(c, HG_ERR_CUDA, "no peer access between the devices");
+                const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_check(c, e, "cudaDeviceEnablePeerAccess");
+                cudaGetLastError();
+            }
+            c->peer.base[q] = ctxs[q]->peer_block;
+        }
+        c->peer_connected = true;
+    }
+    return HG_OK;
+}
+
+int hg_peer_masks(hg_ctx* c, int32_t* mask) {
+    if (!c || !mask || !c->peer_block || !c->filter_done) return set_err(c, HG_ERR_ARG, "hg_peer_masks: no peer-connected run");
+    cudaSetDevice(c->device);
+    std::vector<uint32_t> pk((size_t)c->n_read);
+    HG_TRY(cuda_check(c, cudaMemcpyAsync(pk.data(), c->fs.mask_pk, 4ull * c->n_read, cudaMemcpyDeviceToHost, c->stream), "D2H"));
+    HG_TRY(cuda_check(c, cudaStreamSynchronize(c->stream), "D2H"));
+    for (int i = 0; i < c->n_read; i++) {
+        mask[2 * i] = (int)(pk[i] & 0xffffu) * c->fs.mask_g;
+        mask[2 * i + 1] = (int)(pk[i] >> 16) * c->fs.mask_g;
+    }
+    return HG_OK;
 }
 
 int hg_filter_fetch(hg_ctx* c, int32_t* mask, int32_t* cmask, uint8_t* flags, int64_t* anno_off,

@@ -65,6 +65,15 @@ struct hg_ctx {
     }
     bool ext_mean_cov = false, ext_mask = false, ext_med_hist = false;  // bound to caller-owned memory
 
+    // sharded runs: first / last A-read of the whole .las (hg_set_global_range), -1 = unknown
+    int g_begin = -1, g_end = -1;
+    // phase exchange through peer memory (hg_peer_export / hg_peer_connect)
+    hg::PeerView peer{};          // world <= 1: off
+    uint8_t* peer_block = nullptr;  // this rank's exchange block
+    size_t peer_block_bytes = 0;
+    bool peer_ipc[hg::kMaxPeers] = {};  // base[r] came from cudaIpcOpenMemHandle
+    bool peer_connected = false;
+
     hg::LayoutResult* layout = nullptr;  // result of the last hg_layout
 
     hg::RecView rec_view() const;

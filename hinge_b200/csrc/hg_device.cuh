@@ -42,6 +42,13 @@ constexpr int kReso = 40;
 // (/root/reference/src/lib/LAInterface.cpp:4309-4317)
 __device__ __forceinline__ int cov_bin(int e, int reso) { return e < 0 ? 0 : e / reso + 1; }
 
+// self_cnt[read] (ingest, k_csr_validate): number of A == B records, plus a flag for reads that
+// have a record lying inside one 40-bp bin (abpos / 40 == aepos / 40; never produced by
+// daligner, whose alignments are >= 1000 bp, but legal input)
+constexpr int kSelfDegenerate = 1 << 30;
+__device__ __forceinline__ int self_count(int v) { return v & (kSelfDegenerate - 1); }
+__device__ __forceinline__ bool is_degenerate(int v) { return (v & kSelfDegenerate) != 0; }
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 template <typename T>
@@ -118,6 +125,58 @@ struct MaskView {
     }
 };
 
+// ---- phase exchange of a sharded filter run through NVLink peer memory --------------------
+// Every rank owns one exchange block (cudaMalloc, mapped into the other ranks through CUDA IPC
+// or peer access) and every rank's kernels store straight into all of them:
+//   flags      arrival counters, one per source rank and exchange (epoch numbers, monotone)
+//   hist       the ranks' parts of the mean-coverage histogram (filter.cpp:642-678), one row each
+//   mask_pk    the packed masks of ALL reads (MaskView); K2 stores a read's word into every block
+// A consumer kernel spins on its OWN block's flags (local memory) until every rank's epoch has
+// arrived; a wall-clock limit turns a lost peer into an error instead of a hung GPU.
+constexpr int kMaxPeers = 16;
+constexpr int kPeerHistWords = 4100;  // 4096 bins + valid count + padding
+constexpr size_t kPeerFlagBytes = 256;
+constexpr size_t kPeerHistBytes = sizeof(uint32_t) * kMaxPeers * kPeerHistWords;
+constexpr unsigned long long kPeerTimeoutNs = 4000000000ull;
+
+struct PeerView {
+    int rank, world;  // world <= 1: no exchange
+    unsigned epoch;
+    uint8_t* base[kMaxPeers];
+    __host__ __device__ uint32_t* flag_hist(int r) const { return reinterpret_cast<uint32_t*>(base[r]); }
+    __host__ __device__ uint32_t* flag_mask(int r) const { return reinterpret_cast<uint32_t*>(base[r]) + kMaxPeers; }
+    __host__ __device__ uint32_t* flag_ovf(int r) const { return reinterpret_cast<uint32_t*>(base[r]) + 2 * kMaxPeers; }
+    __host__ __device__ uint32_t* hist(int r, int src) const {
+        return reinterpret_cast<uint32_t*>(base[r] + kPeerFlagBytes) + (size_t)src * kPeerHistWords;
+    }
+    __host__ __device__ uint32_t* mask_pk(int r) const {
+        return reinterpret_cast<uint32_t*>(base[r] + kPeerFlagBytes + kPeerHistBytes);
+    }
+};
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const uint32_t* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Spins until the flag has reached `epoch` (wrap-around safe); false on time-out.
+__device__ __forceinline__ bool peer_wait(const uint32_t* flag, unsigned epoch) {
+    const unsigned long long t0 = global_timer_ns();
+    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+        __nanosleep(100);
+        if (global_timer_ns() - t0 > kPeerTimeoutNs) return false;
+    }
+    return true;
+}
+
 struct MaskAnnoOut {
     int2* mask;        // .mas
     uint32_t* mask_pk; // optional packed copy (MaskView), unit mask_g
@@ -133,11 +192,17 @@ struct MaskAnnoOut {
     int* big_list;     // reads whose profile does not fit the shared-memory path
     int* cov0;         // optional dump of the cut-off-free profile (coverage.txt)
     const int64_t* cov0_off;
+    PeerView peer;     // world > 1: the packed word also goes into every other rank's array
 };
 
 __device__ __forceinline__ void store_mask(const MaskAnnoOut& out, int read, int2 mk) {
     out.mask[read] = mk;
-    if (out.mask_pk) out.mask_pk[read] = (uint32_t)(mk.x / out.mask_g) | ((uint32_t)(mk.y / out.mask_g) << 16);
+    if (out.mask_pk) {
+        const uint32_t w = (uint32_t)(mk.x / out.mask_g) | ((uint32_t)(mk.y / out.mask_g) << 16);
+        out.mask_pk[read] = w;
+        for (int r = 0; r < out.peer.world; r++)  // posted NVLink writes; k_peer_signal publishes them
+            if (r != out.peer.rank) out.peer.mask_pk(r)[read] = w;
+    }
 }
 
 // K4 is a chain of dependent loads per read; everything it needs to get going travels in the

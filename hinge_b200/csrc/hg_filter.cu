@@ -41,6 +41,7 @@ __global__ void k_csr_validate(RecView rv, ReadView rd, int64_t* read_off, int* 
             return;
         }
         if (a == b) atomicAdd(&self_cnt[a], 1);  // inactive in every stage (filter.cpp:538-547); rare
+        if (rv.abpos[k] / kReso == rv.aepos[k] / kReso) atomicOr(&self_cnt[a], kSelfDegenerate);
     }
     // every read in (prev, cur] starts at record k
     for (int r = max(prev + 1, rd.r_lo); r <= cur; r++) read_off[r] = k;
@@ -135,10 +136,10 @@ __device__ void median_pick_block(unsigned int* __restrict__ hist, int est_cov, 
     unsigned int loc[16], tot = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        loc[i] = __ldcg(&hist[16 * t + i]);
+        loc[i] = *(volatile unsigned int*)&hist[16 * t + i];  // global (written by other CTAs) or shared
         tot += loc[i];
     }
-    const unsigned int m = __ldcg(&hist[4096]);
+    const unsigned int m = *(volatile unsigned int*)&hist[4096];
     const unsigned int incl = warp_incl_scan(tot);
     if (lane_id() == 31) wsum[t >> 5] = incl;
     __syncthreads();
@@ -219,6 +220,55 @@ k_median_radix(const int* __restrict__ mean_cov, int n_read, int est_cov, int mi
         if (est_cov != 0) cov_est = est_cov;
         scal[0] = cov_est;
         scal[1] = max(min_cov, cov_est / 3);
+    }
+}
+
+// ------------------------------------------------------------------ peer exchange (sharded runs)
+
+// After k_median_hist (pick = 0) has accumulated the rank's own reads: one CTA stores the rank's
+// part of the histogram into row `rank` of EVERY rank's exchange block (plain stores over NVLink,
+// 16 KB per peer), clears the local accumulator for the next run, and then raises its arrival
+// flag in every block.  Writers fence before the barrier, the flag writers again after it.
+__global__ void __launch_bounds__(1024)
+k_peer_hist_push(unsigned int* __restrict__ hist, PeerView pv) {
+    for (int b = threadIdx.x; b < 4098; b += blockDim.x) {
+        const unsigned v = hist[b];
+        hist[b] = 0;
+        for (int r = 0; r < pv.world; r++) pv.hist(r, pv.rank)[b] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < pv.world) {
+        __threadfence_system();
+        st_release_sys(pv.flag_hist(threadIdx.x) + pv.rank, pv.epoch);
+    }
+}
+
+// Waits for the parts of all ranks, sums them and picks the median (one CTA, 256 threads: thread t
+// owns bins [16 t, 16 t + 16)).  err[0] = 1 when a peer did not arrive in time.
+__global__ void __launch_bounds__(256)
+k_peer_median_pick(PeerView pv, int est_cov, int min_cov, int* __restrict__ scal, int* __restrict__ err) {
+    __shared__ unsigned int sum[4098];
+    if (threadIdx.x < pv.world && !peer_wait(pv.flag_hist(pv.rank) + threadIdx.x, pv.epoch)) atomicExch(err, 1);
+    __syncthreads();
+    for (int b = threadIdx.x; b < 4098; b += blockDim.x) {
+        unsigned v = 0;
+        for (int r = 0; r < pv.world; r++) v += __ldcg(pv.hist(pv.rank, r) + b);
+        sum[b] = v;
+    }
+    __syncthreads();
+    median_pick_block(sum, est_cov, min_cov, scal, false);
+}
+
+// After K2 (both forms): everything this rank stored into the other ranks' mask arrays is
+// complete at the kernel boundary; tell every rank, together with the annotation-pool overflow
+// bit so that all ranks agree on rerunning the stage (HG_RETRY_POOL).
+__global__ void k_peer_signal_masks(PeerView pv, const int* __restrict__ counters) {
+    if (threadIdx.x < pv.world) {
+        __threadfence_system();
+        pv.flag_ovf(threadIdx.x)[pv.rank] = counters[2] ? pv.epoch : pv.epoch - 1;
+        __threadfence_system();
+        st_release_sys(pv.flag_mask(threadIdx.x) + pv.rank, pv.epoch);
     }
 }
 
@@ -642,7 +692,18 @@ __global__ void __launch_bounds__(128, 8)
 k_hinge_call(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
              const int2* __restrict__ anno_ref, const int2* __restrict__ anno_pool,
              int* __restrict__ counters, const int4* __restrict__ work_items, int* __restrict__ exact_list,
-             uint8_t* __restrict__ hinge_keep, uint8_t* scratch, int cap, int4* __restrict__ item_log) {
+             uint8_t* __restrict__ hinge_keep, uint8_t* scratch, int cap, int4* __restrict__ item_log,
+             PeerView pv) {
+    if (pv.world > 1) {
+        // sharded run: the masks of the other ranks' reads arrive through peer memory (store_mask);
+        // every CTA waits on the local arrival flags before its first look-up
+        if (threadIdx.x < pv.world) {
+            if (!peer_wait(pv.flag_mask(pv.rank) + threadIdx.x, pv.epoch)) atomicExch(&counters[15], 1);
+            // a rank whose annotation pool overflowed makes every rank rerun (hg_filter's retry)
+            if (ld_acquire_sys(pv.flag_ovf(pv.rank) + threadIdx.x) == pv.epoch) atomicExch(&counters[2], 1);
+        }
+        __syncthreads();
+    }
     const int lane = lane_id();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1019,10 +1080,26 @@ void launch_median(const ReadView& rd, const hg_filter_params& P, FilterScratch&
     if (mode == 0) k_median_radix<<<1, 1024, 0, st>>>(s.mean_cov, rd.n_read, P.est_cov, P.min_cov, s.scal);
 }
 
+void launch_peer_hist_push(FilterScratch& s, const PeerView& peer, cudaStream_t st) {
+    g_launches += 1;
+    k_peer_hist_push<<<1, 1024, 0, st>>>(s.med_hist, peer);
+}
+
+void launch_peer_median_pick(const hg_filter_params& P, FilterScratch& s, const PeerView& peer, cudaStream_t st) {
+    g_launches += 1;
+    k_peer_median_pick<<<1, 256, 0, st>>>(peer, P.est_cov, P.min_cov, s.scal, s.counters + 15);
+}
+
+void launch_peer_signal_masks(FilterScratch& s, const PeerView& peer, cudaStream_t st) {
+    g_launches += 1;
+    k_peer_signal_masks<<<1, 32, 0, st>>>(peer, s.counters);
+}
+
 void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
                       int r_begin, int r_end, FilterScratch& s, int* cov0, const int64_t* cov0_off,
-                      cudaStream_t st) {
+                      const PeerView& peer, cudaStream_t st) {
     MaskAnnoOut out;
+    out.peer = peer;
     out.mask = s.mask; out.mask_pk = s.mask_pk; out.mask_g = s.mask_g; out.cmask = s.cmask; out.rflags = s.rflags; out.anno_ref = s.anno_ref;
     out.anno_pool = s.anno_pool; out.hinge_keep = s.hinge_keep; out.anno_cap = s.anno_cap; out.counters = s.counters;
     out.work_items = s.work_items; out.big_list = s.big_list; out.cov0 = cov0; out.cov0_off = cov0_off;
@@ -1042,7 +1119,7 @@ void launch_max_pileup(const int64_t* read_off, int n_read, int* out_max, cudaSt
 }
 
 void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
-                       FilterScratch& s, cudaStream_t st) {
+                       FilterScratch& s, const PeerView& peer, cudaStream_t st) {
     if (s.hinge_cap <= 0) return;
     g_launches += 2;
     MaskView mv;
@@ -1051,15 +1128,12 @@ void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_pa
     mv.g = s.mask_g;
     k_hinge_call<<<s.hinge_warps / 4, 128, 0, st>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool,
                                                     s.counters, s.work_items, s.exact_list, s.hinge_keep,
-                                                    s.hinge_scratch, s.hinge_cap, s.item_log);
+                                                    s.hinge_scratch, s.hinge_cap, s.item_log, peer);
     // the few reads that need the exact sort order: shared-memory scratch, one warp each
     constexpr int scap = 1536;
     const int smem = scap * kHingeExactBytesPerRec;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_hinge_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
-    }
+    // function attributes are per device: set it on every launch (cheap), not once per process
+    cudaFuncSetAttribute(k_hinge_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const int grid = s.hinge_warps < 2 * s.num_sms ? s.hinge_warps : 2 * s.num_sms;
     k_hinge_exact<<<grid, 128, smem, st>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters,
                                           s.exact_list, s.hinge_keep, s.hinge_scratch, s.hinge_cap, scap);

@@ -13,6 +13,7 @@ namespace hg {
 struct RecView;
 struct ReadView;
 struct MaskAnnoOut;
+struct PeerView;
 
 enum : uint8_t { kFlagCov = 1, kFlagSelf = 2, kFlagSkipHinge = 4 };
 
@@ -48,6 +49,7 @@ struct FilterScratch {
     uint32_t* flat_prof = nullptr;    // scanned packed profiles, kFlatBins words per batch (K1 -> K2)
     int flat_nbatch = 0;
     int flat_spread = 8;              // record windows per warp in the scatter (tuning aid)
+    int flat_kernel = 0;              // 0: second form of K1 when the cut-off allows it, 1: always the first form
     unsigned long long* big_scratch = nullptr;
     int big_slot_words = 0, big_warps = 0;
     // K4
@@ -65,7 +67,7 @@ void launch_median(const ReadView& rd, const hg_filter_params& P, FilterScratch&
                    cudaStream_t st);
 void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
                       int r_begin, int r_end, FilterScratch& s, int* cov0, const int64_t* cov0_off,
-                      cudaStream_t st);
+                      const PeerView& peer, cudaStream_t st);
 // flat kernels (hg_filter_flat.cu): host-side batch plan + launchers of the two phases
 void flat_plan(const int* rlen, int lo, int hi, int n_read, int cut_off, std::vector<int2>* batch,
                std::vector<int>* rbase);
@@ -74,7 +76,12 @@ void launch_profile(const RecView& rv, const ReadView& rd, const hg_filter_param
 void launch_mask_anno_flat(const RecView& rv, const ReadView& rd, const hg_filter_params& P, int r_begin,
                            int r_end, FilterScratch& s, const MaskAnnoOut& out, cudaStream_t st);
 void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_params& P,
-                       FilterScratch& s, cudaStream_t st);
+                       FilterScratch& s, const PeerView& peer, cudaStream_t st);
+// peer exchange (sharded runs, hg_peer_connect): push the rank's histogram part / pick the median
+// from all parts / publish the masks K2 stored into the other ranks' arrays
+void launch_peer_hist_push(FilterScratch& s, const PeerView& peer, cudaStream_t st);
+void launch_peer_median_pick(const hg_filter_params& P, FilterScratch& s, const PeerView& peer, cudaStream_t st);
+void launch_peer_signal_masks(FilterScratch& s, const PeerView& peer, cudaStream_t st);
 void launch_debug_warp_sort(void* data, const int* off, int count, int descending, int* g, int* l, void* tmp,
                             cudaStream_t st);
 void launch_max_pileup(const int64_t* read_off, int n_read, int* out_max, cudaStream_t st);

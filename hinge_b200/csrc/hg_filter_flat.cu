@@ -85,6 +85,7 @@ struct FlatParams {
     int* __restrict__ big_list;
     const int* __restrict__ scal;        // [1] = MIN_COV (K2 only)
     int r_begin, r_end;                  // first / last A-read with records
+    int v2;                              // K1 ran in its second form (k_profile_flat2)
 };
 
 // Which 4-record group of a 1024-record tile a thread takes.  With the identity map the 32
@@ -111,7 +112,7 @@ __device__ __forceinline__ void finalize_read(const RecView& rv, const ReadView&
     F.cov_maxbin[read] = maxbin;
     F.mean_cov[read] = (rl >= 5000 && read >= F.r_begin && read <= F.r_end) ? mean : -1;
     uint8_t f = 0;
-    if (F.self_cnt[read] > 0) {
+    if (self_count(F.self_cnt[read]) > 0) {
         float cov = 0.0f;
         for (int64_t k = rv.read_off[read]; k < rv.read_off[read + 1]; k++) {
             if (rv.bread[k] != read) continue;
@@ -224,7 +225,7 @@ k_profile_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
     for (int r = tid; r < f1 - f0; r += kFlatThreads) {
         const int read = f0 + r;
         const int base = F.rbase[read];
-        if (F.self_cnt[read] <= 0 || base < 0) continue;
+        if (self_count(F.self_cnt[read]) <= 0 || base < 0) continue;
         int mx = -1, acc = 0;
         for (int64_t k = rv.read_off[read]; k < rv.read_off[read + 1]; k++) {
             const int as = rv.abpos[k], ae = rv.aepos[k];
@@ -295,7 +296,200 @@ k_profile_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
             continue;
         }
         finalize_read(rv, rd, F, read, sh_sum[read - f0],
-                      F.self_cnt[read] > 0 ? sh_max2[read - f0] : sh_max[read - f0]);
+                      self_count(F.self_cnt[read]) > 0 ? sh_max2[read - f0] : sh_max[read - f0]);
+    }
+}
+
+// ------------------------------------------------------------------ K1, second form
+//
+// The first form above is bound by its shared-memory atomics (ncu, round 1: 10.8 M ATOMS warp
+// instructions = 47 M of the 58 M shared-memory wavefronts, l1tex 89 %, HBM 36 %): four per
+// record for the two profiles plus the per-read sum / maximum.  This form needs TWO per record
+// and none per read.
+//
+// Both profiles are differences of the same two counting functions (LAInterface.cpp:4298-4320
+// counts, for entry j, the events at positions < 40 j):
+//     cov0[j] = #{abpos < 40 j}     - #{aepos < 40 j}
+//     covC[j] = #{abpos < 40 j - C} - #{aepos < 40 j + C}
+// so with C a multiple of 20 (nominal: 300) ONE histogram of the record starts and ends on a
+// 20-bp grid (starts in the low half of a word, ends in the high half) and ONE exclusive prefix
+// sum P over it give   cov0[j] = P_S(2 j) - P_E(2 j),   covC[j] = P_S(2 j - C/20) - P_E(2 j + C/20).
+// The prefix sum runs over the whole batch; a read's own counts are differences of P inside its
+// word range (everything before it has both started and ended), taken mod 2^16.
+//
+//   scatter   two ATOMS per record into hist[2 base + pos / 20]
+//   scan      each thread owns 32 histogram words = 16 bins: E[q] = P(2 q), Q[q] = P(2 q + 1),
+//             written back as two arrays so that the look-ups below are unit-stride
+//   per read  one warp per read walks its bins: packs (cov0, covC) into the word K2 expects
+//             (bit-identical to the first form's), stores it, and reduces the profile's sum and
+//             length on the way (filter.cpp:642-656) -- no atomics
+//
+// The profile length is 1 + the last bin with cov0 > 0, which holds unless a record lies inside
+// one 40-bp bin (abpos / 40 == aepos / 40); the ingest flags reads that have such a record
+// (kSelfDegenerate) and their sum / length come from the per-read fallback.  Batches with more
+// than 65535 records (the 16-bit halves of P would run into each other) are left to the
+// fallbacks entirely, here and in K2.
+constexpr int kV2QOff = kFlatBins + 32;                 // where Q starts inside the buffer
+constexpr int kV2Words = 2 * kFlatBins + 64;
+constexpr int kV2MaxBatchRecords = 65535;
+
+// Histogram layout: a thread of the scan owns 32 consecutive words = 8 vectors, so the 8 lanes
+// of a quarter warp are 128 B apart; XOR-ing the vector index with the thread index spreads them
+// over the eight 16-byte bank groups.
+__device__ __forceinline__ int swh(int j) { return j ^ (((j >> 5) & 7) << 2); }
+
+template <int SPREAD>
+__global__ void __launch_bounds__(kFlatThreads)
+k_profile_flat2(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
+    __shared__ __align__(16) uint32_t buf[kV2Words];
+    __shared__ uint32_t wtot[kFlatThreads / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int2 bt = F.batch[blockIdx.x];
+    const int f0 = bt.x, f1 = F.batch[blockIdx.x + 1].x;
+    const int64_t k_begin = bt.y > 0 ? rv.read_off[f0] : 0, k_end = bt.y > 0 ? rv.read_off[f1] : 0;
+    const int nb = (k_end - k_begin > kV2MaxBatchRecords) ? 0 : bt.y;
+
+    if (nb > 0) {
+        // ---- the batch's records: four per thread and step (abpos / aepos; aread for the base)
+        const int64_t g0 = k_begin & ~(int64_t)3;
+        const int grp = flat_group<SPREAD>(tid) * 4;
+        int4 va = make_int4(-1, -1, -1, -1), vs = make_int4(0, 0, 0, 0), ve = vs;
+        auto load4 = [&](int64_t k) {
+            if (k >= k_begin && k + 4 <= k_end) {
+                va = __ldg(reinterpret_cast<const int4*>(rv.aread + k));
+                vs = __ldg(reinterpret_cast<const int4*>(rv.abpos + k));
+                ve = __ldg(reinterpret_cast<const int4*>(rv.aepos + k));
+            } else {  // ragged ends of the batch: records outside it get read id -1
+                int a[4], s[4], e[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int64_t ki = k + i;
+                    const bool in = ki >= k_begin && ki < k_end;
+                    a[i] = in ? __ldg(rv.aread + ki) : -1;
+                    s[i] = in ? __ldg(rv.abpos + ki) : 0;
+                    e[i] = in ? __ldg(rv.aepos + ki) : 0;
+                }
+                va = make_int4(a[0], a[1], a[2], a[3]);
+                vs = make_int4(s[0], s[1], s[2], s[3]);
+                ve = make_int4(e[0], e[1], e[2], e[3]);
+            }
+        };
+        if (g0 < k_end) load4(g0 + grp);  // in flight while the histogram is cleared
+
+        // ---- zero (swh permutes inside aligned 256-word blocks)
+        const int nzero = min((2 * nb + 255) & ~255, 2 * kFlatBins);
+        for (int j = tid * 4; j < nzero; j += kFlatThreads * 4) sts128(buf + j, make_uint4(0, 0, 0, 0));
+        __syncthreads();
+
+        // ---- scatter: start -> low half, end -> high half of hist[2 base + pos / 20]
+        for (int64_t kb = g0; kb < k_end; kb += kFlatThreads * 4) {
+            const int a[4] = {va.x, va.y, va.z, va.w}, s[4] = {vs.x, vs.y, vs.z, vs.w};
+            const int e[4] = {ve.x, ve.y, ve.z, ve.w};
+            if (kb + kFlatThreads * 4 < k_end) load4(kb + kFlatThreads * 4 + grp);
+            // records are sorted by A-read: in most groups one lookup of the read's base serves all four
+            const int base0 = a[0] >= 0 ? __ldg(F.rbase + a[0]) : -1;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int base = base0;
+                if (a[i] != a[0]) base = a[i] >= 0 ? __ldg(F.rbase + a[i]) : -1;
+                if (base < 0) continue;
+                // 0 <= abpos < aepos <= rlen (ingest check)
+                atomicAdd(&buf[swh(2 * base + (int)((unsigned)s[i] / 20u))], 1u);
+                atomicAdd(&buf[swh(2 * base + (int)((unsigned)e[i] / 20u))], 1u << 16);
+            }
+        }
+        // A == B records are inactive (filter.cpp:538-547) and rare; their per-read count comes
+        // from the ingest.  One thread per such read takes their events out again.
+        for (int r = tid; r < f1 - f0; r += kFlatThreads) {
+            const int read = f0 + r;
+            const int base = F.rbase[read];
+            if (self_count(F.self_cnt[read]) <= 0 || base < 0) continue;
+            for (int64_t k = rv.read_off[read]; k < rv.read_off[read + 1]; k++) {
+                if (rv.bread[k] != read) continue;
+                atomicAdd(&buf[swh(2 * base + (int)((unsigned)rv.abpos[k] / 20u))], 0u - 1u);
+                atomicAdd(&buf[swh(2 * base + (int)((unsigned)rv.aepos[k] / 20u))], 0u - (1u << 16));
+            }
+        }
+        __syncthreads();
+
+        // ---- exclusive prefix sum over the 20-bp histogram, one pass: thread t owns bins
+        // [16 t, 16 t + 16) = words [32 t, 32 t + 32)
+        uint32_t he[kFlatItems], ho[kFlatItems];
+        const int q0 = tid * kFlatItems;
+        uint32_t tot = 0;
+        if (q0 < nb) {
+#pragma unroll
+            for (int v = 0; v < 8; v++) {
+                const uint4 x = lds128(buf + 32 * tid + 4 * (v ^ (tid & 7)));
+                he[2 * v] = x.x; ho[2 * v] = x.y; he[2 * v + 1] = x.z; ho[2 * v + 1] = x.w;
+            }
+#pragma unroll
+            for (int i = 0; i < kFlatItems; i++) {
+                const uint32_t e0 = he[i], o0 = ho[i];
+                he[i] = tot;        // E[q] = P(2 q)
+                ho[i] = tot + e0;   // Q[q] = P(2 q + 1)
+                tot += e0 + o0;
+            }
+        }
+        const uint32_t incl = warp_incl_scan(tot);
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();  // every histogram word has been read: the buffer is free for E and Q
+        uint32_t pre = incl - tot, total = 0;
+#pragma unroll
+        for (int w = 0; w < kFlatThreads / 32; w++) {
+            const uint32_t t = wtot[w];
+            if (w < warp) pre += t;
+            total += t;
+        }
+        if (q0 < nb) {
+            const int sx = sw(q0) ^ q0;  // the flipped bits: common to the whole 16-word chunk
+#pragma unroll
+            for (int v = 0; v < kFlatItems / 4; v++) {
+                sts128(buf + ((q0 + 4 * v) ^ sx),
+                       make_uint4(he[4 * v] + pre, he[4 * v + 1] + pre, he[4 * v + 2] + pre, he[4 * v + 3] + pre));
+                sts128(buf + kV2QOff + ((q0 + 4 * v) ^ sx),
+                       make_uint4(ho[4 * v] + pre, ho[4 * v + 1] + pre, ho[4 * v + 2] + pre, ho[4 * v + 3] + pre));
+            }
+        }
+        if (tid == 0 && (nb & (kFlatItems - 1)) == 0) buf[sw(nb)] = total;  // E[nb]: the chunk it is in was skipped
+        __syncthreads();
+    }
+
+    // ---- per read, one warp each: the packed profile words for K2, profile sum and length
+    const int c20 = P.cut_off / 20, h = c20 >> 1, odd = c20 & 1;
+    const uint32_t* const arr = odd ? buf + kV2QOff : buf;  // P at odd / even 20-bp indices
+    const int hs = h + odd;
+    uint32_t* const pw = F.prof + (size_t)blockIdx.x * kFlatBins;
+    for (int read = f0 + warp; read < f1; read += kFlatThreads / 32) {
+        const int base = F.rbase[read];
+        const int64_t nrec = rv.read_off[read + 1] - rv.read_off[read];
+        if (base < 0 || nb == 0 || nrec > Packed<uint32_t>::kMaxCount) {
+            if (lane == 0) F.big_list[atomicAdd(&F.counters1[0], 1)] = read;
+            continue;
+        }
+        const int nbz = bins_needed(rd.rlen[read], P);
+        const uint32_t p_first = buf[sw(base)], p_last = buf[sw(base + nbz)];
+        int sum = 0, last = -1;
+        for (int j = lane; j < nbz; j += 32) {
+            const uint32_t ex = buf[sw(base + j)];
+            const int ms = j - hs, me = j + h;
+            const uint32_t ps = ms < 0 ? p_first : arr[sw(base + ms)];
+            const uint32_t pe = me >= nbz ? p_last : arr[sw(base + me)];
+            const uint32_t c0 = (ex - (ex >> 16)) & 0xffffu;
+            const uint32_t c1 = (ps - (pe >> 16)) & 0xffffu;
+            pw[base + j] = c0 | (c1 << 16);
+            sum += (int)c0;
+            if (c0) last = j;
+        }
+        sum = warp_sum(sum);
+        last = warp_max(last);
+        if (lane == 0) {
+            if (is_degenerate(F.self_cnt[read]))  // a record inside one bin: length from the records
+                F.big_list[atomicAdd(&F.counters1[0], 1)] = read;
+            else
+                finalize_read(rv, rd, F, read, sum, last < 0 ? -1 : last + 1);
+        }
     }
 }
 
@@ -339,8 +533,10 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
     const int f0 = bt.x, f1 = F.batch[blockIdx.x + 1].x;
     const int MIN_COV = F.scal[1];
     constexpr int reso = kReso;
-    // MIN_COV < 0: runs could cross read boundaries, everything goes the generic way
-    const int nb = MIN_COV < 0 ? 0 : bt.y;
+    // MIN_COV < 0: runs could cross read boundaries, everything goes the generic way; so do the
+    // batches the second form of K1 declined (more records than its 16-bit prefix counts hold)
+    const bool declined = F.v2 && bt.y > 0 && rv.read_off[f1] - rv.read_off[f0] > kV2MaxBatchRecords;
+    const int nb = (MIN_COV < 0 || declined) ? 0 : bt.y;
     const int npass = (nb + kFlatPass - 1) / kFlatPass;
     const uint32_t* __restrict__ const pw = F.prof + (size_t)blockIdx.x * kFlatBins;
 
@@ -595,8 +791,14 @@ void flat_plan(const int* rlen, int lo, int hi, int n_read, int cut_off, std::ve
     batch->push_back(make_int2(hi, 0));
 }
 
-static FlatParams flat_params(const FilterScratch& s, int r_begin, int r_end) {
+// The second form of K1 needs the cut-off on the 20-bp grid (nominal: 300).
+static bool use_v2(const FilterScratch& s, const hg_filter_params& P) {
+    return s.flat_kernel != 1 && P.cut_off >= 0 && P.cut_off % 20 == 0;
+}
+
+static FlatParams flat_params(const FilterScratch& s, const hg_filter_params& P, int r_begin, int r_end) {
     FlatParams F;
+    F.v2 = use_v2(s, P) ? 1 : 0;
     F.batch = s.flat_batch;
     F.rbase = s.flat_rbase;
     F.self_cnt = s.self_cnt;
@@ -615,14 +817,20 @@ static FlatParams flat_params(const FilterScratch& s, int r_begin, int r_end) {
 // Phase 1 of the stage: both coverage profiles of every owned read, their lengths and means.
 void launch_profile(const RecView& rv, const ReadView& rd, const hg_filter_params& P, int r_begin,
                     int r_end, FilterScratch& s, cudaStream_t st) {
-    const FlatParams F = flat_params(s, r_begin, r_end);
+    const FlatParams F = flat_params(s, P, r_begin, r_end);
     // the counters of both phases; per-read results of reads outside the planned range were
     // cleared when the plan was made (hg_capi.cu)
     cudaMemsetAsync(s.counters, 0, sizeof(int) * 16, st);
     const int grid = s.flat_nbatch;
     if (grid <= 0) return;
     g_launches += 2;
-    switch (s.flat_spread) {
+    if (F.v2) switch (s.flat_spread) {
+        case 1: k_profile_flat2<1><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;
+        case 4: k_profile_flat2<4><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;
+        case 16: k_profile_flat2<16><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;
+        default: k_profile_flat2<8><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;
+    }
+    else switch (s.flat_spread) {
         case 1: k_profile_flat<1><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;
         case 4: k_profile_flat<4><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;
         case 16: k_profile_flat<16><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;
@@ -635,7 +843,7 @@ void launch_profile(const RecView& rv, const ReadView& rd, const hg_filter_param
 // for the reads it reports is launched by launch_mask_anno, hg_filter.cu).
 void launch_mask_anno_flat(const RecView& rv, const ReadView& rd, const hg_filter_params& P, int r_begin,
                            int r_end, FilterScratch& s, const MaskAnnoOut& out, cudaStream_t st) {
-    const FlatParams F = flat_params(s, r_begin, r_end);
+    const FlatParams F = flat_params(s, P, r_begin, r_end);
     const int grid = s.flat_nbatch;
     if (grid <= 0) return;
     g_launches += 1;

@@ -277,6 +277,8 @@ extern "C" int hg_main_filter(int argc, char** argv) {
     }
     hg_ctx_destroy(ctx);
     timer.lap("fetch results + destroy");
+    timer.note("h2d bytes", 28.0 * (double)las.novl + 4.0 * n + (db.has_qv ? (double)db.qv.size() : 0.0), "B");
+    timer.note("d2h bytes", 17.0 * n + 8.0 * (n + 1) + 9.0 * (double)sum.n_annotations + 4.0 * (double)cov.size(), "B");
 
     const std::string& x = a.prefix;
     {  // filter.cpp:449-457 opens all of these, some stay empty

@@ -32,6 +32,10 @@ struct PhaseTimer {
                 1e3 * (double)(t1.tv_sec - t0.tv_sec) + 1e-6 * (double)(t1.tv_nsec - t0.tv_nsec));
         t0 = t1;
     }
+    // a quantity next to the phase times, same line format (bench.py parses both)
+    void note(const char* what, double value, const char* unit) {
+        if (on) fprintf(stderr, "[hinge_b200 timing] %-28s %8.1f %s\n", what, value, unit);
+    }
 };
 
 bool parse_args(int argc, char** argv, bool layout, Args* a, std::string* err);

@@ -2,75 +2,147 @@
 
 Overlap records of one A-read are contiguous in a LAsort-ed .las
 (thirdparty/DALIGNER/LAsort.c:28-67), so reads — and with them their pile-ups —
-shard by A-read id.  Two per-read arrays cross shards inside `hinge filter`:
+shard by A-read id: every rank owns a contiguous range of A-reads holding about the
+same volume of records.  What crosses shards:
 
-  * the per-read mean coverage, whose global median sets MIN_COV
-    (filter.cpp:642-678).  The median is found by counting, so the ranks only sum
-    their 4096-bin histograms of it                         -> all-reduce, 16 KB
-  * the mask of every B read a pile-up touches
-    (filter.cpp:884-889)                                    -> all-gather, 4 B/read
-    (both bounds are multiples of gcd(40, tspace) and travel as 16-bit units; 8 B/read
-    when a read is too long for that)
+  inside `hinge filter`
+  * the per-read mean coverage, whose global median sets MIN_COV (filter.cpp:642-678).
+    The median is found by counting, so only a 4096-bin histogram travels (16 KB)
+  * the mask of every B read a pile-up touches (filter.cpp:884-889): 4 B per read
+    (both bounds are multiples of gcd(40, tspace) and travel as 16-bit units)
+  Two ways to move them (`exchange`):
+    "peer"  the kernels do it themselves over NVLink peer memory (hg_peer_export /
+            hg_peer_connect): the histogram kernel stores its part into every rank's
+            block, K2 stores each packed mask word into every rank's array, arrival flags
+            replace the barrier — hg_filter stays ONE stream of kernels with no host or
+            NCCL call in between
+    "nccl"  phase-level calls with an all-reduce and an all-gather between them
 
-Both live in padded torch tensors bound into the context (hg_bind_buffer), so
-`torch.distributed.all_gather_into_tensor` moves them over NCCL/NVLink in place.
-This module holds only the host-side plumbing; it runs unchanged on the gloo
+  before `hinge layout` (north_star's "single NCCL all-gather of the hinge / maximal-read
+  bitmaps")
+  * hinge and repeat lists of every read, the maximal-read bitmap
+
+This module holds only the host-side plumbing; the NCCL paths run unchanged on the gloo
 backend with CPU tensors (tests/test_sharding_gloo.py).
 """
+import math
+
+import numpy as np
 import torch
 import torch.distributed as dist
 
 
-def shard_ranges(n_read, world):
-    """Equal read-count slices [lo, hi) per rank plus the padded slice length.
+def shard_ranges(n_read, world, weights=None):
+    """Contiguous read ranges [lo, hi) per rank.
 
-    Equal counts (not equal record counts) keep every rank's slice of the
-    exchanged arrays the same size, which all_gather_into_tensor needs; read ids
-    are in sequencing order, so record counts balance statistically."""
-    chunk = (n_read + world - 1) // world
-    return [(min(n_read, r * chunk), min(n_read, (r + 1) * chunk)) for r in range(world)], chunk
+    weights=None: equal read counts (what `all_gather_into_tensor` needs).
+    weights=w[n_read]: equal cumulative weight — pass the per-read record counts
+    (np.diff(read_off)) or, before the records exist, the read lengths (pile-up depth
+    goes with read length); cuts fall on read boundaries."""
+    if weights is None:
+        chunk = (n_read + world - 1) // world
+        return [(min(n_read, r * chunk), min(n_read, (r + 1) * chunk)) for r in range(world)], chunk
+    cum = np.cumsum(np.asarray(weights, dtype=np.float64))
+    total = float(cum[-1]) if n_read else 0.0
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(cum, total * r / world, side="left")))
+    cuts.append(n_read)
+    for r in range(1, world + 1):  # monotone, non-empty where possible
+        cuts[r] = max(cuts[r], cuts[r - 1])
+    ranges = [(cuts[r], cuts[r + 1]) for r in range(world)]
+    return ranges, max(hi - lo for lo, hi in ranges)
 
 
 class ShardedArrays:
-    """The two exchanged per-read arrays of one rank."""
+    """The exchanged per-read arrays of one rank (NCCL exchange) or the peer-memory
+    connection of its context (peer exchange)."""
 
-    def __init__(self, n_read, rank, world, device):
-        self.rank, self.world = rank, world
-        self.ranges, self.chunk = shard_ranges(n_read, world)
+    def __init__(self, n_read, rank, world, device, weights=None, equal_slices=False):
+        self.rank, self.world, self.n_read, self.device = rank, world, n_read, device
+        self.ranges, self.chunk = shard_ranges(n_read, world, None if equal_slices else weights)
         self.lo, self.hi = self.ranges[rank]
-        self.mean_cov = torch.full((world * self.chunk,), -1, dtype=torch.int32, device=device)
-        self.mask = torch.zeros((world * self.chunk, 2), dtype=torch.int32, device=device)
-        self.hist = torch.zeros((4098,), dtype=torch.int32, device=device)  # HG_BUF_MEDIAN_HIST
-        self.mask_pk = torch.zeros((world * self.chunk,), dtype=torch.int32, device=device)
+        self.exchange = "none"
         self.packed = False
+        self.mask = self.hist = self.mask_pk = None
+        self.g = 1
 
-    def bind(self, ctx):
-        """Makes the context compute straight into the exchanged arrays."""
+    # ---- binding
+    def bind(self, ctx, exchange="nccl", group=None):
+        """Makes the context compute straight into the exchanged arrays (nccl) or connects
+        the contexts of all ranks through peer memory (peer)."""
         from . import api
 
-        if self.world > 1:
-            ctx.bind_buffer(api.HG_BUF_MEDIAN_HIST, self.hist)
-            try:
-                ctx.bind_buffer(api.HG_BUF_MASK_PACKED, self.mask_pk)
-                self.packed = True
-            except Exception:  # a read too long for 16-bit bounds: exchange the full masks
-                self.packed = False
-        if not self.packed:
+        self.ctx = ctx
+        if self.world == 1:
+            return
+        if exchange == "peer":
+            handle = ctx.peer_export(self.rank, self.world)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle, group=group)
+            ctx.peer_connect(b"".join(handles))
+            dist.barrier(group=group)  # every rank has mapped every block before anyone writes
+            self.exchange = "peer"
+            return
+        if any(hi - lo != self.chunk for lo, hi in self.ranges[:-1]):
+            raise ValueError("the NCCL exchange needs equal read-count slices (equal_slices=True)")
+        self.exchange = "nccl"
+        n = self.world * self.chunk
+        self.hist = torch.zeros((4098,), dtype=torch.int32, device=self.device)  # HG_BUF_MEDIAN_HIST
+        ctx.bind_buffer(api.HG_BUF_MEDIAN_HIST, self.hist)
+        self.mask_pk = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        try:
+            ctx.bind_buffer(api.HG_BUF_MASK_PACKED, self.mask_pk)
+            self.packed = True
+        except api.HingeError:  # a read too long for 16-bit bounds: exchange the full masks
+            self.packed = False
+            self.mask = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
             ctx.bind_buffer(api.HG_BUF_MASK, self.mask)
 
-    def exchange(self, t):
+    def set_global_range(self, ctx, first_aread, last_aread, group=None):
+        """The reference's r_begin / r_end are the first and last A-read of the WHOLE .las
+        (filter.cpp:516-517); a shard only sees its own records."""
+        if self.world > 1:
+            t = torch.tensor([-first_aread, last_aread], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            first_aread, last_aread = -int(t[0].item()), int(t[1].item())
+        ctx.set_global_range(first_aread, last_aread)
+
+    def exchange_slices(self, t):
         """All-gather the rank's own slice of `t` into every rank's copy of `t`."""
         if self.world == 1:
             return
         mine = t[self.rank * self.chunk:(self.rank + 1) * self.chunk].clone()
         dist.all_gather_into_tensor(t, mine)
 
+    def gathered_mask(self, n_read):
+        """The masks of ALL reads as this rank holds them after a run (numpy, n_read x 2)."""
+        if self.exchange == "peer":
+            return self.ctx.peer_masks()
+        if self.packed:
+            pk = self.mask_pk[:n_read].cpu().numpy().view(np.uint32)
+            g = math.gcd(40, self.ctx.tspace)
+            return np.stack([(pk & 0xffff).astype(np.int32) * g, (pk >> 16).astype(np.int32) * g], axis=1)
+        return self.mask[:n_read].cpu().numpy()
 
-def run_filter_sharded(ctx, params, arrays):
-    """hg_filter split at its two global dependencies (include/hinge_b200.h)."""
-    ctx.filter_phase1(params)
-    if arrays.world > 1:
+
+def run_filter_sharded(ctx, params, arrays, max_attempts=8):
+    """hg_filter on a shard.  Returns (rc, summary)."""
+    from . import api
+
+    if arrays.world == 1 or arrays.exchange == "peer":
+        # one stream of kernels; with peer exchange the annotation-pool retry is agreed on between
+        # the ranks on the device, so every rank reruns together
+        return 0, ctx.filter(params)
+    for _ in range(max_attempts):
+        ctx.filter_phase1(params)
         dist.all_reduce(arrays.hist)  # the context was bound to arrays.hist (HG_BUF_MEDIAN_HIST)
-    ctx.filter_phase2()
-    arrays.exchange(arrays.mask_pk if arrays.packed else arrays.mask)
-    return ctx.filter_phase3()
+        ctx.filter_phase2()
+        arrays.exchange_slices(arrays.mask_pk if arrays.packed else arrays.mask)
+        rc, s = ctx.filter_phase3()
+        # a pool overflow on one rank reruns the stage on all of them (phase 3 has grown the pool)
+        t = torch.tensor([rc], dtype=torch.int32, device=arrays.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if int(t.item()) != api.HG_RETRY_POOL:
+            return rc, s
+    return api.HG_RETRY_POOL, s

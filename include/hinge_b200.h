@@ -36,14 +36,18 @@ typedef enum hg_status {
 
 enum { HG_MEM_HOST = 0, HG_MEM_DEVICE = 1 };
 
-/* positive, non-fatal: the variable-size annotation pool was too small; the
- * phase-level caller grows it (hg_filter does this itself) and reruns */
+/* positive, non-fatal: the variable-size annotation pool was too small.  hg_filter_phase3 has
+ * already grown it: rerun phases 1-3 (hg_filter does this itself; sharded callers rerun on ALL
+ * ranks, see hinge_b200/sharding.py) */
 #define HG_RETRY_POOL 1
 
 enum hg_option {
     HG_OPT_KEEP_COVERAGE = 1, /* keep the 40-bp coverage profiles (.coverage.txt) */
     HG_OPT_PROFILE = 2,       /* record CUDA events between the kernels of a stage */
-    HG_OPT_SCATTER_SPREAD = 3 /* tuning aid: record windows per warp in the profile scatter (1, 4, 8, 16) */
+    HG_OPT_SCATTER_SPREAD = 3,/* tuning aid: record windows per warp in the profile scatter (1, 4, 8, 16) */
+    HG_OPT_PROFILE_KERNEL = 4 /* tuning aid: 0 = pick the form of the coverage-profile kernel by cut_off
+                                 (20-bp start/end histogram when cut_off % 20 == 0), 1 = always the
+                                 four-event 40-bp form */
 };
 
 enum hg_buffer { /* per-read device arrays a sharded run exchanges between phases */
@@ -107,6 +111,34 @@ int hg_set_overlaps(hg_ctx* ctx, int64_t novl, const int32_t* aread, const int32
                     const int32_t* bepos, const int32_t* diffs, const int32_t* flags,
                     const int64_t* trace_off, const uint8_t* trace, int32_t tbytes, int32_t where,
                     int32_t a_lo, int32_t a_hi);
+
+/* A context that owns a slice of the reads sees only its own records; the reference's
+ * r_begin / r_end are the first and last A-read of the WHOLE .las (filter.cpp:516-517) and
+ * decide which record-less reads still get a mask / a coverage-estimate entry.  Call after
+ * hg_set_overlaps with the global values (min / max over the shards); it stays in force for
+ * later hg_set_overlaps calls whose records lie inside it, until the next hg_set_reads. */
+int hg_set_global_range(hg_ctx* ctx, int32_t first_aread, int32_t last_aread);
+
+/* ---- phase exchange of sharded contexts through NVLink peer memory ------ */
+
+/* Instead of phase-level calls with NCCL collectives in between, the contexts of all ranks can
+ * be connected once; hg_filter on each of them (called collectively) then runs as ONE stream of
+ * kernels: the histogram kernel stores its part into every rank's exchange block, K2 stores
+ * every packed mask word into every rank's array, and arrival flags in peer memory replace the
+ * barriers (a rank that never arrives turns into HG_ERR_CUDA after 4 s, not a hung GPU).
+ *   hg_peer_export   allocates this rank's exchange block; one-process-per-GPU callers get a
+ *                    CUDA IPC handle (HG_PEER_HANDLE_BYTES) to pass to the other ranks
+ *   hg_peer_connect  maps the blocks of all ranks: `handles` = world x HG_PEER_HANDLE_BYTES in
+ *                    rank order (the own entry is ignored); synchronise the ranks afterwards,
+ *                    before the first hg_filter
+ *   hg_peer_connect_local  the same for `world` contexts of ONE process (peer access, no IPC)
+ * Needs 16-bit packable masks (see HG_BUF_MASK_PACKED) and world <= 16. */
+#define HG_PEER_HANDLE_BYTES 64
+int hg_peer_export(hg_ctx* ctx, int32_t rank, int32_t world, void* handle_out);
+int hg_peer_connect(hg_ctx* ctx, const void* handles);
+int hg_peer_connect_local(hg_ctx** ctxs, int32_t world);
+/* The masks of ALL reads as this rank holds them after a peer-connected run (2 ints per read). */
+int hg_peer_masks(hg_ctx* ctx, int32_t* mask);
 
 /* ---- hinge filter (filter.cpp:529-1098) -------------------------------- */
 

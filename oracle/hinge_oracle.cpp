@@ -17,6 +17,9 @@
 #include <map>
 #include <set>
 #include <sstream>
+#include <atomic>
+#include <functional>
+#include <thread>
 #include <unordered_map>
 
 namespace oracle {
@@ -35,9 +38,33 @@ struct Ov {
     int type = UNDEFINED, weight = 0, length = 0;
 };
 
-static void ingest(const Data& d, std::vector<Ov>* ovs) {
+// Loops whose iterations are independent (one read, or one record, each) may be spread over
+// host threads (Params::threads, used by bench.py's verification leg on 100 M-record sets); every
+// iteration computes exactly what the sequential loop computes, so the results do not depend on
+// the thread count.
+static void parallel_for(int64_t lo, int64_t hi, int threads, const std::function<void(int64_t)>& fn) {
+    if (threads <= 1 || hi - lo < 2) {
+        for (int64_t i = lo; i < hi; i++) fn(i);
+        return;
+    }
+    std::atomic<int64_t> next(lo);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(4096, (hi - lo) / (threads * 8)));
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++)
+        th.emplace_back([&]() {
+            for (;;) {
+                const int64_t b = next.fetch_add(chunk);
+                if (b >= hi) break;
+                const int64_t e = std::min(hi, b + chunk);
+                for (int64_t i = b; i < e; i++) fn(i);
+            }
+        });
+    for (auto& t : th) t.join();
+}
+
+static void ingest(const Data& d, std::vector<Ov>* ovs, int threads = 1) {
     ovs->resize((size_t)d.novl);
-    for (int64_t k = 0; k < d.novl; k++) {
+    parallel_for(0, d.novl, threads, [&](int64_t k) {
         Ov& o = (*ovs)[k];
         o.a = d.aread[k];
         o.b = d.bread[k];
@@ -53,7 +80,7 @@ static void ingest(const Data& d, std::vector<Ov>* ovs) {
             o.be = blen - d.bbpos[k];
         }
         o.rec = k;
-    }
+    });
 }
 
 static inline int span(const Ov* o) { return (o->ae - o->as) + (o->be - o->bs); }
@@ -229,8 +256,9 @@ static void qv_masks(const Data& d, std::vector<PII>* qm) {
 
 void run_filter(const Data& d, const Params& p, FilterOut* out) {
     const int n_read = d.n_read;
+    const int T = p.threads;
     std::vector<Ov> ovs;
-    ingest(d, &ovs);
+    ingest(d, &ovs, T);
     std::vector<PII> qm;
     qv_masks(d, &qm);
     const bool use_qv = p.use_qv && d.has_qv;  // filter.cpp:409
@@ -259,14 +287,15 @@ void run_filter(const Data& d, const Params& p, FilterOut* out) {
         cov /= float(d.rlen[it.first]);
         if (cov > 4.5 && d.rlen[it.first] > 10000) self_match.insert(it.first);
     }
-    for (int i = 0; i < n_read; i++)  // filter.cpp:565-567
+    parallel_for(0, n_read, T, [&](int64_t i) {  // filter.cpp:565-567
         std::sort(pile[i].begin(), pile[i].end(), compare_overlap);
+    });
 
     // coverage profiles, filter.cpp:588-614
     out->cov0.assign(n_read, std::vector<PII>());
     out->covc.assign(n_read, std::vector<PII>());
     std::vector<std::vector<PII>> cgs(n_read);
-    for (int i = rb; i <= re; i++) {
+    parallel_for(rb, re + 1, T, [&](int64_t i) {
         profile_coverage(pile[i], &out->covc[i], p.reso, p.cut_off);
         profile_coverage(pile[i], &out->cov0[i], p.reso, 0);
         const std::vector<PII>& c = out->cov0[i];
@@ -275,7 +304,7 @@ void run_filter(const Data& d, const Params& p, FilterOut* out) {
                 cgs[i].push_back(PII(c[j].first, c[j + 1].second - c[j].second));
         else
             cgs[i].push_back(PII(0, 0));
-    }
+    });
 
     // coverage estimate, filter.cpp:633-678
     {
@@ -299,9 +328,9 @@ void run_filter(const Data& d, const Params& p, FilterOut* out) {
     // masks, filter.cpp:696-789
     out->mask.assign(n_read, PII(0, 0));
     out->cmask.assign(n_read, PII(0, 0));
-    std::vector<std::vector<PII>> covc = out->covc;  // thresholded working copy
-    for (int i = rb; i <= re; i++) {
-        std::vector<PII>& cc = covc[i];
+    std::vector<char> cov_flag(n_read, 0), self_flag(n_read, 0);
+    parallel_for(rb, re + 1, T, [&](int64_t i) {
+        std::vector<PII> cc = out->covc[i];  // thresholded working copy
         for (size_t j = 0; j < cc.size(); j++) {
             cc[j].second -= MIN_COV;
             if (cc[j].second < 0) cc[j].second = 0;
@@ -349,8 +378,8 @@ void run_filter(const Data& d, const Params& p, FilterOut* out) {
             }
         }
         if (p.del_telomere_filter) {
-            if (scov >= 10 * ecov || ecov >= 10 * scov) out->cov_flag.push_back(i);
-            if (self_match.count(i)) out->self_flag.push_back(i);
+            if (scov >= 10 * ecov || ecov >= 10 * scov) cov_flag[i] = 1;
+            if (self_match.count((int)i)) self_flag[i] = 1;
         }
         out->cmask[i] = PII(msc, mec);
         if (use_qv && p.use_coverage)
@@ -359,12 +388,16 @@ void run_filter(const Data& d, const Params& p, FilterOut* out) {
             out->mask[i] = PII(maxstart, maxend);
         else
             out->mask[i] = qm[i];
+    });
+    for (int i = rb; i <= re; i++) {
+        if (cov_flag[i]) out->cov_flag.push_back(i);
+        if (self_flag[i]) out->self_flag.push_back(i);
     }
     const std::vector<PII>& mask = out->mask;
 
     // repeat annotation + merge, filter.cpp:796-829
     out->repeats.assign(n_read, std::vector<PII>());
-    for (int i = rb; i <= re; i++) {
+    parallel_for(rb, re + 1, T, [&](int64_t i) {
         std::vector<PII>& anno = out->repeats[i];
         for (size_t j = 0; j + 1 < cgs[i].size(); j++) {
             int pos = cgs[i][j].first;
@@ -391,12 +424,12 @@ void run_filter(const Data& d, const Params& p, FilterOut* out) {
                 it++;
             }
         }
-    }
+    });
 
     // hinge calls, filter.cpp:838-1070
     out->hinges.assign(n_read, std::vector<PII>());
     const int THETA = p.theta, HBL = p.hinge_bin_length, HTL = p.hinge_tolerance_length;
-    for (int i = rb; i <= re; i++) {
+    parallel_for(rb, re + 1, T, [&](int64_t i) {
         int cs = 0, ns = 0, ne = 0, ce = 0;
         for (size_t j = 0; j < out->cov0[i].size(); j++) {
             int pos = out->cov0[i][j].first;
@@ -411,7 +444,7 @@ void run_filter(const Data& d, const Params& p, FilterOut* out) {
         }
         float avg_end = (float)ce / ne;
         float avg_start = (float)cs / ns;
-        if (std::abs(avg_end - avg_start) < 10) continue;
+        if (std::abs(avg_end - avg_start) < 10) return;
 
         for (size_t j = 0; j < out->repeats[i].size(); j++) {
             const int apos = out->repeats[i][j].first;
@@ -487,7 +520,7 @@ void run_filter(const Data& d, const Params& p, FilterOut* out) {
             if (!bridged && support > p.hinge_min_support)
                 out->hinges[i].push_back(PII(apos, out_hinge ? -1 : 1));
         }
-    }
+    });
 }
 
 // ------------------------------------------------------------------ maximal

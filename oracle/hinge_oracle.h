@@ -40,6 +40,7 @@ struct Params {
     int min_cc_size = 8;
     bool use_two_matches = true, keep_only_maximal = true;
     bool del_telomeres_layout = false;  // [layout] del_telomeres (hinging.cpp:803)
+    int threads = 1;  // host threads for the loops with independent iterations (results unchanged)
 };
 
 struct Data {

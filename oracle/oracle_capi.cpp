@@ -54,6 +54,9 @@ int orc_load_ini(void* h, const char* path) {
     return load_ini(path, &((OrcHandle*)h)->p, &err) ? 0 : -1;
 }
 
+// host threads for the loops with independent iterations (results do not depend on it)
+void orc_set_threads(void* h, int threads) { ((OrcHandle*)h)->p.threads = threads < 1 ? 1 : threads; }
+
 int orc_filter(void* hh) {
     OrcHandle* h = (OrcHandle*)hh;
     h->f = FilterOut();

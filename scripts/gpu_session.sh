@@ -1,0 +1,54 @@
+#!/bin/bash
+# One GPU-box session of round 2 (run under gpurun from the repo root):
+#   bash scripts/gpu_session.sh <tag> [steps...]
+# steps: pytest smoke bench bench_old launches ncu_k1 ncu_all sanitize
+set -u
+TAG=${1:-r02}
+shift || true
+STEPS=${*:-"pytest smoke bench"}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/${TAG}_gpu.txt 2>&1
+nproc >> $OUT/${TAG}_gpu.txt; free -g | head -2 >> $OUT/${TAG}_gpu.txt; df -h /tmp | tail -1 >> $OUT/${TAG}_gpu.txt
+SHORT="--steps 3 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-downstream --no-verify"
+for S in $STEPS; do
+  case $S in
+    pytest)
+      timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1
+      echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest_gpu.log; tail -5 $OUT/${TAG}_pytest_gpu.log ;;
+    smoke)
+      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1
+      echo "smoke exit $?" | tee -a $OUT/${TAG}_smoke.log; tail -2 $OUT/${TAG}_smoke.log ;;
+    bench)
+      timeout 1200 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+      echo "bench exit $?"; tail -3 $OUT/${TAG}_bench.err; tail -c 2500 $OUT/${TAG}_bench.json ;;
+    bench_ref)
+      timeout 900 python bench.py --impl reference --steps 1 --warmup 0 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err
+      echo "reference exit $?"; cat $OUT/${TAG}_bench_reference.json ;;
+    bench_old)
+      timeout 900 python bench.py --profile-kernel 1 --no-cpu-baseline --no-downstream --no-verify --e2e-steps 1 > $OUT/${TAG}_bench_k1old.json 2> $OUT/${TAG}_bench_k1old.err
+      echo "bench (old K1) exit $?"
+      python -c "
+import json;d=json.load(open('$OUT/${TAG}_bench_k1old.json'));print('c5',d['ms_per_step'],d['kernel_ms'],d['roofline']['frac']);print('c3',d['c3']['ms_per_step'],d['c3']['kernel_ms'],d['c3']['roofline']['frac'])" ;;
+    launches)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+        --log-file $OUT/${TAG}_launches.csv python bench.py $SHORT > $OUT/${TAG}_launches_bench.log 2>&1
+      echo "launch list exit $?" ;;
+    ncu_k1)
+      for CFG in c5 c3; do
+        timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^k_profile_flat2" -s 4 -c 1 -f \
+          -o $OUT/${TAG}_k_profile_flat2_$CFG python bench.py --config $CFG --also "" $SHORT > $OUT/${TAG}_ncu_k1_$CFG.log 2>&1
+        echo "ncu k_profile_flat2 $CFG exit $?"
+      done ;;
+    ncu_all)
+      for K in k_mask_anno_flat k_hinge_call k_hinge_exact; do
+        timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^$K" -s 4 -c 1 -f \
+          -o $OUT/${TAG}_${K}_c5 python bench.py --config c5 --also "" $SHORT > $OUT/${TAG}_ncu_${K}.log 2>&1
+        echo "ncu $K exit $?"
+      done ;;
+    sanitize)
+      timeout 900 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_memcheck_smoke.log 2>&1
+      echo "memcheck exit $?"; tail -3 $OUT/${TAG}_memcheck_smoke.log ;;
+  esac
+done
+ls -la $OUT | tail -30

@@ -1,5 +1,9 @@
-"""Run under torchrun with N >= 2 ranks: the sharded filter (reads split by A-read id,
-NCCL all-gathers between the phases) must reproduce the single-context result exactly."""
+"""Run under torchrun with N >= 2 ranks: the sharded filter (reads split by A-read id, balanced on
+record volume) must reproduce the single-context result exactly, with both forms of the phase
+exchange: inside the kernels through NVLink peer memory, and NCCL calls between phase-level calls.
+
+  torchrun --nproc-per-node 2 scripts/sharded_check.py [--shape c5]
+"""
 import os
 import sys
 
@@ -18,49 +22,58 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-names = ["aread", "bread", "abpos", "aepos", "bbpos", "bepos", "flags"]
-syn = hgsynth.Synth(genome_len=3_000_000, coverage=40.0, seed=321, n_families=12)
-arrays = ShardedArrays(syn.n_read, rank, world, dev)
-novl = syn.generate(arrays.lo, arrays.hi, want_trace=False, threads=4)
-cols = {k: v.copy() for k, v in syn.cols().items()}
-ctx = api.Context(local, torch.cuda.current_stream().cuda_stream)
-ctx.set_reads(syn.rlen, syn.qv_off, syn.qv, 100)
-arrays.bind(ctx)
-ctx.set_overlaps(novl, cols, a_lo=arrays.lo, a_hi=arrays.hi)
-rc, summ = run_filter_sharded(ctx, api.FilterParams(), arrays)
-assert rc == 0
-mine = ctx.filter_fetch(int(summ.n_annotations))
-parts = [None] * world
-dist.all_gather_object(parts, {k: mine[k] for k in ("cmask", "flags", "anno_off", "anno_pos", "anno_type", "hinge_keep")}
-                       | {"lo": arrays.lo, "hi": arrays.hi, "cov_est": summ.cov_est, "min_cov": summ.min_cov})
+if "c5" in sys.argv:  # long reads, several local alignments per pair (BASELINE configs[4] shape)
+    syn = hgsynth.Synth(genome_len=6_000_000, coverage=40.0, read_mean=24000, read_sd=8000, read_min=2000,
+                        seed=99, frag_prob=1.2, n_families=12)
+else:
+    syn = hgsynth.Synth(genome_len=3_000_000, coverage=40.0, seed=321, n_families=12)
+FIELDS = ("cmask", "flags", "anno_off", "anno_pos", "anno_type", "hinge_keep")
+want = None
 ok = True
-if rank == 0:
-    novl_all = syn.generate(0, syn.n_read, want_trace=False, threads=8)
-    ref = api.Context(local, torch.cuda.current_stream().cuda_stream)
-    ref.set_reads(syn.rlen, syn.qv_off, syn.qv, 100)
-    ref.set_overlaps(novl_all, {k: v.copy() for k, v in syn.cols().items()})
-    s1 = ref.filter(api.FilterParams())
-    want = ref.filter_fetch(int(s1.n_annotations))
-    if arrays.packed:  # both bounds in units of gcd(40, tspace), 16 bits each
-        import math
-
-        pk = arrays.mask_pk[:syn.n_read].cpu().numpy().view(np.uint32)
-        g = math.gcd(40, 100)
-        got_mask = np.stack([(pk & 0xffff).astype(np.int32) * g, (pk >> 16).astype(np.int32) * g], axis=1)
-    else:
-        got_mask = arrays.mask[:syn.n_read].cpu().numpy()
-    ok &= bool(np.array_equal(got_mask, want["mask"]))
-    for p in parts:
-        lo, hi = p["lo"], p["hi"]
-        ok &= (p["cov_est"], p["min_cov"]) == (s1.cov_est, s1.min_cov)
-        ok &= bool(np.array_equal(p["cmask"][lo:hi], want["cmask"][lo:hi]))
-        ok &= bool(np.array_equal(p["flags"][lo:hi], want["flags"][lo:hi]))
-        a0, a1 = want["anno_off"][lo], want["anno_off"][hi]
-        ok &= bool(np.array_equal(np.diff(p["anno_off"][lo:hi + 1]), np.diff(want["anno_off"][lo:hi + 1])))
-        for k in ("anno_pos", "anno_type", "hinge_keep"):
-            ok &= bool(np.array_equal(p[k], want[k][a0:a1]))
-    print("SHARDED_CHECK", "OK" if ok else "MISMATCH", "world", world, "reads", syn.n_read, "overlaps", novl_all,
-          "annotations", int(s1.n_annotations), "hinges", int(want["hinge_keep"].sum()))
-dist.barrier()
+for exchange in ("peer", "nccl"):
+    arrays = ShardedArrays(syn.n_read, rank, world, dev, weights=syn.rlen, equal_slices=(exchange == "nccl"))
+    novl = syn.generate(arrays.lo, arrays.hi, want_trace=False, threads=4)
+    cols = {k: v.copy() for k, v in syn.cols().items()}
+    ctx = api.Context(local, torch.cuda.current_stream().cuda_stream)
+    ctx.set_reads(syn.rlen, syn.qv_off, syn.qv, 100)
+    arrays.bind(ctx, exchange=exchange)
+    ctx.set_overlaps(novl, cols, a_lo=arrays.lo, a_hi=arrays.hi)
+    arrays.set_global_range(ctx, int(cols["aread"][0]), int(cols["aread"][-1]))
+    for rep in range(3):  # several epochs of the arrival flags
+        rc, summ = run_filter_sharded(ctx, api.FilterParams(), arrays)
+        assert rc == 0
+    mine = ctx.filter_fetch(int(summ.n_annotations))
+    part = {k: mine[k] for k in FIELDS}
+    part.update(lo=arrays.lo, hi=arrays.hi, cov_est=summ.cov_est, min_cov=summ.min_cov,
+                mask_all=arrays.gathered_mask(syn.n_read))
+    parts = [None] * world
+    dist.all_gather_object(parts, part)
+    if rank == 0:
+        if want is None:
+            novl_all = syn.generate(0, syn.n_read, want_trace=False, threads=8)
+            ref = api.Context(local, torch.cuda.current_stream().cuda_stream)
+            ref.set_reads(syn.rlen, syn.qv_off, syn.qv, 100)
+            ref.set_overlaps(novl_all, {k: v.copy() for k, v in syn.cols().items()})
+            s1 = ref.filter(api.FilterParams())
+            want = ref.filter_fetch(int(s1.n_annotations))
+            ref.close()
+        good = True
+        for p in parts:
+            lo, hi = p["lo"], p["hi"]
+            good &= (p["cov_est"], p["min_cov"]) == (s1.cov_est, s1.min_cov)
+            good &= bool(np.array_equal(p["mask_all"], want["mask"]))
+            good &= bool(np.array_equal(p["cmask"][lo:hi], want["cmask"][lo:hi]))
+            good &= bool(np.array_equal(p["flags"][lo:hi], want["flags"][lo:hi]))
+            a0, a1 = want["anno_off"][lo], want["anno_off"][hi]
+            good &= bool(np.array_equal(np.diff(p["anno_off"][lo:hi + 1]), np.diff(want["anno_off"][lo:hi + 1])))
+            g0, g1 = p["anno_off"][lo], p["anno_off"][hi]
+            for k in ("anno_pos", "anno_type", "hinge_keep"):
+                good &= bool(np.array_equal(p[k][g0:g1], want[k][a0:a1]))
+        print("SHARDED_CHECK", exchange, "OK" if good else "MISMATCH", "world", world, "ranges",
+              [(p["lo"], p["hi"]) for p in parts], "reads", syn.n_read, "overlaps", novl_all, "annotations",
+              int(s1.n_annotations), "hinges", int(want["hinge_keep"].sum()), flush=True)
+        ok &= good
+    ctx.close()
+    dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -21,6 +21,7 @@ def lib():
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_load_ini.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_filter.argtypes = [C.c_void_p]
+        L.orc_set_threads.argtypes = [C.c_void_p, C.c_int]
         L.orc_filter_results.restype = C.c_int64
         L.orc_filter_results.argtypes = [C.c_void_p] + [C.c_void_p] * 8
         _lib = L
@@ -32,7 +33,7 @@ def _p(a):
 
 
 class Oracle:
-    def __init__(self, rlen, qv_off, qv, tspace, cols, trace_off=None, trace=None, tbytes=1, ini=INI):
+    def __init__(self, rlen, qv_off, qv, tspace, cols, trace_off=None, trace=None, tbytes=1, ini=INI, threads=1):
         L = lib()
         self.n = len(rlen)
         keep = [np.ascontiguousarray(rlen, np.int32)]
@@ -45,6 +46,7 @@ class Oracle:
         self.h = L.orc_create(self.n, _p(keep[0]), _p(keep[1]), _p(keep[2]), tspace, len(cc[0]),
                               *[_p(c) for c in cc], _p(trace_off), _p(trace), tbytes)
         assert L.orc_load_ini(self.h, ini.encode()) == 0
+        L.orc_set_threads(self.h, int(threads))
 
     def filter(self):
         L = lib()

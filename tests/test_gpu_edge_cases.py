@@ -180,3 +180,40 @@ def test_many_tiny_reads_per_batch(built, tmp_path):
     ini = os.path.join(str(tmp_path), "tiny.ini")
     write_ini(ini, {"cut_off": "0", "length_threshold": "50", "aln_threshold": "30", "theta": "10"})
     _run_filter(str(tmp_path), "T", ini=ini)
+
+
+def test_reads_just_under_and_over_the_batch_capacity(built, tmp_path):
+    """(rlen + cut_off) / 40 + 3 coverage bins per read: 163459 bp is the longest read that still fits
+    the 4096-bin batch of the flat kernels (alone in its batch), 163460 bp the shortest that does not."""
+    rng = np.random.default_rng(11)
+    n = 30
+    rlen = [int(x) for x in rng.integers(8000, 14000, n)] + [163459, 163460, 163419, 163420]
+    recs = _tiling(rng, n, rlen[:n], 70000, 0)
+    for big in range(n, n + 4):
+        for i in range(n):
+            ln = min(rlen[i], 7000)
+            at = int(rng.integers(0, rlen[big] - ln))
+            recs += hm.both_directions(big, i, at, at + ln, 0, ln, i % 3 == 0, rlen)
+        # records that reach the very last base: the last event bins of both profiles
+        recs += hm.both_directions(big, 0, rlen[big] - 5000, rlen[big], 100, 5100, 0, rlen)
+    hm.write_fixture(str(tmp_path), "B", rlen, recs, tspace=100, qv="good")
+    _run_filter(str(tmp_path), "B")
+
+
+def test_batch_with_more_records_than_the_prefix_counts_hold(built, tmp_path):
+    """Five reads of 15000 records each: every pile-up fits the packed 16-bit counters, the batch
+    (75000 records) does not fit the 16-bit prefix counts of K1's second form -> both phases leave the
+    whole batch to the per-read fallbacks."""
+    rlen = [6000, 6100, 6200, 6300, 6400, 9000]
+    recs = []
+    for a in range(5):
+        for k in range(15000):
+            b = (a + 1 + k % 4) % 5
+            if b == a:
+                b = 5
+            ab, ae = (k * 7) % 900, rlen[a] - (k * 11) % 900
+            bb, be = (k * 5) % 150, rlen[b] - (k * 13) % 250
+            recs.append((a, b, ab, ae, bb, be, k & 1))
+    recs += hm.both_directions(5, 0, 100, 5000, 200, 5100, 0, rlen)
+    hm.write_fixture(str(tmp_path), "O", rlen, recs, tspace=100, qv="good")
+    _run_filter(str(tmp_path), "O")

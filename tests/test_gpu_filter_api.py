@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
-def _run_both(built, synth_kw, a_ranges=None):
+def _run_both(built, synth_kw, options=()):
     import hgsynth
     import oraclelib
     from hinge_b200 import api
@@ -26,6 +26,8 @@ def _run_both(built, synth_kw, a_ranges=None):
     want = orc.filter()
     orc.close()
     ctx = api.Context(0)
+    for opt, val in options:
+        ctx.set_option(opt, val)
     ctx.set_reads(rlen, qv_off, qv, 100)
     ctx.set_overlaps(len(cols["aread"]), cols)
     summ = ctx.filter(api.FilterParams())
@@ -45,6 +47,27 @@ def test_filter_arrays_match_oracle(built):
     got, want, summ = _run_both(built, dict(genome_len=600000, coverage=40.0, seed=77, n_families=4))
     _assert_equal(got, want, summ)
     assert want["hinge_keep"].sum() > 0, "fixture should call hinges"
+
+
+def test_both_forms_of_the_profile_kernel_match_oracle(built):
+    """HG_OPT_PROFILE_KERNEL = 1 forces the four-event 40-bp form of K1 (the one that also serves
+    cut-offs off the 20-bp grid); the default picks the 20-bp start / end histogram."""
+    from hinge_b200 import api
+
+    kw = dict(genome_len=500000, coverage=45.0, seed=78, n_families=4)
+    for form in (0, 1):
+        got, want, summ = _run_both(built, kw, options=[(api.HG_OPT_PROFILE_KERNEL, form)])
+        _assert_equal(got, want, summ)
+
+
+def test_c5_shaped_long_reads_with_fragmented_alignments(built):
+    """BASELINE configs[4] shape at 1/40 of its size: reads N(24000, 8000) (~600 coverage bins and ~200
+    records each, ~6 reads per batch of the flat kernels), most pairs reported as two or three local
+    alignments."""
+    got, want, summ = _run_both(built, dict(genome_len=7500000, coverage=40.0, read_mean=24000, read_sd=8000,
+                                           read_min=2000, seed=4321, frag_prob=1.2, n_families=20))
+    _assert_equal(got, want, summ)
+    assert len(want["anno_pos"]) > 100 and want["hinge_keep"].sum() > 0
 
 
 def test_tie_heavy_data_uses_order_exact_path(built):

@@ -26,13 +26,38 @@ def test_shard_ranges_tile_the_reads():
             assert all(h - l <= chunk for l, h in ranges)
 
 
+def test_weighted_shard_ranges_balance_the_record_volume():
+    import numpy as np
+
+    from hinge_b200.sharding import shard_ranges
+
+    rng = np.random.default_rng(5)
+    for n, world in ((1, 2), (5, 8), (1000, 3), (50000, 8)):
+        # a few very deep pile-ups among many shallow ones
+        w = rng.integers(1, 200, n).astype(np.int64)
+        w[rng.integers(0, n, max(1, n // 100))] += 20000
+        ranges, chunk = shard_ranges(n, world, weights=w)
+        assert len(ranges) == world and ranges[0][0] == 0 and ranges[-1][1] == n
+        for (l0, h0), (l1, h1) in zip(ranges, ranges[1:]):
+            assert h0 == l1 and l0 <= h0
+        assert chunk == max(h - l for l, h in ranges)
+        if n >= 1000:  # no shard exceeds its share by more than the heaviest read
+            share = w.sum() / world
+            assert all(w[l:h].sum() <= share + w.max() for l, h in ranges)
+
+
 def _worker(rank, world, port, n_read, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from hinge_b200.sharding import ShardedArrays
 
-    arr = ShardedArrays(n_read, rank, world, torch.device("cpu"))
+    arr = ShardedArrays(n_read, rank, world, torch.device("cpu"), equal_slices=True)
+    n = world * arr.chunk
+    arr.mean_cov = torch.full((n,), -1, dtype=torch.int32)
+    arr.mask = torch.zeros((n, 2), dtype=torch.int32)
+    arr.hist = torch.zeros((4098,), dtype=torch.int32)
+    arr.mask_pk = torch.zeros((n,), dtype=torch.int32)
     # every rank fills only the reads it owns, like hg_filter_phase1 / phase2 do
     ids = torch.arange(arr.lo, arr.hi, dtype=torch.int32)
     arr.mean_cov[arr.lo:arr.hi] = ids * 3 + 1
@@ -43,9 +68,9 @@ def _worker(rank, world, port, n_read, q):
     arr.hist[:4096] += torch.bincount((ids % 4096).to(torch.int64), minlength=4096).to(torch.int32)
     arr.hist[4096] += len(ids)
     arr.mask_pk[arr.lo:arr.hi] = (ids // 20) | ((ids // 20 + 7) << 16)
-    arr.exchange(arr.mean_cov)
-    arr.exchange(arr.mask)
-    arr.exchange(arr.mask_pk)
+    arr.exchange_slices(arr.mean_cov)
+    arr.exchange_slices(arr.mask)
+    arr.exchange_slices(arr.mask_pk)
     dist.all_reduce(arr.hist)
     full = torch.arange(n_read, dtype=torch.int32)
     want_hist = torch.bincount((full % 4096).to(torch.int64), minlength=4096).to(torch.int32)
@@ -82,7 +107,7 @@ class _FakeContext:
         from hinge_b200 import api
 
         if which == api.HG_BUF_MASK_PACKED and self.refuse_packed:
-            raise RuntimeError("reads too long for 16-bit mask bounds")
+            raise api.HingeError("reads too long for 16-bit mask bounds")
         self.bound[which] = tensor
 
     def filter_phase1(self, params):
@@ -123,9 +148,9 @@ def _flow_worker(rank, world, port, n_read, refuse_packed, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from hinge_b200.sharding import ShardedArrays, run_filter_sharded
 
-    arr = ShardedArrays(n_read, rank, world, torch.device("cpu"))
+    arr = ShardedArrays(n_read, rank, world, torch.device("cpu"), equal_slices=True)
     ctx = _FakeContext(arr, refuse_packed)
-    arr.bind(ctx)
+    arr.bind(ctx, exchange="nccl")
     rc, _ = run_filter_sharded(ctx, None, arr)
     full = torch.arange(n_read, dtype=torch.int32)
     ok = (rc == 0 and ctx.calls == ["phase1", "phase2", "phase3"]

@@ -36,6 +36,8 @@ typedef struct hgs_params {
     int32_t min_ovl, jitter, tspace;
     double qv_bad_frac;
     uint64_t seed;
+    double frag_prob;  // chance that a pair's alignment comes as two local alignments (as daligner
+                       // reports long noisy overlaps: several records per (A,B) pair)
 } hgs_params;
 }
 
@@ -234,6 +236,21 @@ void overlaps_of(const Synth* S, int a, std::vector<Rec>* out) {
         gs += j1;
         ge -= j2;
         if (ge - gs < p.min_ovl) continue;
+        if (p.frag_prob > 0.0) {
+            // split points and gaps come from the pair's hash, in genome coordinates: A->B and B->A
+            // agree.  frag_prob in (1, 2]: a second split of the right-hand piece with chance frag_prob - 1.
+            uint64_t h2 = h;
+            double pr = p.frag_prob;
+            for (int round = 0; round < 2 && pr > 0.0; round++, pr -= 1.0) {
+                h2 = splitmix(h2 ^ 0x5151);
+                const int gap = 50 + (int)((h2 >> 8) % 300);
+                const int64_t room = ge - gs - 2 * (int64_t)p.min_ovl - gap;
+                if (room < 0 || (h2 >> 40) * (1.0 / 16777216.0) >= pr) break;
+                const int64_t cut = gs + p.min_ovl + (int64_t)((h2 >> 17) % (uint64_t)(room + 1));
+                emit(S, a, b, gs, cut, gs, cut, out);
+                gs = cut + gap;
+            }
+        }
         emit(S, a, b, gs, ge, gs, ge, out);
     }
     // repeat-mediated neighbours: A on copy c, B on another copy c2 of the family
@@ -477,6 +494,7 @@ void hgs_default_params(hgs_params* p) {
     p->min_ovl = 1000; p->jitter = 30; p->tspace = 100;
     p->qv_bad_frac = 0.002;
     p->seed = 1234;
+    p->frag_prob = 0.0;
 }
 
 void* hgs_create(const hgs_params* p) {
@@ -530,6 +548,7 @@ int main(int argc, char** argv) {
         else if (k == "--jitter") p.jitter = atoi(v);
         else if (k == "--qv-bad") p.qv_bad_frac = atof(v);
         else if (k == "--seed") p.seed = strtoull(v, nullptr, 10);
+        else if (k == "--frag") p.frag_prob = atof(v);
         else if (k == "--dir") dir = v;
         else if (k == "--root") root = v;
         else if (k == "--threads") threads = atoi(v);

@@ -15,7 +15,7 @@ class Params(C.Structure):
                 ("n_families", C.c_int32), ("rep_min_len", C.c_int32), ("rep_max_len", C.c_int32),
                 ("rep_min_copies", C.c_int32), ("rep_max_copies", C.c_int32),
                 ("min_ovl", C.c_int32), ("jitter", C.c_int32), ("tspace", C.c_int32),
-                ("qv_bad_frac", C.c_double), ("seed", C.c_uint64)]
+                ("qv_bad_frac", C.c_double), ("seed", C.c_uint64), ("frag_prob", C.c_double)]
 
 
 _lib = None
