@@ -163,7 +163,8 @@ int hg_set_option(hg_ctx* c, int option, int64_t value) {
         return HG_OK;
     }
     if (option == HG_OPT_PROFILE_KERNEL) {
-        if (value != 0 && value != 1) return set_err(c, HG_ERR_ARG, "HG_OPT_PROFILE_KERNEL: 0 or 1");
+        if (value != 0 && value != 1 && value != 5 && value != 6)
+            return set_err(c, HG_ERR_ARG, "HG_OPT_PROFILE_KERNEL: 0, 1, 5 or 6");
         c->fs.flat_kernel = (int)value;
         return HG_OK;
     }

@@ -1,6 +1,8 @@
 // C ABI, part 2: hg_maximal, hg_layout, hg_layout_edges (include/hinge_b200.h).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <numeric>
@@ -57,6 +59,24 @@ struct PairBufs {
     }
 };
 
+// HINGE_B200_TIMING=1: wall time of the steps inside hg_maximal / hg_layout on stderr (each lap
+// synchronises the stream first, so only use it to find out where the time goes)
+struct StepTimer {
+    bool on = getenv("HINGE_B200_TIMING") != nullptr;
+    cudaStream_t st;
+    struct timespec t0;
+    explicit StepTimer(cudaStream_t s) : st(s) { clock_gettime(CLOCK_MONOTONIC, &t0); }
+    void lap(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        struct timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        fprintf(stderr, "[hinge_b200 timing]     %-34s %8.2f ms\n", what,
+                1e3 * (double)(t1.tv_sec - t0.tv_sec) + 1e-6 * (double)(t1.tv_nsec - t0.tv_nsec));
+        t0 = t1;
+    }
+};
+
 static int upload_mask(hg_ctx* c, const int32_t* mask) {
     if (mask)
         return cuda_check(c, cudaMemcpyAsync(c->fs.mask, mask, 8ull * c->n_read, cudaMemcpyHostToDevice, c->stream), "mask H2D");
@@ -86,6 +106,8 @@ int hg_maximal(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, uint8_
     HG_TRY(rtype.alloc(c, (size_t)c->novl, "record types"));
     HG_TRY(remaining.alloc(c, 1, "remaining"));
     int big_cap = 1 << 16, sort_cap = 1 << 20;
+    StepTimer tm(st);
+    tm.lap("maximal: allocations");
     cudaEventRecord(c->ev0, st);
     for (int attempt = 0;; attempt++) {
         PairBufs pb;
@@ -103,7 +125,9 @@ int hg_maximal(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, uint8_
         big_cap = std::max(big_cap, cnt[0] + 1024);
         sort_cap = std::max(sort_cap * 4, cnt[1] + 1024);
     }
+    tm.lap("maximal: classify pairs");
     launch_contain_init(c->rec_view(), c->read_view(), active0.p, rtype.p, state.p, st);
+    tm.lap("maximal: containment init");
     for (int it = 0; it < 100000; it++) {
         int rem = 0;
         launch_contain_step(c->rec_view(), c->read_view(), active0.p, rtype.p, state.p, remaining.p, st);
@@ -111,6 +135,7 @@ int hg_maximal(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, uint8_
         HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "containment"));
         if (rem == 0) break;
     }
+    tm.lap("maximal: containment fixed point");
     cudaEventRecord(c->ev1, st);
     std::vector<uint8_t> hstate(n), hact(n);
     HG_TRY(cuda_check(c, cudaMemcpyAsync(hstate.data(), state.p, n, cudaMemcpyDeviceToHost, st), "D2H"));
@@ -176,6 +201,8 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
     HG_TRY(cuda_check(c, cudaMemcpyAsync(d_active.p, R.active.data(), n, cudaMemcpyHostToDevice, st), "H2D"));
 
     // ---- K5: classify the top two overlaps of every pair of maximal reads
+    StepTimer tm(st);
+    tm.lap("layout: active flags + uploads");
     cudaEventRecord(c->ev0, st);
     int big_cap = 1 << 14, sort_cap = 1 << 18, pair_cap = 1 << 20, cand_cap = 1 << 20;
     std::vector<int4> pairs;
@@ -205,6 +232,7 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
         HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "D2H"));
         break;
     }
+    tm.lap("layout: classify pairs + D2H");
     for (int i = 0; i < n; i++)
         if (contained[i] && R.active[i]) {  // hinging.cpp:598-601
             printf("[contained] Should not happen\n");
@@ -256,6 +284,7 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
         }
     }
 
+    tm.lap("layout: host sorts + hash-order replay");
     // ---- hinges, killed hinges (hinging.cpp:1180-1197)
     R.hin_off.assign(hin_off, hin_off + n + 1);
     R.hin_pos.assign(hin_pos, hin_pos + hin_off[n]);
@@ -274,6 +303,7 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
         R.kil_off[i + 1] = (int64_t)R.kil_pos.size();
     }
     const int64_t nh = hin_off[n], nkil = R.kil_off[n];
+    tm.lap("layout: killed-hinge lists (host)");
 
     // ---- device side of the selection
     const size_t ncand = std::max<size_t>(cands.size(), 1), nord = std::max<size_t>(R.order.size(), 1);
@@ -313,7 +343,9 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
     io.hinge_alive = d_alive.p; io.counters = d_cnt.p; io.chosen = d_chosen.p;
     io.graph = nullptr; io.nkout = nullptr; io.skips = nullptr;
 
+    tm.lap("layout: selection uploads");
     launch_sort_candidates(io, st);  // K6: weight order (hinging.cpp:1066-1071)
+    tm.lap("layout: sort candidates");
 
     // K6: kill pass + hinge graph; list sizes are data dependent: grow and rerun on overflow
     int graph_cap = 1 << 16, nk_cap = 1 << 14;
@@ -344,6 +376,7 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
         HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "D2H"));
         break;
     }
+    tm.lap("layout: kill pass + hinge graph + D2H");
     std::sort(graph.begin(), graph.end(), [](const GraphRec& x, const GraphRec& y) {
         return x.owner != y.owner ? x.owner < y.owner : x.seq < y.seq;
     });
@@ -390,6 +423,7 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
     io.nk.pos = d_npos.p;
     io.nk.type = d_ntype.p;
 
+    tm.lap("layout: components + nk lists (host)");
     // K6: the best-overlap scoring loop
     int skip_cap = 1 << 14;
     std::vector<SkipRec> skips;
@@ -417,6 +451,7 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
         HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "D2H"));
         break;
     }
+    tm.lap("layout: best extension + D2H");
     std::sort(skips.begin(), skips.end(), [](const SkipRec& x, const SkipRec& y) {
         return x.owner != y.owner ? x.owner < y.owner : x.seq < y.seq;
     });

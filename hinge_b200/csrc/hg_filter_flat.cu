@@ -311,40 +311,50 @@ k_profile_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
 // counts, for entry j, the events at positions < 40 j):
 //     cov0[j] = #{abpos < 40 j}     - #{aepos < 40 j}
 //     covC[j] = #{abpos < 40 j - C} - #{aepos < 40 j + C}
-// so with C a multiple of 20 (nominal: 300) ONE histogram of the record starts and ends on a
-// 20-bp grid (starts in the low half of a word, ends in the high half) and ONE exclusive prefix
-// sum P over it give   cov0[j] = P_S(2 j) - P_E(2 j),   covC[j] = P_S(2 j - C/20) - P_E(2 j + C/20).
+// so with C = 300 = 15 x 20 ONE histogram of the record starts and ends on a 20-bp grid (starts in
+// the low half of a word, ends in the high half) and ONE exclusive prefix sum P over it give
+//     cov0[j] = P_S(2 j) - P_E(2 j),      covC[j] = P_S(2 j - 15) - P_E(2 j + 15).
 // The prefix sum runs over the whole batch; a read's own counts are differences of P inside its
 // word range (everything before it has both started and ended), taken mod 2^16.
 //
 //   scatter   two ATOMS per record into hist[2 base + pos / 20]
-//   scan      each thread owns 32 histogram words = 16 bins: E[q] = P(2 q), Q[q] = P(2 q + 1),
-//             written back as two arrays so that the look-ups below are unit-stride
-//   per read  one warp per read walks its bins: packs (cov0, covC) into the word K2 expects
-//             (bit-identical to the first form's), stores it, and reduces the profile's sum and
-//             length on the way (filter.cpp:642-656) -- no atomics
+//   scan      each thread owns 32 histogram words = 16 bins q: E[q] = P(2 q) and Q[q] = P(2 q + 1)
+//             stay in registers; covC needs Q[q - 8] and Q[q + 7], which live in the neighbouring
+//             threads: 15 shuffles (+ a few words through shared memory at the warp seams)
+//   output    the packed (cov0, covC) words K2 expects go to HBM, 64 B per thread
+//   per read  a second block-wide scan, over cov0, leaves its running sum T in shared memory;
+//             one THREAD per read gets the profile sum as T[end] - T[begin] and the profile length
+//             by bisection for the point where T stops growing (filter.cpp:642-656) -- no atomics
+//
+// No read boundaries are needed in the flat phases: the last 9 words of every read's range
+// carry no events (bins_needed), so the look-behind by 8 of a read's first words sees exactly the
+// counts at its own start; the look-ahead by 7 of its last words may see the next read's earliest
+// ends, which only pushes covC further below zero in bins where it already is <= 0 and where
+// nothing but "not above MIN_COV" is ever asked of it (K2 runs this path for MIN_COV >= 0 only).
 //
 // The profile length is 1 + the last bin with cov0 > 0, which holds unless a record lies inside
 // one 40-bp bin (abpos / 40 == aepos / 40); the ingest flags reads that have such a record
 // (kSelfDegenerate) and their sum / length come from the per-read fallback.  Batches with more
-// than 65535 records (the 16-bit halves of P would run into each other) are left to the
-// fallbacks entirely, here and in K2.
-constexpr int kV2QOff = kFlatBins + 32;                 // where Q starts inside the buffer
+// than 32767 records (the 16-bit counts could wrap) are left to the fallbacks entirely, here and
+// in K2.
+constexpr int kV2CutOff = 300;
 constexpr int kV2Words = 2 * kFlatBins + 64;
-constexpr int kV2MaxBatchRecords = 65535;
+constexpr int kV2MaxBatchRecords = 32767;
 
 // Histogram layout: a thread of the scan owns 32 consecutive words = 8 vectors, so the 8 lanes
 // of a quarter warp are 128 B apart; XOR-ing the vector index with the thread index spreads them
 // over the eight 16-byte bank groups.
 __device__ __forceinline__ int swh(int j) { return j ^ (((j >> 5) & 7) << 2); }
 
-template <int SPREAD>
-__global__ void __launch_bounds__(kFlatThreads)
+template <int SPREAD, int MINBLOCKS>
+__global__ void __launch_bounds__(kFlatThreads, MINBLOCKS)
 k_profile_flat2(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
     __shared__ __align__(16) uint32_t buf[kV2Words];
-    __shared__ uint32_t wtot[kFlatThreads / 32];
+    __shared__ uint32_t wtot[2][kFlatThreads / 32];
+    __shared__ uint32_t seam_hi[kFlatThreads / 32][8], seam_lo[kFlatThreads / 32][8];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kFlatThreads / 32;
     const int2 bt = F.batch[blockIdx.x];
     const int f0 = bt.x, f1 = F.batch[blockIdx.x + 1].x;
     const int64_t k_begin = bt.y > 0 ? rv.read_off[f0] : 0, k_end = bt.y > 0 ? rv.read_off[f1] : 0;
@@ -414,11 +424,13 @@ k_profile_flat2(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
         __syncthreads();
 
         // ---- exclusive prefix sum over the 20-bp histogram, one pass: thread t owns bins
-        // [16 t, 16 t + 16) = words [32 t, 32 t + 32)
+        // [16 t, 16 t + 16) = words [32 t, 32 t + 32).  Threads past the batch's last bin carry the
+        // total (their words count as empty): the look-ahead of the last bins reads them.
         uint32_t he[kFlatItems], ho[kFlatItems];
         const int q0 = tid * kFlatItems;
+        const bool mine = q0 < nb;
         uint32_t tot = 0;
-        if (q0 < nb) {
+        if (mine) {
 #pragma unroll
             for (int v = 0; v < 8; v++) {
                 const uint4 x = lds128(buf + 32 * tid + 4 * (v ^ (tid & 7)));
@@ -431,65 +443,116 @@ k_profile_flat2(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
                 ho[i] = tot + e0;   // Q[q] = P(2 q + 1)
                 tot += e0 + o0;
             }
-        }
-        const uint32_t incl = warp_incl_scan(tot);
-        if (lane == 31) wtot[warp] = incl;
-        __syncthreads();  // every histogram word has been read: the buffer is free for E and Q
-        uint32_t pre = incl - tot, total = 0;
+        } else {
 #pragma unroll
-        for (int w = 0; w < kFlatThreads / 32; w++) {
-            const uint32_t t = wtot[w];
-            if (w < warp) pre += t;
-            total += t;
+            for (int i = 0; i < kFlatItems; i++) he[i] = ho[i] = 0;
         }
-        if (q0 < nb) {
-            const int sx = sw(q0) ^ q0;  // the flipped bits: common to the whole 16-word chunk
+        uint32_t batch_total = 0;  // P at the end of the batch: what a look-ahead past the last word sees
+        {
+            const uint32_t incl = warp_incl_scan(tot);
+            if (lane == 31) wtot[0][warp] = incl;
+            __syncthreads();  // every histogram word has been read: the buffer is free for T
+            uint32_t pre = incl - tot;
 #pragma unroll
-            for (int v = 0; v < kFlatItems / 4; v++) {
-                sts128(buf + ((q0 + 4 * v) ^ sx),
-                       make_uint4(he[4 * v] + pre, he[4 * v + 1] + pre, he[4 * v + 2] + pre, he[4 * v + 3] + pre));
-                sts128(buf + kV2QOff + ((q0 + 4 * v) ^ sx),
-                       make_uint4(ho[4 * v] + pre, ho[4 * v + 1] + pre, ho[4 * v + 2] + pre, ho[4 * v + 3] + pre));
+            for (int w = 0; w < NW; w++) {
+                const uint32_t t = wtot[0][w];
+                if (w < warp) pre += t;
+                batch_total += t;
+            }
+#pragma unroll
+            for (int i = 0; i < kFlatItems; i++) {
+                he[i] += pre;
+                ho[i] += pre;
             }
         }
-        if (tid == 0 && (nb & (kFlatItems - 1)) == 0) buf[sw(nb)] = total;  // E[nb]: the chunk it is in was skipped
+        // the Q values the neighbouring warps need: Q[q0 + 8 .. q0 + 15] of a warp's last lane for
+        // the look-behind of the next warp's first lane, Q[q0 .. q0 + 6] of its first lane for the
+        // look-ahead of the previous warp's last lane
+        if (lane == 31) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) seam_hi[warp][i] = ho[8 + i];
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 7; i++) seam_lo[warp][i] = ho[i];
+        }
+        __syncthreads();
+
+        // ---- the packed words: cov0[q] = E_S[q] - E_E[q], covC[q] = Q_S[q - 8] - Q_E[q + 7]
+        uint32_t word[kFlatItems];
+        uint32_t csum = 0;
+#pragma unroll
+        for (int i = 0; i < kFlatItems; i++) {
+            uint32_t ps, pe;
+            if (i < 8) {  // look-behind into the previous thread
+                ps = __shfl_up_sync(0xffffffffu, ho[8 + i], 1);
+                if (lane == 0) ps = warp > 0 ? seam_hi[warp - 1][i] : 0u;
+            } else {
+                ps = ho[i - 8];
+            }
+            if (i + 7 < kFlatItems) {
+                pe = ho[i + 7];
+            } else {  // look-ahead into the next thread
+                pe = __shfl_down_sync(0xffffffffu, ho[i + 7 - kFlatItems], 1);
+                if (lane == 31) pe = warp + 1 < NW ? seam_lo[warp + 1][i + 7 - kFlatItems] : batch_total;
+            }
+            const uint32_t c0 = (he[i] - (he[i] >> 16)) & 0xffffu;
+            const uint32_t c1 = (ps - (pe >> 16)) & 0xffffu;
+            word[i] = c0 | (c1 << 16);
+            he[i] = csum;  // from here on: the thread-local exclusive prefix of cov0
+            csum += c0;
+        }
+        uint32_t* const pw = F.prof + (size_t)blockIdx.x * kFlatBins;
+        if (mine) {
+#pragma unroll
+            for (int v = 0; v < kFlatItems / 4; v++)
+                *reinterpret_cast<uint4*>(pw + q0 + 4 * v) =
+                    make_uint4(word[4 * v], word[4 * v + 1], word[4 * v + 2], word[4 * v + 3]);
+        }
+
+        // ---- T = exclusive prefix sum of cov0 over the batch, into shared memory (swizzled like the
+        // first form's histogram: 16 words per thread)
+        {
+            const uint32_t incl = warp_incl_scan(csum);
+            if (lane == 31) wtot[1][warp] = incl;
+            __syncthreads();
+            uint32_t pre = incl - csum, total = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                const uint32_t t = wtot[1][w];
+                if (w < warp) pre += t;
+                total += t;
+            }
+            if (mine) {
+                const int sx = sw(q0) ^ q0;  // the flipped bits: common to the whole 16-word chunk
+#pragma unroll
+                for (int v = 0; v < kFlatItems / 4; v++)
+                    sts128(buf + ((q0 + 4 * v) ^ sx), make_uint4(he[4 * v] + pre, he[4 * v + 1] + pre,
+                                                                 he[4 * v + 2] + pre, he[4 * v + 3] + pre));
+            }
+            if (tid == 0 && (nb & (kFlatItems - 1)) == 0) buf[sw(nb)] = total;  // T[nb]: its chunk was skipped
+        }
         __syncthreads();
     }
 
-    // ---- per read, one warp each: the packed profile words for K2, profile sum and length
-    const int c20 = P.cut_off / 20, h = c20 >> 1, odd = c20 & 1;
-    const uint32_t* const arr = odd ? buf + kV2QOff : buf;  // P at odd / even 20-bp indices
-    const int hs = h + odd;
-    uint32_t* const pw = F.prof + (size_t)blockIdx.x * kFlatBins;
-    for (int read = f0 + warp; read < f1; read += kFlatThreads / 32) {
+    // ---- per read, one thread each: sum and length of the cut-off-free profile (filter.cpp:642-656)
+    for (int read = f0 + tid; read < f1; read += kFlatThreads) {
         const int base = F.rbase[read];
         const int64_t nrec = rv.read_off[read + 1] - rv.read_off[read];
-        if (base < 0 || nb == 0 || nrec > Packed<uint32_t>::kMaxCount) {
-            if (lane == 0) F.big_list[atomicAdd(&F.counters1[0], 1)] = read;
+        if (base < 0 || nb == 0 || nrec > Packed<uint32_t>::kMaxCount || is_degenerate(F.self_cnt[read])) {
+            // too long / too deep / a record inside one bin: sum and length from the records
+            F.big_list[atomicAdd(&F.counters1[0], 1)] = read;
             continue;
         }
         const int nbz = bins_needed(rd.rlen[read], P);
-        const uint32_t p_first = buf[sw(base)], p_last = buf[sw(base + nbz)];
-        int sum = 0, last = -1;
-        for (int j = lane; j < nbz; j += 32) {
-            const uint32_t ex = buf[sw(base + j)];
-            const int ms = j - hs, me = j + h;
-            const uint32_t ps = ms < 0 ? p_first : arr[sw(base + ms)];
-            const uint32_t pe = me >= nbz ? p_last : arr[sw(base + me)];
-            const uint32_t c0 = (ex - (ex >> 16)) & 0xffffu;
-            const uint32_t c1 = (ps - (pe >> 16)) & 0xffffu;
-            pw[base + j] = c0 | (c1 << 16);
-            sum += (int)c0;
-            if (c0) last = j;
+        const uint32_t t_begin = buf[sw(base)], t_end = buf[sw(base + nbz)];
+        // smallest j with T[base + j] == t_end: bins j - 1 is the last one with cov0 > 0
+        int lo = 0, hi = nbz;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (buf[sw(base + mid)] == t_end) hi = mid; else lo = mid + 1;
         }
-        sum = warp_sum(sum);
-        last = warp_max(last);
-        if (lane == 0) {
-            if (is_degenerate(F.self_cnt[read]))  // a record inside one bin: length from the records
-                F.big_list[atomicAdd(&F.counters1[0], 1)] = read;
-            else
-                finalize_read(rv, rd, F, read, sum, last < 0 ? -1 : last + 1);
-        }
+        finalize_read(rv, rd, F, read, (long long)(t_end - t_begin), lo == 0 ? -1 : lo);
     }
 }
 
@@ -791,9 +854,9 @@ void flat_plan(const int* rlen, int lo, int hi, int n_read, int cut_off, std::ve
     batch->push_back(make_int2(hi, 0));
 }
 
-// The second form of K1 needs the cut-off on the 20-bp grid (nominal: 300).
+// The second form of K1 is written for the nominal cut-off (300: every INI the reference ships).
 static bool use_v2(const FilterScratch& s, const hg_filter_params& P) {
-    return s.flat_kernel != 1 && P.cut_off >= 0 && P.cut_off % 20 == 0;
+    return s.flat_kernel != 1 && P.cut_off == kV2CutOff;
 }
 
 static FlatParams flat_params(const FilterScratch& s, const hg_filter_params& P, int r_begin, int r_end) {
@@ -824,11 +887,14 @@ void launch_profile(const RecView& rv, const ReadView& rd, const hg_filter_param
     const int grid = s.flat_nbatch;
     if (grid <= 0) return;
     g_launches += 2;
-    if (F.v2) switch (s.flat_spread) {
-        case 1: k_profile_flat2<1><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;
-        case 4: k_profile_flat2<4><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;
-        case 16: k_profile_flat2<16><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;
-        default: k_profile_flat2<8><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;
+    if (F.v2) {
+        // tuning aids: resident CTAs per SM the compiler aims for (registers), scatter spread
+        if (s.flat_kernel == 5) k_profile_flat2<8, 5><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
+        else if (s.flat_kernel == 6) k_profile_flat2<8, 6><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
+        else if (s.flat_spread == 1) k_profile_flat2<1, 4><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
+        else if (s.flat_spread == 4) k_profile_flat2<4, 4><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
+        else if (s.flat_spread == 16) k_profile_flat2<16, 4><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
+        else k_profile_flat2<8, 4><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
     }
     else switch (s.flat_spread) {
         case 1: k_profile_flat<1><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;

@@ -203,6 +203,8 @@ int open_context(const ReadDB& db, const LasFile& las, bool with_trace, hg_ctx**
     return rc;
 }
 
+void drop_early_context() { g_early.drop(); }
+
 static void touch(const std::string& path) {
     FILE* f = fopen(path.c_str(), "w");
     if (f) fclose(f);

@@ -42,6 +42,9 @@ bool parse_args(int argc, char** argv, bool layout, Args* a, std::string* err);
 int check_inputs(const Args& a, std::string* las_name);
 int load_inputs(const Args& a, bool want_trace, Ini* ini, ReadDB* db, LasFile* las);
 int open_context(const ReadDB& db, const LasFile& las, bool with_trace, hg_ctx** ctx);
+// load_inputs starts the creation of the CUDA context on a side thread; every error return between
+// load_inputs and open_context must give it back (joins the thread, destroys the context)
+void drop_early_context();
 
 }  // namespace hg
 #endif

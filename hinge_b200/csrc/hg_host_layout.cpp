@@ -124,6 +124,18 @@ void print_greedy12(FILE* g1, FILE* g2, const hg_edge& e) {
             e.read_b[0], e.read_b[1]);
 }
 
+// Output files: an unwritable path must end in exit code 1, not in fprintf(NULL).
+bool g_out_failed = false;
+FILE* open_out(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) {
+        fprintf(stderr, "hinge_b200: cannot write %s\n", path.c_str());
+        g_out_failed = true;
+        f = fopen("/dev/null", "w");
+    }
+    return f;
+}
+
 }  // namespace
 
 extern "C" int hg_main_maximal(int argc, char** argv) {
@@ -146,6 +158,7 @@ extern "C" int hg_main_maximal(int argc, char** argv) {
     std::vector<int32_t> mask;
     if (!read_mask_file(a.prefix + ".mas", n, &mask)) {
         fprintf(stderr, "hinge maximal: cannot read %s.mas (run hinge filter first)\n", a.prefix.c_str());
+        drop_early_context();
         return 1;
     }
     timer.lap("read db + ini + las + mas");
@@ -191,6 +204,7 @@ extern "C" int hg_main_maximal(int argc, char** argv) {
 }
 
 extern "C" int hg_main_layout(int argc, char** argv) {
+    g_out_failed = false;
     mkdir("log", S_IRWXU | S_IRWXG | S_IROTH | S_IXOTH);
     Args a;
     std::string err;
@@ -215,6 +229,7 @@ extern "C" int hg_main_layout(int argc, char** argv) {
     std::vector<int32_t> rep_pos, rep_type, hin_pos, hin_type;
     if (!read_mask_file(x + ".mas", n, &mask)) {
         fprintf(stderr, "hinge layout: cannot read %s.mas (run hinge filter first)\n", x.c_str());
+        drop_early_context();
         return 1;
     }
     read_max_file(x + ".max", n, &maximal);
@@ -257,11 +272,11 @@ extern "C" int hg_main_layout(int argc, char** argv) {
             }
             killed.put_char('\n');
         }
-        FILE* f = fopen((o + ".hgraph").c_str(), "w");  // hinging.cpp:1421-1626
+        FILE* f = open_out(o + ".hgraph");  // hinging.cpp:1421-1626
         for (const GraphRec& g : R.graph)
             fprintf(f, "%d %d %d %d %d %d\n", g.f[0], g.f[1], g.f[2], g.f[3], g.flag, g.rev);
         fclose(f);
-        f = fopen((o + ".hinge.list").c_str(), "w");  // hinging.cpp:1696-1704
+        f = open_out(o + ".hinge.list");  // hinging.cpp:1696-1704
         for (int i = 0; i < n; i++)
             for (int64_t k = R.hin_off[i]; k < R.hin_off[i + 1]; k++)
                 if (R.active[i] && R.hin_alive[k]) fprintf(f, "%d %d %d\n", i, R.hin_pos[k], R.hin_type[k]);
@@ -273,9 +288,9 @@ extern "C" int hg_main_layout(int argc, char** argv) {
 
     hg_edge e;
     {  // debugging dumps in the working directory (hinging.cpp:1073-1151)
-        FILE* g = fopen("edges.g_out.txt", "w");
-        FILE* fb = fopen("edges.fwd.backup.txt", "w");
-        FILE* bb = fopen("edges.bkw.backup.txt", "w");
+        FILE* g = open_out("edges.g_out.txt");
+        FILE* fb = open_out("edges.fwd.backup.txt");
+        FILE* bb = open_out("edges.bkw.backup.txt");
         for (int half = 0; half < 2; half++) {
             if (half) fprintf(g, "bkw\n");
             for (int i = 0; i < n; i++) {
@@ -297,9 +312,9 @@ extern "C" int hg_main_layout(int argc, char** argv) {
         fclose(bb);
     }
     {  // plain greedy graph (hinging.cpp:1724-1860)
-        FILE* g1 = fopen((o + ".edges.1").c_str(), "w");
-        FILE* g2 = fopen((o + ".edges.2").c_str(), "w");
-        FILE* gr = fopen((o + ".edges.greedy").c_str(), "w");
+        FILE* g1 = open_out(o + ".edges.1");
+        FILE* g2 = open_out(o + ".edges.2");
+        FILE* gr = open_out(o + ".edges.greedy");
         for (int i = 0; i < n; i++) {
             if (!R.active[i]) continue;
             for (int half = 0; half < 2; half++) {
@@ -320,9 +335,9 @@ extern "C" int hg_main_layout(int argc, char** argv) {
         fclose(gr);
     }
     {  // the hinge-aware graph (hinging.cpp:1911-2148)
-        FILE* hg = fopen((o + ".edges.hinges").c_str(), "w");
-        FILE* hg2 = fopen((o + ".edges.hinges2").c_str(), "w");
-        FILE* sk = fopen((o + ".edges.skipped").c_str(), "w");
+        FILE* hg = open_out(o + ".edges.hinges");
+        FILE* hg2 = open_out(o + ".edges.hinges2");
+        FILE* sk = open_out(o + ".edges.skipped");
         std::ofstream dead(o + ".deadends.txt");
         for (const SkipRec& s : R.skips) {
             R.fill_edge(s.cand, -1, &e);
@@ -351,5 +366,5 @@ extern "C" int hg_main_layout(int argc, char** argv) {
     }
     hg_ctx_destroy(ctx);
     timer.lap("write output files + destroy");
-    return 0;
+    return g_out_failed ? 1 : 0;
 }

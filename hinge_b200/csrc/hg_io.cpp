@@ -70,7 +70,7 @@ int ReadDB::open(const std::string& db_name) {
         for (int i = 0; i < nfiles; i++) {
             int last;
             char a[10000], b[10000];
-            if (fscanf(f, "  %9d %s %s\n", &last, a, b) != 3) {
+            if (fscanf(f, "  %9d %9999s %9999s\n", &last, a, b) != 3) {
                 fclose(f);
                 error = "Stub file (.db) of " + root + " is junk";
                 return -1;

@@ -287,8 +287,11 @@ __device__ void warp_sort_exact(T* a, int n, Less less, int* idx_g, int* idx_l, 
 // only lane 0 of a warp ever touches.  All threads of the CTA call this with identical
 // arguments; idx_g / idx_l hold n ints each (a range uses its own [first, last) slice), tmp n
 // elements.
+constexpr int kCtaSortStack = 160;   // shared stack of pending sub-ranges
+constexpr int kCtaSortLocal = 64;    // per-warp overflow stack: one entry per level of the introsort
+                                     // recursion at most, and the depth limit is 2 log2(n) <= 62
 struct CtaSortState {
-    int first[160], last[160], depth[160];
+    int first[kCtaSortStack], last[kCtaSortStack], depth[kCtaSortStack];
     int top, busy, lock;
 };
 
@@ -345,6 +348,9 @@ __device__ void cta_sort_exact(T* a, int n, Less less, int* idx_g, int* idx_l, T
         // the range was written by another warp before it pushed it: lane 0's lock acquire + fence
         // orders those writes before lane 0, this orders them before the other 31 lanes
         __syncwarp();
+        // right-hand parts that found the shared stack full wait here and are done by this warp
+        int lf[kCtaSortLocal], ll[kCtaSortLocal], ld[kCtaSortLocal], lsp = 0;
+      next_range:
         while (last - first > 16) {
             if (depth == 0) {
                 if (lane == 0) os_heap_sort(a, first, last, less);
@@ -396,16 +402,34 @@ __device__ void cta_sort_exact(T* a, int n, Less less, int* idx_g, int* idx_l, T
             const int cut = (m < ng && pg[m] < prev_hi) ? pg[m] : prev_hi;
             __syncwarp();
             if (last - cut > 16) {  // right part: for whoever is free (parts of <= 16 need nothing here)
+                int pushed = 0;
                 if (lane == 0) {
                     lock();
-                    const int s = st->top++;
-                    st->first[s] = cut;
-                    st->last[s] = last;
-                    st->depth[s] = depth;
+                    if (st->top < kCtaSortStack) {
+                        const int s = st->top++;
+                        st->first[s] = cut;
+                        st->last[s] = last;
+                        st->depth[s] = depth;
+                        pushed = 1;
+                    }
                     unlock();
+                }
+                pushed = __shfl_sync(0xffffffffu, pushed, 0);
+                if (!pushed) {  // shared stack full: keep it (lsp < kCtaSortLocal, see above)
+                    lf[lsp] = cut;
+                    ll[lsp] = last;
+                    ld[lsp] = depth;
+                    lsp++;
                 }
             }
             last = cut;
+        }
+        if (lsp > 0) {
+            lsp--;
+            first = lf[lsp];
+            last = ll[lsp];
+            depth = ld[lsp];
+            goto next_range;
         }
         if (lane == 0) {
             lock();

@@ -46,8 +46,9 @@ enum hg_option {
     HG_OPT_PROFILE = 2,       /* record CUDA events between the kernels of a stage */
     HG_OPT_SCATTER_SPREAD = 3,/* tuning aid: record windows per warp in the profile scatter (1, 4, 8, 16) */
     HG_OPT_PROFILE_KERNEL = 4 /* tuning aid: 0 = pick the form of the coverage-profile kernel by cut_off
-                                 (20-bp start/end histogram when cut_off % 20 == 0), 1 = always the
-                                 four-event 40-bp form */
+                                 (20-bp start/end histogram for the nominal cut_off 300), 1 = always the
+                                 four-event 40-bp form, 5 / 6 = the 20-bp form compiled for 5 / 6
+                                 resident CTAs per SM */
 };
 
 enum hg_buffer { /* per-read device arrays a sharded run exchanges between phases */

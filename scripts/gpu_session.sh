@@ -30,6 +30,23 @@ for S in $STEPS; do
       echo "bench (old K1) exit $?"
       python -c "
 import json;d=json.load(open('$OUT/${TAG}_bench_k1old.json'));print('c5',d['ms_per_step'],d['kernel_ms'],d['roofline']['frac']);print('c3',d['c3']['ms_per_step'],d['c3']['kernel_ms'],d['c3']['roofline']['frac'])" ;;
+    pytest_filter)
+      timeout 900 python -m pytest tests/test_gpu_filter_api.py tests/test_gpu_edge_cases.py tests/test_gpu_filter_cli.py -m gpu -x -q > $OUT/${TAG}_pytest_filter.log 2>&1
+      echo "pytest (filter) exit $?" | tee -a $OUT/${TAG}_pytest_filter.log; tail -5 $OUT/${TAG}_pytest_filter.log ;;
+    variants)
+      for V in 0 5 6; do
+        timeout 600 python bench.py --profile-kernel $V $SHORT > $OUT/${TAG}_bench_v$V.json 2> $OUT/${TAG}_bench_v$V.err
+        echo "variant $V exit $?"
+        python -c "
+import json;d=json.load(open('$OUT/${TAG}_bench_v$V.json'));print('c5',round(d['ms_per_step'],4),{k:round(v,4) for k,v in d['kernel_ms'].items()},round(d['roofline']['frac'],3));print('c3',round(d['c3']['ms_per_step'],4),{k:round(v,4) for k,v in d['c3']['kernel_ms'].items()},round(d['c3']['roofline']['frac'],3))"
+      done ;;
+    down)
+      for CFG in c3 c5; do
+        HINGE_B200_TIMING=1 timeout 900 python bench.py --config $CFG --also "" --steps 3 --e2e-steps 1 --no-cpu-baseline --no-verify > $OUT/${TAG}_down_$CFG.json 2> $OUT/${TAG}_down_$CFG.err
+        echo "downstream $CFG exit $?"; grep "timing\]" $OUT/${TAG}_down_$CFG.err | tail -40
+        python -c "
+import json;d=json.load(open('$OUT/${TAG}_down_$CFG.json'));print(d.get('downstream_stages'))"
+      done ;;
     launches)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
         --log-file $OUT/${TAG}_launches.csv python bench.py $SHORT > $OUT/${TAG}_launches_bench.log 2>&1

@@ -72,3 +72,13 @@ def test_cli_error_conventions(built, tmp_path):
     r = subprocess.run([ht.HINGE, "filter", "--db", "missing", "--las", "missing", "--config", ht.INI],
                        cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 1 and "Could not open database" in r.stdout
+
+
+def test_missing_mask_file_exits_with_one(built, tmp_path):
+    # maximal / layout before filter: exit code 1 like every other error path; the CUDA context that is
+    # being created beside the input reading must be joined, not left to std::terminate (SIGABRT)
+    root, meta = ht.materialize("dal_small", str(tmp_path))
+    for stage in ("maximal", "layout"):
+        r = ht.run_stage("product", stage, str(tmp_path), root, "nofilter", check=False)
+        assert r.returncode == 1, (stage, r.returncode, r.stdout[-500:])
+        assert "cannot read nofilter.mas" in r.stdout
