@@ -74,6 +74,8 @@ PROTOTYPES = {
     "hg_filter_fetch": (C.c_int, [vp] + [vp] * 7),
     "hg_filter_coverage": (C.c_int, [vp, vp, vp, i64p]),
     "hg_maximal": (C.c_int, [vp, C.POINTER(LayoutParamsC), vp, vp, vp, f32p]),
+    "hg_maximal_phase1": (C.c_int, [vp, C.POINTER(LayoutParamsC), vp, vp, vp, i64, vp, i64, i32p]),
+    "hg_maximal_phase2": (C.c_int, [vp, vp, vp, i32p, i32, i64, vp, i64, vp]),
     "hg_layout": (C.c_int, [vp, C.POINTER(LayoutParamsC)] + [vp] * 8 + [f32p]),
     "hg_layout_edges": (C.c_int, [vp, C.POINTER(EdgeC), i64, i64p]),
     "hg_main_filter": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),

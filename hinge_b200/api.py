@@ -177,6 +177,23 @@ class Context:
                     "hg_maximal")
         return mx, by, ms.value
 
+    def maximal_phase1(self, params, mask, state, unk, pool):
+        """state: uint8[n_read] device tensor; unk: int32[cap, 4]; pool: int32[cap].  Returns (unknown reads,
+        pool entries) -- if either exceeds the tensors' capacity, enlarge them and call again."""
+        counts = (C.c_int32 * 2)()
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.int32)
+        self._check(lib.hg_maximal_phase1(self._h, C.byref(params), _ptr(mask), _ptr(state), _ptr(unk),
+                                          unk.shape[0], _ptr(pool), pool.shape[0], counts), "hg_maximal_phase1")
+        return int(counts[0]), int(counts[1])
+
+    def maximal_phase2(self, state_all, unk_all, counts_all, world, unk_stride, pool_all, pool_stride):
+        mx = np.zeros(self.n_read, np.uint8)
+        cc = (C.c_int32 * (2 * world))(*[int(x) for x in counts_all])
+        self._check(lib.hg_maximal_phase2(self._h, _ptr(state_all), _ptr(unk_all), cc, int(world), int(unk_stride),
+                                          _ptr(pool_all), int(pool_stride), _ptr(mx)), "hg_maximal_phase2")
+        return mx
+
     def layout(self, params, mask, maximal, rep, hin):
         """rep / hin: (off[int64 n+1], pos[int32], type[int32]) CSR triples."""
         ms = C.c_float()

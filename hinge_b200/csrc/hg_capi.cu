@@ -136,6 +136,8 @@ void hg_ctx_destroy(hg_ctx* c) {
     cudaFree(s.big_list); cudaFree(s.exact_list); cudaFree(s.big_scratch); cudaFree(s.hinge_keep); cudaFree(s.hinge_scratch);
     cudaFree(s.item_log); cudaFree(s.flat_batch); cudaFree(s.flat_rbase);
     cudaFree(c->d_cov0); cudaFree(c->d_cov0_off);
+    cudaFree(c->ms.active0); cudaFree(c->ms.state); cudaFree(c->ms.rtype); cudaFree(c->ms.unk); cudaFree(c->ms.pool);
+    cudaFree(c->ms.counters); cudaFree(c->ms.big_pairs); cudaFree(c->ms.sort_scratch);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     free_layout_result(c->layout);
@@ -372,6 +374,8 @@ static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
             std::vector<int> rbase;
             flat_plan(c->h_rlen.data(), lo, std::max(lo, hi), c->n_read, p->cut_off, &batch, &rbase);
             s.flat_nbatch = hi > lo ? (int)batch.size() - 1 : 0;
+            s.flat_bins_total = 0;
+            for (const int2& bt : batch) s.flat_bins_total += bt.y;
             HG_TRY(dev_alloc(c, &s.flat_batch, batch.size(), "flat batches"));
             HG_TRY(dev_alloc(c, &s.flat_rbase, rbase.size(), "flat read offsets"));
             HG_TRY(dev_alloc(c, &s.flat_prof, (size_t)std::max(s.flat_nbatch, 1) * kFlatBins, "coverage profiles"));
@@ -391,6 +395,7 @@ static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
             c->plan_hi = hi;
         }
     }
+    s.flat_bins_per_record = (float)(s.flat_bins_total / (double)std::max<int64_t>(c->novl, 1));
     // the generic path is always armed: very long reads, very deep pile-ups, and reads with more
     // raw annotations than the fast path keeps are rerouted to it at run time
     s.big_slot_words = (bins(c->max_rlen) + 31) & ~31;

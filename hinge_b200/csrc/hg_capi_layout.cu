@@ -89,73 +89,124 @@ void free_layout_result(LayoutResult* r) { delete r; }
 
 }  // namespace hg
 
+
+
+// Scratch of the maximal stage, kept in the context: per-read flags, per-record classes, the
+// containment lists and the (rarely used) buffers of the order-exact pair sort.
+static int maximal_scratch(hg_ctx* c, int unk_cap, int pool_cap, int big_cap, int sort_cap) {
+    hg_ctx::StageScratch& m = c->ms;
+    const int n = c->n_read;
+    if (m.cap_reads < n) {
+        HG_TRY(dev_alloc(c, &m.active0, n, "active"));
+        HG_TRY(dev_alloc(c, &m.state, n, "state"));
+        m.cap_reads = n;
+    }
+    if (m.cap_rtype < c->novl) {
+        HG_TRY(dev_alloc(c, &m.rtype, (size_t)c->novl, "record classes"));
+        m.cap_rtype = c->novl;
+    }
+    if (!m.counters) HG_TRY(dev_alloc(c, &m.counters, 16, "stage counters"));
+    if (m.unk_cap < unk_cap) {
+        HG_TRY(dev_alloc(c, &m.unk, unk_cap, "unknown reads"));
+        m.unk_cap = unk_cap;
+    }
+    if (m.pool_cap < pool_cap) {
+        HG_TRY(dev_alloc(c, &m.pool, pool_cap, "container lists"));
+        m.pool_cap = pool_cap;
+    }
+    if (m.big_cap < big_cap) {
+        HG_TRY(dev_alloc(c, &m.big_pairs, big_cap, "big pairs"));
+        m.big_cap = big_cap;
+    }
+    if (m.sort_cap < sort_cap) {
+        KeyIdx2* p = (KeyIdx2*)m.sort_scratch;
+        HG_TRY(dev_alloc(c, &p, sort_cap, "pair sort scratch"));
+        m.sort_scratch = p;
+        m.sort_cap = sort_cap;
+    }
+    return HG_OK;
+}
+
+// Classification + containment lists of the context's own reads (everything up to the point where
+// a sharded run has to look at other shards).  Leaves state / unk / pool / counters on the device.
+// Returns HG_OK, or a positive value when a list overflowed and was grown: call again.
+static int maximal_local(hg_ctx* c, const hg_layout_params* P, int* n_unknown, int* pool_used) {
+    hg_ctx::StageScratch& m = c->ms;
+    cudaStream_t st = c->stream;
+    const int n = c->n_read;
+    for (int attempt = 0;; attempt++) {
+        HG_TRY(maximal_scratch(c, std::max(m.unk_cap, (c->a_hi - c->a_lo) / 4 + 1024),
+                               std::max(m.pool_cap, c->a_hi - c->a_lo + 4096), std::max(m.big_cap, 1 << 14),
+                               std::max(m.sort_cap, 1 << 18)));
+        PairOut po{};
+        po.counters = m.counters; po.big_pairs = m.big_pairs; po.big_cap = m.big_cap;
+        po.sort_scratch = (KeyIdx2*)m.sort_scratch; po.sort_cap = m.sort_cap;
+        ContainIO io{};
+        io.active0 = m.active0; io.rtype = m.rtype; io.state = m.state; io.unk = m.unk; io.unk_cap = m.unk_cap;
+        io.pool = m.pool; io.pool_cap = m.pool_cap; io.counters = m.counters + 8;
+        k_length_filter<<<(n + 255) / 256, 256, 0, st>>>(c->fs.mask, n, P->length_threshold, m.active0);
+        cudaMemsetAsync(m.state, 0, n, st);  // reads of other shards: unknown until their states arrive
+        // the reference sorts every pair twice before it reads the top two (maximal.cpp:647-654, 791)
+        launch_classify_reads(c->rec_view(), c->read_view(), *P, c->fs.mask, m.active0, 2, m.rtype, po, st);
+        launch_contain_lists(c->rec_view(), c->read_view(), io, st);
+        int cnt[16];
+        HG_TRY(cuda_check(c, cudaGetLastError(), "maximal kernels"));
+        HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, m.counters, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
+        HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "maximal: classify + lists"));
+        if (!cnt[3] && !cnt[10]) {
+            *n_unknown = cnt[8];
+            *pool_used = cnt[9];
+            return HG_OK;
+        }
+        if (attempt > 8) return set_err(c, HG_ERR_NOMEM, "maximal: lists kept overflowing");
+        // grow what overflowed and run again
+        HG_TRY(maximal_scratch(c, std::max(m.unk_cap, cnt[8] + 1024), std::max(m.pool_cap, cnt[9] + 4096),
+                               std::max(m.big_cap, cnt[0] + 1024), cnt[3] ? std::max(m.sort_cap * 4, cnt[1] + 1024) : m.sort_cap));
+    }
+}
+
 extern "C" {
 
 int hg_maximal(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, uint8_t* maximal_out,
                int32_t* contained_by, float* ms_device) {
     if (!c || !P || !maximal_out || c->novl <= 0) return set_err(c, HG_ERR_ARG, "hg_maximal: bad arguments");
     if (!c->has_trace) return set_err(c, HG_ERR_ARG, "hg_maximal needs the trace (pass trace_off/trace to hg_set_overlaps)");
+    if (c->a_lo != 0 || c->a_hi != c->n_read)
+        return set_err(c, HG_ERR_ARG, "hg_maximal on a context that owns a slice of the reads: containment looks at reads "
+                                      "of lower id in other shards; use hg_maximal_phase1 / hg_maximal_phase2");
     cudaSetDevice(c->device);
     cudaStream_t st = c->stream;
     const int n = c->n_read;
     HG_TRY(upload_mask(c, mask));
-    DevBuf<uint8_t> active0, rtype, state;
-    DevBuf<int> remaining;
-    HG_TRY(active0.alloc(c, n, "active"));
-    HG_TRY(state.alloc(c, n, "state"));
-    HG_TRY(rtype.alloc(c, (size_t)c->novl, "record types"));
-    HG_TRY(remaining.alloc(c, 1, "remaining"));
-    int big_cap = 1 << 16, sort_cap = 1 << 20;
     StepTimer tm(st);
-    tm.lap("maximal: allocations");
     cudaEventRecord(c->ev0, st);
-    for (int attempt = 0;; attempt++) {
-        PairBufs pb;
-        HG_TRY(pb.make(c, big_cap, sort_cap, 1, 1));
-        k_length_filter<<<(n + 255) / 256, 256, 0, st>>>(c->fs.mask, n, P->length_threshold, active0.p);
-        cudaMemsetAsync(rtype.p, 0xff, (size_t)c->novl, st);
-        cudaMemsetAsync(state.p, 2, n, st);
-        // the reference sorts every pair twice before it reads the top two (maximal.cpp:647-654, 791)
-        launch_classify(c->rec_view(), c->read_view(), *P, c->fs.mask, active0.p, 0, 2, rtype.p, pb.po, st);
-        int cnt[8];
-        HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, pb.po.counters, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
-        HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "classify"));
-        if (!cnt[3]) break;
-        if (attempt > 6) return set_err(c, HG_ERR_NOMEM, "pair scratch kept overflowing");
-        big_cap = std::max(big_cap, cnt[0] + 1024);
-        sort_cap = std::max(sort_cap * 4, cnt[1] + 1024);
-    }
-    tm.lap("maximal: classify pairs");
-    launch_contain_init(c->rec_view(), c->read_view(), active0.p, rtype.p, state.p, st);
-    tm.lap("maximal: containment init");
-    for (int it = 0; it < 100000; it++) {
-        int rem = 0;
-        launch_contain_step(c->rec_view(), c->read_view(), active0.p, rtype.p, state.p, remaining.p, st);
-        HG_TRY(cuda_check(c, cudaMemcpyAsync(&rem, remaining.p, 4, cudaMemcpyDeviceToHost, st), "D2H"));
-        HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "containment"));
-        if (rem == 0) break;
-    }
-    tm.lap("maximal: containment fixed point");
+    int n_unknown = 0, pool_used = 0;
+    HG_TRY(maximal_local(c, P, &n_unknown, &pool_used));
+    tm.lap("maximal: classify + containment lists");
+    hg_ctx::StageScratch& m = c->ms;
+    launch_contain_resolve(m.unk, m.counters + 8, 1, m.unk_cap, m.pool, m.pool_cap, m.state, m.counters + 12, st);
     cudaEventRecord(c->ev1, st);
     std::vector<uint8_t> hstate(n), hact(n);
-    HG_TRY(cuda_check(c, cudaMemcpyAsync(hstate.data(), state.p, n, cudaMemcpyDeviceToHost, st), "D2H"));
-    HG_TRY(cuda_check(c, cudaMemcpyAsync(hact.data(), active0.p, n, cudaMemcpyDeviceToHost, st), "D2H"));
+    HG_TRY(cuda_check(c, cudaGetLastError(), "containment resolve"));
+    HG_TRY(cuda_check(c, cudaMemcpyAsync(hstate.data(), m.state, n, cudaMemcpyDeviceToHost, st), "D2H"));
+    HG_TRY(cuda_check(c, cudaMemcpyAsync(hact.data(), m.active0, n, cudaMemcpyDeviceToHost, st), "D2H"));
     HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "D2H"));
+    tm.lap("maximal: resolve + D2H");
     if (ms_device) cudaEventElapsedTime(ms_device, c->ev0, c->ev1);
-    for (int i = 0; i < n; i++) maximal_out[i] = (i >= c->a_lo && i < c->a_hi && hstate[i] == 1) ? 1 : 0;
+    for (int i = 0; i < n; i++) maximal_out[i] = hstate[i] == 1 ? 1 : 0;
     if (contained_by) {
         // .contained.txt names the LAST containing read in std::unordered_map iteration order
         // (maximal.cpp:789-857): replay the key sequence into the real container
         std::vector<uint8_t> ht((size_t)c->novl);
         std::vector<int32_t> hb((size_t)c->novl);
         std::vector<int64_t> hoff((size_t)n + 1);
-        HG_TRY(cuda_check(c, cudaMemcpyAsync(ht.data(), rtype.p, (size_t)c->novl, cudaMemcpyDeviceToHost, st), "D2H"));
+        HG_TRY(cuda_check(c, cudaMemcpyAsync(ht.data(), m.rtype, (size_t)c->novl, cudaMemcpyDeviceToHost, st), "D2H"));
         HG_TRY(cuda_check(c, cudaMemcpyAsync(hb.data(), c->d_bread, 4ull * c->novl, cudaMemcpyDeviceToHost, st), "D2H"));
         HG_TRY(cuda_check(c, cudaMemcpyAsync(hoff.data(), c->d_read_off, 8ull * (n + 1), cudaMemcpyDeviceToHost, st), "D2H"));
         HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "D2H"));
         for (int i = 0; i < n; i++) {
             contained_by[i] = -1;
-            if (!(hact[i] && hstate[i] == 2) || i < c->a_lo || i >= c->a_hi) continue;
+            if (!(hact[i] && hstate[i] == 2)) continue;
             std::unordered_map<int, int> um;  // B -> has a BCOVERA record among its top two
             for (int64_t k = hoff[i]; k < hoff[i + 1]; k++) um[hb[k]] = 0;
             for (int64_t k = hoff[i]; k < hoff[i + 1]; k++)
@@ -163,8 +214,59 @@ int hg_maximal(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, uint8_
             for (auto it = um.begin(); it != um.end(); ++it)
                 if (it->second) contained_by[i] = it->first;
         }
+        tm.lap("maximal: .contained.txt replay (host)");
     }
     return HG_OK;
+}
+
+// ---- sharded form -----------------------------------------------------------------------
+// phase 1 (every rank): classification and containment lists of the rank's own reads.
+//   state_out   device, uint8[n_read]: own reads filled (0 unknown / 1 survives / 2 removed), the
+//               others 0 -- a MAX all-reduce over the ranks assembles the array
+//   unk_out     device, int32[4 * unk_cap]; pool_out device, int32[pool_cap]: the lists of this
+//               rank's unknown reads, to be all-gathered (fixed strides); counts[0..1] = entries used
+// phase 2 (every rank, redundantly): the resolve over the gathered lists; maximal_out (host,
+// n_read bytes) is the maximal-read bitmap of ALL reads.
+int hg_maximal_phase1(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, void* state_out,
+                      void* unk_out, int64_t unk_cap, void* pool_out, int64_t pool_cap, int32_t* counts) {
+    if (!c || !P || !state_out || !counts || c->novl <= 0) return set_err(c, HG_ERR_ARG, "hg_maximal_phase1: bad arguments");
+    if (!c->has_trace) return set_err(c, HG_ERR_ARG, "hg_maximal needs the trace (pass trace_off/trace to hg_set_overlaps)");
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    HG_TRY(upload_mask(c, mask));
+    int n_unknown = 0, pool_used = 0;
+    HG_TRY(maximal_local(c, P, &n_unknown, &pool_used));
+    counts[0] = n_unknown;
+    counts[1] = pool_used;
+    hg_ctx::StageScratch& m = c->ms;
+    HG_TRY(cuda_check(c, cudaMemcpyAsync(state_out, m.state, c->n_read, cudaMemcpyDeviceToDevice, st), "state"));
+    if (unk_out && pool_out && n_unknown <= unk_cap && pool_used <= pool_cap) {
+        if (n_unknown) HG_TRY(cuda_check(c, cudaMemcpyAsync(unk_out, m.unk, sizeof(int4) * (size_t)n_unknown, cudaMemcpyDeviceToDevice, st), "lists"));
+        if (pool_used) HG_TRY(cuda_check(c, cudaMemcpyAsync(pool_out, m.pool, sizeof(int) * (size_t)pool_used, cudaMemcpyDeviceToDevice, st), "lists"));
+    }
+    return cuda_check(c, cudaStreamSynchronize(st), "hg_maximal_phase1");
+}
+
+int hg_maximal_phase2(hg_ctx* c, void* state_all, const void* unk_all, const int32_t* counts_all, int32_t world,
+                      int64_t unk_stride, const void* pool_all, int64_t pool_stride, uint8_t* maximal_out) {
+    if (!c || !state_all || !counts_all || world < 1 || !maximal_out)
+        return set_err(c, HG_ERR_ARG, "hg_maximal_phase2: bad arguments");
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    int* d_counts = nullptr;
+    HG_TRY(dev_alloc(c, &d_counts, 2 * (size_t)world, "counts"));
+    int rc = cuda_check(c, cudaMemcpyAsync(d_counts, counts_all, sizeof(int) * 2 * (size_t)world, cudaMemcpyHostToDevice, st), "H2D");
+    if (rc == HG_OK) {
+        launch_contain_resolve((const int4*)unk_all, d_counts, world, (int)unk_stride, (const int*)pool_all,
+                               (int)pool_stride, (uint8_t*)state_all, nullptr, st);
+        std::vector<uint8_t> hstate((size_t)c->n_read);
+        rc = cuda_check(c, cudaMemcpyAsync(hstate.data(), state_all, c->n_read, cudaMemcpyDeviceToHost, st), "D2H");
+        if (rc == HG_OK) rc = cuda_check(c, cudaStreamSynchronize(st), "hg_maximal_phase2");
+        if (rc == HG_OK)
+            for (int i = 0; i < c->n_read; i++) maximal_out[i] = hstate[i] == 1 ? 1 : 0;
+    }
+    cudaFree(d_counts);
+    return rc;
 }
 
 int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const uint8_t* maximal,

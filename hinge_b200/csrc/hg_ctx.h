@@ -74,6 +74,19 @@ struct hg_ctx {
     bool peer_ipc[hg::kMaxPeers] = {};  // base[r] came from cudaIpcOpenMemHandle
     bool peer_connected = false;
 
+    // maximal / layout scratch, kept across calls (grown on demand)
+    struct StageScratch {
+        uint8_t *active0 = nullptr, *state = nullptr, *rtype = nullptr;
+        int64_t cap_reads = 0, cap_rtype = 0;
+        int4* unk = nullptr;
+        int* pool = nullptr;
+        int unk_cap = 0, pool_cap = 0;
+        int* counters = nullptr;   // 16 ints: [0..7] pair lists, [8..11] containment lists, [12] sweeps
+        int64_t* big_pairs = nullptr;
+        void* sort_scratch = nullptr;
+        int big_cap = 0, sort_cap = 0;
+    } ms;
+
     hg::LayoutResult* layout = nullptr;  // result of the last hg_layout
 
     hg::RecView rec_view() const;

@@ -895,7 +895,7 @@ __global__ void __launch_bounds__(128)
 k_hinge_exact(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
               const int2* __restrict__ anno_ref, const int2* __restrict__ anno_pool,
               int* __restrict__ counters, const int* __restrict__ exact_list,
-              uint8_t* __restrict__ hinge_keep, uint8_t* gscratch, int gcap, int scap) {
+              uint8_t* __restrict__ hinge_keep, uint8_t* gscratch, int gcap, int scap, int np_above) {
     extern __shared__ __align__(16) uint8_t sm_exact[];
     __shared__ CtaSortState sort_state;
     __shared__ int sh_w, sh_n;
@@ -912,6 +912,7 @@ k_hinge_exact(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
         const int read = exact_list[w];
         const int64_t o0 = rv.read_off[read], o1 = rv.read_off[read + 1];
         const int np = (int)(o1 - o0);
+        if (np <= np_above) continue;  // shallow pile-ups: k_hinge_exact_warp (uniform over the CTA)
         const bool in_smem = np <= scap;
         const int cap = in_smem ? scap : gcap;
         uint8_t* base = in_smem ? sm_exact : gscratch + (size_t)blockIdx.x * gcap * kHingeSlotBytesPerRec;
@@ -997,6 +998,92 @@ k_hinge_exact(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
             }
             if (threadIdx.x == 0) hinge_keep[ar.x + j] = keep;
             __syncthreads();
+        }
+    }
+}
+
+// The same for pile-ups of at most `cap` records: ONE WARP per read, four reads per CTA, all
+// arrays of a read in its warp's slice of shared memory (48 B per record).  A pile-up of a few
+// hundred records is far too small for a CTA (k_hinge_exact above spends its time in barriers
+// and in the lock of its work stack: 50 us per read, 296 reads at a time -- 3.4 ms for the 20 k
+// reads of the long-read / fragmented-alignment set), while thousands of warps fit the chip.
+// Handles the reads of the list with np_above < pile-up size <= cap; launched once per size tier.
+__global__ void __launch_bounds__(128)
+k_hinge_exact_warp(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
+                   const int2* __restrict__ anno_ref, const int2* __restrict__ anno_pool,
+                   int* __restrict__ counters, int queue_slot, const int* __restrict__ exact_list,
+                   uint8_t* __restrict__ hinge_keep, int np_above, int cap) {
+    extern __shared__ __align__(16) uint8_t sm_exact[];
+    const int lane = lane_id();
+    const unsigned lt = (1u << lane) - 1u;
+    uint8_t* base = sm_exact + (size_t)(threadIdx.x >> 5) * cap * kHingeExactBytesPerRec;
+    int4* rec = reinterpret_cast<int4*>(base);
+    KeyIdx* ord = reinterpret_cast<KeyIdx*>(base + (size_t)cap * 16);
+    int2* ends = reinterpret_cast<int2*>(base + (size_t)cap * 24);
+    int2* tmp = reinterpret_cast<int2*>(base + (size_t)cap * 32);
+    int* gl = reinterpret_cast<int*>(base + (size_t)cap * 40);
+    const int nlist = counters[6];
+    const int THETA = P.theta, HTL = P.hinge_tolerance_length;
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(&counters[queue_slot], 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= nlist) break;
+        const int read = exact_list[w];
+        const int64_t o0 = rv.read_off[read], o1 = rv.read_off[read + 1];
+        const int np = (int)(o1 - o0);
+        if (np <= np_above || np > cap) continue;
+        const int2 mk = mask.full[read];  // the read's own mask: always in the local array
+        const int2 ar = anno_ref[read];
+        // pile-up in file order without the inactive A == B records (filter.cpp:538-547)
+        int n = 0;
+        for (int kb = 0; kb < np; kb += 32) {
+            const int k = kb + lane;
+            PileRec r;
+            r.active = false;
+            if (k < np) r = load_pile_rec(rv, rd, mask, read, o0 + k);
+            const unsigned am = __ballot_sync(0xffffffffu, r.active);
+            if (r.active) {
+                const int s = n + __popc(am & lt);
+                rec[s] = make_int4(r.as, r.ae, r.lo, r.ro);
+                ord[s].key = r.key;
+                ord[s].idx = s;
+            }
+            n += __popc(am);
+        }
+        __syncwarp();
+        // std::sort by total length (filter.cpp:565-567)
+        warp_sort_exact(ord, n, GreaterKey(), gl, gl + cap, reinterpret_cast<KeyIdx*>(tmp));
+        for (int j = 0; j < ar.y; j++) {
+            const int2 an = anno_pool[ar.x + j];
+            const bool out_hinge = an.y == -1;
+            int support = 0;
+            for (int kb = 0; kb < n; kb += 32) {  // selection in pile-up order
+                const int k = kb + lane;
+                bool sel = false;
+                int2 e = make_int2(0, 0);
+                if (k < n) {
+                    const int4 q = rec[ord[k].idx];
+                    PileRec r;
+                    r.as = q.x; r.ae = q.y; r.lo = q.z; r.ro = q.w; r.key = 0; r.active = true;
+                    sel = hinge_select(r, out_hinge, an.x, THETA, HTL, &e);
+                }
+                const unsigned sm = __ballot_sync(0xffffffffu, sel);
+                if (sel) ends[support + __popc(sm & lt)] = e;
+                support += __popc(sm);
+            }
+            __syncwarp();
+            uint8_t keep = 0;
+            if (support >= P.hinge_min_support) {  // filter.cpp:910, 1005
+                if (out_hinge)  // filter.cpp:914 / 1010
+                    warp_sort_exact(ends, support, FirstAsc(), gl, gl + cap, tmp);
+                else
+                    warp_sort_exact(ends, support, FirstDesc(), gl, gl + cap, tmp);
+                keep = hinge_walk_warp(ends, support, out_hinge, mk, P) ? 1 : 0;
+                if (lane == 0) atomicAdd(&counters[4], 1);
+            }
+            if (lane == 0) hinge_keep[ar.x + j] = keep;
+            __syncwarp();
         }
     }
 }
@@ -1134,9 +1221,18 @@ void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_pa
     const int smem = scap * kHingeExactBytesPerRec;
     // function attributes are per device: set it on every launch (cheap), not once per process
     cudaFuncSetAttribute(k_hinge_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    // shallow pile-ups (almost all of them): one warp per read out of shared memory, two size tiers
+    constexpr int capA = 256, capB = 768;
+    const int smemA = 4 * capA * kHingeExactBytesPerRec, smemB = 4 * capB * kHingeExactBytesPerRec;
+    cudaFuncSetAttribute(k_hinge_exact_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, smemB);
+    g_launches += 2;
+    k_hinge_exact_warp<<<4 * s.num_sms, 128, smemA, st>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 12,
+                                                         s.exact_list, s.hinge_keep, 0, capA);
+    k_hinge_exact_warp<<<s.num_sms, 128, smemB, st>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 13,
+                                                     s.exact_list, s.hinge_keep, capA, capB);
     const int grid = s.hinge_warps < 2 * s.num_sms ? s.hinge_warps : 2 * s.num_sms;
     k_hinge_exact<<<grid, 128, smem, st>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters,
-                                          s.exact_list, s.hinge_keep, s.hinge_scratch, s.hinge_cap, scap);
+                                          s.exact_list, s.hinge_keep, s.hinge_scratch, s.hinge_cap, scap, capB);
 }
 
 }  // namespace hg

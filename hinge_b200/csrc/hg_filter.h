@@ -49,7 +49,10 @@ struct FilterScratch {
     uint32_t* flat_prof = nullptr;    // scanned packed profiles, kFlatBins words per batch (K1 -> K2)
     int flat_nbatch = 0;
     int flat_spread = 8;              // record windows per warp in the scatter (tuning aid)
-    int flat_kernel = 0;              // 0: second form of K1 when the cut-off allows it, 1: always the first form
+    int flat_kernel = 0;              // 0: pick the form of K1 by cut-off and shape, 1: always the first form,
+                                      // 5 / 6: second form compiled for 4 / 6 resident CTAs per SM
+    double flat_bins_total = 0;       // coverage bins of the planned reads
+    float flat_bins_per_record = 0;   // ... per record of the context
     unsigned long long* big_scratch = nullptr;
     int big_slot_words = 0, big_warps = 0;
     // K4

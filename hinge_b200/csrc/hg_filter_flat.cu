@@ -855,8 +855,15 @@ void flat_plan(const int* rlen, int lo, int hi, int n_read, int cut_off, std::ve
 }
 
 // The second form of K1 is written for the nominal cut-off (300: every INI the reference ships).
+// It halves the shared-memory atomics per record but handles two histogram words per coverage bin,
+// so it only pays where records outnumber bins (short reads, deep pile-ups: 0.354 vs 0.347 ms on
+// the 62 M-record N(3500,1500) set, a wash); with long reads (3 bins per record on the
+// N(24000,8000) set) the first form is faster (0.92 vs 1.14 ms).  flat_bins_per_record is set
+// when the batch plan is made.
 static bool use_v2(const FilterScratch& s, const hg_filter_params& P) {
-    return s.flat_kernel != 1 && P.cut_off == kV2CutOff;
+    if (s.flat_kernel == 1 || P.cut_off != kV2CutOff) return false;
+    if (s.flat_kernel >= 5) return true;
+    return s.flat_bins_per_record < 1.5f;
 }
 
 static FlatParams flat_params(const FilterScratch& s, const hg_filter_params& P, int r_begin, int r_end) {
@@ -889,12 +896,12 @@ void launch_profile(const RecView& rv, const ReadView& rd, const hg_filter_param
     g_launches += 2;
     if (F.v2) {
         // tuning aids: resident CTAs per SM the compiler aims for (registers), scatter spread
-        if (s.flat_kernel == 5) k_profile_flat2<8, 5><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
+        if (s.flat_kernel == 5) k_profile_flat2<8, 4><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
         else if (s.flat_kernel == 6) k_profile_flat2<8, 6><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
         else if (s.flat_spread == 1) k_profile_flat2<1, 4><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
         else if (s.flat_spread == 4) k_profile_flat2<4, 4><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
         else if (s.flat_spread == 16) k_profile_flat2<16, 4><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
-        else k_profile_flat2<8, 4><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
+        else k_profile_flat2<8, 5><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
     }
     else switch (s.flat_spread) {
         case 1: k_profile_flat<1><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F); break;

@@ -35,36 +35,48 @@ __device__ __forceinline__ int trace_value(const RecView& rv, int64_t off, int k
 
 // ProcessAlignment = trim_overlap + AddTypesAsymmetric
 // (maximal.cpp:65-134; LAInterface.cpp:4552-4683, 4721-4781).
+//
+// trim_overlap walks the trace points (A advances to the next multiple of 100, B by the trace's
+// b-delta) and takes the FIRST point inside both effective reads as the trimmed start and the LAST
+// one as the trimmed end.  The b-deltas are unsigned, so along the walk both coordinates are
+// monotone and the end condition holds for a prefix of the points only; the final point is pushed
+// separately (the match's own end).  That allows two early exits without changing any result:
+//   * the final point satisfies the end condition -> it is the end; walk only until the start is found
+//   * the end condition has turned false          -> the end is known; if the start has not been
+//     found by then the match is inactive (start index >= end index), whatever comes later
+// About half of all overlaps stick out of a mask at their far end and are walked to (almost) the
+// end; the others are done after a few points.
 __device__ Match classify_record(const RecView& rv, const int* __restrict__ rlen,
                                  const int2* __restrict__ mask, int64_t k, int a, int b,
                                  const hg_layout_params& P) {
     Match m;
-    m.as = rv.abpos[k];
-    m.ae = rv.aepos[k];
-    m.comp = rv.flags[k] & 1;
-    m.bs = rv.bbpos[k];
-    m.be = rv.bepos[k];
+    m.as = __ldg(rv.abpos + k);
+    m.ae = __ldg(rv.aepos + k);
+    m.comp = __ldg(rv.flags + k) & 1;
+    m.bs = __ldg(rv.bbpos + k);
+    m.be = __ldg(rv.bepos + k);
     if (m.comp) {
-        const int bl = rlen[b];
+        const int bl = __ldg(rlen + b);
         const int t = bl - m.be;
         m.be = bl - m.bs;
         m.bs = t;
     }
     const int2 EA = mask[a], EB = mask[b];
     m.eas = m.as; m.eae = m.ae; m.ebs = m.bs; m.ebe = m.be;
-    const int64_t toff = rv.trace_off[k];
-    const int tlen = (int)((rv.trace_off[k + 1] - toff) / rv.tbytes);
+    const int64_t toff = __ldg(rv.trace_off + k);
+    const int tlen = (int)((__ldg(rv.trace_off + k + 1) - toff) / rv.tbytes);
     const int inner = max(tlen / 2 - 1, 0);
     const int npts = inner + 2;
     const int sign = 1 - 2 * m.comp;
     int start_idx = npts, end_idx = 0;
     bool have_start = false;
+    // the final point (idx npts - 1): the match's own end
+    const int fa = m.ae, fb = m.comp ? m.bs : m.be;
+    const bool end_final = m.comp ? (fa <= EA.y && fb >= EB.x) : (fa <= EA.y && fb <= EB.y);
+    bool end_alive = true;
     int pa = m.as, pb = m.comp ? m.be : m.bs;
-    for (int idx = 0; idx < npts; idx++) {
-        if (idx == npts - 1) {
-            pa = m.ae;
-            pb = m.comp ? m.bs : m.be;
-        } else if (idx > 0) {
+    for (int idx = 0; idx < npts - 1; idx++) {
+        if (idx > 0) {
             pa = (pa / 100 + 1) * 100;  // next multiple of 100 (LAInterface.cpp:4584-4587)
             pb += sign * trace_value(rv, toff, 2 * (idx - 1) + 1);
         }
@@ -72,17 +84,38 @@ __device__ Match classify_record(const RecView& rv, const int* __restrict__ rlen
             if (!have_start && pa >= EA.x && pb >= EB.x) {
                 m.eas = pa; m.ebs = pb; start_idx = idx; have_start = true;
             }
-            if (pa <= EA.y && pb <= EB.y) {
-                m.eae = pa; m.ebe = pb; end_idx = idx;
+            if (end_alive) {
+                if (pa <= EA.y && pb <= EB.y) {
+                    m.eae = pa; m.ebe = pb; end_idx = idx;
+                } else {
+                    end_alive = false;
+                }
             }
         } else {
             if (!have_start && pa >= EA.x && pb <= EB.y) {
                 m.eas = pa; m.ebe = pb; start_idx = idx; have_start = true;
             }
-            if (pa <= EA.y && pb >= EB.x) {
-                m.eae = pa; m.ebs = pb; end_idx = idx;
+            if (end_alive) {
+                if (pa <= EA.y && pb >= EB.x) {
+                    m.eae = pa; m.ebs = pb; end_idx = idx;
+                } else {
+                    end_alive = false;
+                }
             }
         }
+        if (end_final ? have_start : !end_alive) break;
+    }
+    if (!have_start) {
+        if (!m.comp ? (fa >= EA.x && fb >= EB.x) : (fa >= EA.x && fb <= EB.y)) {
+            m.eas = fa;
+            if (!m.comp) m.ebs = fb; else m.ebe = fb;
+            start_idx = npts - 1;
+        }
+    }
+    if (end_final) {
+        m.eae = fa;
+        if (!m.comp) m.ebe = fb; else m.ebs = fb;
+        end_idx = npts - 1;
     }
     m.active = a != b && !(start_idx >= end_idx);
     m.type = HG_UNDEFINED;
@@ -252,6 +285,68 @@ __global__ void k_classify_big_pairs(RecView rv, ReadView rd, hg_layout_params P
     emit_pair(rv, rd, P, mask, active, mode, a, b, k, top, rtype, po);
 }
 
+// ------------------------------------------------------------------ K5, warp per read (maximal)
+//
+// One warp per active A-read, lanes over its records in file order (coalesced columns).  A lane
+// finds its pair's extent (most pairs have one record: both neighbours differ), ranks its record
+// inside the pair by (length descending, file order) -- which is what the reference's std::sort
+// leaves in front for pairs of at most 16 records (insertion sort: stable) -- and classifies it
+// if it is among the top two.  Larger pairs go to the order-exact kernel below.  Every record of
+// an active read gets its type written (255 = not among the top two).
+__global__ void __launch_bounds__(128)
+k_classify_reads(RecView rv, ReadView rd, hg_layout_params P, const int2* __restrict__ mask,
+                 const uint8_t* __restrict__ active, uint8_t* __restrict__ rtype, PairOut po) {
+    const int lane = lane_id();
+    const int a = rd.r_lo + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (a >= rd.r_hi || !active[a]) return;
+    const int64_t o0 = rv.read_off[a], o1 = rv.read_off[a + 1];
+    const int ntop = P.use_two_matches ? 2 : 1;
+    for (int64_t kb = o0; kb < o1; kb += 32) {
+        const int64_t k = kb + lane;
+        const bool valid = k < o1;
+        const int b = valid ? __ldg(rv.bread + k) : -1;
+        int bp = __shfl_up_sync(0xffffffffu, b, 1), bn = __shfl_down_sync(0xffffffffu, b, 1);
+        if (lane == 0) bp = kb > o0 ? __ldg(rv.bread + kb - 1) : -2;
+        if (lane == 31) bn = kb + 32 < o1 ? __ldg(rv.bread + kb + 32) : -3;
+        if (!valid) continue;
+        bool take = true;
+        if (b == bp || b == bn) {
+            int64_t ps = k, pe = k + 1;
+            while (ps > o0 && __ldg(rv.bread + ps - 1) == b) ps--;
+            while (pe < o1 && __ldg(rv.bread + pe) == b) pe++;
+            if (pe - ps > 16) {
+                // std::sort is only stable up to 16 elements: leave it to the order-exact kernel
+                if (k == ps) {
+                    const int slot = atomicAdd(&po.counters[0], 1);
+                    if (slot < po.big_cap) po.big_pairs[slot] = k; else atomicExch(&po.counters[3], 1);
+                }
+                continue;  // rtype written by k_classify_big_pairs (255 where it does not)
+            }
+            const int key = raw_length(rv, k);
+            int rank = 0;
+            for (int64_t j = ps; j < pe; j++) {
+                if (j == k) continue;
+                const int kj = raw_length(rv, j);
+                rank += (kj > key || (kj == key && j < k)) ? 1 : 0;
+            }
+            take = rank < ntop;
+        }
+        uint8_t t = HG_NOT_CLASSIFIED;
+        if (take) t = (uint8_t)classify_record(rv, rd.rlen, mask, k, a, b, P).type;
+        rtype[k] = t;
+    }
+}
+
+// Records of pairs with more than 16 records: 255 unless the order-exact kernel classifies them.
+__global__ void k_clear_big_pair_types(RecView rv, uint8_t* __restrict__ rtype, PairOut po) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nbig = min(po.counters[0], po.big_cap);
+    if (t >= nbig) return;
+    const int64_t k = po.big_pairs[t];
+    const int a = rv.aread[k], b = rv.bread[k];
+    for (int64_t e = k; e < rv.novl && rv.aread[e] == a && rv.bread[e] == b; e++) rtype[e] = HG_NOT_CLASSIFIED;
+}
+
 // ------------------------------------------------------------------ containment
 
 // state: 0 unknown, 1 survives (maximal), 2 removed
@@ -294,6 +389,114 @@ __global__ void k_contain_step(RecView rv, ReadView rd, const uint8_t* __restric
         state[i] = 1;
     else
         atomicAdd(remaining, 1);
+}
+
+// The same recurrence on compact lists.  Containment (maximal.cpp:780-858) only ever looks at
+// containing reads: a read with an active container of HIGHER id is removed whatever happens
+// (that container has not been visited when the reference visits the read), one without
+// containers survives, and the rest -- "unknown": all containers have lower ids -- depend on the
+// final state of those.  k_contain_lists settles the first two groups and writes, for every
+// unknown read, the list of its lower-id containers; k_contain_resolve then iterates over the
+// unknown reads only (a few per cent of the reads, a handful of list entries each) inside ONE CTA,
+// no host round trips.  Sharded runs gather the lists and states of all ranks before the resolve
+// (hg_maximal_phase1 / hg_maximal_phase2).
+__global__ void __launch_bounds__(128)
+k_contain_lists(RecView rv, ReadView rd, ContainIO io) {
+    const int lane = lane_id();
+    const unsigned lt = (1u << lane) - 1u;
+    const int i = rd.r_lo + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (i >= rd.r_hi) return;
+    if (!io.active0[i]) {
+        if (lane == 0) io.state[i] = 2;
+        return;
+    }
+    const int64_t o0 = rv.read_off[i], o1 = rv.read_off[i + 1];
+    bool hi = false;
+    int nlo = 0;
+    for (int64_t kb = o0; kb < o1; kb += 32) {
+        const int64_t k = kb + lane;
+        bool lo = false;
+        if (k < o1 && io.rtype[k] == HG_BCOVERA) {
+            const int b = __ldg(rv.bread + k);
+            if (io.active0[b]) {
+                // B > A is still active when A is processed (maximal.cpp:809: reads[B]->active)
+                if (b > i) hi = true; else lo = true;
+            }
+        }
+        nlo += __popc(__ballot_sync(0xffffffffu, lo));
+    }
+    hi = __any_sync(0xffffffffu, hi);
+    if (hi || nlo == 0) {
+        if (lane == 0) io.state[i] = hi ? 2 : 1;
+        return;
+    }
+    int slot = 0, off = 0;
+    if (lane == 0) {
+        slot = atomicAdd(&io.counters[0], 1);
+        off = atomicAdd(&io.counters[1], nlo);
+        if (slot >= io.unk_cap || off + nlo > io.pool_cap) {
+            atomicExch(&io.counters[2], 1);
+            slot = -1;
+        } else {
+            io.unk[slot] = make_int4(i, off, nlo, 0);
+        }
+        io.state[i] = 0;
+    }
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (slot < 0) return;
+    int n = 0;
+    for (int64_t kb = o0; kb < o1; kb += 32) {
+        const int64_t k = kb + lane;
+        bool lo = false;
+        int b = 0;
+        if (k < o1 && io.rtype[k] == HG_BCOVERA) {
+            b = __ldg(rv.bread + k);
+            lo = io.active0[b] && b < i;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, lo);
+        if (lo) io.pool[off + n + __popc(m & lt)] = b;
+        n += __popc(m);
+    }
+}
+
+// unk / pool: `world` segments of unk_stride / pool_stride entries, counts[2 r] = unknown reads of
+// segment r.  sweeps_out (may be null) gets the number of sweeps it took.
+__global__ void __launch_bounds__(1024)
+k_contain_resolve(const int4* __restrict__ unk, const int* __restrict__ counts, int world, int unk_stride,
+                  const int* __restrict__ pool, int pool_stride, volatile uint8_t* state, int* sweeps_out) {
+    __shared__ int remaining;
+    int sweeps = 0;
+    for (;;) {
+        if (threadIdx.x == 0) remaining = 0;
+        __syncthreads();
+        for (int r = 0; r < world; r++) {
+            const int n = min(counts[2 * r], unk_stride);
+            for (int e = threadIdx.x; e < n; e += blockDim.x) {
+                const int4 u = unk[(size_t)r * unk_stride + e];
+                if (state[u.x] != 0) continue;
+                const int* lst = pool + (size_t)r * pool_stride + u.y;
+                bool alive = false, unknown = false;
+                for (int c = 0; c < u.z; c++) {
+                    const uint8_t s = state[lst[c]];  // B < A: B's FINAL state decides (maximal.cpp:853-854)
+                    alive = alive || s == 1;
+                    unknown = unknown || s == 0;
+                }
+                if (alive)
+                    state[u.x] = 2;
+                else if (!unknown)
+                    state[u.x] = 1;
+                else
+                    atomicAdd(&remaining, 1);
+            }
+        }
+        sweeps++;
+        __syncthreads();
+        const int rem = remaining;
+        __syncthreads();
+        if (rem == 0 || sweeps > 100000000) break;
+    }
+    if (threadIdx.x == 0 && sweeps_out) *sweeps_out = sweeps;
 }
 
 // ------------------------------------------------------------------ K6: selection
@@ -532,6 +735,31 @@ void launch_classify(const RecView& rv, const ReadView& rd, const hg_layout_para
     k_classify_big_pairs<<<cdiv(po.big_cap, 128), 128, 0, st>>>(rv, rd, P, mask, active, mode,
                                                                 sort_passes, rtype, po);
     g_launches += 2;
+}
+
+void launch_classify_reads(const RecView& rv, const ReadView& rd, const hg_layout_params& P, const int2* mask,
+                           const uint8_t* active, int sort_passes, uint8_t* rtype, const PairOut& po,
+                           cudaStream_t st) {
+    cudaMemsetAsync(po.counters, 0, sizeof(int) * 8, st);
+    const int64_t threads = (int64_t)(rd.r_hi - rd.r_lo) * 32;
+    k_classify_reads<<<cdiv(threads, 128), 128, 0, st>>>(rv, rd, P, mask, active, rtype, po);
+    // the list length lives on the device; one thread per possible entry
+    k_clear_big_pair_types<<<cdiv(po.big_cap, 128), 128, 0, st>>>(rv, rtype, po);
+    k_classify_big_pairs<<<cdiv(po.big_cap, 128), 128, 0, st>>>(rv, rd, P, mask, active, 0, sort_passes, rtype, po);
+    g_launches += 3;
+}
+
+void launch_contain_lists(const RecView& rv, const ReadView& rd, const ContainIO& io, cudaStream_t st) {
+    cudaMemsetAsync(io.counters, 0, sizeof(int) * 4, st);
+    const int64_t threads = (int64_t)(rd.r_hi - rd.r_lo) * 32;
+    k_contain_lists<<<cdiv(threads, 128), 128, 0, st>>>(rv, rd, io);
+    g_launches += 1;
+}
+
+void launch_contain_resolve(const int4* unk, const int* counts, int world, int unk_stride, const int* pool,
+                            int pool_stride, uint8_t* state, int* sweeps_out, cudaStream_t st) {
+    k_contain_resolve<<<1, 1024, 0, st>>>(unk, counts, world, unk_stride, pool, pool_stride, state, sweeps_out);
+    g_launches += 1;
 }
 
 void launch_contain_init(const RecView& rv, const ReadView& rd, const uint8_t* active0,

@@ -41,6 +41,25 @@ struct PairOut {
     uint8_t* contained_flag;  // layout: per read, "[contained] Should not happen"
 };
 
+// containment on compact lists (k_contain_lists / k_contain_resolve)
+struct ContainIO {
+    const uint8_t* active0;  // n_read: long enough to take part (maximal.cpp:541-547)
+    const uint8_t* rtype;    // per record: class of the top-two records of every pair, 255 otherwise
+    uint8_t* state;          // n_read: 0 unknown, 1 survives (maximal), 2 removed
+    int4* unk;               // unknown reads: (read, first list entry, list entries, -)
+    int unk_cap;
+    int* pool;               // lists of lower-id containing reads
+    int pool_cap;
+    int* counters;           // [0] unknown reads [1] pool used [2] overflow
+};
+
+void launch_classify_reads(const RecView& rv, const ReadView& rd, const hg_layout_params& P, const int2* mask,
+                           const uint8_t* active, int sort_passes, uint8_t* rtype, const PairOut& po,
+                           cudaStream_t st);
+void launch_contain_lists(const RecView& rv, const ReadView& rd, const ContainIO& io, cudaStream_t st);
+void launch_contain_resolve(const int4* unk, const int* counts, int world, int unk_stride, const int* pool,
+                            int pool_stride, uint8_t* state, int* sweeps_out, cudaStream_t st);
+
 void launch_classify(const RecView& rv, const ReadView& rd, const hg_layout_params& P,
                      const int2* mask, const uint8_t* active, int mode, int sort_passes,
                      uint8_t* rtype, const PairOut& po, cudaStream_t st);

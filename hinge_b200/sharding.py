@@ -146,3 +146,36 @@ def run_filter_sharded(ctx, params, arrays, max_attempts=8):
         if int(t.item()) != api.HG_RETRY_POOL:
             return rc, s
     return api.HG_RETRY_POOL, s
+
+
+def run_maximal_sharded(ctx, params, arrays, mask, group=None):
+    """hg_maximal on shards: local classification + containment lists, then ONE exchange round over
+    NCCL (MAX all-reduce of the per-read states, all-gather of the unknown reads' lists) and the
+    resolve on every rank.  Returns the maximal-read bitmap of ALL reads (numpy uint8[n_read])."""
+    dev, world, n = arrays.device, arrays.world, arrays.n_read
+    state = torch.zeros((n,), dtype=torch.uint8, device=dev)
+    unk_cap, pool_cap = max(1024, (arrays.hi - arrays.lo) // 4), max(4096, arrays.hi - arrays.lo)
+    while True:
+        unk = torch.zeros((unk_cap, 4), dtype=torch.int32, device=dev)
+        pool = torch.zeros((pool_cap,), dtype=torch.int32, device=dev)
+        n_unk, n_pool = ctx.maximal_phase1(params, mask, state, unk, pool)
+        if n_unk <= unk_cap and n_pool <= pool_cap:
+            break
+        unk_cap, pool_cap = max(unk_cap, n_unk), max(pool_cap, n_pool)
+    if world == 1:
+        return ctx.maximal_phase2(state, unk, [n_unk, n_pool], 1, unk_cap, pool, pool_cap)
+    counts = torch.tensor([n_unk, n_pool], dtype=torch.int64, device=dev)
+    counts_all = torch.zeros((world, 2), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts_all, counts, group=group)
+    counts_all = counts_all.cpu().numpy()
+    unk_stride, pool_stride = max(1, int(counts_all[:, 0].max())), max(1, int(counts_all[:, 1].max()))
+    mine_unk = torch.zeros((unk_stride, 4), dtype=torch.int32, device=dev)
+    mine_unk[:n_unk] = unk[:n_unk]
+    mine_pool = torch.zeros((pool_stride,), dtype=torch.int32, device=dev)
+    mine_pool[:n_pool] = pool[:n_pool]
+    unk_all = torch.empty((world * unk_stride, 4), dtype=torch.int32, device=dev)
+    pool_all = torch.empty((world * pool_stride,), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(unk_all, mine_unk, group=group)
+    dist.all_gather_into_tensor(pool_all, mine_pool, group=group)
+    dist.all_reduce(state, op=dist.ReduceOp.MAX, group=group)  # slices are disjoint; 0 elsewhere
+    return ctx.maximal_phase2(state, unk_all, counts_all.reshape(-1), world, unk_stride, pool_all, pool_stride)

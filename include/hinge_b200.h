@@ -45,10 +45,11 @@ enum hg_option {
     HG_OPT_KEEP_COVERAGE = 1, /* keep the 40-bp coverage profiles (.coverage.txt) */
     HG_OPT_PROFILE = 2,       /* record CUDA events between the kernels of a stage */
     HG_OPT_SCATTER_SPREAD = 3,/* tuning aid: record windows per warp in the profile scatter (1, 4, 8, 16) */
-    HG_OPT_PROFILE_KERNEL = 4 /* tuning aid: 0 = pick the form of the coverage-profile kernel by cut_off
-                                 (20-bp start/end histogram for the nominal cut_off 300), 1 = always the
-                                 four-event 40-bp form, 5 / 6 = the 20-bp form compiled for 5 / 6
-                                 resident CTAs per SM */
+    HG_OPT_PROFILE_KERNEL = 4 /* tuning aid: 0 = pick the form of the coverage-profile kernel by cut_off and
+                                 data shape (20-bp start/end histogram for the nominal cut_off 300 when
+                                 records outnumber coverage bins), 1 = always the four-event 40-bp form,
+                                 5 / 6 = always the 20-bp form, compiled for 4 / 6 resident CTAs per SM
+                                 (default: 5) */
 };
 
 enum hg_buffer { /* per-read device arrays a sharded run exchanges between phases */
@@ -186,6 +187,23 @@ int hg_filter_coverage(hg_ctx* ctx, int64_t* cov_off, int32_t* cov, int64_t* n_b
  * (.contained.txt). */
 int hg_maximal(hg_ctx* ctx, const hg_layout_params* params, const int32_t* mask,
                uint8_t* maximal_out, int32_t* contained_by, float* ms_device);
+
+/* The same stage for contexts that own a slice of the reads.  Containment is a recurrence over
+ * ascending read ids (maximal.cpp:809,853): a read with an active container of higher id is
+ * removed, one without containers survives, the others depend on the final state of containers
+ * with LOWER ids, which may live in other shards.  Phase 1 settles what is local and leaves, on
+ * the device, the per-read states (uint8[n_read]: own reads 0 unknown / 1 survives / 2 removed,
+ * other reads 0) and the lists of the unknown reads (unk: int32[4] per read = read, first list
+ * entry, entries, 0; pool: int32 ids of lower-id containers); counts[0..1] = entries used.  The
+ * caller MAX-all-reduces the states and all-gathers unk / pool with fixed strides (the
+ * "all-gather of the maximal-read bitmap" of BASELINE.json's north_star, over NCCL); phase 2 runs
+ * the resolve on every rank and returns the bitmap of ALL reads.  All pointers but counts /
+ * counts_all / maximal_out are device pointers. */
+int hg_maximal_phase1(hg_ctx* ctx, const hg_layout_params* params, const int32_t* mask, void* state_out,
+                      void* unk_out, int64_t unk_cap, void* pool_out, int64_t pool_cap, int32_t* counts);
+int hg_maximal_phase2(hg_ctx* ctx, void* state_all, const void* unk_all, const int32_t* counts_all,
+                      int32_t world, int64_t unk_stride, const void* pool_all, int64_t pool_stride,
+                      uint8_t* maximal_out);
 
 /* ---- layout: candidate extensions + best-overlap selection ------------- */
 
