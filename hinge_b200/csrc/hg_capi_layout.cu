@@ -84,8 +84,28 @@ static int upload_mask(hg_ctx* c, const int32_t* mask) {
     return HG_OK;
 }
 
-const LayoutResult* layout_result(const hg_ctx* c) { return c->layout; }
-void free_layout_result(LayoutResult* r) { delete r; }
+// Copies the device-resident candidate lists of the last hg_layout to the host (the file writers of
+// `hinge layout` print every candidate; the array-level API only needs the chosen ones).
+const LayoutResult* layout_result(hg_ctx* c) {
+    LayoutResult* R = c->layout;
+    if (!R || R->materialized) return R;
+    cudaSetDevice(c->device);
+    R->cands.resize((size_t)R->n_cand_slots);
+    R->order.resize((size_t)R->n_cand_slots);
+    R->ranges.resize((size_t)R->n_read);
+    cudaMemcpy(R->cands.data(), R->d_cands, sizeof(Cand) * (size_t)R->n_cand_slots, cudaMemcpyDeviceToHost);
+    cudaMemcpy(R->order.data(), R->d_order, sizeof(int) * (size_t)R->n_cand_slots, cudaMemcpyDeviceToHost);
+    cudaMemcpy(R->ranges.data(), R->d_ranges, sizeof(int4) * (size_t)R->n_read, cudaMemcpyDeviceToHost);
+    R->materialized = true;
+    return R;
+}
+void free_layout_result(LayoutResult* r) {
+    if (!r) return;
+    cudaFree(r->d_cands);
+    cudaFree(r->d_order);
+    cudaFree(r->d_ranges);
+    delete r;
+}
 
 }  // namespace hg
 
@@ -269,6 +289,24 @@ int hg_maximal_phase2(hg_ctx* c, void* state_all, const void* unk_all, const int
     return rc;
 }
 
+// Bucket-count schedule of this toolchain's std::unordered_map<int, T> (see hash_iteration_order,
+// hg_order.h), read off the real container: at[i] = element count whose insertion makes the bucket
+// count bkt[i].
+static void hash_growth_schedule(int max_elements, std::vector<int>* at, std::vector<int>* bkt) {
+    std::unordered_map<int, int> m;
+    size_t cur = m.bucket_count();
+    at->clear();
+    bkt->clear();
+    for (int k = 1; k <= max_elements; k++) {
+        m[k] = 0;
+        if (m.bucket_count() != cur) {
+            cur = m.bucket_count();
+            at->push_back(k);
+            bkt->push_back((int)cur);
+        }
+    }
+}
+
 int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const uint8_t* maximal,
               const int64_t* rep_off, const int32_t* rep_pos, const int32_t* rep_type,
               const int64_t* hin_off, const int32_t* hin_pos, const int32_t* hin_type,
@@ -286,6 +324,7 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
     LayoutResult& R = *c->layout;
     R.n_read = n;
     R.mask.assign(mask, mask + 2 * (size_t)n);
+    StepTimer tm(st);
 
     // ---- who takes part (hinging.cpp:877-913, 954-960, 398-412)
     R.active.assign(n, 1);
@@ -297,97 +336,7 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
         }
         R.active[i] = R.active[i] && maximal[i];
     }
-    HG_TRY(upload_mask(c, mask));
-    DevBuf<uint8_t> d_active;
-    HG_TRY(d_active.alloc(c, n, "active"));
-    HG_TRY(cuda_check(c, cudaMemcpyAsync(d_active.p, R.active.data(), n, cudaMemcpyHostToDevice, st), "H2D"));
-
-    // ---- K5: classify the top two overlaps of every pair of maximal reads
-    StepTimer tm(st);
-    tm.lap("layout: active flags + uploads");
-    cudaEventRecord(c->ev0, st);
-    int big_cap = 1 << 14, sort_cap = 1 << 18, pair_cap = 1 << 20, cand_cap = 1 << 20;
-    std::vector<int4> pairs;
-    std::vector<Cand> cands;
-    std::vector<uint8_t> contained(n);
-    for (int attempt = 0;; attempt++) {
-        PairBufs pb;
-        HG_TRY(pb.make(c, big_cap, sort_cap, pair_cap, cand_cap));
-        cudaMemsetAsync(pb.po.contained_flag, 0, n, st);
-        launch_classify(c->rec_view(), c->read_view(), *P, c->fs.mask, d_active.p, 1, 1, nullptr, pb.po, st);
-        int cnt[8];
-        HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, pb.po.counters, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
-        HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "classify"));
-        if (cnt[3]) {
-            if (attempt > 6) return set_err(c, HG_ERR_NOMEM, "candidate buffers kept overflowing");
-            big_cap = std::max(big_cap, cnt[0] + 1024);
-            sort_cap = std::max(sort_cap * 4, cnt[1] + 1024);
-            pair_cap = std::max(pair_cap, cnt[4] + 1024);
-            cand_cap = std::max(cand_cap, cnt[5] + 1024);
-            continue;
-        }
-        pairs.resize(cnt[4]);
-        cands.resize(cnt[5]);
-        if (cnt[4]) HG_TRY(cuda_check(c, cudaMemcpyAsync(pairs.data(), pb.po.pairs, sizeof(int4) * (size_t)cnt[4], cudaMemcpyDeviceToHost, st), "D2H"));
-        if (cnt[5]) HG_TRY(cuda_check(c, cudaMemcpyAsync(cands.data(), pb.po.cands, sizeof(Cand) * (size_t)cnt[5], cudaMemcpyDeviceToHost, st), "D2H"));
-        HG_TRY(cuda_check(c, cudaMemcpyAsync(contained.data(), pb.po.contained_flag, n, cudaMemcpyDeviceToHost, st), "D2H"));
-        HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "D2H"));
-        break;
-    }
-    tm.lap("layout: classify pairs + D2H");
-    for (int i = 0; i < n; i++)
-        if (contained[i] && R.active[i]) {  // hinging.cpp:598-601
-            printf("[contained] Should not happen\n");
-            R.active[i] = 0;
-        }
-    HG_TRY(cuda_check(c, cudaMemcpyAsync(d_active.p, R.active.data(), n, cudaMemcpyHostToDevice, st), "H2D"));
-
-    // ---- pre-sort order of each read's candidates = iteration order of the reference's
-    // std::unordered_map<int, ...> keyed by B (hinging.cpp:532): replay the keys, in file order,
-    // into the real container
-    auto first_of = [](const int4& p) { return ((int64_t)p.w << 31) | (int64_t)p.z; };
-    std::sort(pairs.begin(), pairs.end(), [&](const int4& x, const int4& y) { return first_of(x) < first_of(y); });
-    std::sort(cands.begin(), cands.end(), [](const Cand& x, const Cand& y) {
-        if (x.a != y.a) return x.a < y.a;
-        if (x.b != y.b) return x.b < y.b;
-        return x.rank < y.rank;
-    });
-    R.cands = cands;
-    R.ranges.assign(n, make_int4(0, 0, 0, 0));
-    R.order.clear();
-    {
-        size_t pi = 0, ci = 0;
-        for (int a = 0; a < n; a++) {
-            const size_t p0 = pi;
-            while (pi < pairs.size() && pairs[pi].x == a) pi++;
-            const size_t c0 = ci;
-            while (ci < cands.size() && cands[ci].a == a) ci++;
-            if (p0 == pi) continue;
-            std::unordered_map<int, int> um;
-            for (size_t k = p0; k < pi; k++) um[pairs[k].y] = 0;
-            std::vector<int> fwd, bwd;
-            for (auto it = um.begin(); it != um.end(); ++it) {
-                const int b = it->first;
-                size_t lo = std::lower_bound(cands.begin() + c0, cands.begin() + ci, b,
-                                             [](const Cand& x, int v) { return x.b < v; }) - cands.begin();
-                for (size_t k = lo; k < ci && cands[k].b == b; k++) {
-                    const bool f = cands[k].type == HG_FORWARD || cands[k].type == HG_FORWARD_INTERNAL;
-                    (f ? fwd : bwd).push_back((int)k);
-                }
-            }
-            int4 r;
-            r.x = (int)R.order.size();
-            R.order.insert(R.order.end(), fwd.begin(), fwd.end());
-            r.y = (int)R.order.size();
-            r.z = r.y;
-            R.order.insert(R.order.end(), bwd.begin(), bwd.end());
-            r.w = (int)R.order.size();
-            R.ranges[a] = r;
-        }
-    }
-
-    tm.lap("layout: host sorts + hash-order replay");
-    // ---- hinges, killed hinges (hinging.cpp:1180-1197)
+    // ---- hinges, killed hinges = annotations that are not hinges (hinging.cpp:1180-1197)
     R.hin_off.assign(hin_off, hin_off + n + 1);
     R.hin_pos.assign(hin_pos, hin_pos + hin_off[n]);
     R.hin_type.assign(hin_type, hin_type + hin_off[n]);
@@ -395,61 +344,119 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
     R.kil_pos.clear();
     R.kil_type.clear();
     for (int i = 0; i < n; i++) {
-        std::set<std::pair<int, int>> surviving;
-        for (int64_t k = hin_off[i]; k < hin_off[i + 1]; k++) surviving.insert(std::make_pair(hin_pos[k], hin_type[k]));
-        for (int64_t k = rep_off[i]; k < rep_off[i + 1]; k++)
-            if (!surviving.count(std::make_pair(rep_pos[k], rep_type[k]))) {
+        for (int64_t k = rep_off[i]; k < rep_off[i + 1]; k++) {
+            bool is_hinge = false;
+            for (int64_t h = hin_off[i]; h < hin_off[i + 1] && !is_hinge; h++)
+                is_hinge = hin_pos[h] == rep_pos[k] && hin_type[h] == rep_type[k];
+            if (!is_hinge) {
                 R.kil_pos.push_back(rep_pos[k]);
                 R.kil_type.push_back(rep_type[k]);
             }
+        }
         R.kil_off[i + 1] = (int64_t)R.kil_pos.size();
     }
     const int64_t nh = hin_off[n], nkil = R.kil_off[n];
-    tm.lap("layout: killed-hinge lists (host)");
+    std::vector<int> grow_at, grow_bkt;
+    hash_growth_schedule(std::max(c->max_pileup, 16) + 2, &grow_at, &grow_bkt);
+    tm.lap("layout: active flags, killed-hinge lists (host)");
 
-    // ---- device side of the selection
-    const size_t ncand = std::max<size_t>(cands.size(), 1), nord = std::max<size_t>(R.order.size(), 1);
-    DevBuf<Cand> d_cands;
-    DevBuf<int4> d_ranges;
-    DevBuf<int> d_order, d_hpos, d_htype, d_kpos, d_ktype, d_npos, d_ntype, d_cnt;
+    HG_TRY(upload_mask(c, mask));
+    DevBuf<uint8_t> d_active, d_contained, d_alive;
+    DevBuf<int2> d_pair_ref, d_cand_ref, d_chosen;
+    DevBuf<int> d_bkt_ref, d_cnt, d_grow, d_hpos, d_htype, d_kpos, d_ktype, d_npos, d_ntype;
     DevBuf<int64_t> d_hoff, d_koff, d_noff;
-    DevBuf<KeyIdx2> d_sort;
-    DevBuf<uint8_t> d_alive;
-    DevBuf<int2> d_chosen;
-    HG_TRY(d_cands.alloc(c, ncand, "cands")); HG_TRY(d_ranges.alloc(c, n, "ranges"));
-    HG_TRY(d_order.alloc(c, nord, "order")); HG_TRY(d_sort.alloc(c, nord, "sort scratch"));
+    DevBuf<unsigned long long> d_total;
+    HG_TRY(d_active.alloc(c, n, "active")); HG_TRY(d_contained.alloc(c, n, "contained flags"));
+    HG_TRY(d_pair_ref.alloc(c, n, "pair refs")); HG_TRY(d_cand_ref.alloc(c, n, "candidate refs"));
+    HG_TRY(d_bkt_ref.alloc(c, n, "bucket refs")); HG_TRY(d_cnt.alloc(c, 16, "counters"));
+    HG_TRY(d_total.alloc(c, 1, "pair total")); HG_TRY(d_grow.alloc(c, 2 * grow_at.size() + 2, "hash schedule"));
     HG_TRY(d_hoff.alloc(c, n + 1, "hinge off")); HG_TRY(d_hpos.alloc(c, nh, "hinge pos")); HG_TRY(d_htype.alloc(c, nh, "hinge type"));
     HG_TRY(d_koff.alloc(c, n + 1, "killed off")); HG_TRY(d_kpos.alloc(c, nkil, "killed pos")); HG_TRY(d_ktype.alloc(c, nkil, "killed type"));
-    HG_TRY(d_noff.alloc(c, n + 1, "nk off"));
-    HG_TRY(d_alive.alloc(c, nh, "hinge alive")); HG_TRY(d_cnt.alloc(c, 8, "counters")); HG_TRY(d_chosen.alloc(c, 2 * (size_t)n, "chosen"));
+    HG_TRY(d_noff.alloc(c, n + 1, "nk off")); HG_TRY(d_alive.alloc(c, nh, "hinge alive"));
+    HG_TRY(d_chosen.alloc(c, 2 * (size_t)n, "chosen"));
     auto h2d = [&](void* d, const void* h, size_t bytes) {
         return bytes ? cuda_check(c, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st), "H2D") : HG_OK;
     };
-    HG_TRY(h2d(d_cands.p, cands.data(), sizeof(Cand) * cands.size()));
-    HG_TRY(h2d(d_ranges.p, R.ranges.data(), sizeof(int4) * n));
-    HG_TRY(h2d(d_order.p, R.order.data(), 4 * R.order.size()));
+    HG_TRY(h2d(d_active.p, R.active.data(), n));
+    HG_TRY(h2d(d_grow.p, grow_at.data(), 4 * grow_at.size()));
+    HG_TRY(h2d(d_grow.p + grow_at.size(), grow_bkt.data(), 4 * grow_bkt.size()));
     HG_TRY(h2d(d_hoff.p, R.hin_off.data(), 8 * ((size_t)n + 1)));
     HG_TRY(h2d(d_hpos.p, R.hin_pos.data(), 4 * (size_t)nh));
     HG_TRY(h2d(d_htype.p, R.hin_type.data(), 4 * (size_t)nh));
     HG_TRY(h2d(d_koff.p, R.kil_off.data(), 8 * ((size_t)n + 1)));
     HG_TRY(h2d(d_kpos.p, R.kil_pos.data(), 4 * (size_t)nkil));
     HG_TRY(h2d(d_ktype.p, R.kil_type.data(), 4 * (size_t)nkil));
-    cudaMemsetAsync(d_alive.p, 1, std::max<size_t>((size_t)nh, 1), st);
+    cudaMemsetAsync(d_contained.p, 0, n, st);
+    tm.lap("layout: uploads");
+
+    // ---- K5: pairs between maximal reads, their top two classified, candidates in the reference's order
+    cudaEventRecord(c->ev0, st);
+    launch_layout_count_pairs(c->rec_view(), c->read_view(), d_active.p, d_pair_ref.p, d_total.p, st);
+    unsigned long long total_pairs = 0;
+    HG_TRY(cuda_check(c, cudaMemcpyAsync(&total_pairs, d_total.p, 8, cudaMemcpyDeviceToHost, st), "D2H"));
+    HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "count pairs"));
+    if (total_pairs > 1000000000ull) return set_err(c, HG_ERR_NOMEM, "hg_layout: more than 1e9 pairs between maximal reads");
+    const size_t np_total = std::max<size_t>((size_t)total_pairs, 1), nc_slots = 2 * np_total;
+    // bucket scratch: the count after the last insertion is below 2 n + 13 per read
+    const size_t nbkt = 2 * np_total + 16 * (size_t)n + 64;
+    DevBuf<int2> d_pairs;
+    DevBuf<int> d_hnext, d_hout, d_hbkt;
+    DevBuf<KeyIdx2> d_sort, d_bigsort;
+    HG_TRY(d_pairs.alloc(c, np_total, "pairs")); HG_TRY(d_hnext.alloc(c, np_total, "hash next"));
+    HG_TRY(d_hout.alloc(c, np_total, "hash order")); HG_TRY(d_hbkt.alloc(c, nbkt, "hash buckets"));
+    HG_TRY(d_sort.alloc(c, nc_slots, "sort scratch"));
+    Cand* d_cands = nullptr;
+    int* d_order = nullptr;
+    int4* d_ranges = nullptr;
+    HG_TRY(dev_alloc(c, &d_cands, nc_slots, "candidates"));
+    R.d_cands = d_cands;
+    HG_TRY(dev_alloc(c, &d_order, nc_slots, "candidate order"));
+    R.d_order = d_order;
+    HG_TRY(dev_alloc(c, &d_ranges, n, "candidate ranges"));
+    R.d_ranges = d_ranges;
+    R.n_cand_slots = (int64_t)nc_slots;
 
     SelectIO io;
-    io.n_read = n; io.active = d_active.p; io.cands = d_cands.p; io.ranges = d_ranges.p;
-    io.order = d_order.p; io.sort_scratch = d_sort.p;
+    io.n_read = n; io.active = d_active.p; io.cands = d_cands; io.ranges = d_ranges; io.ranges_out = d_ranges;
+    io.order = d_order; io.sort_scratch = d_sort.p;
     io.hv.off = d_hoff.p; io.hv.pos = d_hpos.p; io.hv.type = d_htype.p;
     io.kv.off = d_koff.p; io.kv.pos = d_kpos.p; io.kv.type = d_ktype.p;
     io.nk.off = d_noff.p; io.nk.pos = nullptr; io.nk.type = nullptr;
-    io.hinge_alive = d_alive.p; io.counters = d_cnt.p; io.chosen = d_chosen.p;
+    io.hinge_alive = d_alive.p; io.counters = d_cnt.p + 8; io.chosen = d_chosen.p;
     io.graph = nullptr; io.nkout = nullptr; io.skips = nullptr;
 
-    tm.lap("layout: selection uploads");
-    launch_sort_candidates(io, st);  // K6: weight order (hinging.cpp:1066-1071)
-    tm.lap("layout: sort candidates");
+    int big_sort_cap = 1 << 16;
+    for (int attempt = 0;; attempt++) {
+        HG_TRY(d_bigsort.alloc(c, big_sort_cap, "pair sort scratch"));
+        LayoutLists L;
+        L.pair_ref = d_pair_ref.p; L.cand_ref = d_cand_ref.p; L.bkt_ref = d_bkt_ref.p; L.pairs = d_pairs.p;
+        L.cands = d_cands; L.hash_next = d_hnext.p; L.hash_out = d_hout.p; L.hash_bkt = d_hbkt.p;
+        L.contained_flag = d_contained.p; L.counters = d_cnt.p; L.sort_scratch = d_bigsort.p; L.sort_cap = big_sort_cap;
+        L.grow_at = d_grow.p; L.grow_bkt = d_grow.p + grow_at.size(); L.ngrow = (int)grow_at.size();
+        launch_layout_pairs(c->rec_view(), c->read_view(), *P, c->fs.mask, d_active.p, L, st);
+        // "[contained] Should not happen" (hinging.cpp:598-601): such reads leave the layout
+        launch_apply_contained(n, d_contained.p, d_active.p, d_cnt.p + 7, st);
+        launch_order_candidates(L, io, st);
+        int cnt[8];
+        HG_TRY(cuda_check(c, cudaGetLastError(), "layout pairs"));
+        HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, d_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
+        HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "layout pairs"));
+        if (cnt[2] > (long long)nbkt) return set_err(c, HG_ERR_NOMEM, "hg_layout: hash bucket scratch too small");
+        if (!cnt[3]) {
+            R.n_contained = cnt[7];
+            break;
+        }
+        if (attempt > 6) return set_err(c, HG_ERR_NOMEM, "pair sort scratch kept overflowing");
+        big_sort_cap = std::max(big_sort_cap * 4, cnt[4] + 1024);
+        // the contained flags are sticky and the pair counts were overwritten: restore and run again
+        HG_TRY(h2d(d_active.p, R.active.data(), n));
+        cudaMemsetAsync(d_contained.p, 0, n, st);
+        launch_layout_count_pairs(c->rec_view(), c->read_view(), d_active.p, d_pair_ref.p, d_total.p, st);
+    }
+    for (int i = 0; i < R.n_contained; i++) printf("[contained] Should not happen\n");
+    tm.lap("layout: pairs, candidates, order (device)");
 
-    // K6: kill pass + hinge graph; list sizes are data dependent: grow and rerun on overflow
+    // ---- K6: kill pass + hinge graph; list sizes are data dependent: grow and rerun on overflow
     int graph_cap = 1 << 16, nk_cap = 1 << 14;
     std::vector<GraphRec> graph;
     std::vector<NkRec> nks;
@@ -463,7 +470,7 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
         cudaMemsetAsync(d_alive.p, 1, std::max<size_t>((size_t)nh, 1), st);
         launch_hinge_graph(c->rec_view(), *P, io, st);
         int cnt[8];
-        HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, d_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
+        HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, io.counters, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
         HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "hinge graph"));
         if (cnt[3]) {
             if (attempt > 8) return set_err(c, HG_ERR_NOMEM, "hinge graph buffers kept overflowing");
@@ -485,7 +492,6 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
     std::sort(nks.begin(), nks.end(), [](const NkRec& x, const NkRec& y) {
         return x.owner != y.owner ? x.owner < y.owner : x.seq < y.seq;
     });
-    R.graph = graph;
 
     // connected components of the hinge graph (hinging.cpp:1644-1675): only sizes matter
     R.hin_alive.assign((size_t)std::max<int64_t>(nh, 1), 1);
@@ -524,21 +530,29 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
     HG_TRY(h2d(d_ntype.p, ntype.data(), 4 * nks.size()));
     io.nk.pos = d_npos.p;
     io.nk.type = d_ntype.p;
-
+    R.graph.swap(graph);
     tm.lap("layout: components + nk lists (host)");
-    // K6: the best-overlap scoring loop
+
+    // ---- K6: the best-overlap scoring loop
     int skip_cap = 1 << 14;
     std::vector<SkipRec> skips;
     R.chosen.assign(2 * (size_t)n, make_int2(-1, -1));
+    DevBuf<Cand> d_edges;
+    DevBuf<int2> d_edge_ref;
+    HG_TRY(d_edges.alloc(c, 2 * (size_t)n, "edges"));
+    HG_TRY(d_edge_ref.alloc(c, 2 * (size_t)n, "edge refs"));
     for (int attempt = 0;; attempt++) {
         DevBuf<SkipRec> d_skip;
         HG_TRY(d_skip.alloc(c, skip_cap, "skip records"));
         io.skips = d_skip.p;
         io.skip_cap = skip_cap;
-        cudaMemsetAsync(d_cnt.p, 0, sizeof(int) * 8, st);
+        cudaMemsetAsync(io.counters, 0, sizeof(int) * 8, st);
         launch_best_extension(*P, io, st);
+        launch_gather_chosen(n, d_chosen.p, d_cands, d_edges.p, d_edge_ref.p, io.counters + 6, st);
+        cudaEventRecord(c->ev1, st);
         int cnt[8];
-        HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, d_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
+        HG_TRY(cuda_check(c, cudaGetLastError(), "best extension"));
+        HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, io.counters, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
         HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "best extension"));
         if (cnt[3]) {
             if (attempt > 8) return set_err(c, HG_ERR_NOMEM, "skip buffer kept overflowing");
@@ -546,18 +560,37 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
             continue;
         }
         skips.resize(cnt[2]);
+        R.edge_cands.resize(cnt[6]);
+        R.edge_ref.resize(cnt[6]);
         if (cnt[2]) HG_TRY(cuda_check(c, cudaMemcpyAsync(skips.data(), d_skip.p, sizeof(SkipRec) * (size_t)cnt[2], cudaMemcpyDeviceToHost, st), "D2H"));
+        if (cnt[6]) {
+            HG_TRY(cuda_check(c, cudaMemcpyAsync(R.edge_cands.data(), d_edges.p, sizeof(Cand) * (size_t)cnt[6], cudaMemcpyDeviceToHost, st), "D2H"));
+            HG_TRY(cuda_check(c, cudaMemcpyAsync(R.edge_ref.data(), d_edge_ref.p, sizeof(int2) * (size_t)cnt[6], cudaMemcpyDeviceToHost, st), "D2H"));
+        }
         HG_TRY(cuda_check(c, cudaMemcpyAsync(R.chosen.data(), d_chosen.p, sizeof(int2) * 2 * (size_t)n, cudaMemcpyDeviceToHost, st), "D2H"));
-        if (!R.order.empty()) HG_TRY(cuda_check(c, cudaMemcpyAsync(R.order.data(), d_order.p, 4 * R.order.size(), cudaMemcpyDeviceToHost, st), "D2H"));
-        cudaEventRecord(c->ev1, st);
+        HG_TRY(cuda_check(c, cudaMemcpyAsync(R.active.data(), d_active.p, n, cudaMemcpyDeviceToHost, st), "D2H"));
         HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "D2H"));
         break;
     }
-    tm.lap("layout: best extension + D2H");
     std::sort(skips.begin(), skips.end(), [](const SkipRec& x, const SkipRec& y) {
         return x.owner != y.owner ? x.owner < y.owner : x.seq < y.seq;
     });
-    R.skips = skips;
+    R.skips.swap(skips);
+    // edges in output order: by read, forward before backward
+    {
+        std::vector<int> idx(R.edge_ref.size());
+        std::iota(idx.begin(), idx.end(), 0);
+        std::sort(idx.begin(), idx.end(), [&](int x, int y) { return R.edge_ref[x].x < R.edge_ref[y].x; });
+        std::vector<Cand> ec(idx.size());
+        std::vector<int2> er(idx.size());
+        for (size_t k = 0; k < idx.size(); k++) {
+            ec[k] = R.edge_cands[idx[k]];
+            er[k] = R.edge_ref[idx[k]];
+        }
+        R.edge_cands.swap(ec);
+        R.edge_ref.swap(er);
+    }
+    tm.lap("layout: best extension + D2H");
     if (ms_device) cudaEventElapsedTime(ms_device, c->ev0, c->ev1);
     return HG_OK;
 }
@@ -565,15 +598,9 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
 int hg_layout_edges(hg_ctx* c, hg_edge* edges, int64_t capacity, int64_t* n_edges) {
     if (!c || !c->layout || !n_edges) return set_err(c, HG_ERR_ARG, "hg_layout_edges: run hg_layout first");
     const LayoutResult& R = *c->layout;
-    int64_t k = 0;
-    for (int i = 0; i < R.n_read; i++)
-        for (int half = 0; half < 2; half++) {
-            const int2 ch = R.chosen[2 * (size_t)i + half];
-            if (ch.x < 0) continue;
-            if (edges && k < capacity) R.fill_edge(ch.x, ch.y, &edges[k]);
-            k++;
-        }
-    *n_edges = k;
+    const int64_t n = (int64_t)R.edge_cands.size();
+    for (int64_t k = 0; k < n && edges && k < capacity; k++) R.fill_edge(R.edge_cands[k], R.edge_ref[k].y, &edges[k]);
+    *n_edges = n;
     return HG_OK;
 }
 

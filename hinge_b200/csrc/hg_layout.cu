@@ -347,6 +347,238 @@ __global__ void k_clear_big_pair_types(RecView rv, uint8_t* __restrict__ rtype, 
     for (int64_t e = k; e < rv.novl && rv.aread[e] == a && rv.bread[e] == b; e++) rtype[e] = HG_NOT_CLASSIFIED;
 }
 
+// ------------------------------------------------------------------ K5, warp per read (layout)
+//
+// Pairs between maximal reads and their classified top-two overlaps, device-resident and in the
+// reference's order: one warp per active A-read, lanes over its records.  Pair leaders whose B is
+// active get consecutive pair slots (ballot prefix: file order = ascending B, the insertion order of
+// the reference's idx_ab[A], hinging.cpp:477-480), the leader classifies the pair's top two and the
+// FORWARD / BACKWARD(_INTERNAL) ones become candidates in consecutive slots of the read's block.
+
+// pairs per read: first pass of the same loop, so the blocks can be laid out without guessing
+__global__ void __launch_bounds__(128)
+k_layout_count_pairs(RecView rv, ReadView rd, const uint8_t* __restrict__ active, int2* __restrict__ pair_ref,
+                     unsigned long long* __restrict__ total) {
+    const int lane = lane_id();
+    const int a = rd.r_lo + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (a >= rd.r_hi) return;
+    int np = 0;
+    if (active[a]) {
+        const int64_t o0 = rv.read_off[a], o1 = rv.read_off[a + 1];
+        for (int64_t kb = o0; kb < o1; kb += 32) {
+            const int64_t k = kb + lane;
+            const int b = k < o1 ? __ldg(rv.bread + k) : -1;
+            int bp = __shfl_up_sync(0xffffffffu, b, 1);
+            if (lane == 0) bp = kb > o0 ? __ldg(rv.bread + kb - 1) : -2;
+            const bool lead = k < o1 && b != bp && active[b];
+            np += __popc(__ballot_sync(0xffffffffu, lead));
+        }
+    }
+    if (lane == 0) {
+        pair_ref[a] = make_int2(0, np);
+        if (np) atomicAdd(total, (unsigned long long)np);
+    }
+}
+
+__device__ __forceinline__ int hash_buckets_for(int n, const int* __restrict__ grow_at,
+                                                const int* __restrict__ grow_bkt, int ngrow) {
+    int nb = 1;
+    for (int i = 0; i < ngrow && grow_at[i] <= n; i++) nb = grow_bkt[i];
+    return nb;
+}
+
+__device__ __forceinline__ void store_cand(Cand* dst, const Match& m, int a, int b, int64_t rec, int rank) {
+    Cand c;
+    c.a = a; c.b = b; c.type = m.type; c.comp = m.comp; c.weight = m.weight; c.length = m.length;
+    c.eas = m.eas; c.eae = m.eae; c.ebs = m.ebs; c.ebe = m.ebe;
+    c.as = m.as; c.ae = m.ae; c.bs = m.bs; c.be = m.be;
+    c.rec = rec;
+    c.rank = rank;
+    c.pad = 0;
+    *dst = c;
+}
+
+__global__ void __launch_bounds__(128)
+k_layout_pairs(RecView rv, ReadView rd, hg_layout_params P, const int2* __restrict__ mask,
+               const uint8_t* __restrict__ active, LayoutLists L) {
+    const int lane = lane_id();
+    const unsigned lt = (1u << lane) - 1u;
+    const int a = rd.r_lo + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (a >= rd.r_hi) return;
+    const int np = L.pair_ref[a].y;
+    if (np == 0) {
+        if (lane == 0) {
+            L.cand_ref[a] = make_int2(0, 0);
+            L.bkt_ref[a] = 0;
+        }
+        return;
+    }
+    int poff = 0, coff = 0, boff = 0;
+    if (lane == 0) {
+        poff = atomicAdd(&L.counters[0], np);
+        coff = atomicAdd(&L.counters[1], 2 * np);
+        boff = atomicAdd(&L.counters[2], hash_buckets_for(np, L.grow_at, L.grow_bkt, L.ngrow));
+    }
+    poff = __shfl_sync(0xffffffffu, poff, 0);
+    coff = __shfl_sync(0xffffffffu, coff, 0);
+    boff = __shfl_sync(0xffffffffu, boff, 0);
+    const int64_t o0 = rv.read_off[a], o1 = rv.read_off[a + 1];
+    int pi = 0, ci = 0;
+    for (int64_t kb = o0; kb < o1; kb += 32) {
+        const int64_t k = kb + lane;
+        const int b = k < o1 ? __ldg(rv.bread + k) : -1;
+        int bp = __shfl_up_sync(0xffffffffu, b, 1);
+        if (lane == 0) bp = kb > o0 ? __ldg(rv.bread + kb - 1) : -2;
+        const bool lead = k < o1 && b != bp && active[b];
+        const unsigned lm = __ballot_sync(0xffffffffu, lead);
+        Match m0, m1;
+        int64_t top[2] = {k, -1};
+        int v0 = 0, v1 = 0;
+        if (lead) {
+            int64_t e = k + 1;
+            while (e < o1 && __ldg(rv.bread + e) == b) e++;
+            const int m = (int)(e - k);
+            if (m > 16) {
+                // std::sort is only stable up to 16 elements: libstdc++'s introsort on (length, index),
+                // once (hinging.cpp:534), in a slice of the sort scratch
+                const int off = atomicAdd(&L.counters[4], m);
+                if (off + m > L.sort_cap) {
+                    atomicExch(&L.counters[3], 1);
+                } else {
+                    KeyIdx2* sc = L.sort_scratch + off;
+                    for (int i = 0; i < m; i++) {
+                        sc[i].key = raw_length(rv, k + i);
+                        sc[i].idx = i;
+                    }
+                    std_sort_exact(sc, m, KeyIdx2Greater());
+                    top[0] = k + sc[0].idx;
+                    top[1] = k + sc[1].idx;
+                }
+            } else if (m > 1) {
+                // insertion sort by length, descending, is stable: best = earliest maximum,
+                // second = next in (length desc, file order)
+                int k1 = raw_length(rv, k), k2 = -2147483647 - 1;
+                int64_t i2 = -1;
+                for (int64_t i = k + 1; i < e; i++) {
+                    const int key = raw_length(rv, i);
+                    if (key > k1) {
+                        k2 = k1; i2 = top[0];
+                        k1 = key; top[0] = i;
+                    } else if (i2 < 0 || key > k2) {
+                        k2 = key; i2 = i;
+                    }
+                }
+                top[1] = i2;
+            }
+            m0 = classify_record(rv, rd.rlen, mask, top[0], a, b, P);
+            v0 = (m0.type == HG_FORWARD || m0.type == HG_FORWARD_INTERNAL || m0.type == HG_BACKWARD ||
+                  m0.type == HG_BACKWARD_INTERNAL) ? 1 : 0;
+            bool bcov = m0.type == HG_BCOVERA;
+            if (top[1] >= 0 && P.use_two_matches) {
+                m1 = classify_record(rv, rd.rlen, mask, top[1], a, b, P);
+                v1 = (m1.type == HG_FORWARD || m1.type == HG_FORWARD_INTERNAL || m1.type == HG_BACKWARD ||
+                      m1.type == HG_BACKWARD_INTERNAL) ? 1 : 0;
+                bcov = bcov || m1.type == HG_BCOVERA;
+            }
+            if (bcov) L.contained_flag[a] = 1;  // hinging.cpp:598 (B is active here)
+        }
+        // consecutive candidate slots in lane (= pair) order
+        const int nc = v0 + v1;
+        int incl = nc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lead) {
+            const int start = ci + incl - nc;
+            if (v0) store_cand(L.cands + coff + start, m0, a, b, top[0], 0);
+            if (v1) store_cand(L.cands + coff + start + v0, m1, a, b, top[1], 1);
+            L.pairs[poff + pi + __popc(lm & lt)] = make_int2(b, (start << 2) | nc);
+        }
+        pi += __popc(lm);
+        ci += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+        L.pair_ref[a] = make_int2(poff, np);
+        L.cand_ref[a] = make_int2(coff, ci);
+        L.bkt_ref[a] = boff;
+    }
+}
+
+// Pre-sort order + weight sort of every read's candidate lists, one thread per read:
+// the reference fills matches_forward / matches_backward while iterating idx_ab[A], a
+// std::unordered_map keyed by B (hinging.cpp:532-592), and then std::sorts both by weight
+// (hinging.cpp:1066-1071; unstable: ties keep an order that depends on the input order).  The
+// iteration order is replayed by hash_iteration_order (hg_order.h), the sort by std_sort_exact.
+__global__ void __launch_bounds__(128)
+k_order_candidates(LayoutLists L, SelectIO io) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= io.n_read) return;
+    int4 rg = make_int4(0, 0, 0, 0);
+    const int2 pr = L.pair_ref[a];
+    if (io.active[a] && pr.y > 0) {
+        const int2 cr = L.cand_ref[a];
+        const int2* pairs = L.pairs + pr.x;
+        int* out = L.hash_out + pr.x;
+        hash_iteration_order([&](int i) { return pairs[i].x; }, pr.y, L.grow_at, L.grow_bkt, L.ngrow,
+                             L.hash_next + pr.x, L.hash_bkt + L.bkt_ref[a], out);
+        int n = 0;
+        for (int half = 0; half < 2; half++) {
+            const int lo = n;
+            for (int t = 0; t < pr.y; t++) {
+                const int info = pairs[out[t]].y;
+                for (int r = 0; r < (info & 3); r++) {
+                    const int ci = cr.x + (info >> 2) + r;
+                    const int ty = io.cands[ci].type;
+                    const bool fwd = ty == HG_FORWARD || ty == HG_FORWARD_INTERNAL;
+                    if (fwd == (half == 0)) io.order[cr.x + n++] = ci;
+                }
+            }
+            if (half == 0) {
+                rg.x = cr.x + lo;
+                rg.y = cr.x + n;
+            } else {
+                rg.z = cr.x + lo;
+                rg.w = cr.x + n;
+            }
+            const int cnt = n - lo;
+            if (cnt > 1) {
+                KeyIdx2* s = io.sort_scratch + cr.x + lo;
+                for (int t = 0; t < cnt; t++) {
+                    s[t].idx = io.order[cr.x + lo + t];
+                    s[t].key = io.cands[s[t].idx].weight;
+                }
+                std_sort_exact(s, cnt, KeyIdx2Greater());
+                for (int t = 0; t < cnt; t++) io.order[cr.x + lo + t] = s[t].idx;
+            }
+        }
+    }
+    io.ranges_out[a] = rg;
+}
+
+// active &= !contained ("[contained] Should not happen", hinging.cpp:598-601); counts them
+__global__ void k_apply_contained(int n, const uint8_t* __restrict__ contained, uint8_t* __restrict__ active,
+                                  int* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && contained[i] && active[i]) {
+        active[i] = 0;
+        atomicAdd(count, 1);
+    }
+}
+
+// the chosen candidates, compacted for the host: (candidate, hinge_pos) per read and direction
+__global__ void k_gather_chosen(int n_read, const int2* __restrict__ chosen, const Cand* __restrict__ cands,
+                                Cand* __restrict__ out, int2* __restrict__ out_ref, int* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n_read) return;
+    const int2 ch = chosen[i];
+    if (ch.x < 0) return;
+    const int slot = atomicAdd(count, 1);
+    out[slot] = cands[ch.x];
+    out_ref[slot] = make_int2(i, ch.y);
+}
+
 // ------------------------------------------------------------------ containment
 
 // state: 0 unknown, 1 survives (maximal), 2 removed
@@ -759,6 +991,38 @@ void launch_contain_lists(const RecView& rv, const ReadView& rd, const ContainIO
 void launch_contain_resolve(const int4* unk, const int* counts, int world, int unk_stride, const int* pool,
                             int pool_stride, uint8_t* state, int* sweeps_out, cudaStream_t st) {
     k_contain_resolve<<<1, 1024, 0, st>>>(unk, counts, world, unk_stride, pool, pool_stride, state, sweeps_out);
+    g_launches += 1;
+}
+
+void launch_layout_count_pairs(const RecView& rv, const ReadView& rd, const uint8_t* active, int2* pair_ref,
+                               unsigned long long* total, cudaStream_t st) {
+    cudaMemsetAsync(total, 0, sizeof(unsigned long long), st);
+    k_layout_count_pairs<<<cdiv((int64_t)(rd.r_hi - rd.r_lo) * 32, 128), 128, 0, st>>>(rv, rd, active, pair_ref, total);
+    g_launches += 1;
+}
+
+void launch_layout_pairs(const RecView& rv, const ReadView& rd, const hg_layout_params& P, const int2* mask,
+                         const uint8_t* active, const LayoutLists& L, cudaStream_t st) {
+    cudaMemsetAsync(L.counters, 0, sizeof(int) * 8, st);
+    k_layout_pairs<<<cdiv((int64_t)(rd.r_hi - rd.r_lo) * 32, 128), 128, 0, st>>>(rv, rd, P, mask, active, L);
+    g_launches += 1;
+}
+
+void launch_order_candidates(const LayoutLists& L, const SelectIO& io, cudaStream_t st) {
+    k_order_candidates<<<cdiv(io.n_read, 128), 128, 0, st>>>(L, io);
+    g_launches += 1;
+}
+
+void launch_apply_contained(int n, const uint8_t* contained, uint8_t* active, int* count, cudaStream_t st) {
+    cudaMemsetAsync(count, 0, sizeof(int), st);
+    k_apply_contained<<<cdiv(n, 256), 256, 0, st>>>(n, contained, active, count);
+    g_launches += 1;
+}
+
+void launch_gather_chosen(int n_read, const int2* chosen, const Cand* cands, Cand* out, int2* out_ref, int* count,
+                          cudaStream_t st) {
+    cudaMemsetAsync(count, 0, sizeof(int), st);
+    k_gather_chosen<<<cdiv(2 * (int64_t)n_read, 256), 256, 0, st>>>(n_read, chosen, cands, out, out_ref, count);
     g_launches += 1;
 }
 

@@ -94,6 +94,7 @@ struct SelectIO {
     const uint8_t* active;   // reads
     const Cand* cands;
     const int4* ranges;      // per read: fwd [x,y), bwd [z,w) into order[]
+    int4* ranges_out;        // written by k_order_candidates
     int* order;              // candidate indices, sorted by weight per list
     KeyIdx2* sort_scratch;   // one per candidate
     HingeView hv, kv, nk;    // hinges, killed hinges, new killed hinges
@@ -108,6 +109,33 @@ struct SelectIO {
     int2* chosen;            // per read x 2 (fwd, bwd): (candidate index or -1, hinge_pos)
 };
 
+// device-resident pair / candidate lists of the layout stage (k_layout_pairs, k_order_candidates)
+struct LayoutLists {
+    int2* pair_ref;          // per read: (first pair slot, pairs with an active B)
+    int2* cand_ref;          // per read: (first candidate slot, candidates)
+    int* bkt_ref;            // per read: first slot of its hash-bucket scratch
+    int2* pairs;             // per pair: (B, first candidate relative to the read's block << 2 | candidates)
+    Cand* cands;
+    int* hash_next;          // scratch of hash_iteration_order: one int per pair ...
+    int* hash_out;
+    int* hash_bkt;           // ... and one per bucket
+    uint8_t* contained_flag; // per read: "[contained] Should not happen" (hinging.cpp:598)
+    int* counters;           // [0] pair slots [1] candidate slots [2] bucket slots [3] overflow [4] sort scratch
+    KeyIdx2* sort_scratch;   // pairs with more than 16 records
+    int sort_cap;
+    const int* grow_at;      // bucket-count schedule of std::unordered_map (hash_growth_schedule)
+    const int* grow_bkt;
+    int ngrow;
+};
+
+void launch_layout_count_pairs(const RecView& rv, const ReadView& rd, const uint8_t* active, int2* pair_ref,
+                               unsigned long long* total, cudaStream_t st);
+void launch_layout_pairs(const RecView& rv, const ReadView& rd, const hg_layout_params& P, const int2* mask,
+                         const uint8_t* active, const LayoutLists& L, cudaStream_t st);
+void launch_order_candidates(const LayoutLists& L, const SelectIO& io, cudaStream_t st);
+void launch_apply_contained(int n, const uint8_t* contained, uint8_t* active, int* count, cudaStream_t st);
+void launch_gather_chosen(int n_read, const int2* chosen, const Cand* cands, Cand* out, int2* out_ref, int* count,
+                          cudaStream_t st);
 void launch_sort_candidates(const SelectIO& io, cudaStream_t st);
 void launch_hinge_graph(const RecView& rv, const hg_layout_params& P, const SelectIO& io,
                         cudaStream_t st);

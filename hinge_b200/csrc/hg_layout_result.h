@@ -25,9 +25,19 @@ struct LayoutResult {
     std::vector<GraphRec> graph;    // .hgraph, in output order
     std::vector<SkipRec> skips;     // .edges.skipped, in output order
     std::vector<int2> chosen;       // per read x 2: (candidate, hinge_pos)
+    // the chosen candidates themselves (always fetched): slot -> (2 * read + direction, hinge_pos)
+    std::vector<Cand> edge_cands;
+    std::vector<int2> edge_ref;
+    int n_contained = 0;            // "[contained] Should not happen" events (hinging.cpp:598-601)
+    // the full candidate lists stay on the device until a file writer asks for them (materialize)
+    Cand* d_cands = nullptr;
+    int* d_order = nullptr;
+    int4* d_ranges = nullptr;
+    int64_t n_cand_slots = 0;
+    bool materialized = false;
 
-    void fill_edge(int cand, int hinge_pos, hg_edge* e) const {
-        const Cand& c = cands[cand];
+    void fill_edge(int cand, int hinge_pos, hg_edge* e) const { fill_edge(cands[cand], hinge_pos, e); }
+    void fill_edge(const Cand& c, int hinge_pos, hg_edge* e) const {
         e->a = c.a; e->b = c.b; e->length = c.length; e->comp = c.comp; e->type = c.type;
         e->weight = c.weight;
         e->eff_a[0] = c.eas; e->eff_a[1] = c.eae; e->eff_b[0] = c.ebs; e->eff_b[1] = c.ebe;
@@ -38,7 +48,8 @@ struct LayoutResult {
     }
 };
 
-const LayoutResult* layout_result(const hg_ctx* c);
+// The result of the last hg_layout with the candidate lists copied to the host (first call).
+const LayoutResult* layout_result(hg_ctx* c);
 
 }  // namespace hg
 #endif

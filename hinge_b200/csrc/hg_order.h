@@ -178,6 +178,72 @@ HG_HD void std_sort_exact(T* a, int n, Less less) {
 }
 
 
+// ---------------------------------------------------------------- std::unordered_map<int, T> order
+//
+// Iteration order of a default-constructed std::unordered_map<int, T> after inserting n DISTINCT
+// non-negative keys one at a time (operator[]), as GCC 13's libstdc++ does it (bits/hashtable.h):
+//   * std::hash<int> is the identity, bucket = key % bucket_count
+//   * a new node goes to the FRONT of its bucket's run in the singly linked element list; into an
+//     empty bucket it goes to the front of the whole list (_M_insert_bucket_begin)
+//   * before the insertion that would exceed the load factor the table is rehashed to the next
+//     bucket count of _Prime_rehash_policy; the rehash walks the list and re-inserts every node
+//     by the same two rules (_M_rehash_aux, unique keys)
+// The bucket-count schedule (1, 13, 29, 59, 127, 257, ...: "next prime" table of the library's
+// binary) is not restated: hash_growth_schedule() reads it off the real container at run time
+// (grow_at[i] = number of elements whose insertion makes the count grow_bkt[i]).
+// next[n] and bucket[max bucket count] are scratch; out[n] receives the indices (insertion
+// numbers) in iteration order.
+constexpr int kHashBeforeBegin = -2, kHashEmpty = -1;
+
+template <class KeyAt>
+HG_HD void hash_iteration_order(KeyAt key_at, int n, const int* grow_at, const int* grow_bkt, int ngrow,
+                                int* next, int* bucket, int* out) {
+    int head = -1, nb = 1, gi = 0;
+    bucket[0] = kHashEmpty;
+    for (int k = 0; k < n; k++) {
+        while (gi < ngrow && grow_at[gi] <= k + 1) {  // rehash before linking element k + 1
+            const int newb = grow_bkt[gi++];
+            for (int i = 0; i < newb; i++) bucket[i] = kHashEmpty;
+            int p = head, bbegin = 0;
+            head = -1;
+            while (p >= 0) {
+                const int nx = next[p];
+                const int b = key_at(p) % newb;
+                if (bucket[b] == kHashEmpty) {
+                    next[p] = head;
+                    head = p;
+                    bucket[b] = kHashBeforeBegin;
+                    if (next[p] >= 0) bucket[bbegin] = p;
+                    bbegin = b;
+                } else if (bucket[b] == kHashBeforeBegin) {
+                    next[p] = head;
+                    head = p;
+                } else {
+                    next[p] = next[bucket[b]];
+                    next[bucket[b]] = p;
+                }
+                p = nx;
+            }
+            nb = newb;
+        }
+        const int b = key_at(k) % nb;
+        if (bucket[b] == kHashEmpty) {
+            next[k] = head;
+            head = k;
+            if (next[k] >= 0) bucket[key_at(next[k]) % nb] = k;
+            bucket[b] = kHashBeforeBegin;
+        } else if (bucket[b] == kHashBeforeBegin) {
+            next[k] = head;
+            head = k;
+        } else {
+            next[k] = next[bucket[b]];
+            next[bucket[b]] = k;
+        }
+    }
+    int i = 0;
+    for (int p = head; p >= 0; p = next[p]) out[i++] = p;
+}
+
 #if defined(__CUDACC__)
 // ------------------------------------------------- std::sort, one warp, same result
 //

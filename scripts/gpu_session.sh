@@ -47,6 +47,19 @@ import json;d=json.load(open('$OUT/${TAG}_bench_v$V.json'));print('c5',round(d['
         python -c "
 import json;d=json.load(open('$OUT/${TAG}_down_$CFG.json'));print(d.get('downstream_stages'))"
       done ;;
+    pytest_pipeline)
+      timeout 900 python -m pytest tests/test_gpu_pipeline_cli.py tests/test_gpu_edge_cases.py -m gpu -x -q > $OUT/${TAG}_pytest_pipeline.log 2>&1
+      echo "pytest (pipeline) exit $?" | tee -a $OUT/${TAG}_pytest_pipeline.log; tail -15 $OUT/${TAG}_pytest_pipeline.log ;;
+    launches_down)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+        --log-file $OUT/${TAG}_launches_down.csv python bench.py --config c3 --also "" --steps 1 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-verify > $OUT/${TAG}_launches_down.log 2>&1
+      echo "launch list (downstream) exit $?" ;;
+    ncu_down)
+      for K in k_classify_reads k_layout_pairs k_order_candidates k_hinge_exact_warp; do
+        timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^$K" -s 1 -c 1 -f \
+          -o $OUT/${TAG}_${K}_c3 python bench.py --config c3 --also "" --steps 2 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-verify > $OUT/${TAG}_ncu_${K}.log 2>&1
+        echo "ncu $K exit $?"
+      done ;;
     launches)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
         --log-file $OUT/${TAG}_launches.csv python bench.py $SHORT > $OUT/${TAG}_launches_bench.log 2>&1
