@@ -164,6 +164,10 @@ int hg_set_option(hg_ctx* c, int option, int64_t value) {
         c->fs.flat_spread = (int)value;
         return HG_OK;
     }
+    if (option == HG_OPT_KEEP_MASKS) {
+        c->keep_masks = value != 0;
+        return HG_OK;
+    }
     if (option == HG_OPT_PROFILE_KERNEL) {
         if (value != 0 && value != 1 && value != 5 && value != 6)
             return set_err(c, HG_ERR_ARG, "HG_OPT_PROFILE_KERNEL: 0, 1, 5 or 6");
@@ -385,7 +389,7 @@ static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
             cudaMemsetAsync(s.cov_maxbin, 0xff, sizeof(int) * c->n_read, c->stream);
             cudaMemsetAsync(s.mean_cov, 0xff, sizeof(int) * c->n_read, c->stream);
             cudaMemsetAsync(s.rflags, 0, c->n_read, c->stream);
-            cudaMemsetAsync(s.mask, 0, sizeof(int2) * c->n_read, c->stream);
+            if (!c->keep_masks) cudaMemsetAsync(s.mask, 0, sizeof(int2) * c->n_read, c->stream);
             cudaMemsetAsync(s.cmask, 0, sizeof(int2) * c->n_read, c->stream);
             cudaMemsetAsync(s.anno_ref, 0, sizeof(int2) * c->n_read, c->stream);
             HG_TRY(cuda_check(c, cudaStreamSynchronize(c->stream), "flat plan"));  // the vectors go away

@@ -92,7 +92,7 @@ static void say(const char* fmt, const std::string& s = std::string()) {
 }
 
 // Flag-combination checks shared by the three stages (filter.cpp:212-241).
-int check_inputs(const Args& a, std::string* las_name) {
+int check_inputs(const Args& a, std::vector<std::string>* las_names) {
     const bool db_and_las = !a.db.empty() && !a.las.empty();
     const bool db_or_las = !a.db.empty() || !a.las.empty();
     const bool fa_and_paf = !a.fasta.empty() && !a.paf.empty();
@@ -109,13 +109,23 @@ int check_inputs(const Args& a, std::string* las_name) {
         fprintf(stderr, "hinge_b200: the fasta + paf input path is outside the B200 hot path (DESIGN.md, out of scope)\n");
         return 1;
     }
-    if (a.mlas) {
-        fprintf(stderr, "hinge_b200: --mlas is not supported: merge the parts with LAmerge; the reference's multi-part "
-                        "results differ from its single-file results (SURVEY.md section 5)\n");
-        return 1;
+    las_names->clear();
+    if (a.mlas) {  // the parts <las>.1.las, <las>.2.las, ... as far as they exist (filter.cpp:35-63)
+        for (int i = 1;; i++) {
+            const std::string name = a.las + "." + std::to_string(i) + ".las";
+            struct stat st;
+            if (stat(name.c_str(), &st) != 0) break;
+            las_names->push_back(name);
+        }
+        if (las_names->empty()) {
+            fprintf(stderr, "hinge_b200: --mlas: no file %s.1.las\n", a.las.c_str());
+            return 1;
+        }
+        return 0;
     }
-    *las_name = a.las;
-    if (las_name->size() < 4 || las_name->compare(las_name->size() - 4, 4, ".las") != 0) *las_name += ".las";
+    std::string name = a.las;
+    if (name.size() < 4 || name.compare(name.size() - 4, 4, ".las") != 0) name += ".las";
+    las_names->push_back(name);
     return 0;
 }
 
@@ -145,21 +155,24 @@ struct EarlyContext {
 } g_early;
 }  // namespace
 
-static int load_inputs_inner(const Args& a, bool want_trace, Ini* ini, ReadDB* db, LasFile* las);
+static int load_inputs_inner(const Args& a, bool want_trace, Ini* ini, ReadDB* db, LasFile* las,
+                             std::vector<std::pair<int32_t, int32_t>>* part_ranges, bool load_las);
 
-int load_inputs(const Args& a, bool want_trace, Ini* ini, ReadDB* db, LasFile* las) {
-    std::string las_name;
-    int rc = check_inputs(a, &las_name);
+int load_inputs(const Args& a, bool want_trace, Ini* ini, ReadDB* db, LasFile* las,
+                std::vector<std::pair<int32_t, int32_t>>* part_ranges, bool load_las) {
+    std::vector<std::string> las_names;
+    int rc = check_inputs(a, &las_names);
     if (rc) return rc;
     g_early.start();
-    rc = load_inputs_inner(a, want_trace, ini, db, las);
+    rc = load_inputs_inner(a, want_trace, ini, db, las, part_ranges, load_las);
     if (rc) g_early.drop();
     return rc;
 }
 
-static int load_inputs_inner(const Args& a, bool want_trace, Ini* ini, ReadDB* db, LasFile* las) {
-    std::string las_name;
-    check_inputs(a, &las_name);
+static int load_inputs_inner(const Args& a, bool want_trace, Ini* ini, ReadDB* db, LasFile* las,
+                             std::vector<std::pair<int32_t, int32_t>>* part_ranges, bool load_las) {
+    std::vector<std::string> las_names;
+    check_inputs(a, &las_names);
     if (db->open(a.db) != 0) {  // LAInterface::openDB exits 1
         fprintf(stderr, "%s\n", db->error.c_str());
         return 1;
@@ -169,7 +182,8 @@ static int load_inputs_inner(const Args& a, bool want_trace, Ini* ini, ReadDB* d
         fprintf(stderr, "Can't load %s\n", a.config.c_str());
         return 1;
     }
-    if (las->open(las_name, want_trace) != 0) {
+    if (!load_las) return 0;
+    if (las->open_parts(las_names, want_trace, part_ranges) != 0) {
         fprintf(stderr, "%s\n", las->error.c_str());
         return 1;
     }
@@ -230,139 +244,191 @@ extern "C" int hg_main_filter(int argc, char** argv) {
     PhaseTimer timer;
     Ini ini;
     ReadDB db;
-    LasFile las;
-    int rc = load_inputs(a, false, &ini, &db, &las);
-    if (rc) return rc;
-    timer.lap("read db + ini + las");
+    std::vector<std::string> las_names;
+    if (check_inputs(a, &las_names)) return 1;
+    {
+        LasFile none;
+        const int rc = load_inputs(a, false, &ini, &db, &none, nullptr, false);  // DB + INI; starts the CUDA context
+        if (rc) return rc;
+    }
     hg_filter_params fp;
     load_filter_params(ini, db.has_qv, &fp);
-
-    hg_ctx* ctx = nullptr;
-    if (open_context(db, las, false, &ctx) != HG_OK) {
-        hg_ctx_destroy(ctx);
-        return 1;
-    }
-    timer.lap("context + H2D + CSR");
-    const bool want_cov = getenv("HINGE_B200_SKIP_COVERAGE_TXT") == nullptr;
-    hg_set_option(ctx, HG_OPT_KEEP_COVERAGE, want_cov);
-    hg_filter_summary sum;
-    rc = hg_filter(ctx, &fp, &sum);
-    if (rc != HG_OK) {
-        fprintf(stderr, "hinge_b200: filter failed: %s\n", hg_last_error(ctx));
-        hg_ctx_destroy(ctx);
-        return 1;
-    }
-    say("Estimated median coverage: %s", std::to_string(sum.cov_est));
-    timer.lap("hg_filter");
-
     const int n = db.n_read;
-    std::vector<int32_t> mask(2 * (size_t)n), cmask(2 * (size_t)n);
-    std::vector<uint8_t> flags(n);
-    std::vector<int64_t> anno_off((size_t)n + 1);
-    std::vector<int32_t> apos((size_t)sum.n_annotations + 1), atype((size_t)sum.n_annotations + 1);
-    std::vector<uint8_t> keep((size_t)sum.n_annotations + 1);
-    rc = hg_filter_fetch(ctx, mask.data(), cmask.data(), flags.data(), anno_off.data(), apos.data(),
-                         atype.data(), keep.data());
-    std::vector<int64_t> cov_off;
-    std::vector<int32_t> cov;
-    if (rc == HG_OK && want_cov) {
-        int64_t nb = 0;
-        cov_off.resize((size_t)n + 1);
-        rc = hg_filter_coverage(ctx, cov_off.data(), nullptr, &nb);
-        cov.resize((size_t)nb + 1);
-        if (rc == HG_OK) rc = hg_filter_coverage(ctx, nullptr, cov.data(), &nb);
-    }
-    if (rc != HG_OK) {
-        fprintf(stderr, "hinge_b200: fetching results failed: %s\n", hg_last_error(ctx));
-        hg_ctx_destroy(ctx);
-        return 1;
-    }
-    hg_ctx_destroy(ctx);
-    timer.lap("fetch results + destroy");
-    timer.note("h2d bytes", 28.0 * (double)las.novl + 4.0 * n + (db.has_qv ? (double)db.qv.size() : 0.0), "B");
-    timer.note("d2h bytes", 17.0 * n + 8.0 * (n + 1) + 9.0 * (double)sum.n_annotations + 4.0 * (double)cov.size(), "B");
-
+    const bool want_cov = getenv("HINGE_B200_SKIP_COVERAGE_TXT") == nullptr;
     const std::string& x = a.prefix;
-    {  // filter.cpp:449-457 opens all of these, some stay empty
-        touch(x + ".homologous.txt");
-        touch(x + ".filtered.fasta");
-        touch("debug.txt");
-        TextOut fcov(x + ".coverage.txt"), fmask(x + ".mas"), fcmask(x + ".cmas");
-        TextOut frep(x + ".repeat.txt"), fhg(x + ".hinges.txt");
-        TextOut fcf(x + ".cov.flag"), fsf(x + ".self.flag");
-        int64_t hinges = 0;
-        if (want_cov) {
-            // .coverage.txt (filter.cpp:599-602) is ~11 bytes per 40-bp bin of every read, by far the
-            // largest output: formatted by all cores, a block of reads at a time, written in order
-            int workers = (int)std::thread::hardware_concurrency();
-            if (const char* v = getenv("HINGE_B200_IO_THREADS")) workers = atoi(v);
-            workers = std::max(1, std::min(workers, 32));
-            const int block = 4096 * workers;
-            std::vector<std::vector<char>> bufs((size_t)workers);
-            auto put_int = [](std::vector<char>& b, long v) {
-                char tmp[24];
-                int n = 0;
-                unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
-                do {
-                    tmp[n++] = (char)('0' + u % 10);
-                    u /= 10;
-                } while (u);
-                if (v < 0) b.push_back('-');
-                while (n) b.push_back(tmp[--n]);
-            };
-            for (int b0 = sum.r_begin; b0 <= sum.r_end; b0 += block) {
-                const int b1 = std::min(sum.r_end + 1, b0 + block);
-                std::vector<std::thread> pool;
-                for (int w = 0; w < workers; w++)
-                    pool.emplace_back([&, w]() {
-                        std::vector<char>& out = bufs[w];
-                        out.clear();
-                        const int per = (b1 - b0 + workers - 1) / workers;
-                        for (int i = b0 + w * per; i < std::min(b1, b0 + (w + 1) * per); i++) {
-                            const char* head = "read ";
-                            out.insert(out.end(), head, head + 5);
-                            put_int(out, i);
-                            out.push_back(' ');
-                            for (int64_t k = cov_off[i]; k < cov_off[i + 1]; k++) {
-                                put_int(out, (long)(k - cov_off[i]) * fp.reso);
-                                out.push_back(',');
-                                put_int(out, cov[k]);
+    hg_ctx* ctx = nullptr;
+    bool out_failed = false;
+    double h2d_bytes = 0, d2h_bytes = 0;
+    int64_t all_hinges = 0;
+
+    // One pass per part.  A single .las is one part; with --mlas the reference loops over the parts and
+    // carries state from one to the next (filter.cpp:474-1109), which makes its results differ from a
+    // single-file run -- and this loop reproduces exactly that:
+    //   * MIN_COV only ever grows: every part raises it to a third of ITS median coverage (:677-678)
+    //   * the masks of the reads of earlier parts stay known; those of later parts are still (0,0)
+    //     when a part calls its hinges (:534, 884-889)                         -> HG_OPT_KEEP_MASKS
+    //   * .repeat.txt is closed after part 0 (:1086); every part's last read has no .hinges.txt line
+    //     (:1091); all other files are appended to part after part
+    for (size_t part = 0; part < las_names.size(); part++) {
+        LasFile las;
+        if (las.open(las_names[part], false) != 0) {
+            fprintf(stderr, "%s\n", las.error.c_str());
+            if (ctx) hg_ctx_destroy(ctx); else drop_early_context();
+            return 1;
+        }
+        say("# Alignments: %s", std::to_string(las.novl));
+        if (las.novl == 0) {  // filter.cpp:505-508
+            fprintf(stderr, "No alignments!\n");
+            if (ctx) hg_ctx_destroy(ctx); else drop_early_context();
+            return 1;
+        }
+        timer.lap(part == 0 ? "read db + ini + las" : "read las part");
+        int rc = HG_OK;
+        if (part == 0) {
+            rc = open_context(db, las, false, &ctx);
+        } else {
+            rc = hg_set_overlaps(ctx, las.novl, las.aread.data(), las.bread.data(), las.abpos.data(), las.aepos.data(),
+                                 las.bbpos.data(), las.bepos.data(), las.diffs.data(), las.flags.data(), nullptr,
+                                 nullptr, las.tbytes, HG_MEM_HOST, 0, n);
+            if (rc != HG_OK) fprintf(stderr, "hinge_b200: %s\n", hg_last_error(ctx));
+        }
+        if (rc != HG_OK) {
+            hg_ctx_destroy(ctx);
+            return 1;
+        }
+        timer.lap("context + H2D + CSR");
+        hg_set_option(ctx, HG_OPT_KEEP_COVERAGE, want_cov);
+        hg_set_option(ctx, HG_OPT_KEEP_MASKS, part > 0);
+        hg_filter_summary sum;
+        rc = hg_filter(ctx, &fp, &sum);
+        if (rc != HG_OK) {
+            fprintf(stderr, "hinge_b200: filter failed: %s\n", hg_last_error(ctx));
+            hg_ctx_destroy(ctx);
+            return 1;
+        }
+        fp.min_cov = sum.min_cov;  // carried into the next part
+        say("Estimated median coverage: %s", std::to_string(sum.cov_est));
+        timer.lap("hg_filter");
+
+        std::vector<int32_t> mask(2 * (size_t)n), cmask(2 * (size_t)n);
+        std::vector<uint8_t> flags(n);
+        std::vector<int64_t> anno_off((size_t)n + 1);
+        std::vector<int32_t> apos((size_t)sum.n_annotations + 1), atype((size_t)sum.n_annotations + 1);
+        std::vector<uint8_t> keep((size_t)sum.n_annotations + 1);
+        rc = hg_filter_fetch(ctx, mask.data(), cmask.data(), flags.data(), anno_off.data(), apos.data(),
+                             atype.data(), keep.data());
+        std::vector<int64_t> cov_off;
+        std::vector<int32_t> cov;
+        if (rc == HG_OK && want_cov) {
+            int64_t nb = 0;
+            cov_off.resize((size_t)n + 1);
+            rc = hg_filter_coverage(ctx, cov_off.data(), nullptr, &nb);
+            cov.resize((size_t)nb + 1);
+            if (rc == HG_OK) rc = hg_filter_coverage(ctx, nullptr, cov.data(), &nb);
+        }
+        if (rc != HG_OK) {
+            fprintf(stderr, "hinge_b200: fetching results failed: %s\n", hg_last_error(ctx));
+            hg_ctx_destroy(ctx);
+            return 1;
+        }
+        const bool last_part = part + 1 == las_names.size();
+        if (last_part) {
+            hg_ctx_destroy(ctx);
+            ctx = nullptr;
+        }
+        timer.lap(last_part ? "fetch results + destroy" : "fetch results");
+        h2d_bytes += 28.0 * (double)las.novl + (part == 0 ? 4.0 * n + (db.has_qv ? (double)db.qv.size() : 0.0) : 0.0);
+        d2h_bytes += 17.0 * n + 8.0 * (n + 1) + 9.0 * (double)sum.n_annotations + 4.0 * (double)cov.size();
+
+        {  // filter.cpp:449-457 opens all of these before the part loop, some stay empty
+            const bool app = part > 0;
+            if (!app) {
+                touch(x + ".homologous.txt");
+                touch(x + ".filtered.fasta");
+                touch("debug.txt");
+            }
+            TextOut fcov(x + ".coverage.txt", app), fmask(x + ".mas", app), fcmask(x + ".cmas", app);
+            TextOut fhg(x + ".hinges.txt", app), fcf(x + ".cov.flag", app), fsf(x + ".self.flag", app);
+            TextOut frep(app ? std::string("/dev/null") : x + ".repeat.txt");  // closed after part 0 (filter.cpp:1086)
+            int64_t hinges = 0;
+            if (want_cov) {
+                // .coverage.txt (filter.cpp:599-602) is ~11 bytes per 40-bp bin of every read, by far the
+                // largest output: formatted by all cores, a block of reads at a time, written in order
+                int workers = (int)std::thread::hardware_concurrency();
+                if (const char* v = getenv("HINGE_B200_IO_THREADS")) workers = atoi(v);
+                workers = std::max(1, std::min(workers, 32));
+                const int block = 4096 * workers;
+                std::vector<std::vector<char>> bufs((size_t)workers);
+                auto put_int = [](std::vector<char>& b, long v) {
+                    char tmp[24];
+                    int n = 0;
+                    unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
+                    do {
+                        tmp[n++] = (char)('0' + u % 10);
+                        u /= 10;
+                    } while (u);
+                    if (v < 0) b.push_back('-');
+                    while (n) b.push_back(tmp[--n]);
+                };
+                for (int b0 = sum.r_begin; b0 <= sum.r_end; b0 += block) {
+                    const int b1 = std::min(sum.r_end + 1, b0 + block);
+                    std::vector<std::thread> pool;
+                    for (int w = 0; w < workers; w++)
+                        pool.emplace_back([&, w]() {
+                            std::vector<char>& out = bufs[w];
+                            out.clear();
+                            const int per = (b1 - b0 + workers - 1) / workers;
+                            for (int i = b0 + w * per; i < std::min(b1, b0 + (w + 1) * per); i++) {
+                                const char* head = "read ";
+                                out.insert(out.end(), head, head + 5);
+                                put_int(out, i);
                                 out.push_back(' ');
+                                for (int64_t k = cov_off[i]; k < cov_off[i + 1]; k++) {
+                                    put_int(out, (long)(k - cov_off[i]) * fp.reso);
+                                    out.push_back(',');
+                                    put_int(out, cov[k]);
+                                    out.push_back(' ');
+                                }
+                                out.push_back('\n');
                             }
-                            out.push_back('\n');
+                        });
+                    for (auto& th : pool) th.join();
+                    for (int w = 0; w < workers; w++) fcov.put_bytes(bufs[w].data(), bufs[w].size());
+                }
+            }
+            for (int i = sum.r_begin; i <= sum.r_end; i++) {
+                fcmask.put_int(i); fcmask.put_char(' '); fcmask.put_int(cmask[2 * i]); fcmask.put_char(' ');
+                fcmask.put_int(cmask[2 * i + 1]); fcmask.put_char('\n');
+                fmask.put_int(i); fmask.put_char(' '); fmask.put_int(mask[2 * i]); fmask.put_char(' ');
+                fmask.put_int(mask[2 * i + 1]); fmask.put_char('\n');
+                if (flags[i] & 1) { fcf.put_int(i); fcf.put_char('\n'); }
+                if (flags[i] & 2) { fsf.put_int(i); fsf.put_char('\n'); }
+                frep.put_int(i);  // filter.cpp:1078-1085
+                frep.put_char(' ');
+                for (int64_t k = anno_off[i]; k < anno_off[i + 1]; k++) {
+                    frep.put_int(apos[k]); frep.put_char(' '); frep.put_int(atype[k]); frep.put_char(' ');
+                }
+                frep.put_char('\n');
+                if (i < sum.r_end) {  // filter.cpp:1091: the last read (of every part) gets no line
+                    fhg.put_int(i);
+                    fhg.put_char(' ');
+                    for (int64_t k = anno_off[i]; k < anno_off[i + 1]; k++)
+                        if (keep[k]) {
+                            fhg.put_int(apos[k]); fhg.put_char(' '); fhg.put_int(atype[k]); fhg.put_char(' ');
+                            hinges++;
                         }
-                    });
-                for (auto& th : pool) th.join();
-                for (int w = 0; w < workers; w++) fcov.put_bytes(bufs[w].data(), bufs[w].size());
+                    fhg.put_char('\n');
+                }
             }
+            out_failed = out_failed || !fcov.ok() || !fmask.ok() || !fcmask.ok() || !fhg.ok() || !fcf.ok() || !fsf.ok() ||
+                         !frep.ok();
+            all_hinges += hinges;
+            say("Number of hinges before filtering: %s", std::to_string(sum.n_annotations));
+            say("Number of hinges: %s", std::to_string(hinges));
         }
-        for (int i = sum.r_begin; i <= sum.r_end; i++) {
-            fcmask.put_int(i); fcmask.put_char(' '); fcmask.put_int(cmask[2 * i]); fcmask.put_char(' ');
-            fcmask.put_int(cmask[2 * i + 1]); fcmask.put_char('\n');
-            fmask.put_int(i); fmask.put_char(' '); fmask.put_int(mask[2 * i]); fmask.put_char(' ');
-            fmask.put_int(mask[2 * i + 1]); fmask.put_char('\n');
-            if (flags[i] & 1) { fcf.put_int(i); fcf.put_char('\n'); }
-            if (flags[i] & 2) { fsf.put_int(i); fsf.put_char('\n'); }
-            frep.put_int(i);  // filter.cpp:1078-1085
-            frep.put_char(' ');
-            for (int64_t k = anno_off[i]; k < anno_off[i + 1]; k++) {
-                frep.put_int(apos[k]); frep.put_char(' '); frep.put_int(atype[k]); frep.put_char(' ');
-            }
-            frep.put_char('\n');
-            if (i < sum.r_end) {  // filter.cpp:1091: the last read gets no line
-                fhg.put_int(i);
-                fhg.put_char(' ');
-                for (int64_t k = anno_off[i]; k < anno_off[i + 1]; k++)
-                    if (keep[k]) {
-                        fhg.put_int(apos[k]); fhg.put_char(' '); fhg.put_int(atype[k]); fhg.put_char(' ');
-                        hinges++;
-                    }
-                fhg.put_char('\n');
-            }
-        }
-        say("Number of hinges before filtering: %s", std::to_string(sum.n_annotations));
-        say("Number of hinges: %s", std::to_string(hinges));
+        timer.lap("write output files");
     }
-    timer.lap("write output files");
-    return 0;
+    timer.note("h2d bytes", h2d_bytes, "B");
+    timer.note("d2h bytes", d2h_bytes, "B");
+    return out_failed ? 1 : 0;
 }

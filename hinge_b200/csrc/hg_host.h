@@ -6,6 +6,8 @@
 #include <time.h>
 
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/hinge_b200.h"
 #include "hg_io.h"
@@ -39,8 +41,13 @@ struct PhaseTimer {
 };
 
 bool parse_args(int argc, char** argv, bool layout, Args* a, std::string* err);
-int check_inputs(const Args& a, std::string* las_name);
-int load_inputs(const Args& a, bool want_trace, Ini* ini, ReadDB* db, LasFile* las);
+// las_names: the single <las>[.las], or the parts <las>.1.las, <las>.2.las, ... of a --mlas run
+// (filter.cpp:35-63,228-241)
+int check_inputs(const Args& a, std::vector<std::string>* las_names);
+// Reads the DB, the INI and (load_las) all records -- the parts of a --mlas run taken together, with
+// part_ranges = [first, last] A-read of every part.  Starts the creation of the CUDA context beside it.
+int load_inputs(const Args& a, bool want_trace, Ini* ini, ReadDB* db, LasFile* las,
+                std::vector<std::pair<int32_t, int32_t>>* part_ranges = nullptr, bool load_las = true);
 int open_context(const ReadDB& db, const LasFile& las, bool with_trace, hg_ctx** ctx);
 // load_inputs starts the creation of the CUDA context on a side thread; every error return between
 // load_inputs and open_context must give it back (joins the thread, destroys the context)

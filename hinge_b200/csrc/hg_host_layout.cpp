@@ -150,7 +150,11 @@ extern "C" int hg_main_maximal(int argc, char** argv) {
     Ini ini;
     ReadDB db;
     LasFile las;
-    int rc = load_inputs(a, true, &ini, &db, &las);
+    // --mlas: the parts hold disjoint, ascending A-read ranges and the reference's part loop only shares
+    // the per-read active flags (maximal.cpp:562-900), so the records are taken together; the part
+    // ranges still decide which reads .max lists
+    std::vector<std::pair<int32_t, int32_t>> part_ranges;
+    int rc = load_inputs(a, true, &ini, &db, &las, &part_ranges);
     if (rc) return rc;
     hg_layout_params lp;
     load_layout_params(ini, &lp);
@@ -180,24 +184,24 @@ extern "C" int hg_main_maximal(int argc, char** argv) {
     }
     timer.lap("hg_maximal");
     hg_ctx_destroy(ctx);
-    const int r_begin = las.aread.front(), r_end = las.aread.back();
     touch(a.prefix + ".homologous.txt");  // maximal.cpp:515-517 reopens (truncates) these
     touch(a.prefix + ".filtered.fasta");
     TextOut fmax(a.prefix + ".max"), fcont(a.prefix + ".contained.txt");
     int kept = 0;
-    for (int i = r_begin; i <= r_end; i++) {
-        if (by[i] >= 0) {  // maximal.cpp:853-857
-            fcont.put_int(i);
-            fcont.put_char('\t');
-            fcont.put_int(by[i]);
-            fcont.put_char('\n');
+    for (const auto& pr : part_ranges)
+        for (int i = pr.first; i <= pr.second; i++) {
+            if (by[i] >= 0) {  // maximal.cpp:853-857
+                fcont.put_int(i);
+                fcont.put_char('\t');
+                fcont.put_int(by[i]);
+                fcont.put_char('\n');
+            }
+            if (maximal[i]) {  // maximal.cpp:873-878
+                fmax.put_int(i);
+                fmax.put_char('\n');
+                kept++;
+            }
         }
-        if (maximal[i]) {  // maximal.cpp:873-878
-            fmax.put_int(i);
-            fmax.put_char('\n');
-            kept++;
-        }
-    }
     printf("[hinge_b200] removed contained reads, active reads: %d (%.3f ms on device)\n", kept, ms);
     timer.lap("destroy + write output files");
     return 0;

@@ -254,6 +254,53 @@ void walk_records(const uint8_t* base, size_t fsize, size_t begin, size_t stop, 
 
 }  // namespace
 
+int LasFile::open_parts(const std::vector<std::string>& names, bool want_trace,
+                        std::vector<std::pair<int32_t, int32_t>>* ranges) {
+    if (names.size() == 1) {
+        const int rc = open(names[0], want_trace);
+        if (rc == 0 && ranges && novl > 0) ranges->assign(1, std::make_pair(aread.front(), aread.back()));
+        return rc;
+    }
+    std::vector<LasFile> parts(names.size());
+    int64_t total = 0, ttotal = 0;
+    for (size_t i = 0; i < names.size(); i++) {
+        if (parts[i].open(names[i], want_trace) != 0) {
+            error = parts[i].error;
+            return -1;
+        }
+        if (i > 0 && parts[i].tspace != parts[0].tspace) {
+            error = "parts of a split .las disagree on the trace spacing: " + names[i];
+            return -1;
+        }
+        total += parts[i].novl;
+        ttotal += parts[i].trace_off[(size_t)parts[i].novl];
+    }
+    novl = total;
+    tspace = parts[0].tspace;
+    tbytes = parts[0].tbytes;
+    const size_t n = (size_t)total;
+    aread.resize(n); bread.resize(n); abpos.resize(n); aepos.resize(n);
+    bbpos.resize(n); bepos.resize(n); diffs.resize(n); flags.resize(n);
+    trace_off.resize(n + 1);
+    if (want_trace) trace.resize((size_t)ttotal);
+    if (ranges) ranges->clear();
+    size_t at = 0;
+    int64_t tat = 0;
+    for (LasFile& p : parts) {
+        const size_t m = (size_t)p.novl;
+        RawColumn<int32_t>* dst[8] = {&aread, &bread, &abpos, &aepos, &bbpos, &bepos, &diffs, &flags};
+        RawColumn<int32_t>* src[8] = {&p.aread, &p.bread, &p.abpos, &p.aepos, &p.bbpos, &p.bepos, &p.diffs, &p.flags};
+        for (int c = 0; c < 8; c++) memcpy(dst[c]->data() + at, src[c]->data(), m * sizeof(int32_t));
+        for (size_t i = 0; i < m; i++) trace_off[at + i] = tat + p.trace_off[i];
+        if (want_trace && p.trace_off[m] > 0) memcpy(trace.data() + tat, p.trace.data(), (size_t)p.trace_off[m]);
+        if (ranges && m > 0) ranges->push_back(std::make_pair(p.aread.front(), p.aread.back()));
+        at += m;
+        tat += p.trace_off[m];
+    }
+    trace_off[n] = tat;
+    return 0;
+}
+
 int LasFile::open(const std::string& las_name, bool want_trace) {
     int fd = ::open(las_name.c_str(), O_RDONLY);
     if (fd < 0) {
@@ -583,7 +630,14 @@ void load_layout_params(const Ini& ini, hg_layout_params* p) {
 
 // ---------------------------------------------------------------- TextOut
 
-TextOut::TextOut(const std::string& path) : buf_(1 << 20) { fp_ = fopen(path.c_str(), "w"); }
+TextOut::TextOut(const std::string& path, bool append) : buf_(1 << 20) {
+    fp_ = fopen(path.c_str(), append ? "a" : "w");
+    if (!fp_) {  // an unwritable path must not end in fwrite(NULL): report it, swallow the output
+        fprintf(stderr, "hinge_b200: cannot write %s\n", path.c_str());
+        failed_ = true;
+        fp_ = fopen("/dev/null", "w");
+    }
+}
 TextOut::~TextOut() { close(); }
 
 void TextOut::flush() {

@@ -69,6 +69,10 @@ struct LasFile {
     // Mirrors LAInterface::openAlignmentFile + getOverlap(0, n_read)
     // (/root/reference/src/lib/LAInterface.cpp:595-621,1519-1634).
     int open(const std::string& las_name, bool want_trace);
+    // The parts of a split .las (--mlas: <base>.1.las, <base>.2.las, ...) taken together, in order;
+    // ranges gets the [first, last] A-read of every part.
+    int open_parts(const std::vector<std::string>& names, bool want_trace,
+                   std::vector<std::pair<int32_t, int32_t>>* ranges);
 };
 
 // inih-compatible INI reader (/root/reference/src/lib/ini.c, INIReader.cpp):
@@ -97,9 +101,9 @@ void load_layout_params(const Ini& ini, hg_layout_params* p);
 // single characters); much faster than iostream, same bytes.
 class TextOut {
 public:
-    explicit TextOut(const std::string& path);
+    explicit TextOut(const std::string& path, bool append = false);
     ~TextOut();
-    bool ok() const { return fp_ != nullptr; }
+    bool ok() const { return fp_ != nullptr && !failed_; }
     void put_int(long v);
     void put_char(char c);
     void put_str(const char* s);
@@ -109,6 +113,7 @@ public:
 private:
     void flush();
     void* fp_ = nullptr;
+    bool failed_ = false;
     std::vector<char> buf_;
     size_t len_ = 0;
 };

@@ -67,55 +67,61 @@ __device__ Match classify_record(const RecView& rv, const int* __restrict__ rlen
     const int tlen = (int)((__ldg(rv.trace_off + k + 1) - toff) / rv.tbytes);
     const int inner = max(tlen / 2 - 1, 0);
     const int npts = inner + 2;
+    // Point idx of the walk (LAInterface.cpp:4569-4590): A = abpos for idx 0, then the multiples of
+    // 100 above it, (abpos / 100 + idx) * 100; B = its start plus / minus the first idx b-deltas.
+    // u = +B (or -B for a complemented match) grows along the walk, so do the A coordinates, and all
+    // four mask tests become "index >= / <= a bound known up front" and "u >= / <= a bound":
+    //   start (first point inside both effective reads):  idx >= ia_s  and  u >= u_s
+    //   end   (last such point):                          idx <= ia_e  and  u <= u_e
     const int sign = 1 - 2 * m.comp;
+    const int u_s = m.comp ? -EB.y : EB.x, u_e = m.comp ? -EB.x : EB.y;
+    const int a100 = m.as / 100;
+    const int ia_s = m.as >= EA.x ? 0 : max(1, (EA.x + 99) / 100 - a100);   // EA.x > as >= 0 here
+    const int ia_e = EA.y < m.as ? -1 : (EA.y < 0 ? -1 : max(0, min(inner, EA.y / 100 - a100)));
     int start_idx = npts, end_idx = 0;
     bool have_start = false;
     // the final point (idx npts - 1): the match's own end
     const int fa = m.ae, fb = m.comp ? m.bs : m.be;
-    const bool end_final = m.comp ? (fa <= EA.y && fb >= EB.x) : (fa <= EA.y && fb <= EB.y);
+    const int fu = sign * fb;
+    const bool end_final = fa <= EA.y && fu <= u_e;
     bool end_alive = true;
-    int pa = m.as, pb = m.comp ? m.be : m.bs;
-    for (int idx = 0; idx < npts - 1; idx++) {
-        if (idx > 0) {
-            pa = (pa / 100 + 1) * 100;  // next multiple of 100 (LAInterface.cpp:4584-4587)
-            pb += sign * trace_value(rv, toff, 2 * (idx - 1) + 1);
+    int u = sign * (m.comp ? m.be : m.bs), u_start = 0, u_end = 0;
+    const uint8_t* __restrict__ t8 = rv.trace + toff;
+    const uint16_t* __restrict__ t16 = reinterpret_cast<const uint16_t*>(rv.trace + toff);
+    const bool wide = rv.tbytes != 1;
+    for (int idx = 0; idx <= inner; idx++) {
+        if (idx > 0) u += wide ? (int)t16[2 * idx - 1] : (int)t8[2 * idx - 1];
+        if (!have_start && idx >= ia_s && u >= u_s) {
+            start_idx = idx;
+            u_start = u;
+            have_start = true;
         }
-        if (!m.comp) {
-            if (!have_start && pa >= EA.x && pb >= EB.x) {
-                m.eas = pa; m.ebs = pb; start_idx = idx; have_start = true;
-            }
-            if (end_alive) {
-                if (pa <= EA.y && pb <= EB.y) {
-                    m.eae = pa; m.ebe = pb; end_idx = idx;
-                } else {
-                    end_alive = false;
-                }
-            }
-        } else {
-            if (!have_start && pa >= EA.x && pb <= EB.y) {
-                m.eas = pa; m.ebe = pb; start_idx = idx; have_start = true;
-            }
-            if (end_alive) {
-                if (pa <= EA.y && pb >= EB.x) {
-                    m.eae = pa; m.ebs = pb; end_idx = idx;
-                } else {
-                    end_alive = false;
-                }
+        if (end_alive) {
+            if (idx <= ia_e && u <= u_e) {
+                end_idx = idx;
+                u_end = u;
+            } else {
+                end_alive = false;
             }
         }
         if (end_final ? have_start : !end_alive) break;
     }
-    if (!have_start) {
-        if (!m.comp ? (fa >= EA.x && fb >= EB.x) : (fa >= EA.x && fb <= EB.y)) {
-            m.eas = fa;
-            if (!m.comp) m.ebs = fb; else m.ebe = fb;
-            start_idx = npts - 1;
-        }
+    if (have_start) {
+        m.eas = start_idx == 0 ? m.as : (a100 + start_idx) * 100;
+        if (!m.comp) m.ebs = u_start; else m.ebe = -u_start;
+    } else if (fa >= EA.x && fu >= u_s) {
+        m.eas = fa;
+        if (!m.comp) m.ebs = fb; else m.ebe = fb;
+        start_idx = npts - 1;
     }
     if (end_final) {
         m.eae = fa;
         if (!m.comp) m.ebe = fb; else m.ebs = fb;
         end_idx = npts - 1;
+    } else if (ia_e >= 0 && (end_idx > 0 || (m.as <= EA.y && sign * (m.comp ? m.be : m.bs) <= u_e))) {
+        // the last cumulative point that passed (idx 0 included)
+        m.eae = end_idx == 0 ? m.as : (a100 + end_idx) * 100;
+        if (!m.comp) m.ebe = u_end; else m.ebs = -u_end;
     }
     m.active = a != b && !(start_idx >= end_idx);
     m.type = HG_UNDEFINED;

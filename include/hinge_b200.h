@@ -45,6 +45,9 @@ enum hg_option {
     HG_OPT_KEEP_COVERAGE = 1, /* keep the 40-bp coverage profiles (.coverage.txt) */
     HG_OPT_PROFILE = 2,       /* record CUDA events between the kernels of a stage */
     HG_OPT_SCATTER_SPREAD = 3,/* tuning aid: record windows per warp in the profile scatter (1, 4, 8, 16) */
+    HG_OPT_KEEP_MASKS = 5,    /* multi-part runs (--mlas): hg_set_overlaps + hg_filter on the next part keep the
+                                 masks the earlier parts computed (reads of later parts still have (0,0)),
+                                 as the reference's part loop does (filter.cpp:534,884-889) */
     HG_OPT_PROFILE_KERNEL = 4 /* tuning aid: 0 = pick the form of the coverage-profile kernel by cut_off and
                                  data shape (20-bp start/end histogram for the nominal cut_off 300 when
                                  records outnumber coverage bins), 1 = always the four-event 40-bp form,

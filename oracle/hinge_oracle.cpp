@@ -254,7 +254,7 @@ static void qv_masks(const Data& d, std::vector<PII>* qm) {
     }
 }
 
-void run_filter(const Data& d, const Params& p, FilterOut* out) {
+void run_filter(const Data& d, const Params& p, FilterOut* out, FilterCarry* carry) {
     const int n_read = d.n_read;
     const int T = p.threads;
     std::vector<Ov> ovs;
@@ -262,7 +262,7 @@ void run_filter(const Data& d, const Params& p, FilterOut* out) {
     std::vector<PII> qm;
     qv_masks(d, &qm);
     const bool use_qv = p.use_qv && d.has_qv;  // filter.cpp:409
-    int MIN_COV = p.min_cov;
+    int MIN_COV = (carry && carry->started) ? carry->min_cov : p.min_cov;
 
     out->r_begin = ovs.front().a;  // filter.cpp:516-517
     out->r_end = ovs.back().a;
@@ -327,6 +327,7 @@ void run_filter(const Data& d, const Params& p, FilterOut* out) {
 
     // masks, filter.cpp:696-789
     out->mask.assign(n_read, PII(0, 0));
+    if (carry && carry->started) out->mask = carry->mask;  // reads of earlier parts keep their masks
     out->cmask.assign(n_read, PII(0, 0));
     std::vector<char> cov_flag(n_read, 0), self_flag(n_read, 0);
     parallel_for(rb, re + 1, T, [&](int64_t i) {
@@ -521,6 +522,11 @@ void run_filter(const Data& d, const Params& p, FilterOut* out) {
                 out->hinges[i].push_back(PII(apos, out_hinge ? -1 : 1));
         }
     });
+    if (carry) {
+        carry->started = true;
+        carry->min_cov = MIN_COV;
+        carry->mask = out->mask;
+    }
 }
 
 // ------------------------------------------------------------------ maximal
@@ -848,12 +854,14 @@ static void print_pairs(std::ofstream& f, int i, const std::vector<PII>& v) {
 }
 
 // filter.cpp:599-602,775-788,1078-1098
-void write_filter_files(const FilterOut& o, const Params& p, int n_read, const std::string& x) {
+void write_filter_files(const FilterOut& o, const Params& p, int n_read, const std::string& x, int part) {
     (void)p;
     (void)n_read;
-    std::ofstream cov(x + ".coverage.txt"), homo(x + ".homologous.txt"), rep(x + ".repeat.txt");
-    std::ofstream filtered(x + ".filtered.fasta"), hg(x + ".hinges.txt"), mask(x + ".mas");
-    std::ofstream comask(x + ".cmas"), covflag(x + ".cov.flag"), selfflag(x + ".self.flag");
+    const std::ios_base::openmode mode = part > 0 ? std::ios_base::app : std::ios_base::trunc;
+    std::ofstream cov(x + ".coverage.txt", mode), homo(x + ".homologous.txt", mode), rep;
+    if (part <= 0) rep.open(x + ".repeat.txt", mode);  // closed inside the part loop: part 0 only (filter.cpp:1086)
+    std::ofstream filtered(x + ".filtered.fasta", mode), hg(x + ".hinges.txt", mode), mask(x + ".mas", mode);
+    std::ofstream comask(x + ".cmas", mode), covflag(x + ".cov.flag", mode), selfflag(x + ".self.flag", mode);
     for (int i = o.r_begin; i <= o.r_end; i++) {
         cov << "read " << i << " ";
         for (size_t j = 0; j < o.cov0[i].size(); j++)
@@ -861,7 +869,7 @@ void write_filter_files(const FilterOut& o, const Params& p, int n_read, const s
         cov << std::endl;
         comask << i << " " << o.cmask[i].first << " " << o.cmask[i].second << std::endl;
         mask << i << " " << o.mask[i].first << " " << o.mask[i].second << std::endl;
-        print_pairs(rep, i, o.repeats[i]);
+        if (part <= 0) print_pairs(rep, i, o.repeats[i]);
         if (i < o.r_end) print_pairs(hg, i, o.hinges[i]);  // filter.cpp:1091 `i < r_end`
     }
     for (size_t k = 0; k < o.cov_flag.size(); k++) covflag << o.cov_flag[k] << std::endl;
@@ -869,12 +877,13 @@ void write_filter_files(const FilterOut& o, const Params& p, int n_read, const s
 }
 
 // maximal.cpp:853-878
-void write_maximal_files(const MaximalOut& o, int r_begin, int r_end, const std::string& x) {
+void write_maximal_files(const MaximalOut& o, const std::vector<PII>& ranges, const std::string& x) {
     std::ofstream cont(x + ".contained.txt"), mx(x + ".max");
     for (size_t k = 0; k < o.contained.size(); k++)
         cont << o.contained[k].first << "\t" << o.contained[k].second << std::endl;
-    for (int i = r_begin; i <= r_end; i++)
-        if (o.active[i]) mx << i << std::endl;
+    for (const PII& r : ranges)
+        for (int i = r.first; i <= r.second; i++)
+            if (o.active[i]) mx << i << std::endl;
 }
 
 // hinging.cpp:188-248
@@ -937,6 +946,19 @@ void write_layout_files(const LayoutOut& o, int n_read, const std::string& x, co
     f = fopen((out + ".edges.greedy").c_str(), "w");
     for (size_t k = 0; k < o.greedy.size(); k++) print_edge(f, o.greedy[k]);
     fclose(f);
+    // .edges.1 / .edges.2: the same greedy edges in the older two-file format (hinging.cpp:1739-1786,
+    // 1805-1852; forward and backward edges print the same way)
+    f = fopen((out + ".edges.1").c_str(), "w");
+    f2 = fopen((out + ".edges.2").c_str(), "w");
+    for (size_t k = 0; k < o.greedy.size(); k++) {
+        const Edge& e = o.greedy[k];
+        fprintf(f, e.comp == 0 ? "%d %d %d [%d %d] [%d %d] [%d %d] [%d %d]\n" : "%d %d' %d [%d %d] [%d %d] [%d %d] [%d %d]\n",
+                e.a, e.b, e.length, e.eas, e.eae, e.ebs, e.ebe, e.ras, e.rae, e.rbs, e.rbe);
+        fprintf(f2, e.comp == 0 ? "%d' %d' %d [%d %d] [%d %d] [%d %d] [%d %d]\n" : "%d %d' %d [%d %d] [%d %d] [%d %d] [%d %d]\n",
+                e.b, e.a, e.length, e.eas, e.eae, e.ebs, e.ebe, e.ras, e.rae, e.rbs, e.rbe);
+    }
+    fclose(f);
+    fclose(f2);
 }
 
 void read_mask_file(const std::string& path, int n_read, std::vector<PII>* mask) {

@@ -93,9 +93,17 @@ struct LayoutOut {
 
 bool load_ini(const std::string& path, Params* p, std::string* err);
 bool load_db(const std::string& name, Data* d, std::string* err);
-bool load_las(const std::string& name, Data* d, std::string* err);
+bool load_las(const std::string& name, Data* d, std::string* err, bool append = false);
 
-void run_filter(const Data& d, const Params& p, FilterOut* out);
+// State the reference carries from one part of a multi-part run (--mlas, filter.cpp:474-1109) to the
+// next: MIN_COV only ever grows (filter.cpp:677-678) and the masks of the reads of earlier parts stay
+// known, while those of later parts are still (0,0) when a part calls its hinges (filter.cpp:534,884-889).
+struct FilterCarry {
+    int min_cov = 0;
+    std::vector<PII> mask;
+    bool started = false;
+};
+void run_filter(const Data& d, const Params& p, FilterOut* out, FilterCarry* carry = nullptr);
 void run_maximal(const Data& d, const Params& p, const std::vector<PII>& mask, int r_begin,
                  int r_end, MaximalOut* out);
 void run_layout(const Data& d, const Params& p, const std::vector<PII>& mask,
@@ -103,8 +111,13 @@ void run_layout(const Data& d, const Params& p, const std::vector<PII>& mask,
                 const std::vector<std::vector<PII>>& hinges, LayoutOut* out);
 
 // text writers: byte-identical to the reference's files
-void write_filter_files(const FilterOut& o, const Params& p, int n_read, const std::string& prefix);
-void write_maximal_files(const MaximalOut& o, int r_begin, int r_end, const std::string& prefix);
+// part < 0: single .las.  part >= 0: part number of a --mlas run: files are truncated by part 0 and
+// appended to by the others; .repeat.txt is closed after part 0 (filter.cpp:1086) and every part's
+// last read gets no .hinges.txt line (filter.cpp:1091).
+void write_filter_files(const FilterOut& o, const Params& p, int n_read, const std::string& prefix, int part = -1);
+// ranges: the [first, last] A-read of every part (one entry for a single .las): .max lists the
+// surviving reads of those ranges only (maximal.cpp:873-878 runs inside the part loop)
+void write_maximal_files(const MaximalOut& o, const std::vector<PII>& ranges, const std::string& prefix);
 void write_layout_files(const LayoutOut& o, int n_read, const std::string& prefix,
                         const std::string& out_prefix);
 

@@ -177,7 +177,7 @@ bool load_db(const std::string& name, Data* d, std::string* err) {
     return true;
 }
 
-bool load_las(const std::string& name, Data* d, std::string* err) {
+bool load_las(const std::string& name, Data* d, std::string* err, bool append) {
     FILE* f = fopen(name.c_str(), "rb");
     if (!f) {
         *err = "cannot open " + name;
@@ -190,14 +190,19 @@ bool load_las(const std::string& name, Data* d, std::string* err) {
         *err = "short .las";
         return false;
     }
+    const int64_t base = append ? d->novl : 0;  // parts of a split .las: appended in order
+    if (!append) {
+        d->trace_off.assign(1, 0);
+        d->trace.clear();
+    }
+    novl += base;
     d->novl = novl;
     d->tspace = tspace;
     d->tbytes = tspace <= 125 ? 1 : 2;
     d->aread.resize(novl); d->bread.resize(novl); d->abpos.resize(novl); d->aepos.resize(novl);
     d->bbpos.resize(novl); d->bepos.resize(novl); d->flags.resize(novl);
-    d->trace_off.assign(novl + 1, 0);
-    d->trace.clear();
-    for (int64_t k = 0; k < novl; k++) {
+    d->trace_off.resize(novl + 1, 0);
+    for (int64_t k = base; k < novl; k++) {
         int rec[10];
         if (fread(rec, 40, 1, f) != 1) {
             fclose(f);

@@ -60,6 +60,23 @@ import json;d=json.load(open('$OUT/${TAG}_down_$CFG.json'));print(d.get('downstr
           -o $OUT/${TAG}_${K}_c3 python bench.py --config c3 --also "" --steps 2 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-verify > $OUT/${TAG}_ncu_${K}.log 2>&1
         echo "ncu $K exit $?"
       done ;;
+    sharded)
+      for SHAPE in c3 c5; do
+        timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29641 \
+          scripts/sharded_check.py $SHAPE > $OUT/${TAG}_sharded_$SHAPE.log 2>&1
+        echo "sharded_check $SHAPE exit $?"; grep SHARDED_CHECK $OUT/${TAG}_sharded_$SHAPE.log; tail -3 $OUT/${TAG}_sharded_$SHAPE.log
+      done ;;
+    bench2)
+      timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29642 \
+        bench.py --gpus 2 --no-downstream > $OUT/${TAG}_bench_n2.json 2> $OUT/${TAG}_bench_n2.err
+      echo "bench N=2 exit $?"; tail -5 $OUT/${TAG}_bench_n2.err; tail -c 1500 $OUT/${TAG}_bench_n2.json
+      timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29643 \
+        bench.py --gpus 2 --no-downstream --exchange nccl --no-verify > $OUT/${TAG}_bench_n2_nccl.json 2> $OUT/${TAG}_bench_n2_nccl.err
+      echo "bench N=2 nccl exit $?"
+      python -c "
+import json
+for f in ('$OUT/${TAG}_bench_n2.json','$OUT/${TAG}_bench_n2_nccl.json'):
+    d=json.load(open(f)); print(f, 'c5', round(d['ms_per_step'],4), d['kernel_ms'], d.get('parity'), 'c3', round(d['c3']['ms_per_step'],4), d['c3'].get('parity'))" ;;
     launches)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
         --log-file $OUT/${TAG}_launches.csv python bench.py $SHORT > $OUT/${TAG}_launches_bench.log 2>&1

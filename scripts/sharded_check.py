@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import hgsynth  # noqa: E402
 from hinge_b200 import api  # noqa: E402
-from hinge_b200.sharding import ShardedArrays, run_filter_sharded  # noqa: E402
+from hinge_b200.sharding import ShardedArrays, run_filter_sharded, run_maximal_sharded  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -75,5 +75,37 @@ for exchange in ("peer", "nccl"):
         ok &= good
     ctx.close()
     dist.barrier()
+
+# ---- maximal reads: classification and containment lists per shard, one NCCL exchange round
+# (states + lists), resolve on every rank == hg_maximal on one context
+arrays = ShardedArrays(syn.n_read, rank, world, dev, weights=syn.rlen)
+novl = syn.generate(arrays.lo, arrays.hi, want_trace=True, threads=4)
+cols = {k: v.copy() for k, v in syn.cols().items()}
+toff, tr = syn.trace()
+toff, tr = toff.copy(), tr.copy()
+ctx = api.Context(local, torch.cuda.current_stream().cuda_stream)
+ctx.set_reads(syn.rlen, syn.qv_off, syn.qv, 100)
+ctx.set_overlaps(novl, cols, trace_off=toff, trace=tr, a_lo=arrays.lo, a_hi=arrays.hi)
+masks = [want["mask"] if rank == 0 else None]
+dist.broadcast_object_list(masks, src=0)
+lp = api.LayoutParams()
+got_max = run_maximal_sharded(ctx, lp, arrays, masks[0])
+ctx.close()
+all_max = [None] * world
+dist.all_gather_object(all_max, got_max)
+if rank == 0:
+    novl_all = syn.generate(0, syn.n_read, want_trace=True, threads=8)
+    cols_all = {k: v.copy() for k, v in syn.cols().items()}
+    toff_all, tr_all = syn.trace()
+    ref = api.Context(local, torch.cuda.current_stream().cuda_stream)
+    ref.set_reads(syn.rlen, syn.qv_off, syn.qv, 100)
+    ref.set_overlaps(novl_all, cols_all, trace_off=toff_all, trace=tr_all)
+    want_max, _, _ = ref.maximal(lp, masks[0])
+    ref.close()
+    good = all(bool(np.array_equal(m, want_max)) for m in all_max)
+    print("SHARDED_CHECK maximal", "OK" if good else "MISMATCH", "world", world, "maximal reads", int(want_max.sum()),
+          "of", syn.n_read, flush=True)
+    ok &= good
+dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

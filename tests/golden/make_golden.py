@@ -11,7 +11,9 @@
 
 For every fixture `expected/` holds the reference's output files (small ones
 verbatim) and SHA256SUMS lists the digest of every output, large ones included.
-Only this container has /root/reference; the GPU box uses the committed files.
+Only this container has /root/reference; the GPU box uses the committed files.  dal_small cannot
+be re-run against the reference binaries on the GPU box at all: they load the bases (.D.bps),
+which are not committed -- re-derive it here (this script) instead.
 """
 import hashlib
 import json
@@ -30,7 +32,7 @@ INI = os.path.join(HERE, "nominal.ini")
 
 OUTPUTS = ["mas", "cmas", "coverage.txt", "repeat.txt", "hinges.txt", "cov.flag", "self.flag", "max",
            "contained.txt", "edges.hinges", "edges.hinges2", "hinge.list", "hgraph", "killed.hinges",
-           "edges.skipped", "edges.greedy", "deadends.txt", "garbage.txt"]
+           "edges.skipped", "edges.greedy", "edges.1", "edges.2", "deadends.txt", "garbage.txt"]
 KEEP_VERBATIM_BELOW = 200_000
 
 SYNTH_FIXTURES = {
@@ -40,6 +42,9 @@ SYNTH_FIXTURES = {
                    "--read-sd", "4000", "--read-min", "2000", "--families", "4", "--rep-max", "20000"],
     "synth_noqv": ["--genome", "300000", "--cov", "40", "--seed", "23", "--qv", "0", "--families", "2",
                    "--jitter", "0"],
+    # BASELINE configs[4] shape in small: long reads, most pairs reported as two or three local alignments
+    "synth_frag": ["--genome", "1500000", "--cov", "40", "--seed", "4321", "--read-mean", "24000",
+                   "--read-sd", "8000", "--read-min", "2000", "--frag", "1.2", "--families", "6"],
 }
 
 

@@ -21,8 +21,8 @@ LIB = os.path.join(ROOT, "hinge_b200", "_build", "libhinge_b200.so")
 FILTER_OUT = ["mas", "cmas", "coverage.txt", "repeat.txt", "hinges.txt", "cov.flag", "self.flag"]
 MAXIMAL_OUT = ["max", "contained.txt"]
 LAYOUT_OUT = ["edges.hinges", "edges.hinges2", "hinge.list", "hgraph", "killed.hinges", "edges.skipped",
-              "edges.greedy", "deadends.txt", "garbage.txt"]
-FIXTURES = ["dal_small", "synth_small", "synth_long", "synth_noqv"]
+              "edges.greedy", "edges.1", "edges.2", "deadends.txt", "garbage.txt"]
+FIXTURES = ["dal_small", "synth_small", "synth_long", "synth_noqv", "synth_frag"]
 
 
 def build_all():
@@ -133,3 +133,53 @@ def assert_matches_golden(name, workdir, prefix, exts):
             want = os.path.join(GOLDEN, name, "expected", "out." + ext)
             bad.append("%s: %s" % (ext, first_diff(g, want) if os.path.exists(want) else "sha256 mismatch"))
     assert not bad, "differs from the reference's golden output (%s):\n%s" % (name, "\n".join(bad))
+
+
+def split_las(path, base, nparts):
+    """LAsplit stand-in: cuts a .las into `nparts` files base.1.las ... at A-read boundaries, about the
+    same number of records each (thirdparty/DALIGNER/LAsplit.c:189-194 splits on A-reads too)."""
+    import struct
+
+    data = open(path, "rb").read()
+    novl, tspace = struct.unpack_from("<qi", data, 0)
+    tb = 1 if tspace <= 125 else 2
+    pos, starts, areads = 12, [], []
+    for _ in range(novl):
+        tlen, = struct.unpack_from("<i", data, pos)
+        aread, = struct.unpack_from("<i", data, pos + 28)
+        starts.append(pos)
+        areads.append(aread)
+        pos += 40 + tlen * tb
+    starts.append(pos)
+    cuts = [0]
+    for p in range(1, nparts):
+        k = max(cuts[-1] + 1, novl * p // nparts)
+        while k < novl and areads[k] == areads[k - 1]:
+            k += 1
+        cuts.append(min(k, novl))
+    cuts.append(novl)
+    names = []
+    for p in range(nparts):
+        lo, hi = cuts[p], cuts[p + 1]
+        assert hi > lo, "too many parts for this .las"
+        name = "%s.%d.las" % (base, p + 1)
+        with open(name, "wb") as f:
+            f.write(struct.pack("<qi", hi - lo, tspace))
+            f.write(data[starts[lo]:starts[hi]])
+        names.append(name)
+    return names
+
+
+def stage_cmd_mlas(kind, stage, root, base, prefix, out=None, ini=INI):
+    cmd = stage_cmd(kind, stage, root, prefix, out, ini)
+    i = cmd.index("--las")
+    cmd[i + 1] = base
+    return cmd + ["--mlas"]
+
+
+def run_stage_mlas(kind, stage, workdir, root, base, prefix, out=None, ini=INI, check=True):
+    r = subprocess.run(stage_cmd_mlas(kind, stage, root, base, prefix, out, ini), cwd=workdir, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    if check and r.returncode != 0:
+        raise AssertionError("%s %s --mlas failed (%d):\n%s" % (kind, stage, r.returncode, r.stdout[-4000:]))
+    return r

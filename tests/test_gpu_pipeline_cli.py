@@ -45,3 +45,17 @@ def test_stages_match_oracle_on_fresh_synthetic(built, tmp_path, args):
     for stage in ("filter", "maximal", "layout"):
         ht.run_stage("product", stage, work, "S", "gpu")
     ht.assert_same_files(work, "gpu", "ora", ALL)
+
+
+@pytest.mark.parametrize("name,nparts", [("synth_small", 3), ("synth_long", 4), ("dal_small", 2)])
+def test_mlas_pipeline_matches_oracle(built, tmp_path, name, nparts):
+    """`--mlas` (what every demo script of the reference passes, demo/ecoli_demo/run.sh:21-25): the .las
+    split at A-read boundaries; all three stages, all output files, against the oracle's restatement of
+    the reference's part loop (pinned to the reference binaries in tests/test_oracle_golden.py)."""
+    work = str(tmp_path)
+    root, _ = ht.materialize(name, work)
+    ht.split_las(os.path.join(work, root + ".las"), os.path.join(work, "P"), nparts)
+    for stage in ("filter", "maximal", "layout"):
+        ht.run_stage_mlas("oracle", stage, work, root, "P", "ora")
+        ht.run_stage_mlas("product", stage, work, root, "P", "gpu")
+    ht.assert_same_files(work, "gpu", "ora", ALL)

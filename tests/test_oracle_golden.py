@@ -69,3 +69,26 @@ def test_oracle_equals_reference_on_edge_cases(built, tmp_path):
             ec.test_ini_variants(True, pathlib.Path(d), ov)
     finally:
         ec._run_all = saved
+
+
+@pytest.mark.skipif(not ht.have_reference(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("name,nparts", [("synth_small", 3), ("synth_long", 2)])
+def test_oracle_equals_reference_with_mlas(built, tmp_path, name, nparts):
+    """--mlas: the .las split at A-read boundaries (LAsplit).  The reference loops over the parts and
+    carries MIN_COV and the masks from part to part, closes .repeat.txt after part 0 and drops the last
+    read of every part from .hinges.txt (filter.cpp:474-1109), so its results differ from a single-file
+    run; the oracle restates exactly that (FilterCarry) and must write the same bytes."""
+    import json
+
+    work = str(tmp_path)
+    meta = json.load(open(os.path.join(ht.GOLDEN, name, "fixture.json")))
+    root = meta["root"]
+    ht.synth(work, meta["synth_args"], root)  # with the bases: the reference loads them
+    ht.split_las(os.path.join(work, root + ".las"), os.path.join(work, "P"), nparts)
+    for stage in ("filter", "maximal", "layout"):
+        ht.run_stage_mlas("reference", stage, work, root, "P", "ref", out="ref")
+        ht.run_stage_mlas("oracle", stage, work, root, "P", "ora")
+    ht.assert_same_files(work, "ora", "ref", ALL)
+    # and the multi-part run really is a different computation
+    ht.run_stage("oracle", "filter", work, root, "one")
+    assert ht.sha256(os.path.join(work, "one.hinges.txt")) != ht.sha256(os.path.join(work, "ora.hinges.txt"))
