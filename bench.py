@@ -467,7 +467,14 @@ class Bench:
             # (rlen + 300) / 40 + 3 bins per read) and 9 B per read; K2 (mask + annotation) reads the
             # profiles back plus ~60 B per read of inputs and results.
             bins = float(((rlen[a_lo:a_hi].astype(np.int64) + params.cut_off) // 40 + 3).sum())
-            kbytes = {"profile": 12.0 * novl + 4.0 * bins + 39.0 * owned, "mask_anno": 4.0 * bins + 60.0 * owned}
+            # K4 (hinge calls): per annotation of an annotated read one pass over a 4-byte position column
+            # of its pile-up (the selection's first step), 48 B of work item per read; the second step
+            # (24 B + two gathers per record near the annotation) touches a few per cent of that
+            n_anno = np.diff(result["anno_off"][a_lo:a_hi + 1])
+            pile = np.bincount(cols_np["aread"] - a_lo, minlength=owned)[:owned]
+            k4 = float((n_anno * pile).sum()) * 4.0 + 48.0 * float((n_anno > 0).sum())
+            kbytes = {"profile": 12.0 * novl + 4.0 * bins + 39.0 * owned, "mask_anno": 4.0 * bins + 60.0 * owned,
+                      "hinge_call": k4}
             dom = max(kbytes, key=lambda k: kavg[k])
             achieved = kbytes[dom] / (kavg[dom] * 1e-3) / 1e9
             traffic = None
@@ -488,7 +495,10 @@ class Bench:
                            "generate_s": round(t_gen, 2)},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": self.peak, "unit": "GB/s",
                              "frac": achieved / self.peak, "traffic": traffic, "peak_source": self.peak_src,
-                             "algorithmic_bytes_per_launch": kbytes[dom], "kernel_ms": kavg[dom]},
+                             "algorithmic_bytes_per_launch": kbytes[dom], "kernel_ms": kavg[dom],
+                             "all_kernels": {k: {"ms": kavg[k], "algorithmic_bytes": kbytes[k],
+                                                 "frac": kbytes[k] / (kavg[k] * 1e-3) / 1e9 / self.peak}
+                                             for k in kbytes}},
                 "kernel_ms": kavg,
                 "filter_scan": {"bytes_per_overlap": 32, "gbs": 32.0 * novl / (ms_step * 1e-3) / 1e9,
                                 "frac_of_peak": 32.0 * novl / (ms_step * 1e-3) / 1e9 / self.peak},

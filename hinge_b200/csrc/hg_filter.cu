@@ -894,8 +894,8 @@ constexpr int kHingeExactBytesPerRec = 16 + 8 + 8 + 8 + 8;
 __global__ void __launch_bounds__(128)
 k_hinge_exact(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
               const int2* __restrict__ anno_ref, const int2* __restrict__ anno_pool,
-              int* __restrict__ counters, const int* __restrict__ exact_list,
-              uint8_t* __restrict__ hinge_keep, uint8_t* gscratch, int gcap, int scap, int np_above) {
+              int* __restrict__ counters, int queue_slot, const int* __restrict__ exact_list,
+              uint8_t* __restrict__ hinge_keep, uint8_t* gscratch, int gcap, int scap, int np_above, int np_upto) {
     extern __shared__ __align__(16) uint8_t sm_exact[];
     __shared__ CtaSortState sort_state;
     __shared__ int sh_w, sh_n;
@@ -904,7 +904,7 @@ k_hinge_exact(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
     const int nlist = counters[6];
     const int THETA = P.theta, HTL = P.hinge_tolerance_length;
     for (;;) {
-        if (threadIdx.x == 0) sh_w = atomicAdd(&counters[7], 1);
+        if (threadIdx.x == 0) sh_w = atomicAdd(&counters[queue_slot], 1);
         __syncthreads();
         const int w = sh_w;
         __syncthreads();
@@ -912,7 +912,7 @@ k_hinge_exact(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
         const int read = exact_list[w];
         const int64_t o0 = rv.read_off[read], o1 = rv.read_off[read + 1];
         const int np = (int)(o1 - o0);
-        if (np <= np_above) continue;  // shallow pile-ups: k_hinge_exact_warp (uniform over the CTA)
+        if (np <= np_above || np > np_upto) continue;  // another size tier's read (uniform over the CTA)
         const bool in_smem = np <= scap;
         const int cap = in_smem ? scap : gcap;
         uint8_t* base = in_smem ? sm_exact : gscratch + (size_t)blockIdx.x * gcap * kHingeSlotBytesPerRec;
@@ -1216,23 +1216,38 @@ void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_pa
     k_hinge_call<<<s.hinge_warps / 4, 128, 0, st>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool,
                                                     s.counters, s.work_items, s.exact_list, s.hinge_keep,
                                                     s.hinge_scratch, s.hinge_cap, s.item_log, peer);
-    // the few reads that need the exact sort order: shared-memory scratch, one warp each
-    constexpr int scap = 1536;
-    const int smem = scap * kHingeExactBytesPerRec;
-    // function attributes are per device: set it on every launch (cheap), not once per process
-    cudaFuncSetAttribute(k_hinge_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    // shallow pile-ups (almost all of them): one warp per read out of shared memory, two size tiers
-    constexpr int capA = 256, capB = 768;
-    const int smemA = 4 * capA * kHingeExactBytesPerRec, smemB = 4 * capB * kHingeExactBytesPerRec;
-    cudaFuncSetAttribute(k_hinge_exact_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, smemB);
-    g_launches += 2;
+    // The reads that need the exact sort order, in three size tiers that run side by side on forked
+    // streams (they work on different reads of one list; each has its own queue cursor):
+    //   A  pile-ups of at most 256 records: one WARP per read, 12 KB of shared memory each
+    //   B  257 .. 768 records: one CTA per read, 36 KB (six CTAs per SM)
+    //   C  deeper: one CTA per read, 72 KB, global scratch beyond 1536 records
+    constexpr int capA = 256, capB = 768, capC = 1536;
+    const int smemA = 4 * capA * kHingeExactBytesPerRec, smemB = capB * kHingeExactBytesPerRec;
+    const int smemC = capC * kHingeExactBytesPerRec;
+    // function attributes are per device: set them on every launch (cheap), not once per process
+    cudaFuncSetAttribute(k_hinge_exact_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, smemA);
+    cudaFuncSetAttribute(k_hinge_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, smemC);
+    g_launches += 3;
+    cudaStream_t sB = s.side_stream[0] ? s.side_stream[0] : st, sC = s.side_stream[1] ? s.side_stream[1] : st;
+    if (sB != st) {
+        cudaEventRecord(s.side_event[0], st);
+        cudaStreamWaitEvent(sB, s.side_event[0], 0);
+        cudaStreamWaitEvent(sC, s.side_event[0], 0);
+    }
     k_hinge_exact_warp<<<4 * s.num_sms, 128, smemA, st>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 12,
                                                          s.exact_list, s.hinge_keep, 0, capA);
-    k_hinge_exact_warp<<<s.num_sms, 128, smemB, st>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 13,
-                                                     s.exact_list, s.hinge_keep, capA, capB);
-    const int grid = s.hinge_warps < 2 * s.num_sms ? s.hinge_warps : 2 * s.num_sms;
-    k_hinge_exact<<<grid, 128, smem, st>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters,
-                                          s.exact_list, s.hinge_keep, s.hinge_scratch, s.hinge_cap, scap, capB);
+    k_hinge_exact<<<6 * s.num_sms, 128, smemB, sB>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 13,
+                                                    s.exact_list, s.hinge_keep, s.hinge_scratch, s.hinge_cap, capB,
+                                                    capA, capB);
+    const int gridC = s.hinge_warps < 2 * s.num_sms ? s.hinge_warps : 2 * s.num_sms;
+    k_hinge_exact<<<gridC, 128, smemC, sC>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 7, s.exact_list,
+                                            s.hinge_keep, s.hinge_scratch, s.hinge_cap, capC, capB, 0x7fffffff);
+    if (sB != st) {
+        cudaEventRecord(s.side_event[1], sB);
+        cudaEventRecord(s.side_event[2], sC);
+        cudaStreamWaitEvent(st, s.side_event[1], 0);
+        cudaStreamWaitEvent(st, s.side_event[2], 0);
+    }
 }
 
 }  // namespace hg

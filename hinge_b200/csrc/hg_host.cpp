@@ -5,8 +5,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
 #include <sys/stat.h>
 #include <time.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <string>
@@ -353,7 +355,15 @@ extern "C" int hg_main_filter(int argc, char** argv) {
             int64_t hinges = 0;
             if (want_cov) {
                 // .coverage.txt (filter.cpp:599-602) is ~11 bytes per 40-bp bin of every read, by far the
-                // largest output: formatted by all cores, a block of reads at a time, written in order
+                // largest output: all cores format a block of reads at a time and write their pieces
+                // straight to their places in the file (pwrite), no single-threaded copy in between
+                fcov.close();
+                const int fd = ::open((x + ".coverage.txt").c_str(), O_WRONLY | O_CREAT | (app ? 0 : O_TRUNC), 0644);
+                if (fd < 0) {
+                    fprintf(stderr, "hinge_b200: cannot write %s.coverage.txt\n", x.c_str());
+                    out_failed = true;
+                }
+                off_t file_pos = fd >= 0 ? lseek(fd, 0, SEEK_END) : 0;
                 int workers = (int)std::thread::hardware_concurrency();
                 if (const char* v = getenv("HINGE_B200_IO_THREADS")) workers = atoi(v);
                 workers = std::max(1, std::min(workers, 32));
@@ -370,7 +380,7 @@ extern "C" int hg_main_filter(int argc, char** argv) {
                     if (v < 0) b.push_back('-');
                     while (n) b.push_back(tmp[--n]);
                 };
-                for (int b0 = sum.r_begin; b0 <= sum.r_end; b0 += block) {
+                for (int b0 = sum.r_begin; b0 <= sum.r_end && fd >= 0; b0 += block) {
                     const int b1 = std::min(sum.r_end + 1, b0 + block);
                     std::vector<std::thread> pool;
                     for (int w = 0; w < workers; w++)
@@ -393,8 +403,22 @@ extern "C" int hg_main_filter(int argc, char** argv) {
                             }
                         });
                     for (auto& th : pool) th.join();
-                    for (int w = 0; w < workers; w++) fcov.put_bytes(bufs[w].data(), bufs[w].size());
+                    pool.clear();
+                    std::vector<off_t> at((size_t)workers + 1, file_pos);
+                    for (int w = 0; w < workers; w++) at[w + 1] = at[w] + (off_t)bufs[w].size();
+                    for (int w = 0; w < workers; w++)
+                        pool.emplace_back([&, w]() {
+                            size_t done = 0;
+                            while (done < bufs[w].size()) {
+                                const ssize_t r = pwrite(fd, bufs[w].data() + done, bufs[w].size() - done, at[w] + (off_t)done);
+                                if (r <= 0) break;
+                                done += (size_t)r;
+                            }
+                        });
+                    for (auto& th : pool) th.join();
+                    file_pos = at[workers];
                 }
+                if (fd >= 0) ::close(fd);
             }
             for (int i = sum.r_begin; i <= sum.r_end; i++) {
                 fcmask.put_int(i); fcmask.put_char(' '); fcmask.put_int(cmask[2 * i]); fcmask.put_char(' ');
