@@ -349,7 +349,8 @@ extern "C" int hg_main_filter(int argc, char** argv) {
                 touch(x + ".filtered.fasta");
                 touch("debug.txt");
             }
-            TextOut fcov(x + ".coverage.txt", app), fmask(x + ".mas", app), fcmask(x + ".cmas", app);
+            TextOut fmask(x + ".mas", app), fcmask(x + ".cmas", app);
+            if (!want_cov && !app) touch(x + ".coverage.txt");
             TextOut fhg(x + ".hinges.txt", app), fcf(x + ".cov.flag", app), fsf(x + ".self.flag", app);
             TextOut frep(app ? std::string("/dev/null") : x + ".repeat.txt");  // closed after part 0 (filter.cpp:1086)
             int64_t hinges = 0;
@@ -357,7 +358,6 @@ extern "C" int hg_main_filter(int argc, char** argv) {
                 // .coverage.txt (filter.cpp:599-602) is ~11 bytes per 40-bp bin of every read, by far the
                 // largest output: all cores format a block of reads at a time and write their pieces
                 // straight to their places in the file (pwrite), no single-threaded copy in between
-                fcov.close();
                 const int fd = ::open((x + ".coverage.txt").c_str(), O_WRONLY | O_CREAT | (app ? 0 : O_TRUNC), 0644);
                 if (fd < 0) {
                     fprintf(stderr, "hinge_b200: cannot write %s.coverage.txt\n", x.c_str());
@@ -444,7 +444,7 @@ extern "C" int hg_main_filter(int argc, char** argv) {
                     fhg.put_char('\n');
                 }
             }
-            out_failed = out_failed || !fcov.ok() || !fmask.ok() || !fcmask.ok() || !fhg.ok() || !fcf.ok() || !fsf.ok() ||
+            out_failed = out_failed || !fmask.ok() || !fcmask.ok() || !fhg.ok() || !fcf.ok() || !fsf.ok() ||
                          !frep.ok();
             all_hinges += hinges;
             say("Number of hinges before filtering: %s", std::to_string(sum.n_annotations));

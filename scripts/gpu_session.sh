@@ -87,6 +87,12 @@ for f in ('$OUT/${TAG}_bench_n2.json','$OUT/${TAG}_bench_n2_nccl.json'):
           -o $OUT/${TAG}_k_profile_flat2_$CFG python bench.py --config $CFG --also "" $SHORT > $OUT/${TAG}_ncu_k1_$CFG.log 2>&1
         echo "ncu k_profile_flat2 $CFG exit $?"
       done ;;
+    ncu_k4)
+      for K in k_hinge_exact_warp k_hinge_call; do
+        timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^$K" -s 4 -c 1 -f \
+          -o $OUT/${TAG}_${K}_c5 python bench.py --config c5 --also "" $SHORT > $OUT/${TAG}_ncu_${K}.log 2>&1
+        echo "ncu $K exit $?"
+      done ;;
     ncu_all)
       for K in k_mask_anno_flat k_hinge_call k_hinge_exact; do
         timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^$K" -s 4 -c 1 -f \
