@@ -43,6 +43,10 @@ class FilterSummaryC(C.Structure):
                 ("n_exact_order", i32)]
 
 
+class GraphRecC(C.Structure):
+    _fields_ = [("owner", i32), ("seq", i32), ("f", i32 * 4), ("flag", i32), ("rev", i32), ("u", i32), ("v", i32)]
+
+
 class EdgeC(C.Structure):
     _fields_ = [(n, i32) for n in ("a", "b", "length", "comp", "type", "weight")] + \
                [(n, i32 * 2) for n in ("eff_a", "eff_b", "read_a", "read_b", "raw_a", "raw_b")] + \
@@ -78,6 +82,10 @@ PROTOTYPES = {
     "hg_maximal_phase2": (C.c_int, [vp, vp, vp, i32p, i32, i64, vp, i64, vp]),
     "hg_layout": (C.c_int, [vp, C.POINTER(LayoutParamsC)] + [vp] * 8 + [f32p]),
     "hg_layout_edges": (C.c_int, [vp, C.POINTER(EdgeC), i64, i64p]),
+    "hg_layout_phase1": (C.c_int, [vp, C.POINTER(LayoutParamsC)] + [vp] * 8 + [vp]),
+    "hg_layout_phase2": (C.c_int, [vp, vp, vp, i64p]),
+    "hg_layout_graph": (C.c_int, [vp, vp, i64]),
+    "hg_layout_phase3": (C.c_int, [vp, vp, vp, i64, f32p]),
     "hg_main_filter": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "hg_main_maximal": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "hg_main_layout": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),

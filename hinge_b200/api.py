@@ -6,7 +6,7 @@ import sys
 
 import numpy as np
 
-from ._lib import (EdgeC, FilterParamsC, FilterSummaryC, HingeError, LayoutParamsC, lib)
+from ._lib import (EdgeC, FilterParamsC, FilterSummaryC, GraphRecC, HingeError, LayoutParamsC, lib)
 
 HG_MEM_HOST, HG_MEM_DEVICE = 0, 1
 HG_OPT_KEEP_COVERAGE, HG_OPT_PROFILE, HG_OPT_SCATTER_SPREAD, HG_OPT_PROFILE_KERNEL, HG_OPT_KEEP_MASKS = 1, 2, 3, 4, 5
@@ -207,6 +207,49 @@ class Context:
         edges = (EdgeC * max(n.value, 1))()
         self._check(lib.hg_layout_edges(self._h, edges, n.value, C.byref(n)), "hg_layout_edges")
         return list(edges)[:n.value], ms.value
+
+
+def _layout_args(mask, maximal, rep, hin):
+    args = [np.ascontiguousarray(mask, np.int32), np.ascontiguousarray(maximal, np.uint8)]
+    for off, pos, typ in (rep, hin):
+        # pointers must be valid even for empty lists
+        args += [np.ascontiguousarray(off, np.int64), np.ascontiguousarray(np.append(pos, 0), np.int32),
+                 np.ascontiguousarray(np.append(typ, 0), np.int32)]
+    return args
+
+
+def layout_phase1(ctx, params, mask, maximal, rep, hin):
+    """Sharded hg_layout, phase 1.  Returns the "[contained]" flags of the context's own reads (uint8[n_read])."""
+    args = _layout_args(mask, maximal, rep, hin)
+    contained = np.zeros(ctx.n_read, np.uint8)
+    ctx._check(lib.hg_layout_phase1(ctx._h, C.byref(params), *[_ptr(a) for a in args], _ptr(contained)), "hg_layout_phase1")
+    ctx._layout_keep = args
+    return contained
+
+
+def layout_phase2(ctx, contained_all, n_hinges):
+    """Returns (alive flags of all hinges after this rank's kill pass, this rank's hinge-graph records as a
+    structured numpy array)."""
+    alive = np.ones(max(n_hinges, 1), np.uint8)
+    n = C.c_int64()
+    ctx._check(lib.hg_layout_phase2(ctx._h, _ptr(np.ascontiguousarray(contained_all, np.uint8)), _ptr(alive), C.byref(n)),
+               "hg_layout_phase2")
+    graph = np.zeros((max(n.value, 1), 10), np.int32)
+    ctx._check(lib.hg_layout_graph(ctx._h, _ptr(graph), n.value), "hg_layout_graph")
+    return alive[:n_hinges], graph[:n.value]
+
+
+def layout_phase3(ctx, alive_all, graph_all):
+    ms = C.c_float()
+    alive_all = np.ascontiguousarray(np.append(alive_all, 1), np.uint8)
+    graph_all = np.ascontiguousarray(graph_all, np.int32).reshape(-1, 10)
+    g = np.ascontiguousarray(np.vstack([graph_all, np.zeros((1, 10), np.int32)]))
+    ctx._check(lib.hg_layout_phase3(ctx._h, _ptr(alive_all), _ptr(g), len(graph_all), C.byref(ms)), "hg_layout_phase3")
+    n = C.c_int64()
+    ctx._check(lib.hg_layout_edges(ctx._h, None, 0, C.byref(n)), "hg_layout_edges")
+    edges = (EdgeC * max(n.value, 1))()
+    ctx._check(lib.hg_layout_edges(ctx._h, edges, n.value, C.byref(n)), "hg_layout_edges")
+    return list(edges)[:n.value], ms.value
 
 
 def launch_count():

@@ -87,8 +87,8 @@ int hg_ctx_create(int device, void* stream, hg_ctx** out) {
     c->fs.num_sms = c->num_sms;
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
-    for (int i = 0; i < 2; i++) cudaStreamCreateWithFlags(&c->fs.side_stream[i], cudaStreamNonBlocking);
-    for (int i = 0; i < 3; i++) cudaEventCreateWithFlags(&c->fs.side_event[i], cudaEventDisableTiming);
+    for (int i = 0; i < 3; i++) cudaStreamCreateWithFlags(&c->fs.side_stream[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&c->fs.side_event[i], cudaEventDisableTiming);
     int rc = dev_alloc(c, &c->d_err, 4, "err flag");
     if (rc == HG_OK) rc = dev_alloc(c, &c->fs.scal, 8, "scalars");
     if (rc == HG_OK) rc = dev_alloc(c, &c->fs.counters, 16, "counters");
@@ -142,10 +142,11 @@ void hg_ctx_destroy(hg_ctx* c) {
     cudaFree(c->ms.counters); cudaFree(c->ms.big_pairs); cudaFree(c->ms.sort_scratch);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    for (int i = 0; i < 2; i++)
-        if (c->fs.side_stream[i]) cudaStreamDestroy(c->fs.side_stream[i]);
     for (int i = 0; i < 3; i++)
+        if (c->fs.side_stream[i]) cudaStreamDestroy(c->fs.side_stream[i]);
+    for (int i = 0; i < 4; i++)
         if (c->fs.side_event[i]) cudaEventDestroy(c->fs.side_event[i]);
+    free_layout_run(c->layout_run);
     free_layout_result(c->layout);
     delete c;
 }

@@ -307,18 +307,51 @@ static void hash_growth_schedule(int max_elements, std::vector<int>* at, std::ve
     }
 }
 
-int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const uint8_t* maximal,
-              const int64_t* rep_off, const int32_t* rep_pos, const int32_t* rep_type,
-              const int64_t* hin_off, const int32_t* hin_pos, const int32_t* hin_type,
-              float* ms_device) {
-    if (!c || !P || !mask || !maximal || !rep_off || !hin_off || c->novl <= 0)
-        return set_err(c, HG_ERR_ARG, "hg_layout: bad arguments");
-    if (!c->has_trace) return set_err(c, HG_ERR_ARG, "hg_layout needs the trace (pass trace_off/trace to hg_set_overlaps)");
-    if (c->a_lo != 0 || c->a_hi != c->n_read)
-        return set_err(c, HG_ERR_ARG, "hg_layout runs on a context that owns all reads (gather the shards' results first)");
-    cudaSetDevice(c->device);
+}  // extern "C"
+
+namespace hg {
+
+// One run of the layout stage: the device buffers that live from the pair pass to the best-extension
+// pass.  A context that owns all reads runs the three phases back to back (hg_layout); a sharded run
+// exchanges two small per-read / per-hinge arrays and the hinge-graph records between them
+// (hg_layout_phase1..3).
+struct LayoutRun {
+    hg_ctx* c = nullptr;
+    hg_layout_params P;
+    int n = 0;
+    int64_t nh = 0;
+    DevBuf<uint8_t> d_active, d_contained, d_alive;
+    DevBuf<int2> d_pair_ref, d_cand_ref, d_chosen, d_pairs;
+    DevBuf<int> d_bkt_ref, d_cnt, d_grow, d_hpos, d_htype, d_kpos, d_ktype, d_npos, d_ntype, d_hnext, d_hout, d_hbkt;
+    DevBuf<int64_t> d_hoff, d_koff, d_noff;
+    DevBuf<unsigned long long> d_total;
+    DevBuf<KeyIdx2> d_sort, d_bigsort;
+    SelectIO io;
+    LayoutLists L;
+    std::vector<uint8_t> active0;   // before the "[contained]" fix-up
+    std::vector<GraphRec> graph;    // this context's records (phase 2)
+    std::vector<NkRec> nks;
+    int ngrow = 0;
+
+    int h2d(void* d, const void* h, size_t bytes) {
+        return bytes ? cuda_check(c, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream), "H2D") : HG_OK;
+    }
+    int phase1(const hg_layout_params* params, const int32_t* mask, const uint8_t* maximal, const int64_t* rep_off,
+               const int32_t* rep_pos, const int32_t* rep_type, const int64_t* hin_off, const int32_t* hin_pos,
+               const int32_t* hin_type, uint8_t* contained_out);
+    int phase2(const uint8_t* contained_all, uint8_t* alive_out);
+    int phase3(const uint8_t* alive_all, const GraphRec* graph_all, int64_t n_graph_all);
+};
+
+void free_layout_run(LayoutRun* r) { delete r; }
+
+int LayoutRun::phase1(const hg_layout_params* params, const int32_t* mask, const uint8_t* maximal,
+                      const int64_t* rep_off, const int32_t* rep_pos, const int32_t* rep_type,
+                      const int64_t* hin_off, const int32_t* hin_pos, const int32_t* hin_type,
+                      uint8_t* contained_out) {
+    P = *params;
     cudaStream_t st = c->stream;
-    const int n = c->n_read;
+    n = c->n_read;
     free_layout_result(c->layout);
     c->layout = new LayoutResult();
     LayoutResult& R = *c->layout;
@@ -329,13 +362,14 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
     // ---- who takes part (hinging.cpp:877-913, 954-960, 398-412)
     R.active.assign(n, 1);
     for (int i = 0; i < n; i++) {
-        if (P->delete_telomeres && rep_off[i + 1] - rep_off[i] > P->num_events_telomere) R.active[i] = 0;
-        if (mask[2 * i + 1] - mask[2 * i] < P->length_threshold) {
+        if (P.delete_telomeres && rep_off[i + 1] - rep_off[i] > P.num_events_telomere) R.active[i] = 0;
+        if (mask[2 * i + 1] - mask[2 * i] < P.length_threshold) {
             R.active[i] = 0;
             R.garbage.push_back(i);
         }
         R.active[i] = R.active[i] && maximal[i];
     }
+    active0 = R.active;
     // ---- hinges, killed hinges = annotations that are not hinges (hinging.cpp:1180-1197)
     R.hin_off.assign(hin_off, hin_off + n + 1);
     R.hin_pos.assign(hin_pos, hin_pos + hin_off[n]);
@@ -355,17 +389,14 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
         }
         R.kil_off[i + 1] = (int64_t)R.kil_pos.size();
     }
-    const int64_t nh = hin_off[n], nkil = R.kil_off[n];
+    nh = hin_off[n];
+    const int64_t nkil = R.kil_off[n];
     std::vector<int> grow_at, grow_bkt;
     hash_growth_schedule(std::max(c->max_pileup, 16) + 2, &grow_at, &grow_bkt);
+    ngrow = (int)grow_at.size();
     tm.lap("layout: active flags, killed-hinge lists (host)");
 
     HG_TRY(upload_mask(c, mask));
-    DevBuf<uint8_t> d_active, d_contained, d_alive;
-    DevBuf<int2> d_pair_ref, d_cand_ref, d_chosen;
-    DevBuf<int> d_bkt_ref, d_cnt, d_grow, d_hpos, d_htype, d_kpos, d_ktype, d_npos, d_ntype;
-    DevBuf<int64_t> d_hoff, d_koff, d_noff;
-    DevBuf<unsigned long long> d_total;
     HG_TRY(d_active.alloc(c, n, "active")); HG_TRY(d_contained.alloc(c, n, "contained flags"));
     HG_TRY(d_pair_ref.alloc(c, n, "pair refs")); HG_TRY(d_cand_ref.alloc(c, n, "candidate refs"));
     HG_TRY(d_bkt_ref.alloc(c, n, "bucket refs")); HG_TRY(d_cnt.alloc(c, 16, "counters"));
@@ -374,9 +405,6 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
     HG_TRY(d_koff.alloc(c, n + 1, "killed off")); HG_TRY(d_kpos.alloc(c, nkil, "killed pos")); HG_TRY(d_ktype.alloc(c, nkil, "killed type"));
     HG_TRY(d_noff.alloc(c, n + 1, "nk off")); HG_TRY(d_alive.alloc(c, nh, "hinge alive"));
     HG_TRY(d_chosen.alloc(c, 2 * (size_t)n, "chosen"));
-    auto h2d = [&](void* d, const void* h, size_t bytes) {
-        return bytes ? cuda_check(c, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st), "H2D") : HG_OK;
-    };
     HG_TRY(h2d(d_active.p, R.active.data(), n));
     HG_TRY(h2d(d_grow.p, grow_at.data(), 4 * grow_at.size()));
     HG_TRY(h2d(d_grow.p + grow_at.size(), grow_bkt.data(), 4 * grow_bkt.size()));
@@ -387,6 +415,8 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
     HG_TRY(h2d(d_kpos.p, R.kil_pos.data(), 4 * (size_t)nkil));
     HG_TRY(h2d(d_ktype.p, R.kil_type.data(), 4 * (size_t)nkil));
     cudaMemsetAsync(d_contained.p, 0, n, st);
+    cudaMemsetAsync(d_pair_ref.p, 0, sizeof(int2) * (size_t)n, st);  // reads of other shards: no pairs here
+    cudaMemsetAsync(d_cand_ref.p, 0, sizeof(int2) * (size_t)n, st);
     tm.lap("layout: uploads");
 
     // ---- K5: pairs between maximal reads, their top two classified, candidates in the reference's order
@@ -399,9 +429,6 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
     const size_t np_total = std::max<size_t>((size_t)total_pairs, 1), nc_slots = 2 * np_total;
     // bucket scratch: the count after the last insertion is below 2 n + 13 per read
     const size_t nbkt = 2 * np_total + 16 * (size_t)n + 64;
-    DevBuf<int2> d_pairs;
-    DevBuf<int> d_hnext, d_hout, d_hbkt;
-    DevBuf<KeyIdx2> d_sort, d_bigsort;
     HG_TRY(d_pairs.alloc(c, np_total, "pairs")); HG_TRY(d_hnext.alloc(c, np_total, "hash next"));
     HG_TRY(d_hout.alloc(c, np_total, "hash order")); HG_TRY(d_hbkt.alloc(c, nbkt, "hash buckets"));
     HG_TRY(d_sort.alloc(c, nc_slots, "sort scratch"));
@@ -416,7 +443,6 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
     R.d_ranges = d_ranges;
     R.n_cand_slots = (int64_t)nc_slots;
 
-    SelectIO io;
     io.n_read = n; io.active = d_active.p; io.cands = d_cands; io.ranges = d_ranges; io.ranges_out = d_ranges;
     io.order = d_order; io.sort_scratch = d_sort.p;
     io.hv.off = d_hoff.p; io.hv.pos = d_hpos.p; io.hv.type = d_htype.p;
@@ -428,38 +454,42 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
     int big_sort_cap = 1 << 16;
     for (int attempt = 0;; attempt++) {
         HG_TRY(d_bigsort.alloc(c, big_sort_cap, "pair sort scratch"));
-        LayoutLists L;
         L.pair_ref = d_pair_ref.p; L.cand_ref = d_cand_ref.p; L.bkt_ref = d_bkt_ref.p; L.pairs = d_pairs.p;
         L.cands = d_cands; L.hash_next = d_hnext.p; L.hash_out = d_hout.p; L.hash_bkt = d_hbkt.p;
         L.contained_flag = d_contained.p; L.counters = d_cnt.p; L.sort_scratch = d_bigsort.p; L.sort_cap = big_sort_cap;
-        L.grow_at = d_grow.p; L.grow_bkt = d_grow.p + grow_at.size(); L.ngrow = (int)grow_at.size();
-        launch_layout_pairs(c->rec_view(), c->read_view(), *P, c->fs.mask, d_active.p, L, st);
-        // "[contained] Should not happen" (hinging.cpp:598-601): such reads leave the layout
-        launch_apply_contained(n, d_contained.p, d_active.p, d_cnt.p + 7, st);
-        launch_order_candidates(L, io, st);
+        L.grow_at = d_grow.p; L.grow_bkt = d_grow.p + ngrow; L.ngrow = ngrow;
+        launch_layout_pairs(c->rec_view(), c->read_view(), P, c->fs.mask, d_active.p, L, st);
         int cnt[8];
         HG_TRY(cuda_check(c, cudaGetLastError(), "layout pairs"));
         HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, d_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
+        if (contained_out) HG_TRY(cuda_check(c, cudaMemcpyAsync(contained_out, d_contained.p, n, cudaMemcpyDeviceToHost, st), "D2H"));
         HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "layout pairs"));
         if (cnt[2] > (long long)nbkt) return set_err(c, HG_ERR_NOMEM, "hg_layout: hash bucket scratch too small");
-        if (!cnt[3]) {
-            R.n_contained = cnt[7];
-            break;
-        }
+        if (!cnt[3]) break;
         if (attempt > 6) return set_err(c, HG_ERR_NOMEM, "pair sort scratch kept overflowing");
         big_sort_cap = std::max(big_sort_cap * 4, cnt[4] + 1024);
         // the contained flags are sticky and the pair counts were overwritten: restore and run again
-        HG_TRY(h2d(d_active.p, R.active.data(), n));
         cudaMemsetAsync(d_contained.p, 0, n, st);
+        cudaMemsetAsync(d_pair_ref.p, 0, sizeof(int2) * (size_t)n, st);
         launch_layout_count_pairs(c->rec_view(), c->read_view(), d_active.p, d_pair_ref.p, d_total.p, st);
     }
-    for (int i = 0; i < R.n_contained; i++) printf("[contained] Should not happen\n");
-    tm.lap("layout: pairs, candidates, order (device)");
+    tm.lap("layout: pairs + candidates (device)");
+    return HG_OK;
+}
+
+// contained_all: the "[contained]" flags of ALL reads (null: this context's own are all there is)
+int LayoutRun::phase2(const uint8_t* contained_all, uint8_t* alive_out) {
+    cudaStream_t st = c->stream;
+    LayoutResult& R = *c->layout;
+    StepTimer tm(st);
+    if (contained_all) HG_TRY(h2d(d_contained.p, contained_all, n));
+    // "[contained] Should not happen" (hinging.cpp:598-601): such reads leave the layout
+    launch_apply_contained(n, d_contained.p, d_active.p, d_cnt.p + 7, st);
+    launch_order_candidates(L, io, st);
+    HG_TRY(cuda_check(c, cudaMemcpyAsync(&R.n_contained, d_cnt.p + 7, 4, cudaMemcpyDeviceToHost, st), "D2H"));
 
     // ---- K6: kill pass + hinge graph; list sizes are data dependent: grow and rerun on overflow
     int graph_cap = 1 << 16, nk_cap = 1 << 14;
-    std::vector<GraphRec> graph;
-    std::vector<NkRec> nks;
     for (int attempt = 0;; attempt++) {
         DevBuf<GraphRec> d_graph;
         DevBuf<NkRec> d_nk;
@@ -468,7 +498,7 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
         io.graph = d_graph.p; io.graph_cap = graph_cap; io.nkout = d_nk.p; io.nk_cap = nk_cap;
         io.skips = nullptr; io.skip_cap = 0;
         cudaMemsetAsync(d_alive.p, 1, std::max<size_t>((size_t)nh, 1), st);
-        launch_hinge_graph(c->rec_view(), *P, io, st);
+        launch_hinge_graph(c->rec_view(), P, io, st);
         int cnt[8];
         HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, io.counters, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
         HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "hinge graph"));
@@ -485,18 +515,30 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
         HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "D2H"));
         break;
     }
-    tm.lap("layout: kill pass + hinge graph + D2H");
+    for (int i = 0; i < R.n_contained; i++) printf("[contained] Should not happen\n");
+    R.hin_alive.assign((size_t)std::max<int64_t>(nh, 1), 1);
+    if (nh) HG_TRY(cuda_check(c, cudaMemcpyAsync(R.hin_alive.data(), d_alive.p, (size_t)nh, cudaMemcpyDeviceToHost, st), "D2H"));
+    HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "D2H"));
+    if (alive_out && nh) memcpy(alive_out, R.hin_alive.data(), (size_t)nh);
+    tm.lap("layout: order + kill pass + hinge graph + D2H");
+    return HG_OK;
+}
+
+// alive_all / graph_all: the kill-pass result and the hinge-graph records of ALL ranks (null: this
+// context's own)
+int LayoutRun::phase3(const uint8_t* alive_all, const GraphRec* graph_all, int64_t n_graph_all) {
+    cudaStream_t st = c->stream;
+    LayoutResult& R = *c->layout;
+    StepTimer tm(st);
+    if (graph_all) graph.assign(graph_all, graph_all + n_graph_all);
+    if (alive_all && nh) memcpy(R.hin_alive.data(), alive_all, (size_t)nh);
     std::sort(graph.begin(), graph.end(), [](const GraphRec& x, const GraphRec& y) {
         return x.owner != y.owner ? x.owner < y.owner : x.seq < y.seq;
     });
     std::sort(nks.begin(), nks.end(), [](const NkRec& x, const NkRec& y) {
         return x.owner != y.owner ? x.owner < y.owner : x.seq < y.seq;
     });
-
     // connected components of the hinge graph (hinging.cpp:1644-1675): only sizes matter
-    R.hin_alive.assign((size_t)std::max<int64_t>(nh, 1), 1);
-    if (nh) HG_TRY(cuda_check(c, cudaMemcpyAsync(R.hin_alive.data(), d_alive.p, (size_t)nh, cudaMemcpyDeviceToHost, st), "D2H"));
-    HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "D2H"));
     {
         std::vector<int> parent((size_t)nh), size((size_t)nh, 0);
         std::iota(parent.begin(), parent.end(), 0);
@@ -511,7 +553,7 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
             if (g.flag == 1) parent[find(g.u)] = find(g.v);
         for (int64_t v = 0; v < nh; v++) size[find((int)v)]++;
         for (int64_t v = 0; v < nh; v++)
-            if (size[find((int)v)] < P->min_connected_component_size) R.hin_alive[v] = 0;
+            if (size[find((int)v)] < P.min_connected_component_size) R.hin_alive[v] = 0;
     }
     HG_TRY(h2d(d_alive.p, R.hin_alive.data(), (size_t)nh));
     // new_killed_hinges_vec as a CSR
@@ -547,8 +589,8 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
         io.skips = d_skip.p;
         io.skip_cap = skip_cap;
         cudaMemsetAsync(io.counters, 0, sizeof(int) * 8, st);
-        launch_best_extension(*P, io, st);
-        launch_gather_chosen(n, d_chosen.p, d_cands, d_edges.p, d_edge_ref.p, io.counters + 6, st);
+        launch_best_extension(P, io, st);
+        launch_gather_chosen(n, d_chosen.p, R.d_cands, d_edges.p, d_edge_ref.p, io.counters + 6, st);
         cudaEventRecord(c->ev1, st);
         int cnt[8];
         HG_TRY(cuda_check(c, cudaGetLastError(), "best extension"));
@@ -591,8 +633,88 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
         R.edge_ref.swap(er);
     }
     tm.lap("layout: best extension + D2H");
-    if (ms_device) cudaEventElapsedTime(ms_device, c->ev0, c->ev1);
     return HG_OK;
+}
+
+}  // namespace hg
+
+extern "C" {
+
+static int layout_args_ok(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const uint8_t* maximal,
+                          const int64_t* rep_off, const int64_t* hin_off) {
+    if (!c || !P || !mask || !maximal || !rep_off || !hin_off || c->novl <= 0)
+        return set_err(c, HG_ERR_ARG, "hg_layout: bad arguments");
+    if (!c->has_trace) return set_err(c, HG_ERR_ARG, "hg_layout needs the trace (pass trace_off/trace to hg_set_overlaps)");
+    return HG_OK;
+}
+
+int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const uint8_t* maximal,
+              const int64_t* rep_off, const int32_t* rep_pos, const int32_t* rep_type,
+              const int64_t* hin_off, const int32_t* hin_pos, const int32_t* hin_type,
+              float* ms_device) {
+    HG_TRY(layout_args_ok(c, P, mask, maximal, rep_off, hin_off));
+    if (c->a_lo != 0 || c->a_hi != c->n_read)
+        return set_err(c, HG_ERR_ARG, "hg_layout on a context that owns a slice of the reads: use hg_layout_phase1..3 "
+                                      "and exchange the flags between them");
+    cudaSetDevice(c->device);
+    free_layout_run(c->layout_run);
+    c->layout_run = new LayoutRun();
+    c->layout_run->c = c;
+    int rc = c->layout_run->phase1(P, mask, maximal, rep_off, rep_pos, rep_type, hin_off, hin_pos, hin_type, nullptr);
+    if (rc == HG_OK) rc = c->layout_run->phase2(nullptr, nullptr);
+    if (rc == HG_OK) rc = c->layout_run->phase3(nullptr, nullptr, 0);
+    if (rc == HG_OK && ms_device) cudaEventElapsedTime(ms_device, c->ev0, c->ev1);
+    free_layout_run(c->layout_run);  // the candidate lists live on in c->layout
+    c->layout_run = nullptr;
+    return rc;
+}
+
+// ---- sharded form: every rank classifies the pairs of its own reads and picks their edges; what
+// crosses shards is small and travels as host arrays through the caller's collectives (hinge_b200/
+// sharding.py, NCCL):
+//   phase 1 -> contained_out[n_read]  "[contained]" flags of the own reads      : MAX all-reduce
+//   phase 2 -> alive_out[n_hinges]    hinges the own reads' matches killed (0)  : MIN all-reduce
+//              graph records (hg_layout_graph)                                  : all-gather
+//   phase 3    components of the whole hinge graph, best extension of the own reads
+int hg_layout_phase1(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const uint8_t* maximal,
+                     const int64_t* rep_off, const int32_t* rep_pos, const int32_t* rep_type,
+                     const int64_t* hin_off, const int32_t* hin_pos, const int32_t* hin_type,
+                     uint8_t* contained_out) {
+    HG_TRY(layout_args_ok(c, P, mask, maximal, rep_off, hin_off));
+    if (!contained_out) return set_err(c, HG_ERR_ARG, "hg_layout_phase1: contained_out is null");
+    cudaSetDevice(c->device);
+    free_layout_run(c->layout_run);
+    c->layout_run = new LayoutRun();
+    c->layout_run->c = c;
+    return c->layout_run->phase1(P, mask, maximal, rep_off, rep_pos, rep_type, hin_off, hin_pos, hin_type, contained_out);
+}
+
+int hg_layout_phase2(hg_ctx* c, const uint8_t* contained_all, uint8_t* alive_out, int64_t* n_graph) {
+    if (!c || !c->layout_run || !contained_all || !n_graph) return set_err(c, HG_ERR_ARG, "hg_layout_phase2 before phase1");
+    cudaSetDevice(c->device);
+    HG_TRY(c->layout_run->phase2(contained_all, alive_out));
+    *n_graph = (int64_t)c->layout_run->graph.size();
+    return HG_OK;
+}
+
+int hg_layout_graph(hg_ctx* c, hg_graph_rec* out, int64_t capacity) {
+    if (!c || !c->layout_run || (!out && capacity > 0)) return set_err(c, HG_ERR_ARG, "hg_layout_graph before phase2");
+    static_assert(sizeof(hg_graph_rec) == sizeof(GraphRec), "graph record layout");
+    const int64_t m = std::min<int64_t>(capacity, (int64_t)c->layout_run->graph.size());
+    if (m > 0) memcpy(out, c->layout_run->graph.data(), sizeof(GraphRec) * (size_t)m);
+    return HG_OK;
+}
+
+int hg_layout_phase3(hg_ctx* c, const uint8_t* alive_all, const hg_graph_rec* graph_all, int64_t n_graph_all,
+                     float* ms_device) {
+    if (!c || !c->layout_run || !alive_all || (!graph_all && n_graph_all > 0))
+        return set_err(c, HG_ERR_ARG, "hg_layout_phase3 before phase2");
+    cudaSetDevice(c->device);
+    const int rc = c->layout_run->phase3(alive_all, reinterpret_cast<const GraphRec*>(graph_all), n_graph_all);
+    if (rc == HG_OK && ms_device) cudaEventElapsedTime(ms_device, c->ev0, c->ev1);
+    free_layout_run(c->layout_run);
+    c->layout_run = nullptr;
+    return rc;
 }
 
 int hg_layout_edges(hg_ctx* c, hg_edge* edges, int64_t capacity, int64_t* n_edges) {

@@ -14,6 +14,8 @@
 namespace hg {
 struct LayoutResult;
 void free_layout_result(LayoutResult* r);
+struct LayoutRun;
+void free_layout_run(LayoutRun* r);
 }
 
 struct hg_ctx {
@@ -89,6 +91,7 @@ struct hg_ctx {
     } ms;
 
     hg::LayoutResult* layout = nullptr;  // result of the last hg_layout
+    hg::LayoutRun* layout_run = nullptr; // between the phases of a sharded hg_layout
 
     hg::RecView rec_view() const;
     hg::ReadView read_view() const;

@@ -1216,37 +1216,43 @@ void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_pa
     k_hinge_call<<<s.hinge_warps / 4, 128, 0, st>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool,
                                                     s.counters, s.work_items, s.exact_list, s.hinge_keep,
                                                     s.hinge_scratch, s.hinge_cap, s.item_log, peer);
-    // The reads that need the exact sort order, in three size tiers that run side by side on forked
-    // streams (they work on different reads of one list; each has its own queue cursor):
-    //   A  pile-ups of at most 256 records: one WARP per read, 12 KB of shared memory each
-    //   B  257 .. 768 records: one CTA per read, 36 KB (six CTAs per SM)
-    //   C  deeper: one CTA per read, 72 KB, global scratch beyond 1536 records
-    constexpr int capA = 256, capB = 768, capC = 1536;
-    const int smemA = 4 * capA * kHingeExactBytesPerRec, smemB = capB * kHingeExactBytesPerRec;
-    const int smemC = capC * kHingeExactBytesPerRec;
+    // The reads that need the exact sort order, in size tiers that run side by side on forked streams
+    // (they work on different reads of one list; each has its own queue cursor).  One WARP per read out
+    // of shared memory (48 B per record) is by far the fastest form -- 18 us per read and thousands in
+    // flight, against ~270 us per read for the CTA form on a few hundred records (ncu, long-read set:
+    // 15 k reads in 115 us vs 5 k reads in 1.5 ms) -- so it takes everything that fits a warp's slice:
+    //   A   <= 256 records: 12 KB per warp, 16 warps per SM       B   <= 384: 18 KB, 12 warps per SM
+    //   C   <= 768: 36 KB, 4 warps per SM
+    //   D   deeper: one CTA per read (sub-ranges of the introsort on different warps), 72 KB, global
+    //       scratch beyond 1536 records
+    constexpr int capA = 256, capB = 384, capC = 768, capD = 1536;
+    const int smemD = capD * kHingeExactBytesPerRec;
     // function attributes are per device: set them on every launch (cheap), not once per process
-    cudaFuncSetAttribute(k_hinge_exact_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, smemA);
-    cudaFuncSetAttribute(k_hinge_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, smemC);
-    g_launches += 3;
-    cudaStream_t sB = s.side_stream[0] ? s.side_stream[0] : st, sC = s.side_stream[1] ? s.side_stream[1] : st;
-    if (sB != st) {
+    cudaFuncSetAttribute(k_hinge_exact_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * capC * kHingeExactBytesPerRec);
+    cudaFuncSetAttribute(k_hinge_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, smemD);
+    g_launches += 4;
+    const bool fork = s.side_stream[0] != nullptr;
+    cudaStream_t sB = fork ? s.side_stream[0] : st, sC = fork ? s.side_stream[1] : st, sD = fork ? s.side_stream[2] : st;
+    if (fork) {
         cudaEventRecord(s.side_event[0], st);
         cudaStreamWaitEvent(sB, s.side_event[0], 0);
         cudaStreamWaitEvent(sC, s.side_event[0], 0);
+        cudaStreamWaitEvent(sD, s.side_event[0], 0);
     }
-    k_hinge_exact_warp<<<4 * s.num_sms, 128, smemA, st>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 12,
-                                                         s.exact_list, s.hinge_keep, 0, capA);
-    k_hinge_exact<<<6 * s.num_sms, 128, smemB, sB>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 13,
-                                                    s.exact_list, s.hinge_keep, s.hinge_scratch, s.hinge_cap, capB,
-                                                    capA, capB);
-    const int gridC = s.hinge_warps < 2 * s.num_sms ? s.hinge_warps : 2 * s.num_sms;
-    k_hinge_exact<<<gridC, 128, smemC, sC>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 7, s.exact_list,
-                                            s.hinge_keep, s.hinge_scratch, s.hinge_cap, capC, capB, 0x7fffffff);
-    if (sB != st) {
-        cudaEventRecord(s.side_event[1], sB);
-        cudaEventRecord(s.side_event[2], sC);
-        cudaStreamWaitEvent(st, s.side_event[1], 0);
-        cudaStreamWaitEvent(st, s.side_event[2], 0);
+    k_hinge_exact_warp<<<4 * s.num_sms, 128, 4 * capA * kHingeExactBytesPerRec, st>>>(
+        rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 12, s.exact_list, s.hinge_keep, 0, capA);
+    k_hinge_exact_warp<<<3 * s.num_sms, 128, 4 * capB * kHingeExactBytesPerRec, sB>>>(
+        rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 13, s.exact_list, s.hinge_keep, capA, capB);
+    k_hinge_exact_warp<<<s.num_sms, 128, 4 * capC * kHingeExactBytesPerRec, sC>>>(
+        rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 14, s.exact_list, s.hinge_keep, capB, capC);
+    const int gridD = s.hinge_warps < 2 * s.num_sms ? s.hinge_warps : 2 * s.num_sms;
+    k_hinge_exact<<<gridD, 128, smemD, sD>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 7, s.exact_list,
+                                            s.hinge_keep, s.hinge_scratch, s.hinge_cap, capD, capC, 0x7fffffff);
+    if (fork) {
+        for (int i = 0; i < 3; i++) {
+            cudaEventRecord(s.side_event[1 + i], i == 0 ? sB : (i == 1 ? sC : sD));
+            cudaStreamWaitEvent(st, s.side_event[1 + i], 0);
+        }
     }
 }
 

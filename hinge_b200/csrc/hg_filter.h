@@ -60,8 +60,8 @@ struct FilterScratch {
     uint8_t* hinge_scratch = nullptr;
     int hinge_cap = 0, hinge_warps = 0;
     int4* item_log = nullptr;       // HG_OPT_PROFILE: (read, cycles, support, exact n) per work item
-    cudaStream_t side_stream[2] = {nullptr, nullptr};  // the size tiers of the exact-order kernels run side by side
-    cudaEvent_t side_event[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t side_stream[3] = {nullptr, nullptr, nullptr};  // the size tiers of the exact-order kernels run side by side
+    cudaEvent_t side_event[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 void launch_csr_validate(const RecView& rv, const ReadView& rd, int64_t* read_off, int* self_cnt, int* err,

@@ -179,3 +179,29 @@ def run_maximal_sharded(ctx, params, arrays, mask, group=None):
     dist.all_gather_into_tensor(pool_all, mine_pool, group=group)
     dist.all_reduce(state, op=dist.ReduceOp.MAX, group=group)  # slices are disjoint; 0 elsewhere
     return ctx.maximal_phase2(state, unk_all, counts_all.reshape(-1), world, unk_stride, pool_all, pool_stride)
+
+
+def run_layout_sharded(ctx, params, arrays, mask, maximal, rep, hin, group=None):
+    """hg_layout on shards.  mask / maximal / rep / hin are the GLOBAL arrays (the filter's results of all
+    shards gathered, the bitmap of run_maximal_sharded): north_star's "single NCCL all-gather of the hinge /
+    maximal-read bitmaps before layout".  Between the phases two small flag arrays are reduced and the
+    hinge-graph records gathered.  Returns this rank's edges (list of EdgeC, read order) and the device ms."""
+    from . import api
+
+    dev, world = arrays.device, arrays.world
+    n_hinges = int(hin[0][-1])
+    contained = api.layout_phase1(ctx, params, mask, maximal, rep, hin)
+    if world > 1:
+        t = torch.from_numpy(contained).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        contained = t.cpu().numpy()
+    alive, graph = api.layout_phase2(ctx, contained, n_hinges)
+    if world > 1:
+        t = torch.from_numpy(np.ascontiguousarray(alive)).to(dev) if n_hinges else None
+        if t is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            alive = t.cpu().numpy()
+        parts = [None] * world
+        dist.all_gather_object(parts, graph, group=group)
+        graph = np.vstack([p.reshape(-1, 10) for p in parts])
+    return api.layout_phase3(ctx, alive, graph)

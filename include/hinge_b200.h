@@ -231,6 +231,25 @@ int hg_layout(hg_ctx* ctx, const hg_layout_params* params, const int32_t* mask,
               const int32_t* hin_type, float* ms_device);
 int hg_layout_edges(hg_ctx* ctx, hg_edge* edges, int64_t capacity, int64_t* n_edges);
 
+/* The same stage for contexts that own a slice of the reads: every rank classifies the pairs of its
+ * own reads and picks their edges; mask, maximal and the annotation / hinge lists are the global
+ * arrays (gathered before: the filter's results of all shards, the bitmap of hg_maximal_phase2).
+ * What crosses shards in between is small and travels as HOST arrays through the caller's collectives:
+ *   phase 1 -> contained_out[n_read]: reads found contained after all (hinging.cpp:598-601)  MAX all-reduce
+ *   phase 2 -> alive_out[n_hinges]:   0 = hinge killed by a match of an own read (:1262-1321) MIN all-reduce
+ *              *n_graph records of the hinge graph (hg_layout_graph, :1365-1640)            all-gather
+ *   phase 3    components of the WHOLE hinge graph (:1644-1691), best extension of the own reads;
+ *              hg_layout_edges then returns this rank's edges (rank order = read order) */
+typedef struct hg_graph_rec { int32_t owner, seq, f[4], flag, rev, u, v; } hg_graph_rec;
+int hg_layout_phase1(hg_ctx* ctx, const hg_layout_params* params, const int32_t* mask, const uint8_t* maximal,
+                     const int64_t* rep_off, const int32_t* rep_pos, const int32_t* rep_type,
+                     const int64_t* hin_off, const int32_t* hin_pos, const int32_t* hin_type,
+                     uint8_t* contained_out);
+int hg_layout_phase2(hg_ctx* ctx, const uint8_t* contained_all, uint8_t* alive_out, int64_t* n_graph);
+int hg_layout_graph(hg_ctx* ctx, hg_graph_rec* out, int64_t capacity);
+int hg_layout_phase3(hg_ctx* ctx, const uint8_t* alive_all, const hg_graph_rec* graph_all, int64_t n_graph_all,
+                     float* ms_device);
+
 /* ---- file-level drivers: what the three executables do ------------------ */
 
 /* Same flags, inputs, outputs and exit conventions as Reads_filter,

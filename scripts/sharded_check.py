@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import hgsynth  # noqa: E402
 from hinge_b200 import api  # noqa: E402
-from hinge_b200.sharding import ShardedArrays, run_filter_sharded, run_maximal_sharded  # noqa: E402
+from hinge_b200.sharding import ShardedArrays, run_filter_sharded, run_layout_sharded, run_maximal_sharded  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -90,9 +90,30 @@ masks = [want["mask"] if rank == 0 else None]
 dist.broadcast_object_list(masks, src=0)
 lp = api.LayoutParams()
 got_max = run_maximal_sharded(ctx, lp, arrays, masks[0])
-ctx.close()
 all_max = [None] * world
 dist.all_gather_object(all_max, got_max)
+
+# ---- layout on shards: global annotation / hinge lists (rank 0's single-context filter result stands in
+# for the gathered per-shard lists, which the checks above proved identical), maximal bitmap from above
+def csr(res):
+    n = len(res["anno_off"]) - 1
+    keep = res["hinge_keep"].astype(bool)
+    per_read = np.repeat(np.arange(n), np.diff(res["anno_off"]))
+    hin_off = np.zeros(n + 1, np.int64)
+    np.cumsum(np.bincount(per_read[keep], minlength=n), out=hin_off[1:])
+    return ((res["anno_off"], res["anno_pos"], res["anno_type"]),
+            (hin_off, res["anno_pos"][keep], res["anno_type"][keep]))
+
+
+lists = [csr(want) if rank == 0 else None]
+dist.broadcast_object_list(lists, src=0)
+rep_csr, hin_csr = lists[0]
+my_edges, _ = run_layout_sharded(ctx, lp, arrays, masks[0], got_max, rep_csr, hin_csr)
+ctx.close()
+edge_key = lambda e: (e.a, e.b, e.length, e.comp, e.type, e.weight, tuple(e.eff_a), tuple(e.eff_b), tuple(e.raw_a),
+                      tuple(e.raw_b), e.hinge_pos)
+all_edges = [None] * world
+dist.all_gather_object(all_edges, [edge_key(e) for e in my_edges])
 if rank == 0:
     novl_all = syn.generate(0, syn.n_read, want_trace=True, threads=8)
     cols_all = {k: v.copy() for k, v in syn.cols().items()}
@@ -101,10 +122,16 @@ if rank == 0:
     ref.set_reads(syn.rlen, syn.qv_off, syn.qv, 100)
     ref.set_overlaps(novl_all, cols_all, trace_off=toff_all, trace=tr_all)
     want_max, _, _ = ref.maximal(lp, masks[0])
-    ref.close()
     good = all(bool(np.array_equal(m, want_max)) for m in all_max)
     print("SHARDED_CHECK maximal", "OK" if good else "MISMATCH", "world", world, "maximal reads", int(want_max.sum()),
           "of", syn.n_read, flush=True)
+    ok &= good
+    want_edges, _ = ref.layout(lp, masks[0], want_max, rep_csr, hin_csr)
+    ref.close()
+    got_edges = [e for part in all_edges for e in part]  # rank order = read order
+    good = got_edges == [edge_key(e) for e in want_edges]
+    print("SHARDED_CHECK layout", "OK" if good else "MISMATCH", "world", world, "edges", len(want_edges),
+          "hinged", sum(1 for e in want_edges if e.hinge_pos >= 0), flush=True)
     ok &= good
 dist.barrier()
 dist.destroy_process_group()

@@ -21,5 +21,5 @@ def test_two_rank_filter_matches_single_context(built):
                         "--master-addr", "127.0.0.1", "--master-port", "29631",
                         os.path.join(ROOT, "scripts", "sharded_check.py")],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert r.returncode == 0 and all("SHARDED_CHECK %s OK" % k in r.stdout for k in ("peer", "nccl", "maximal")), \
+    assert r.returncode == 0 and all("SHARDED_CHECK %s OK" % k in r.stdout for k in ("peer", "nccl", "maximal", "layout")), \
         r.stdout[-3000:]
