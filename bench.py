@@ -385,7 +385,8 @@ class Bench:
                                              equal_slices=(args.exchange == "nccl"))
         a_lo, a_hi = arrays.lo, arrays.hi
         novl = syn.generate(a_lo, a_hi, want_trace=False, threads=host_threads(world))
-        cols_np = syn.cols()
+        cols_np = syn.cols()  # views into the generator's buffers: valid until its next generate()
+        pile = np.bincount(cols_np["aread"] - a_lo, minlength=a_hi - a_lo)[:a_hi - a_lo]  # records per owned read
         t_gen = time.perf_counter() - t_gen
 
         ctx = api.Context(self.local, self.stream.cuda_stream)
@@ -471,7 +472,6 @@ class Bench:
             # of its pile-up (the selection's first step), 48 B of work item per read; the second step
             # (24 B + two gathers per record near the annotation) touches a few per cent of that
             n_anno = np.diff(result["anno_off"][a_lo:a_hi + 1])
-            pile = np.bincount(cols_np["aread"] - a_lo, minlength=owned)[:owned]
             k4 = float((n_anno * pile).sum()) * 4.0 + 48.0 * float((n_anno > 0).sum())
             kbytes = {"profile": 12.0 * novl + 4.0 * bins + 39.0 * owned, "mask_anno": 4.0 * bins + 60.0 * owned,
                       "hinge_call": k4}

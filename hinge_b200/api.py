@@ -9,7 +9,7 @@ import numpy as np
 from ._lib import (EdgeC, FilterParamsC, FilterSummaryC, GraphRecC, HingeError, LayoutParamsC, lib)
 
 HG_MEM_HOST, HG_MEM_DEVICE = 0, 1
-HG_OPT_KEEP_COVERAGE, HG_OPT_PROFILE, HG_OPT_SCATTER_SPREAD, HG_OPT_PROFILE_KERNEL, HG_OPT_KEEP_MASKS = 1, 2, 3, 4, 5
+HG_OPT_KEEP_COVERAGE, HG_OPT_PROFILE, HG_OPT_SCATTER_SPREAD, HG_OPT_PROFILE_KERNEL, HG_OPT_KEEP_MASKS, HG_OPT_ANNO_POOL = 1, 2, 3, 4, 5, 6
 HG_BUF_MEAN_COV, HG_BUF_MASK, HG_BUF_READ_FLAGS, HG_BUF_MEDIAN_HIST, HG_BUF_MASK_PACKED = 1, 2, 3, 4, 5
 HG_RETRY_POOL = 1
 HG_PEER_HANDLE_BYTES = 64

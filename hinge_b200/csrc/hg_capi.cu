@@ -171,6 +171,12 @@ int hg_set_option(hg_ctx* c, int option, int64_t value) {
         c->fs.flat_spread = (int)value;
         return HG_OK;
     }
+    if (option == HG_OPT_ANNO_POOL) {
+        if (value < 1 || value > (1ll << 30)) return set_err(c, HG_ERR_ARG, "HG_OPT_ANNO_POOL: 1 .. 2^30 entries");
+        c->anno_pool_hint = (int)value;
+        c->fs.anno_cap = 0;  // reallocated by the next hg_set_overlaps
+        return HG_OK;
+    }
     if (option == HG_OPT_KEEP_MASKS) {
         c->keep_masks = value != 0;
         return HG_OK;
@@ -344,7 +350,7 @@ int hg_set_overlaps(hg_ctx* c, int64_t novl, const int32_t* aread, const int32_t
 
     // scratch that depends on the shape of the data
     FilterScratch& s = c->fs;
-    if (s.anno_cap == 0) HG_TRY(alloc_anno_pool(c, 2 * (a_hi - a_lo) + (1 << 16)));
+    if (s.anno_cap == 0) HG_TRY(alloc_anno_pool(c, c->anno_pool_hint > 0 ? c->anno_pool_hint : 2 * (a_hi - a_lo) + (1 << 16)));
     // K4: one slot of 56 B per pile-up record and warp
     s.hinge_cap = (std::max(c->max_pileup, 32) + 3) & ~3;  // keeps every slot 16-byte aligned
     {

@@ -332,6 +332,34 @@ struct LayoutRun {
     std::vector<GraphRec> graph;    // this context's records (phase 2)
     std::vector<NkRec> nks;
     int ngrow = 0;
+    // device time of the kernels alone: event pairs around every stretch of launches (the host steps
+    // between them -- allocation, the list-size round trips, union-find -- are not in it)
+    cudaEvent_t seg[8] = {};
+    int nseg = 0;
+    float kernel_ms = 0;
+    void seg_begin() {
+        if (nseg + 2 > 8) return;
+        for (int i = 0; i < 2; i++)
+            if (!seg[nseg + i]) cudaEventCreate(&seg[nseg + i]);
+        cudaEventRecord(seg[nseg], c->stream);
+    }
+    void seg_end() {
+        if (nseg + 2 > 8) return;
+        cudaEventRecord(seg[nseg + 1], c->stream);
+        nseg += 2;
+    }
+    float kernel_time() {  // call after a synchronisation
+        float total = 0;
+        for (int i = 0; i + 1 < nseg; i += 2) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, seg[i], seg[i + 1]) == cudaSuccess) total += ms;
+        }
+        return total;
+    }
+    ~LayoutRun() {
+        for (int i = 0; i < 8; i++)
+            if (seg[i]) cudaEventDestroy(seg[i]);
+    }
 
     int h2d(void* d, const void* h, size_t bytes) {
         return bytes ? cuda_check(c, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream), "H2D") : HG_OK;
@@ -421,7 +449,9 @@ int LayoutRun::phase1(const hg_layout_params* params, const int32_t* mask, const
 
     // ---- K5: pairs between maximal reads, their top two classified, candidates in the reference's order
     cudaEventRecord(c->ev0, st);
+    seg_begin();
     launch_layout_count_pairs(c->rec_view(), c->read_view(), d_active.p, d_pair_ref.p, d_total.p, st);
+    seg_end();
     unsigned long long total_pairs = 0;
     HG_TRY(cuda_check(c, cudaMemcpyAsync(&total_pairs, d_total.p, 8, cudaMemcpyDeviceToHost, st), "D2H"));
     HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "count pairs"));
@@ -458,7 +488,9 @@ int LayoutRun::phase1(const hg_layout_params* params, const int32_t* mask, const
         L.cands = d_cands; L.hash_next = d_hnext.p; L.hash_out = d_hout.p; L.hash_bkt = d_hbkt.p;
         L.contained_flag = d_contained.p; L.counters = d_cnt.p; L.sort_scratch = d_bigsort.p; L.sort_cap = big_sort_cap;
         L.grow_at = d_grow.p; L.grow_bkt = d_grow.p + ngrow; L.ngrow = ngrow;
+        if (attempt == 0) seg_begin();
         launch_layout_pairs(c->rec_view(), c->read_view(), P, c->fs.mask, d_active.p, L, st);
+        if (attempt == 0) seg_end();
         int cnt[8];
         HG_TRY(cuda_check(c, cudaGetLastError(), "layout pairs"));
         HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, d_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
@@ -484,8 +516,10 @@ int LayoutRun::phase2(const uint8_t* contained_all, uint8_t* alive_out) {
     StepTimer tm(st);
     if (contained_all) HG_TRY(h2d(d_contained.p, contained_all, n));
     // "[contained] Should not happen" (hinging.cpp:598-601): such reads leave the layout
+    seg_begin();
     launch_apply_contained(n, d_contained.p, d_active.p, d_cnt.p + 7, st);
     launch_order_candidates(L, io, st);
+    seg_end();
     HG_TRY(cuda_check(c, cudaMemcpyAsync(&R.n_contained, d_cnt.p + 7, 4, cudaMemcpyDeviceToHost, st), "D2H"));
 
     // ---- K6: kill pass + hinge graph; list sizes are data dependent: grow and rerun on overflow
@@ -498,7 +532,9 @@ int LayoutRun::phase2(const uint8_t* contained_all, uint8_t* alive_out) {
         io.graph = d_graph.p; io.graph_cap = graph_cap; io.nkout = d_nk.p; io.nk_cap = nk_cap;
         io.skips = nullptr; io.skip_cap = 0;
         cudaMemsetAsync(d_alive.p, 1, std::max<size_t>((size_t)nh, 1), st);
+        if (attempt == 0) seg_begin();
         launch_hinge_graph(c->rec_view(), P, io, st);
+        if (attempt == 0) seg_end();
         int cnt[8];
         HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, io.counters, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
         HG_TRY(cuda_check(c, cudaStreamSynchronize(st), "hinge graph"));
@@ -589,8 +625,10 @@ int LayoutRun::phase3(const uint8_t* alive_all, const GraphRec* graph_all, int64
         io.skips = d_skip.p;
         io.skip_cap = skip_cap;
         cudaMemsetAsync(io.counters, 0, sizeof(int) * 8, st);
+        if (attempt == 0) seg_begin();
         launch_best_extension(P, io, st);
         launch_gather_chosen(n, d_chosen.p, R.d_cands, d_edges.p, d_edge_ref.p, io.counters + 6, st);
+        if (attempt == 0) seg_end();
         cudaEventRecord(c->ev1, st);
         int cnt[8];
         HG_TRY(cuda_check(c, cudaGetLastError(), "best extension"));
@@ -633,6 +671,7 @@ int LayoutRun::phase3(const uint8_t* alive_all, const GraphRec* graph_all, int64
         R.edge_ref.swap(er);
     }
     tm.lap("layout: best extension + D2H");
+    kernel_ms = kernel_time();
     return HG_OK;
 }
 
@@ -663,7 +702,7 @@ int hg_layout(hg_ctx* c, const hg_layout_params* P, const int32_t* mask, const u
     int rc = c->layout_run->phase1(P, mask, maximal, rep_off, rep_pos, rep_type, hin_off, hin_pos, hin_type, nullptr);
     if (rc == HG_OK) rc = c->layout_run->phase2(nullptr, nullptr);
     if (rc == HG_OK) rc = c->layout_run->phase3(nullptr, nullptr, 0);
-    if (rc == HG_OK && ms_device) cudaEventElapsedTime(ms_device, c->ev0, c->ev1);
+    if (rc == HG_OK && ms_device) *ms_device = c->layout_run->kernel_ms;
     free_layout_run(c->layout_run);  // the candidate lists live on in c->layout
     c->layout_run = nullptr;
     return rc;
@@ -711,7 +750,7 @@ int hg_layout_phase3(hg_ctx* c, const uint8_t* alive_all, const hg_graph_rec* gr
         return set_err(c, HG_ERR_ARG, "hg_layout_phase3 before phase2");
     cudaSetDevice(c->device);
     const int rc = c->layout_run->phase3(alive_all, reinterpret_cast<const GraphRec*>(graph_all), n_graph_all);
-    if (rc == HG_OK && ms_device) cudaEventElapsedTime(ms_device, c->ev0, c->ev1);
+    if (rc == HG_OK && ms_device) *ms_device = c->layout_run->kernel_ms;
     free_layout_run(c->layout_run);
     c->layout_run = nullptr;
     return rc;

@@ -55,6 +55,7 @@ struct hg_ctx {
     int reads_version = 0, plan_reads_version = -1, plan_cut_off = 0, plan_lo = 0, plan_hi = 0;  // flat K2 plan
     int keep_cov = 0;
     bool keep_masks = false;  // HG_OPT_KEEP_MASKS
+    int anno_pool_hint = 0;   // HG_OPT_ANNO_POOL
     int* d_cov0 = nullptr;
     int64_t* d_cov0_off = nullptr;
     std::vector<int64_t> h_cov0_off;

@@ -11,6 +11,8 @@
 //   K6 hinge_graph      hinge kill pass + hinge-graph edges through the trace
 //                       (hinging.cpp:1262-1321,1365-1640; LAInterface.cpp:4498-4546)
 //   K6 best_extension   the best-overlap scoring loop  (hinging.cpp:1911-2148)
+#include <algorithm>
+
 #include "hg_device.cuh"
 #include "hg_layout.h"
 #include "hg_order.h"
@@ -698,6 +700,30 @@ k_contain_lists(RecView rv, ReadView rd, ContainIO io) {
     }
 }
 
+// One sweep over the unknown reads with the whole grid: settles every read whose containers are all
+// settled.  Most chains are one or two links long, so a few of these leave only a handful of reads to
+// the single-CTA loop below.
+__global__ void __launch_bounds__(256)
+k_contain_sweep(const int4* __restrict__ unk, const int* __restrict__ counts, int world, int unk_stride,
+                const int* __restrict__ pool, int pool_stride, volatile uint8_t* state) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (r >= world || e >= min(counts[2 * r], unk_stride)) return;
+    const int4 u = unk[(size_t)r * unk_stride + e];
+    if (state[u.x] != 0) return;
+    const int* lst = pool + (size_t)r * pool_stride + u.y;
+    bool alive = false, unknown = false;
+    for (int c = 0; c < u.z; c++) {
+        const uint8_t s = state[lst[c]];
+        alive = alive || s == 1;
+        unknown = unknown || s == 0;
+    }
+    if (alive)
+        state[u.x] = 2;
+    else if (!unknown)
+        state[u.x] = 1;
+}
+
 // unk / pool: `world` segments of unk_stride / pool_stride entries, counts[2 r] = unknown reads of
 // segment r.  sweeps_out (may be null) gets the number of sweeps it took.
 __global__ void __launch_bounds__(1024)
@@ -996,8 +1022,13 @@ void launch_contain_lists(const RecView& rv, const ReadView& rd, const ContainIO
 
 void launch_contain_resolve(const int4* unk, const int* counts, int world, int unk_stride, const int* pool,
                             int pool_stride, uint8_t* state, int* sweeps_out, cudaStream_t st) {
+    // racing reads of `state` inside a sweep are harmless: a state only ever goes from 0 to its final
+    // value, and a read that still sees 0 just leaves its entry for the next sweep
+    const dim3 grid((unsigned)cdiv(std::max(unk_stride, 1), 256), (unsigned)world);
+    for (int i = 0; i < 3; i++)
+        k_contain_sweep<<<grid, 256, 0, st>>>(unk, counts, world, unk_stride, pool, pool_stride, state);
     k_contain_resolve<<<1, 1024, 0, st>>>(unk, counts, world, unk_stride, pool, pool_stride, state, sweeps_out);
-    g_launches += 1;
+    g_launches += 4;
 }
 
 void launch_layout_count_pairs(const RecView& rv, const ReadView& rd, const uint8_t* active, int2* pair_ref,

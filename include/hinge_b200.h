@@ -48,6 +48,8 @@ enum hg_option {
     HG_OPT_KEEP_MASKS = 5,    /* multi-part runs (--mlas): hg_set_overlaps + hg_filter on the next part keep the
                                  masks the earlier parts computed (reads of later parts still have (0,0)),
                                  as the reference's part loop does (filter.cpp:534,884-889) */
+    HG_OPT_ANNO_POOL = 6,     /* initial capacity of the annotation pool (entries; default 2 per owned read + 64 K);
+                                 a pool that turns out too small is grown and the stage rerun (HG_RETRY_POOL) */
     HG_OPT_PROFILE_KERNEL = 4 /* tuning aid: 0 = pick the form of the coverage-profile kernel by cut_off and
                                  data shape (20-bp start/end histogram for the nominal cut_off 300 when
                                  records outnumber coverage bins), 1 = always the four-event 40-bp form,
@@ -224,7 +226,9 @@ typedef struct hg_edge {      /* one line of .edges.hinges (hinging.cpp:188-248)
  * best-overlap scoring loop (:1911-2148).  Inputs are the inter-stage files'
  * content: mask (2 ints/read), maximal (1 byte/read), repeat annotations and
  * hinges as CSR (off has n_read+1 entries; pos/type per entry).  Results are
- * written by the hg_layout_write_* helpers or fetched with hg_layout_edges. */
+ * fetched with hg_layout_edges (the file-level driver prints every candidate list).
+ * ms_device: device time of the kernels alone (CUDA events around every stretch of launches; the
+ * host steps between them -- allocation, list-size round trips, union-find -- are not in it). */
 int hg_layout(hg_ctx* ctx, const hg_layout_params* params, const int32_t* mask,
               const uint8_t* maximal, const int64_t* rep_off, const int32_t* rep_pos,
               const int32_t* rep_type, const int64_t* hin_off, const int32_t* hin_pos,

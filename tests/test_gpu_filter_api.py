@@ -70,6 +70,17 @@ def test_c5_shaped_long_reads_with_fragmented_alignments(built):
     assert len(want["anno_pos"]) > 100 and want["hinge_keep"].sum() > 0
 
 
+def test_annotation_pool_overflow_is_retried(built):
+    """A pool of 16 entries for a batch with hundreds of annotations: hg_filter grows it and reruns the
+    stage (HG_RETRY_POOL inside), the results are the oracle's."""
+    from hinge_b200 import api
+
+    got, want, summ = _run_both(built, dict(genome_len=600000, coverage=40.0, seed=77, n_families=4),
+                                options=[(api.HG_OPT_ANNO_POOL, 16)])
+    assert len(want["anno_pos"]) > 64
+    _assert_equal(got, want, summ)
+
+
 def test_tie_heavy_data_uses_order_exact_path(built):
     # no end jitter: every repeat-induced alignment starts exactly on the repeat
     # boundary, and reads longer than the repeats see both boundaries, so end lists
