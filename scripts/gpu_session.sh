@@ -77,6 +77,14 @@ import json;d=json.load(open('$OUT/${TAG}_down_$CFG.json'));print(d.get('downstr
 import json
 for f in ('$OUT/${TAG}_bench_n2.json','$OUT/${TAG}_bench_n2_nccl.json'):
     d=json.load(open(f)); print(f, 'c5', round(d['ms_per_step'],4), d['kernel_ms'], d.get('parity'), 'c3', round(d['c3']['ms_per_step'],4), d['c3'].get('parity'))" ;;
+    benchN)
+      NG=${NGPUS:-4}
+      timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29651 \
+        bench.py --gpus $NG --no-downstream > $OUT/${TAG}_bench_n$NG.json 2> $OUT/${TAG}_bench_n$NG.err
+      echo "bench N=$NG exit $?"; grep -v "^\*\|^$\|OMP_NUM" $OUT/${TAG}_bench_n$NG.err | tail -5
+      python -c "
+import json
+d=json.load(open('$OUT/${TAG}_bench_n$NG.json')); print('c5 value %.4g ms %.4f'%(d['value'],d['ms_per_step']), d['kernel_ms'], d.get('parity'), d['config']['overlaps_rank0']); print('c3 value %.4g ms %.4f'%(d['c3']['value'],d['c3']['ms_per_step']), d['c3']['kernel_ms'], d['c3'].get('parity')); print('e2e', d['e2e']['value'], d['e2e']['ms_per_step'])" ;;
     launches)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
         --log-file $OUT/${TAG}_launches.csv python bench.py $SHORT > $OUT/${TAG}_launches_bench.log 2>&1

@@ -1,10 +1,10 @@
 #!/usr/bin/env python3
-"""Turns one `scripts/profile_gpu.sh <tag>` session (gpurun_out/<tag>_*) into the tracked
-summaries under profiles/: bench lines, the per-kernel share of a step from the ncu launch
-list, the key `ncu --set full` metrics of each captured kernel and profiles/traffic.json
-(DRAM bytes per launch, read by bench.py for `roofline.traffic`).
+"""Turns files of `scripts/gpu_session.sh` sessions (gpurun_out/) into the tracked summaries under
+profiles/: bench lines, the per-kernel share of a step from ncu launch lists, the key
+`ncu --set full` metrics of each captured kernel and profiles/traffic.json (DRAM bytes per launch and
+workload, read by bench.py for `roofline.traffic`).
 
-    python scripts/summarise_profiles.py r01a [r01]      (source tag, name under profiles/)
+    python scripts/summarise_profiles.py r02 gpurun_out/r02x_k_profile_flat2_c3.ncu-rep gpurun_out/r02x_launches.csv ...
 """
 import csv
 import io
@@ -76,67 +76,81 @@ def short_name(full):
     return m.group(1) if m else full[:40]
 
 
+def launch_table(path, title):
+    """Per-kernel device time of ONE steady-state filter step (from one K1 launch to the next) out of an
+    `ncu --metrics gpu__time_duration.sum` launch list."""
+    rows = list(csv.reader(open(path)))
+    hdr = next((r for r in rows if r and r[0] == "ID"), None)
+    if hdr is None:
+        return None
+    ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    body = [r for r in rows if len(r) > iv and r[0].isdigit()]
+    names = [short_name(r[ik]) for r in body]
+    ns = [float(r[iv].replace(",", "")) for r in body]
+    starts = [i for i, n in enumerate(names) if n.startswith("k_profile_flat")]
+    lines = ["# %s" % title, "",
+             "`ncu --metrics gpu__time_duration.sum --clock-control none` serialises launches and runs them with a",
+             "cold cache, so only the SHARES are comparable with the CUDA-event times in the bench line (the size",
+             "tiers of the exact-order hinge kernels, for one, overlap on forked streams in a real run).", ""]
+    if len(starts) >= 3:
+        a, b = starts[1], starts[2]
+        agg = {}
+        for n, t in zip(names[a:b], ns[a:b]):
+            agg.setdefault(n, [0, 0.0])
+            agg[n][0] += 1
+            agg[n][1] += t
+        tot = sum(v[1] for v in agg.values())
+        lines += ["| kernel | launches | time (us) | share |", "|---|---|---|---|"]
+        for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            lines.append("| %s | %d | %.1f | %.1f %% |" % (n, c, t / 1e3, 100 * t / tot))
+        lines.append("| **total** | %d | %.1f | |" % (b - a, tot / 1e3))
+    lines += ["", "all %d launches of the capture: the .csv next to this file" % len(body)]
+    return "\n".join(lines) + "\n"
+
+
+ALIAS = {"k_mask_anno_flat": "mask_anno", "k_profile_flat": "profile", "k_profile_flat2": "profile",
+         "k_hinge_call": "hinge_call"}
+
+
 def main():
-    src = sys.argv[1]
-    dst = sys.argv[2] if len(sys.argv) > 2 else src
+    """summarise_profiles.py <name under profiles/> <file> ...
+    files: gpurun_out/*.ncu-rep (a `_c3` / `_c5` suffix names the workload), *_launches*.csv, anything else
+    is copied as is."""
+    dst = sys.argv[1]
     os.makedirs(PROF, exist_ok=True)
-    for suffix in ("bench.json", "bench_reference.json", "pytest_gpu.log", "smoke.log", "gpu.txt", "launches.csv"):
-        p = os.path.join(OUT, "%s_%s" % (src, suffix))
-        if os.path.exists(p):
-            shutil.copy(p, os.path.join(PROF, "%s_%s" % (dst, suffix)))
-
-    # ---- launch list -> per-kernel share of the steady-state step
-    lp = os.path.join(OUT, "%s_launches.csv" % src)
-    if os.path.exists(lp):
-        rows = [r for r in csv.reader(open(lp)) if len(r) > 14 and r[0].isdigit()]
-        names = [short_name(r[4]) if "hg::" in r[4] else "torch:" + r[4][:48] for r in rows]
-        ns = [float(r[14].replace(",", "")) for r in rows]
-        # one step = from a k_profile_flat launch to the next; the second one is a warm, device-resident step
-        # (later ones belong to the end-to-end arm, which re-ingests: k_csr_validate, k_max_pileup)
-        starts = [i for i, n in enumerate(names) if n == "k_profile_flat"]
-        lines = ["# ncu launch list (%s): per-kernel device time of ONE steady-state filter step" % dst, "",
-                 "`ncu --metrics gpu__time_duration.sum --clock-control none` serialises launches and runs them with a",
-                 "cold cache, so only the SHARES are comparable with the CUDA-event times in the bench line.", ""]
-        if len(starts) >= 3:
-            a, b = starts[1], starts[2]
-            agg = {}
-            for n, t in zip(names[a:b], ns[a:b]):
-                agg.setdefault(n, [0, 0.0])
-                agg[n][0] += 1
-                agg[n][1] += t
-            tot = sum(v[1] for v in agg.values())
-            lines += ["| kernel | launches | time (us) | share |", "|---|---|---|---|"]
-            for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-                lines.append("| %s | %d | %.1f | %.1f %% |" % (n, c, t / 1e3, 100 * t / tot))
-            lines.append("| **total** | %d | %.1f | |" % (b - a, tot / 1e3))
-        lines += ["", "all %d launches seen: see %s_launches.csv" % (len(rows), dst)]
-        open(os.path.join(PROF, "%s_launches.md" % dst), "w").write("\n".join(lines) + "\n")
-
-    # ---- ncu --set full captures
     traffic_path = os.path.join(PROF, "traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
-    alias = {"k_mask_anno_flat": "mask_anno", "k_profile_flat": "profile", "k_hinge_call": "hinge_call",
-             "k_classify_pairs": "classify_pairs"}
-    for f in sorted(os.listdir(OUT)):
-        if not (f.startswith(src + "_k_") and f.endswith(".ncu-rep")):
-            continue
-        for d in ncu_raw(os.path.join(OUT, f)):
-            kname = short_name(d["Kernel Name"][0])
-            lines = ["# ncu --set full: %s (%s)" % (d["Kernel Name"][0], dst), ""]
-            for k in KEYS:
-                if k in d and d[k][0] != "":
-                    lines.append("%-80s %s %s" % (k, d[k][0], d[k][1]))
-            open(os.path.join(PROF, "%s_%s_ncu.txt" % (dst, kname)), "w").write("\n".join(lines) + "\n")
-            try:
-                rd = float(d["dram__bytes_read.sum"][0].replace(",", "")) * SCALE[d["dram__bytes_read.sum"][1]]
-                wr = float(d["dram__bytes_write.sum"][0].replace(",", "")) * SCALE[d["dram__bytes_write.sum"][1]]
-                if kname in alias:
-                    traffic[alias[kname]] = rd + wr
-                    traffic[alias[kname] + "_source"] = "%s_%s_ncu.txt" % (dst, kname)
-            except (KeyError, ValueError):
-                pass
+    traffic = {k: v for k, v in traffic.items() if isinstance(v, dict)}  # round-1 layout: flat keys
+    for f in sys.argv[2:]:
+        base = os.path.basename(f)
+        tail = base.split("_", 1)[1] if "_" in base else base
+        if base.endswith(".ncu-rep"):
+            cfg = "c5" if "_c5" in base else ("c3" if "_c3" in base else "")
+            for d in ncu_raw(f):
+                kname = short_name(d["Kernel Name"][0])
+                lines = ["# ncu --set full: %s (%s%s)" % (d["Kernel Name"][0], dst, ", workload " + cfg if cfg else ""), ""]
+                for k in KEYS:
+                    if k in d and d[k][0] != "":
+                        lines.append("%-80s %s %s" % (k, d[k][0], d[k][1]))
+                name = "%s_%s%s_ncu.txt" % (dst, kname, "_" + cfg if cfg else "")
+                open(os.path.join(PROF, name), "w").write("\n".join(lines) + "\n")
+                try:
+                    rd = float(d["dram__bytes_read.sum"][0].replace(",", "")) * SCALE[d["dram__bytes_read.sum"][1]]
+                    wr = float(d["dram__bytes_write.sum"][0].replace(",", "")) * SCALE[d["dram__bytes_write.sum"][1]]
+                    if kname in ALIAS and cfg:
+                        traffic.setdefault(cfg, {})[ALIAS[kname]] = rd + wr
+                        traffic[cfg][ALIAS[kname] + "_source"] = name
+                except (KeyError, ValueError):
+                    pass
+        elif "launches" in base and base.endswith(".csv"):
+            shutil.copy(f, os.path.join(PROF, "%s_%s" % (dst, tail)))
+            md = launch_table(f, "ncu launch list (%s, %s): per-kernel device time of one steady-state filter step" % (dst, tail))
+            if md:
+                open(os.path.join(PROF, "%s_%s" % (dst, tail.replace(".csv", ".md"))), "w").write(md)
+        else:
+            shutil.copy(f, os.path.join(PROF, "%s_%s" % (dst, tail)))
     json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
-    print("profiles/ updated from", src)
+    print("profiles/ updated:", dst)
 
 
 if __name__ == "__main__":
