@@ -357,8 +357,8 @@ int hg_set_overlaps(hg_ctx* c, int64_t novl, const int32_t* aread, const int32_t
         const size_t slot = (size_t)s.hinge_cap * 56;
         size_t warps = (size_t)c->num_sms * 48;  // the kernel is latency bound: many warps, few reads each
         const size_t budget = (size_t)768 << 20;
-        if (warps * slot > budget) warps = std::max<size_t>(4, budget / slot);
-        warps = std::max<size_t>(4, warps & ~(size_t)3);
+        if (warps * slot > budget) warps = std::max<size_t>(32, budget / slot);
+        warps = std::max<size_t>(32, warps & ~(size_t)3);  // >= 8 CTA slots: the exact-order tiers share them
         s.hinge_warps = (int)warps;
         if (warps * slot > c->cap_hinge_scratch) {
             HG_TRY(dev_alloc(c, &s.hinge_scratch, warps * slot, "hinge scratch"));

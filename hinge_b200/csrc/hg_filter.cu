@@ -14,6 +14,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "hg_device.cuh"
 #include "hg_filter.h"
 #include "hg_order.h"
@@ -1002,26 +1004,33 @@ k_hinge_exact(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
     }
 }
 
-// The same for pile-ups of at most `cap` records: ONE WARP per read, four reads per CTA, all
-// arrays of a read in its warp's slice of shared memory (48 B per record).  A pile-up of a few
-// hundred records is far too small for a CTA (k_hinge_exact above spends its time in barriers
-// and in the lock of its work stack: 50 us per read, 296 reads at a time -- 3.4 ms for the 20 k
-// reads of the long-read / fragmented-alignment set), while thousands of warps fit the chip.
+// The same for pile-ups of at most `cap` records: ONE WARP per read, four reads per CTA.  A pile-up
+// of a few hundred records is far too small for a CTA (k_hinge_exact above spends its time in
+// barriers and in the lock of its work stack: ~270 us per read, 296 reads at a time -- 3.4 ms for the
+// 20 k reads of the long-read / fragmented-alignment set); a warp takes 50-100 us, most of it the
+// fixed cost of the ~n/8 partition steps of the introsort emulation (latency, not throughput), so
+// what counts is how many warps are in flight.  Shared memory per record is therefore kept to 28
+// bytes -- sort keys, end list, sort scratch and 16-bit position lists; the records themselves sit
+// in the warp's slot of the global scratch k_hinge_call has finished with (read once per
+// annotation, L1-resident) -- which allows 32 / 21 / 10 warps per SM for the three size tiers.
 // Handles the reads of the list with np_above < pile-up size <= cap; launched once per size tier.
+constexpr int kHingeWarpBytesPerRec = 8 + 8 + 8 + 4;
+
 __global__ void __launch_bounds__(128)
 k_hinge_exact_warp(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
                    const int2* __restrict__ anno_ref, const int2* __restrict__ anno_pool,
                    int* __restrict__ counters, int queue_slot, const int* __restrict__ exact_list,
-                   uint8_t* __restrict__ hinge_keep, int np_above, int cap) {
+                   uint8_t* __restrict__ hinge_keep, uint8_t* gscratch, int gcap, int np_above, int cap) {
     extern __shared__ __align__(16) uint8_t sm_exact[];
     const int lane = lane_id();
     const unsigned lt = (1u << lane) - 1u;
-    uint8_t* base = sm_exact + (size_t)(threadIdx.x >> 5) * cap * kHingeExactBytesPerRec;
-    int4* rec = reinterpret_cast<int4*>(base);
-    KeyIdx* ord = reinterpret_cast<KeyIdx*>(base + (size_t)cap * 16);
-    int2* ends = reinterpret_cast<int2*>(base + (size_t)cap * 24);
-    int2* tmp = reinterpret_cast<int2*>(base + (size_t)cap * 32);
-    int* gl = reinterpret_cast<int*>(base + (size_t)cap * 40);
+    uint8_t* base = sm_exact + (size_t)(threadIdx.x >> 5) * cap * kHingeWarpBytesPerRec;
+    KeyIdx* ord = reinterpret_cast<KeyIdx*>(base);
+    int2* ends = reinterpret_cast<int2*>(base + (size_t)cap * 8);
+    int2* tmp = reinterpret_cast<int2*>(base + (size_t)cap * 16);
+    uint16_t* gl = reinterpret_cast<uint16_t*>(base + (size_t)cap * 24);
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int4* rec = reinterpret_cast<int4*>(gscratch + (size_t)gwarp * gcap * kHingeSlotBytesPerRec);
     const int nlist = counters[6];
     const int THETA = P.theta, HTL = P.hinge_tolerance_length;
     for (;;) {
@@ -1217,18 +1226,16 @@ void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_pa
                                                     s.counters, s.work_items, s.exact_list, s.hinge_keep,
                                                     s.hinge_scratch, s.hinge_cap, s.item_log, peer);
     // The reads that need the exact sort order, in size tiers that run side by side on forked streams
-    // (they work on different reads of one list; each has its own queue cursor).  One WARP per read out
-    // of shared memory (48 B per record) is by far the fastest form -- 18 us per read and thousands in
-    // flight, against ~270 us per read for the CTA form on a few hundred records (ncu, long-read set:
-    // 15 k reads in 115 us vs 5 k reads in 1.5 ms) -- so it takes everything that fits a warp's slice:
-    //   A   <= 256 records: 12 KB per warp, 16 warps per SM       B   <= 384: 18 KB, 12 warps per SM
-    //   C   <= 768: 36 KB, 4 warps per SM
+    // (they work on different reads of one list; each has its own queue cursor).  One WARP per read
+    // (k_hinge_exact_warp) takes everything that fits a warp's slice of shared memory:
+    //   A   <= 256 records: 7 KB per warp, 32 warps per SM        B   <= 384: 10.5 KB, 21 warps per SM
+    //   C   <= 768: 21 KB, 10 warps per SM
     //   D   deeper: one CTA per read (sub-ranges of the introsort on different warps), 72 KB, global
     //       scratch beyond 1536 records
     constexpr int capA = 256, capB = 384, capC = 768, capD = 1536;
     const int smemD = capD * kHingeExactBytesPerRec;
     // function attributes are per device: set them on every launch (cheap), not once per process
-    cudaFuncSetAttribute(k_hinge_exact_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * capC * kHingeExactBytesPerRec);
+    cudaFuncSetAttribute(k_hinge_exact_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * capC * kHingeWarpBytesPerRec);
     cudaFuncSetAttribute(k_hinge_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, smemD);
     g_launches += 4;
     const bool fork = s.side_stream[0] != nullptr;
@@ -1239,15 +1246,25 @@ void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_pa
         cudaStreamWaitEvent(sC, s.side_event[0], 0);
         cudaStreamWaitEvent(sD, s.side_event[0], 0);
     }
-    k_hinge_exact_warp<<<4 * s.num_sms, 128, 4 * capA * kHingeExactBytesPerRec, st>>>(
-        rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 12, s.exact_list, s.hinge_keep, 0, capA);
-    k_hinge_exact_warp<<<3 * s.num_sms, 128, 4 * capB * kHingeExactBytesPerRec, sB>>>(
-        rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 13, s.exact_list, s.hinge_keep, capA, capB);
-    k_hinge_exact_warp<<<s.num_sms, 128, 4 * capC * kHingeExactBytesPerRec, sC>>>(
-        rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 14, s.exact_list, s.hinge_keep, capB, capC);
-    const int gridD = s.hinge_warps < 2 * s.num_sms ? s.hinge_warps : 2 * s.num_sms;
+    // a warp of these kernels keeps the records in its slot of the global scratch: the tiers' grids
+    // share the hinge_warps slots (B behind A, C behind B; D only uses slots when it leaves shared memory)
+    const int slots = s.hinge_warps / 4;  // in CTAs of four warps
+    const int gA = std::max(1, std::min(8 * s.num_sms, slots / 2)), gB = std::max(1, std::min(5 * s.num_sms, slots / 4));
+    const int gC = std::max(1, std::min(2 * s.num_sms, slots / 8));
+    const size_t slot_bytes = (size_t)s.hinge_cap * kHingeSlotBytesPerRec * 4;  // per CTA
+    k_hinge_exact_warp<<<gA, 128, 4 * capA * kHingeWarpBytesPerRec, st>>>(
+        rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 12, s.exact_list, s.hinge_keep, s.hinge_scratch,
+        s.hinge_cap, 0, capA);
+    k_hinge_exact_warp<<<gB, 128, 4 * capB * kHingeWarpBytesPerRec, sB>>>(
+        rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 13, s.exact_list, s.hinge_keep,
+        s.hinge_scratch + slot_bytes * gA, s.hinge_cap, capA, capB);
+    k_hinge_exact_warp<<<gC, 128, 4 * capC * kHingeWarpBytesPerRec, sC>>>(
+        rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 14, s.exact_list, s.hinge_keep,
+        s.hinge_scratch + slot_bytes * (gA + gB), s.hinge_cap, capB, capC);
+    const int gridD = std::max(1, std::min(2 * s.num_sms, slots / 8));
     k_hinge_exact<<<gridD, 128, smemD, sD>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 7, s.exact_list,
-                                            s.hinge_keep, s.hinge_scratch, s.hinge_cap, capD, capC, 0x7fffffff);
+                                            s.hinge_keep, s.hinge_scratch + slot_bytes * (gA + gB + gC) , s.hinge_cap,
+                                            capD, capC, 0x7fffffff);
     if (fork) {
         for (int i = 0; i < 3; i++) {
             cudaEventRecord(s.side_event[1 + i], i == 0 ? sB : (i == 1 ? sC : sD));

@@ -260,9 +260,9 @@ HG_HD void hash_iteration_order(KeyAt key_at, int n, const int* grow_at, const i
 //     <= 16-element block (blocks are mutually ordered after the introsort loop):
 //     every lane ranks its elements inside a +-15 window.
 //   * median-of-3 and the heap-sort fallback (depth limit) stay on lane 0.
-// Scratch: idx_g / idx_l hold n ints each, tmp holds n elements.
-template <class T, class Less>
-__device__ void warp_sort_exact(T* a, int n, Less less, int* idx_g, int* idx_l, T* tmp) {
+// Scratch: idx_g / idx_l hold n indices each (16-bit ones do for n < 65536), tmp holds n elements.
+template <class T, class Less, class Idx>
+__device__ void warp_sort_exact(T* a, int n, Less less, Idx* idx_g, Idx* idx_l, T* tmp) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     if (n <= 1) return;
@@ -309,19 +309,19 @@ __device__ void warp_sort_exact(T* a, int n, Less less, int* idx_g, int* idx_l, 
                     le = !less(pivot, v);
                 }
                 const unsigned mg = __ballot_sync(0xffffffffu, ge), ml = __ballot_sync(0xffffffffu, le);
-                if (ge) idx_g[ng + __popc(mg & lt)] = p;
-                if (le) idx_l[nl + __popc(ml & lt)] = p;
+                if (ge) idx_g[ng + __popc(mg & lt)] = (Idx)p;
+                if (le) idx_l[nl + __popc(ml & lt)] = (Idx)p;
                 ng += __popc(mg);
                 nl += __popc(ml);
             }
             __syncwarp();
             const int lim = ng < nl ? ng : nl;
             int cnt = 0;
-            for (int i = lane; i < lim; i += 32) cnt += idx_g[i] < idx_l[nl - 1 - i] ? 1 : 0;
+            for (int i = lane; i < lim; i += 32) cnt += (int)idx_g[i] < (int)idx_l[nl - 1 - i] ? 1 : 0;
             const int m = __reduce_add_sync(0xffffffffu, cnt);
-            for (int i = lane; i < m; i += 32) os_swap(a, idx_g[i], idx_l[nl - 1 - i]);
-            const int prev_hi = m > 0 ? idx_l[nl - m] : last;
-            const int cut = (m < ng && idx_g[m] < prev_hi) ? idx_g[m] : prev_hi;
+            for (int i = lane; i < m; i += 32) os_swap(a, (int)idx_g[i], (int)idx_l[nl - 1 - i]);
+            const int prev_hi = m > 0 ? (int)idx_l[nl - m] : last;
+            const int cut = (m < ng && (int)idx_g[m] < prev_hi) ? (int)idx_g[m] : prev_hi;
             __syncwarp();
             stack_first[sp] = cut;
             stack_last[sp] = last;
