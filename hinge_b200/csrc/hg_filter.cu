@@ -1030,7 +1030,7 @@ k_hinge_exact_warp(RecView rv, ReadView rd, hg_filter_params P, MaskView mask,
     int2* tmp = reinterpret_cast<int2*>(base + (size_t)cap * 16);
     uint16_t* gl = reinterpret_cast<uint16_t*>(base + (size_t)cap * 24);
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int4* rec = reinterpret_cast<int4*>(gscratch + (size_t)gwarp * gcap * kHingeSlotBytesPerRec);
+    int4* rec = reinterpret_cast<int4*>(gscratch + (size_t)gwarp * gcap * sizeof(int4));
     const int nlist = counters[6];
     const int THETA = P.theta, HTL = P.hinge_tolerance_length;
     for (;;) {
@@ -1246,25 +1246,27 @@ void launch_hinge_call(const RecView& rv, const ReadView& rd, const hg_filter_pa
         cudaStreamWaitEvent(sC, s.side_event[0], 0);
         cudaStreamWaitEvent(sD, s.side_event[0], 0);
     }
-    // a warp of these kernels keeps the records in its slot of the global scratch: the tiers' grids
-    // share the hinge_warps slots (B behind A, C behind B; D only uses slots when it leaves shared memory)
-    const int slots = s.hinge_warps / 4;  // in CTAs of four warps
-    const int gA = std::max(1, std::min(8 * s.num_sms, slots / 2)), gB = std::max(1, std::min(5 * s.num_sms, slots / 4));
-    const int gC = std::max(1, std::min(2 * s.num_sms, slots / 8));
-    const size_t slot_bytes = (size_t)s.hinge_cap * kHingeSlotBytesPerRec * 4;  // per CTA
+    // The global scratch k_hinge_call has finished with (hinge_warps slots of 56 B per record) is
+    // carved up again: tier D's CTAs keep full slots, a warp of the other tiers only needs 16 B per
+    // record for the records themselves.
+    const size_t total = (size_t)s.hinge_warps * s.hinge_cap * kHingeSlotBytesPerRec;
+    const size_t slotD = (size_t)s.hinge_cap * kHingeSlotBytesPerRec, slotW = (size_t)s.hinge_cap * sizeof(int4) * 4;
+    const int gridD = (int)std::max<size_t>(1, std::min<size_t>(2 * s.num_sms, total / 4 / slotD));
+    const size_t ctas = (total - slotD * gridD) / slotW;  // CTAs of four warps the rest can serve
+    const int gA = (int)std::max<size_t>(1, std::min<size_t>(8 * s.num_sms, ctas / 2));
+    const int gB = (int)std::max<size_t>(1, std::min<size_t>(5 * s.num_sms, ctas / 4));
+    const int gC = (int)std::max<size_t>(1, std::min<size_t>(2 * s.num_sms, ctas / 8));
+    uint8_t* const baseW = s.hinge_scratch + slotD * gridD;
     k_hinge_exact_warp<<<gA, 128, 4 * capA * kHingeWarpBytesPerRec, st>>>(
-        rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 12, s.exact_list, s.hinge_keep, s.hinge_scratch,
-        s.hinge_cap, 0, capA);
+        rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 12, s.exact_list, s.hinge_keep, baseW, s.hinge_cap, 0, capA);
     k_hinge_exact_warp<<<gB, 128, 4 * capB * kHingeWarpBytesPerRec, sB>>>(
-        rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 13, s.exact_list, s.hinge_keep,
-        s.hinge_scratch + slot_bytes * gA, s.hinge_cap, capA, capB);
+        rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 13, s.exact_list, s.hinge_keep, baseW + slotW * gA,
+        s.hinge_cap, capA, capB);
     k_hinge_exact_warp<<<gC, 128, 4 * capC * kHingeWarpBytesPerRec, sC>>>(
-        rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 14, s.exact_list, s.hinge_keep,
-        s.hinge_scratch + slot_bytes * (gA + gB), s.hinge_cap, capB, capC);
-    const int gridD = std::max(1, std::min(2 * s.num_sms, slots / 8));
+        rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 14, s.exact_list, s.hinge_keep, baseW + slotW * (gA + gB),
+        s.hinge_cap, capB, capC);
     k_hinge_exact<<<gridD, 128, smemD, sD>>>(rv, rd, P, mv, s.anno_ref, s.anno_pool, s.counters, 7, s.exact_list,
-                                            s.hinge_keep, s.hinge_scratch + slot_bytes * (gA + gB + gC) , s.hinge_cap,
-                                            capD, capC, 0x7fffffff);
+                                            s.hinge_keep, s.hinge_scratch, s.hinge_cap, capD, capC, 0x7fffffff);
     if (fork) {
         for (int i = 0; i < 3; i++) {
             cudaEventRecord(s.side_event[1 + i], i == 0 ? sB : (i == 1 ? sC : sD));

@@ -148,6 +148,32 @@ def run_filter_sharded(ctx, params, arrays, max_attempts=8):
     return api.HG_RETRY_POOL, s
 
 
+def gather_filter_lists(result, arrays, group=None):
+    """All-gather-v of the shards' repeat-annotation / hinge lists ("after K4"):
+    `result` is this rank's hg_filter_fetch; returns the GLOBAL CSRs (rep, hin), each (off[n+1], pos, type),
+    identical on every rank -- what `.repeat.txt` / `.hinges.txt` hold in a single-process run."""
+    n, lo, hi = arrays.n_read, arrays.lo, arrays.hi
+    a0, a1 = int(result["anno_off"][lo]), int(result["anno_off"][hi])
+    mine = (lo, hi, np.diff(result["anno_off"][lo:hi + 1]).astype(np.int64), result["anno_pos"][a0:a1],
+            result["anno_type"][a0:a1], result["hinge_keep"][a0:a1].astype(bool))
+    parts = [mine]
+    if arrays.world > 1:
+        parts = [None] * arrays.world
+        dist.all_gather_object(parts, mine, group=group)
+    counts = np.zeros(n, np.int64)
+    for plo, phi, cnt, _, _, _ in parts:
+        counts[plo:phi] = cnt
+    pos = np.concatenate([p[3] for p in parts]).astype(np.int32)
+    typ = np.concatenate([p[4] for p in parts]).astype(np.int32)
+    keep = np.concatenate([p[5] for p in parts])
+    rep_off = np.zeros(n + 1, np.int64)
+    np.cumsum(counts, out=rep_off[1:])
+    per_read = np.repeat(np.arange(n), counts)
+    hin_off = np.zeros(n + 1, np.int64)
+    np.cumsum(np.bincount(per_read[keep], minlength=n), out=hin_off[1:])
+    return (rep_off, pos, typ), (hin_off, pos[keep], typ[keep])
+
+
 def run_maximal_sharded(ctx, params, arrays, mask, group=None):
     """hg_maximal on shards: local classification + containment lists, then ONE exchange round over
     NCCL (MAX all-reduce of the per-read states, all-gather of the unknown reads' lists) and the

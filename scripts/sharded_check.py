@@ -16,7 +16,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import hgsynth  # noqa: E402
 from hinge_b200 import api  # noqa: E402
-from hinge_b200.sharding import ShardedArrays, run_filter_sharded, run_layout_sharded, run_maximal_sharded  # noqa: E402
+from hinge_b200.sharding import (ShardedArrays, gather_filter_lists, run_filter_sharded, run_layout_sharded,  # noqa: E402
+                                 run_maximal_sharded)
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -43,6 +44,8 @@ for exchange in ("peer", "nccl"):
         rc, summ = run_filter_sharded(ctx, api.FilterParams(), arrays)
         assert rc == 0
     mine = ctx.filter_fetch(int(summ.n_annotations))
+    lists = gather_filter_lists(mine, arrays)  # the last exchange's lists feed the layout check below
+    masks_all = arrays.gathered_mask(syn.n_read)
     part = {k: mine[k] for k in FIELDS}
     part.update(lo=arrays.lo, hi=arrays.hi, cov_est=summ.cov_est, min_cov=summ.min_cov,
                 mask_all=arrays.gathered_mask(syn.n_read))
@@ -86,28 +89,15 @@ toff, tr = toff.copy(), tr.copy()
 ctx = api.Context(local, torch.cuda.current_stream().cuda_stream)
 ctx.set_reads(syn.rlen, syn.qv_off, syn.qv, 100)
 ctx.set_overlaps(novl, cols, trace_off=toff, trace=tr, a_lo=arrays.lo, a_hi=arrays.hi)
-masks = [want["mask"] if rank == 0 else None]
-dist.broadcast_object_list(masks, src=0)
+masks = [masks_all]  # as every rank holds them after the sharded filter (checked against `want` above)
 lp = api.LayoutParams()
 got_max = run_maximal_sharded(ctx, lp, arrays, masks[0])
 all_max = [None] * world
 dist.all_gather_object(all_max, got_max)
 
-# ---- layout on shards: global annotation / hinge lists (rank 0's single-context filter result stands in
-# for the gathered per-shard lists, which the checks above proved identical), maximal bitmap from above
-def csr(res):
-    n = len(res["anno_off"]) - 1
-    keep = res["hinge_keep"].astype(bool)
-    per_read = np.repeat(np.arange(n), np.diff(res["anno_off"]))
-    hin_off = np.zeros(n + 1, np.int64)
-    np.cumsum(np.bincount(per_read[keep], minlength=n), out=hin_off[1:])
-    return ((res["anno_off"], res["anno_pos"], res["anno_type"]),
-            (hin_off, res["anno_pos"][keep], res["anno_type"][keep]))
-
-
-lists = [csr(want) if rank == 0 else None]
-dist.broadcast_object_list(lists, src=0)
-rep_csr, hin_csr = lists[0]
+# ---- layout on shards: the annotation / hinge lists all-gathered from the shards' filter results, the
+# maximal bitmap from above
+rep_csr, hin_csr = lists
 my_edges, _ = run_layout_sharded(ctx, lp, arrays, masks[0], got_max, rep_csr, hin_csr)
 ctx.close()
 edge_key = lambda e: (e.a, e.b, e.length, e.comp, e.type, e.weight, tuple(e.eff_a), tuple(e.eff_b), tuple(e.raw_a),
@@ -126,7 +116,12 @@ if rank == 0:
     print("SHARDED_CHECK maximal", "OK" if good else "MISMATCH", "world", world, "maximal reads", int(want_max.sum()),
           "of", syn.n_read, flush=True)
     ok &= good
-    want_edges, _ = ref.layout(lp, masks[0], want_max, rep_csr, hin_csr)
+    keep = want["hinge_keep"].astype(bool)
+    per_read = np.repeat(np.arange(syn.n_read), np.diff(want["anno_off"]))
+    hin_off = np.zeros(syn.n_read + 1, np.int64)
+    np.cumsum(np.bincount(per_read[keep], minlength=syn.n_read), out=hin_off[1:])
+    want_edges, _ = ref.layout(lp, want["mask"], want_max, (want["anno_off"], want["anno_pos"], want["anno_type"]),
+                               (hin_off, want["anno_pos"][keep], want["anno_type"][keep]))
     ref.close()
     got_edges = [e for part in all_edges for e in part]  # rank order = read order
     good = got_edges == [edge_key(e) for e in want_edges]

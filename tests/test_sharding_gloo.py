@@ -174,3 +174,47 @@ def test_sharded_filter_flow_exchanges_between_the_phases(refuse_packed):
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def _lists_worker(rank, world, port, n_read, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+
+    from hinge_b200.sharding import ShardedArrays, gather_filter_lists
+
+    # the whole result as one process would see it: read i carries i % 3 annotations, every second one a hinge
+    counts = np.arange(n_read) % 3
+    off = np.zeros(n_read + 1, np.int64)
+    np.cumsum(counts, out=off[1:])
+    pos = (np.arange(off[-1]) * 40).astype(np.int32)
+    typ = np.where(np.arange(off[-1]) % 2 == 0, 1, -1).astype(np.int32)
+    keep = (np.arange(off[-1]) % 2 == 1).astype(np.uint8)
+    arr = ShardedArrays(n_read, rank, world, torch.device("cpu"), weights=np.arange(1, n_read + 1))
+    # this rank's fetch: offsets are global-sized, but only the annotations of its own reads are there
+    a0, a1 = off[arr.lo], off[arr.hi]
+    mine_off = np.clip(off, a0, a1) - a0
+    mine = {"anno_off": mine_off, "anno_pos": pos[a0:a1], "anno_type": typ[a0:a1], "hinge_keep": keep[a0:a1]}
+    (rep_off, rep_pos, rep_typ), (hin_off, hin_pos, hin_typ) = gather_filter_lists(mine, arr)
+    k = keep.astype(bool)
+    per_read = np.repeat(np.arange(n_read), counts)
+    want_hin_off = np.zeros(n_read + 1, np.int64)
+    np.cumsum(np.bincount(per_read[k], minlength=n_read), out=want_hin_off[1:])
+    ok = (np.array_equal(rep_off, off) and np.array_equal(rep_pos, pos) and np.array_equal(rep_typ, typ)
+          and np.array_equal(hin_off, want_hin_off) and np.array_equal(hin_pos, pos[k]) and np.array_equal(hin_typ, typ[k]))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_annotation_lists_are_gathered_into_global_csrs():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 23
+    procs = [ctx.Process(target=_lists_worker, args=(r, 2, port, 203, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)]
