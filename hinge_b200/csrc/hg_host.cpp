@@ -368,39 +368,61 @@ extern "C" int hg_main_filter(int argc, char** argv) {
                 if (const char* v = getenv("HINGE_B200_IO_THREADS")) workers = atoi(v);
                 workers = std::max(1, std::min(workers, 32));
                 const int block = 4096 * workers;
+                // raw buffers + a two-digits-at-a-time itoa: the text is ~11 bytes per bin and there are tens of
+                // millions of bins, so the formatter is worth its own few lines
                 std::vector<std::vector<char>> bufs((size_t)workers);
-                auto put_int = [](std::vector<char>& b, long v) {
-                    char tmp[24];
+                static const char kDigits[] =
+                    "00010203040506070809101112131415161718192021222324252627282930313233343536373839"
+                    "40414243444546474849505152535455565758596061626364656667686970717273747576777879"
+                    "8081828384858687888990919293949596979899";
+                auto put_u = [](char* p, unsigned v) -> char* {  // v < 2^31
+                    char tmp[12];
                     int n = 0;
-                    unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
-                    do {
-                        tmp[n++] = (char)('0' + u % 10);
-                        u /= 10;
-                    } while (u);
-                    if (v < 0) b.push_back('-');
-                    while (n) b.push_back(tmp[--n]);
+                    while (v >= 100) {
+                        const unsigned r = v % 100;
+                        v /= 100;
+                        tmp[n++] = kDigits[2 * r + 1];
+                        tmp[n++] = kDigits[2 * r];
+                    }
+                    if (v >= 10) {
+                        tmp[n++] = kDigits[2 * v + 1];
+                        tmp[n++] = kDigits[2 * v];
+                    } else {
+                        tmp[n++] = (char)('0' + v);
+                    }
+                    while (n) *p++ = tmp[--n];
+                    return p;
                 };
                 for (int b0 = sum.r_begin; b0 <= sum.r_end && fd >= 0; b0 += block) {
                     const int b1 = std::min(sum.r_end + 1, b0 + block);
                     std::vector<std::thread> pool;
                     for (int w = 0; w < workers; w++)
                         pool.emplace_back([&, w]() {
-                            std::vector<char>& out = bufs[w];
-                            out.clear();
                             const int per = (b1 - b0 + workers - 1) / workers;
-                            for (int i = b0 + w * per; i < std::min(b1, b0 + (w + 1) * per); i++) {
-                                const char* head = "read ";
-                                out.insert(out.end(), head, head + 5);
-                                put_int(out, i);
-                                out.push_back(' ');
-                                for (int64_t k = cov_off[i]; k < cov_off[i + 1]; k++) {
-                                    put_int(out, (long)(k - cov_off[i]) * fp.reso);
-                                    out.push_back(',');
-                                    put_int(out, cov[k]);
-                                    out.push_back(' ');
+                            const int lo = std::min(b1, b0 + w * per), hi = std::min(b1, b0 + (w + 1) * per);
+                            // "read <i> " + per bin "<pos>,<cov> " (at most 10 + 1 + 11 + 1 bytes) + newline
+                            std::vector<char>& out = bufs[w];
+                            out.resize((size_t)(hi - lo) * 32 + (size_t)(cov_off[hi] - cov_off[lo]) * 24 + 64);
+                            char* p = out.data();
+                            for (int i = lo; i < hi; i++) {
+                                memcpy(p, "read ", 5);
+                                p = put_u(p + 5, (unsigned)i);
+                                *p++ = ' ';
+                                unsigned pos = 0;
+                                for (int64_t k = cov_off[i]; k < cov_off[i + 1]; k++, pos += (unsigned)fp.reso) {
+                                    p = put_u(p, pos);
+                                    *p++ = ',';
+                                    int v = cov[k];
+                                    if (v < 0) {
+                                        *p++ = '-';
+                                        v = -v;
+                                    }
+                                    p = put_u(p, (unsigned)v);
+                                    *p++ = ' ';
                                 }
-                                out.push_back('\n');
+                                *p++ = '\n';
                             }
+                            out.resize((size_t)(p - out.data()));
                         });
                     for (auto& th : pool) th.join();
                     pool.clear();
