@@ -205,6 +205,11 @@ def file_to_file(p, steps, warmup, with_cli):
             mine = [exe, "filter", "--db", "S", "--las", "S.las", "-x", "gpu", "--config", ini]
             env = dict(os.environ, HINGE_B200_TIMING="1")
             runs = []
+            # clocks are sampled over this timed region too; the running nvidia-smi also keeps the driver
+            # attached to the GPU between the runs (on a box without persistence mode every process start
+            # would otherwise pay the driver's own cold start, ~0.7 s, which is not the executable's doing)
+            sampler = ClockSampler(0)
+            time.sleep(0.3)
             for _ in range(3):
                 t0 = time.perf_counter()
                 r = subprocess.run(mine, cwd=work, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE,
@@ -212,7 +217,8 @@ def file_to_file(p, steps, warmup, with_cli):
                 runs.append((time.perf_counter() - t0, r.stderr))
             runs = runs[1:]  # the first run pages the executable and the CUDA libraries in
             best, phases = min(runs, key=lambda x: x[0])
-            cli = {"seconds": best, "seconds_all": [round(x[0], 3) for x in runs], "overlaps_per_s": novl / best,
+            cli_clocks = sampler.stop()
+            cli = {"seconds": best, "clocks": cli_clocks, "seconds_all": [round(x[0], 3) for x in runs], "overlaps_per_s": novl / best,
                    "phases_ms": parse_phases(phases)}
         cmd = [ref] + (["filter"] if kind == "port" else []) + ["--db", "S", "--las", "S.las", "-x", "ref",
                                                                  "--config", ini]
@@ -309,19 +315,33 @@ def compare_results(np, got, want, lo=0, hi=None):
     of the arrays that differ.  `got` may hold only the annotations of its own reads."""
     n = len(want["anno_off"]) - 1
     hi = n if hi is None else hi
-    bad = []
-    for k in ("mask", "cmask", "flags"):
-        if not np.array_equal(got[k][lo:hi], want[k][lo:hi]):
-            bad.append(k)
-    if not np.array_equal(np.diff(got["anno_off"][lo:hi + 1]), np.diff(want["anno_off"][lo:hi + 1])):
+    return compare_slice(np, slice_result(np, got, lo, hi), want)
+
+
+def slice_result(np, res, lo, hi):
+    """The part of a filter result that belongs to the reads [lo, hi) (what a rank sends for checking)."""
+    a0, a1 = int(res["anno_off"][lo]), int(res["anno_off"][hi])
+    return {"lo": lo, "hi": hi, "mask": res["mask"][lo:hi].copy(), "cmask": res["cmask"][lo:hi].copy(),
+            "flags": res["flags"][lo:hi].copy(), "anno_cnt": np.diff(res["anno_off"][lo:hi + 1]),
+            "anno_pos": res["anno_pos"][a0:a1].copy(), "anno_type": res["anno_type"][a0:a1].copy(),
+            "hinge_keep": res["hinge_keep"][a0:a1].copy()}
+
+
+def compare_slice(np, part, want):
+    lo, hi = part["lo"], part["hi"]
+    bad = [k for k in ("mask", "cmask", "flags") if not np.array_equal(part[k], want[k][lo:hi])]
+    if not np.array_equal(part["anno_cnt"], np.diff(want["anno_off"][lo:hi + 1])):
         bad.append("anno_off")
     else:
-        g0, g1 = got["anno_off"][lo], got["anno_off"][hi]
         w0, w1 = want["anno_off"][lo], want["anno_off"][hi]
-        for k in ("anno_pos", "anno_type", "hinge_keep"):
-            if not np.array_equal(got[k][g0:g1], want[k][w0:w1]):
-                bad.append(k)
+        bad += [k for k in ("anno_pos", "anno_type", "hinge_keep") if not np.array_equal(part[k], want[k][w0:w1])]
     return bad
+
+
+def digest(np, a):
+    import hashlib
+
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
 class Bench:
@@ -522,11 +542,11 @@ class Bench:
         world, rank = self.world, self.rank
         t0 = time.perf_counter()
         info = {"checked": True, "identical": None, "against": [], "differing": []}
-        mine = {k: result[k] for k in FIELDS}
-        mine.update(lo=arrays.lo, hi=arrays.hi, cov_est=int(summary.cov_est), min_cov=int(summary.min_cov))
+        mine = slice_result(np, result, arrays.lo, arrays.hi)
+        mine.update(cov_est=int(summary.cov_est), min_cov=int(summary.min_cov))
         if world > 1:
-            # the shards' masks were exchanged during the run: every rank holds all of them
-            mine["mask_all"] = arrays.gathered_mask(syn.n_read)
+            # the shards' masks were exchanged during the run: every rank holds all of them (digest travels)
+            mine["mask_all_sha256"] = digest(np, arrays.gathered_mask(syn.n_read))
             parts = [None] * world if rank == 0 else None
             dist.gather_object(mine, parts, dst=0)
         else:
@@ -543,11 +563,12 @@ class Bench:
                 full = ref.filter_fetch(int(s1.n_annotations))
                 full["summary"] = np.array([s1.r_begin, s1.r_end, s1.cov_est, s1.min_cov])
                 ref.close()
+                want_digest = digest(np, full["mask"])
                 for r, part in enumerate(parts):
-                    bad = compare_results(np, part, full, part["lo"], part["hi"])
+                    bad = compare_slice(np, part, full)
                     if (part["cov_est"], part["min_cov"]) != (int(s1.cov_est), int(s1.min_cov)):
                         bad.append("cov_est/min_cov")
-                    if not np.array_equal(part["mask_all"], full["mask"]):
+                    if part["mask_all_sha256"] != want_digest:
                         bad.append("exchanged masks")
                     info["differing"] += ["rank%d:%s" % (r, b) for b in bad]
                 info["against"].append("single-context GPU run of the whole set (%d overlaps) vs the %d shards"
@@ -628,7 +649,8 @@ def main():
                            "page cache -> all output files (process start and CUDA context creation included)",
                            "same_files_as_cpu_baseline": True, "overlaps": f2f["sample_overlaps"],
                            "outputs_identical_to_reference": cli["outputs_identical_to_reference"],
-                           "phases_ms": cli["phases_ms"], "reference_seconds": cli["reference_seconds"]}
+                           "phases_ms": cli["phases_ms"], "reference_seconds": cli["reference_seconds"],
+                           "seconds_all": cli["seconds_all"], "clocks": cli["clocks"]}
         else:
             line["e2e"] = dict(main_res["e2e_arrays"], path="array-level C ABI, pinned host buffers (file-to-file "
                                "leg skipped: N > 1 or --no-cpu-baseline)")

@@ -581,235 +581,6 @@ k_cov_big(RecView rv, ReadView rd, FlatParams F) {
     }
 }
 
-// ------------------------------------------------------------------ K2, per read, warp-wide
-//
-// The per-read part of K2 for LONG reads.  With N(24000, 8000) reads a batch holds six reads of
-// ~600 bins each: one thread per read (below) leaves 250 of 256 threads idle while six walk their
-// bit maps and chase dependent loads through the annotation candidates (ncu: 0.61 ms for 1.2 GB on
-// the long-read set, 15 k cycles per CTA).  Here a warp takes a read: lanes own bit-map words
-// (covered-run search: a max-gap-between-zeros reduction) or bits of one word (annotation candidates:
-// coverage words loaded side by side, types by ballot, only the few survivors go through the
-// sequential merge).  Same results as the thread-per-read form, bit for bit.
-struct WarpAnnoState {  // the streaming merge of filter.cpp:817-829 (see the thread form below)
-    unsigned cur;
-    bool have;
-    int n;
-};
-
-__device__ __forceinline__ void flat_read_warp(const hg_filter_params& P, const FlatParams& F, const MaskAnnoOut& out,
-                                               const RecView& rv, const ReadView& rd, const uint32_t* __restrict__ pw,
-                                               const uint32_t* zmap, const uint32_t* cmap, int MIN_COV, int read, int base,
-                                               int64_t nrec) {
-    const int lane = lane_id();
-    constexpr int reso = kReso;
-    const int nbz = bins_needed(rd.rlen[read], P);
-    const int L0 = F.cov_maxbin[read] + 1;  // length of the cut-off-free profile
-    auto H = [&](int j) { return __ldg(pw + base + j); };
-
-    // ---- longest run of covered bins (filter.cpp:696-728): zeros z in ascending order, the run before z
-    // scores z - p (p = the zero before it, bin 0 to begin with); strictly greater keeps the earliest
-    const int end = base + nbz;
-    unsigned long long best = 0;  // (gap << 32) | (0x7fffffff - z)
-    int carry_last = base;        // last zero seen in earlier chunks of 32 words
-    for (int w0 = base >> 5; w0 <= (end - 1) >> 5; w0 += 32) {
-        const int w = w0 + lane;
-        uint32_t m = w <= (end - 1) >> 5 ? map_word(zmap, w, base + 1, end) : 0u;
-        int first = -1, last = -1;
-        unsigned long long mine = 0;
-        if (m) {
-            first = (w << 5) + __ffs(m) - 1;
-            last = (w << 5) + 31 - __clz(m);
-            int p = first;
-            uint32_t r = m & (m - 1);
-            while (r) {  // gaps between the zeros inside this word
-                const int z = (w << 5) + __ffs(r) - 1;
-                const unsigned long long cand = ((unsigned long long)(z - p) << 32) | (unsigned)(0x7fffffff - z);
-                if (cand > mine) mine = cand;
-                p = z;
-                r &= r - 1;
-            }
-        }
-        // the zero before this word's first one: the last zero of the nearest lower lane that has any
-        int prev = last;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, prev, d);
-            if (lane >= d) prev = max(prev, o);
-        }
-        const int incl = prev;
-        prev = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) prev = -1;
-        prev = max(prev, carry_last);
-        if (m) {
-            const unsigned long long cand = ((unsigned long long)(first - prev) << 32) | (unsigned)(0x7fffffff - first);
-            if (cand > mine) mine = cand;
-        }
-        best = max(best, warp_max_u64(mine));
-        carry_last = max(carry_last, __shfl_sync(0xffffffffu, incl, 31));
-    }
-    const int bestgap = (int)(best >> 32), bestz = 0x7fffffff - (int)(best & 0xffffffffu);
-    int maxstart = 0, maxend = 0, msc = 0, mec = 0;
-    if (bestgap >= 3) {
-        const int z = bestz - base, pz = z - bestgap;
-        msc = pz + 1;
-        mec = z - 1;
-        maxstart = reso * (pz + 1);
-        maxend = reso * (z - 1);
-    }
-
-    // ---- telomere / coverage-imbalance flag (filter.cpp:731-760)
-    uint8_t flags = 0;
-    if (P.delete_telomere) {
-        flags = out.rflags[read] & kFlagSelf;
-        int limit, div;
-        if (mec - msc + 1 > 20) {
-            limit = 10;
-            div = 10;
-        } else {
-            limit = (mec - msc) / 2;
-            div = limit;
-        }
-        int sc = 0, ec = 0;
-        for (int t = lane; t < limit; t += 32) {
-            sc += max(f_hi(H(msc + t)), MIN_COV);
-            ec += max(f_hi(H(mec - t)), MIN_COV);
-        }
-        sc = warp_sum(sc);
-        ec = warp_sum(ec);
-        if (div == 0) {
-            sc = 0;
-            ec = 0;
-        } else {
-            sc /= div;
-            ec /= div;
-        }
-        if (sc >= 10 * ec || ec >= 10 * sc) flags |= kFlagCov;
-    }
-
-    // ---- final mask (filter.cpp:777-788)
-    const int2 q = rd.qvmask[read];
-    int2 mk;
-    if (P.use_qv_mask && P.use_coverage_mask)
-        mk = make_int2(max(maxstart, q.x), min(maxend, q.y));
-    else if (P.use_coverage_mask && !P.use_qv_mask)
-        mk = make_int2(maxstart, maxend);
-    else
-        mk = q;
-
-    // ---- repeat annotation (filter.cpp:796-813) + merge pass (filter.cpp:817-829): count, then write
-    const int NHR = P.no_hinge_region;
-    const int MINT = P.min_repeat_annotation_threshold, MAXT = P.max_repeat_annotation_threshold;
-    const int ja_lo = mk.x + NHR <= 0 ? 0 : (mk.x + NHR + reso - 1) / reso;
-    const int ja_hi = mk.y - NHR < 0 ? -1 : min((mk.y - NHR) / reso, L0 - 3);
-    const int GAP = P.repeat_annotation_gap_threshold;
-    int kept = 0, off = 0;
-    for (int wr = 0; wr < 2; wr++) {
-        WarpAnnoState st;
-        st.cur = 0;
-        st.have = false;
-        st.n = 0;
-        if (ja_hi >= ja_lo) {
-            const int lo = base + ja_lo + 1, hi = base + ja_hi + 2;  // map entry j + 1 flags the jump cov0[j + 1] - cov0[j]
-            for (int w = lo >> 5; w <= (hi - 1) >> 5; w++) {
-                const uint32_t m = map_word(cmap, w, lo, hi);  // uniform
-                if (!m) continue;
-                // lane b looks at bit b: bin j = 32 w + b - 1 - base
-                unsigned nxt = 0;
-                bool cand = false;
-                if ((m >> lane) & 1u) {
-                    const int j = (w << 5) + lane - 1 - base;
-                    const int c0 = f_lo(H(j));
-                    const int g = f_lo(H(j + 1)) - c0;
-                    const int thr = min(max((c0 + MIN_COV) / P.coverage_fraction, MINT), MAXT);
-                    const int type = g > thr ? 1 : (g < -thr ? -1 : 0);
-                    cand = type != 0;
-                    nxt = ((unsigned)(reso * j) << 2) | (unsigned)(type + 1);
-                }
-                unsigned am = __ballot_sync(0xffffffffu, cand);
-                while (am) {  // the survivors, in position order, through the merge (all lanes alike)
-                    const int src = __ffs(am) - 1;
-                    am &= am - 1;
-                    const unsigned nx = __shfl_sync(0xffffffffu, nxt, src);
-                    if (!st.have) {
-                        st.cur = nx;
-                        st.have = true;
-                        continue;
-                    }
-                    const int ct = (int)(st.cur & 3u) - 1, nt = (int)(nx & 3u) - 1;
-                    const int gap = (int)(nx >> 2) - (int)(st.cur >> 2);
-                    if (ct == 1 && nt == 1 && gap < GAP) {
-                        continue;      // +1,+1 close together: the later one goes
-                    } else if (ct == -1 && nt == -1 && gap < GAP) {
-                        st.cur = nx;   // -1,-1 close together: the earlier one goes
-                    } else {
-                        if (wr && lane == 0) {
-                            out.anno_pool[off + st.n] = make_int2((int)(st.cur >> 2), (int)(st.cur & 3u) - 1);
-                            out.hinge_keep[off + st.n] = 0;
-                        }
-                        st.n++;
-                        st.cur = nx;
-                    }
-                }
-            }
-        }
-        if (st.have) {
-            if (wr && lane == 0) {
-                out.anno_pool[off + st.n] = make_int2((int)(st.cur >> 2), (int)(st.cur & 3u) - 1);
-                out.hinge_keep[off + st.n] = 0;
-            }
-            st.n++;
-        }
-        if (wr == 0) {
-            kept = st.n;
-            if (kept == 0) break;
-            if (lane == 0) {
-                off = atomicAdd(&out.counters[0], kept);
-                if (off + kept > out.anno_cap) {
-                    atomicExch(&out.counters[2], 1);
-                    off = -1;
-                }
-            }
-            off = __shfl_sync(0xffffffffu, off, 0);
-            if (off < 0) break;
-        }
-    }
-    __syncwarp();  // lane 0 reads the first annotations back for the work item
-
-    // ---- hinge pre-test: mean coverage near both mask ends (filter.cpp:842-865)
-    bool skip_hinges = false;
-    if (kept > 0) {
-        int cs = 0, ns = 0, ce = 0, ne = 0;
-        int jlo = mk.x <= 0 ? 0 : (mk.x + reso - 1) / reso;  // bins with mk.x <= 40 j <= mk.x + NHR
-        int jhi = mk.x + NHR < 0 ? -1 : min((mk.x + NHR) / reso, L0 - 1);
-        for (int j = jlo + lane; j <= jhi; j += 32) {
-            cs += f_lo(H(j));
-            ns++;
-        }
-        jlo = mk.y - NHR <= 0 ? 0 : (mk.y - NHR + reso - 1) / reso;  // mk.y - NHR <= 40 j <= mk.y
-        jhi = mk.y < 0 ? -1 : min(mk.y / reso, L0 - 1);
-        for (int j = jlo + lane; j <= jhi; j += 32) {
-            ce += f_lo(H(j));
-            ne++;
-        }
-        cs = warp_sum(cs);
-        ns = warp_sum(ns);
-        ce = warp_sum(ce);
-        ne = warp_sum(ne);
-        // float on purpose: 0/0 = NaN makes the '< 10' test false (filter.cpp:861-865)
-        const float avg_end = __fdiv_rn((float)ce, (float)ne);
-        const float avg_start = __fdiv_rn((float)cs, (float)ns);
-        skip_hinges = fabsf(__fsub_rn(avg_end, avg_start)) < 10.0f;
-    }
-    if (lane == 0) {
-        store_mask(out, read, mk);
-        out.cmask[read] = make_int2(msc, mec);
-        out.rflags[read] = flags | (skip_hinges ? kFlagSkipHinge : 0);
-        out.anno_ref[read] = make_int2(off, kept);
-        if (kept > 0 && !skip_hinges && off >= 0)
-            push_work_item(out, read, rv.read_off[read], (int)nrec, mk, off, kept);
-    }
-}
-
 // ------------------------------------------------------------------ K2
 
 template <bool DUMP>
@@ -866,22 +637,18 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
     }
     __syncthreads();
 
-    // ---- per read: a warp each when the batch holds few (long) reads, else a thread each
-    const bool warp_per_read = f1 - f0 <= 2 * (kFlatThreads / 32);
-    if (warp_per_read) {
-        for (int read = f0 + warp; read < f1; read += kFlatThreads / 32) {
-            const int base = F.rbase[read];
-            const int64_t nrec = rv.read_off[read + 1] - rv.read_off[read];
-            if (base < 0 || nb == 0 || nrec > Packed<uint32_t>::kMaxCount) {
-                if (lane == 0) out.big_list[atomicAdd(&out.counters[3], 1)] = read;
-                continue;
-            }
-            flat_read_warp(P, F, out, rv, rd, pw, zmap, cmap, MIN_COV, read, base, nrec);
-        }
-    }
+    // ---- per read, one thread each.  A read's walk is a chain of dependent steps (bit-map words,
+    // coverage look-ups behind the annotation candidates), so the reads of a batch are dealt out
+    // round-robin over the CTA's WARPS: consecutive thread ids would put a long-read batch's six reads
+    // into one warp -- one instruction stream per CTA, eight per SM -- where this gives six.  (A
+    // warp-wide form of the walk, lanes over bit-map words and candidate bits, was tried on the
+    // long-read set and lost: 0.95 ms against 0.61 ms; the walk is short on parallel work and the
+    // reductions cost more issue slots than they save.)
     const int NHR = P.no_hinge_region;
     const int MINT = P.min_repeat_annotation_threshold, MAXT = P.max_repeat_annotation_threshold;
-    for (int read = f0 + tid; read < f1 && !warp_per_read; read += kFlatThreads) {
+    constexpr int kWarps = kFlatThreads / 32;
+    for (int slot = lane * kWarps + warp; slot < f1 - f0; slot += kFlatThreads) {
+        const int read = f0 + slot;
         const int base = F.rbase[read];
         const int64_t nrec = rv.read_off[read + 1] - rv.read_off[read];
         if (base < 0 || nb == 0 || nrec > Packed<uint32_t>::kMaxCount) {

@@ -91,22 +91,39 @@ __device__ Match classify_record(const RecView& rv, const int* __restrict__ rlen
     const uint8_t* __restrict__ t8 = rv.trace + toff;
     const uint16_t* __restrict__ t16 = reinterpret_cast<const uint16_t*>(rv.trace + toff);
     const bool wide = rv.tbytes != 1;
-    for (int idx = 0; idx <= inner; idx++) {
-        if (idx > 0) u += wide ? (int)t16[2 * idx - 1] : (int)t8[2 * idx - 1];
-        if (!have_start && idx >= ia_s && u >= u_s) {
-            start_idx = idx;
-            u_start = u;
-            have_start = true;
+    // four trace values are fetched side by side (the exits depend on the values, so a one-at-a-time
+    // loop is a chain of load latencies: a third of this kernel's stall samples, ncu round 2)
+    bool done = false;
+    for (int idx0 = 0; idx0 <= inner && !done; idx0 += 4) {
+        int d[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int idx = idx0 + i;
+            d[i] = (idx > 0 && idx <= inner) ? (wide ? (int)t16[2 * idx - 1] : (int)t8[2 * idx - 1]) : 0;
         }
-        if (end_alive) {
-            if (idx <= ia_e && u <= u_e) {
-                end_idx = idx;
-                u_end = u;
-            } else {
-                end_alive = false;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int idx = idx0 + i;
+            if (idx > inner) break;
+            u += d[i];
+            if (!have_start && idx >= ia_s && u >= u_s) {
+                start_idx = idx;
+                u_start = u;
+                have_start = true;
+            }
+            if (end_alive) {
+                if (idx <= ia_e && u <= u_e) {
+                    end_idx = idx;
+                    u_end = u;
+                } else {
+                    end_alive = false;
+                }
+            }
+            if (end_final ? have_start : !end_alive) {
+                done = true;
+                break;
             }
         }
-        if (end_final ? have_start : !end_alive) break;
     }
     if (have_start) {
         m.eas = start_idx == 0 ? m.as : (a100 + start_idx) * 100;

@@ -101,8 +101,12 @@ d=json.load(open('$OUT/${TAG}_bench_n$NG.json')); print('c5 value %.4g ms %.4f'%
           -o $OUT/${TAG}_${K}_c5 python bench.py --config c5 --also "" $SHORT > $OUT/${TAG}_ncu_${K}.log 2>&1
         echo "ncu $K exit $?"
       done ;;
+    ncu_maximal)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^k_classify_reads" -s 1 -c 1 -f \
+        -o $OUT/${TAG}_k_classify_reads_c3 python bench.py --config c3 --also "" --steps 2 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-verify > $OUT/${TAG}_ncu_k_classify_reads.log 2>&1
+      echo "ncu k_classify_reads exit $?" ;;
     ncu_all)
-      for K in k_mask_anno_flat k_hinge_call k_hinge_exact; do
+      for K in k_mask_anno_flat k_hinge_call k_hinge_exact_warp k_profile_flat; do
         timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^$K" -s 4 -c 1 -f \
           -o $OUT/${TAG}_${K}_c5 python bench.py --config c5 --also "" $SHORT > $OUT/${TAG}_ncu_${K}.log 2>&1
         echo "ncu $K exit $?"
