@@ -53,7 +53,7 @@ NAMES = ["aread", "bread", "abpos", "aepos", "bbpos", "bepos", "flags"]
 PRESETS = {
     # BASELINE.json configs[4] / SURVEY.md section 8(d) "S-100M"
     "c5": dict(genome_mb=300.0, cov=40.0, read_mean=24000, read_sd=8000, read_min=2000, frag=1.2, seed=4321,
-               scaling="strong", sample_mb=24.0,
+               scaling="strong", sample_mb=64.0,
                name="synthetic 300 Mb genome, 40x, reads N(24000,8000)>=2000, ~100 M overlaps (BASELINE configs[4])"),
     # BASELINE.json configs[2] / "S-50M"
     "c3": dict(genome_mb=50.0, cov=50.0, read_mean=3500, read_sd=1500, read_min=1000, frag=0.0, seed=1234,
@@ -493,7 +493,10 @@ class Bench:
             # (24 B + two gathers per record near the annotation) touches a few per cent of that
             n_anno = np.diff(result["anno_off"][a_lo:a_hi + 1])
             k4 = float((n_anno * pile).sum()) * 4.0 + 48.0 * float((n_anno > 0).sum())
-            kbytes = {"profile": 12.0 * novl + 4.0 * bins + 39.0 * owned, "mask_anno": 4.0 * bins + 60.0 * owned,
+            # the TMA-staged form of K1 (default) reads abpos / aepos only: 8 B per record; K2 also writes and
+            # reads back two bits per bin (its two kernels' bit maps)
+            rec_b = 12.0 if args.profile_kernel in (1, 2, 5, 6) else 8.0
+            kbytes = {"profile": rec_b * novl + 4.0 * bins + 39.0 * owned, "mask_anno": 4.5 * bins + 60.0 * owned,
                       "hinge_call": k4}
             dom = max(kbytes, key=lambda k: kavg[k])
             achieved = kbytes[dom] / (kavg[dom] * 1e-3) / 1e9

@@ -85,6 +85,11 @@ int hg_ctx_create(int device, void* stream, hg_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
     c->fs.num_sms = c->num_sms;
+    // tuning aid for the executables (the ABI has HG_OPT_PROFILE_KERNEL): form of the coverage-profile kernel
+    if (const char* v = getenv("HINGE_B200_PROFILE_KERNEL")) {
+        const int k = atoi(v);
+        if (k == 0 || k == 1 || k == 3 || k == 5 || k == 6) c->fs.flat_kernel = k;
+    }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
     for (int i = 0; i < 3; i++) cudaStreamCreateWithFlags(&c->fs.side_stream[i], cudaStreamNonBlocking);
@@ -128,6 +133,7 @@ void hg_ctx_destroy(hg_ctx* c) {
     cudaFree(c->d_rlen); cudaFree(c->d_qvmask); cudaFree(c->d_read_off); cudaFree(c->d_err);
     FilterScratch& s = c->fs;
     cudaFree(s.cov_maxbin); cudaFree(s.self_cnt); cudaFree(s.flat_prof);
+    cudaFree(s.flat_rbatch); cudaFree(s.flat_cpre); cudaFree(s.flat_desc); cudaFree(s.flat_zmap); cudaFree(s.flat_cmap);
     if (!c->ext_mean_cov) cudaFree(s.mean_cov);
     if (!c->ext_mask) cudaFree(s.mask);
     for (int i = 0; i < hg_ctx::kMarks; i++)
@@ -182,8 +188,8 @@ int hg_set_option(hg_ctx* c, int option, int64_t value) {
         return HG_OK;
     }
     if (option == HG_OPT_PROFILE_KERNEL) {
-        if (value != 0 && value != 1 && value != 5 && value != 6)
-            return set_err(c, HG_ERR_ARG, "HG_OPT_PROFILE_KERNEL: 0, 1, 5 or 6");
+        if (value != 0 && value != 1 && value != 3 && value != 5 && value != 6)
+            return set_err(c, HG_ERR_ARG, "HG_OPT_PROFILE_KERNEL: 0, 1, 3, 5 or 6");
         c->fs.flat_kernel = (int)value;
         return HG_OK;
     }
@@ -207,7 +213,7 @@ int hg_set_reads(hg_ctx* c, int32_t n_read, const int32_t* rlen, const int64_t* 
         c->rlen_q999 = srt[(size_t)((double)(n_read - 1) * 0.999)];
         if (srt.front() < 0) return set_err(c, HG_ERR_INPUT, "negative read length");
     }
-    HG_TRY(dev_alloc(c, &c->d_rlen, n_read, "rlen"));
+    HG_TRY(dev_alloc(c, &c->d_rlen, (size_t)n_read + 8, "rlen"));  // + slack: bulk copies of 16-byte multiples (k_profile_tma)
     HG_TRY(dev_alloc(c, &c->d_qvmask, n_read, "qv mask"));
     HG_TRY(cuda_check(c, cudaMemcpyAsync(c->d_rlen, rlen, sizeof(int) * n_read, cudaMemcpyHostToDevice, st), "rlen H2D"));
     c->has_qv = qv_off != nullptr && qv != nullptr;
@@ -243,7 +249,7 @@ int hg_set_reads(hg_ctx* c, int32_t n_read, const int32_t* rlen, const int64_t* 
     HG_TRY(dev_alloc(c, &s.work_items, 3 * (size_t)n_read, "work items"));
     HG_TRY(dev_alloc(c, &s.big_list, n_read, "big_list"));
     HG_TRY(dev_alloc(c, &s.exact_list, n_read, "exact_list"));
-    HG_TRY(dev_alloc(c, &c->d_read_off, (size_t)n_read + 1, "read_off"));
+    HG_TRY(dev_alloc(c, &c->d_read_off, (size_t)n_read + 1 + 4, "read_off"));  // + slack, as above
     cudaMemsetAsync(s.mean_cov, 0xff, sizeof(int) * n_read, st);
     cudaMemsetAsync(s.rflags, 0, n_read, st);
     s.anno_cap = 0;
@@ -386,18 +392,40 @@ static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
         // batches of kFlatBins histogram words; the plan only depends on read lengths and cut_off
         const int lo = std::max(c->a_lo, c->r_begin), hi = std::min(c->a_hi, c->r_end + 1);  // r_begin / r_end: global when set
         if (c->plan_reads_version != c->reads_version || c->plan_cut_off != p->cut_off ||
-            c->plan_lo != lo || c->plan_hi != hi) {
-            std::vector<int2> batch;
-            std::vector<int> rbase;
-            flat_plan(c->h_rlen.data(), lo, std::max(lo, hi), c->n_read, p->cut_off, &batch, &rbase);
+            c->plan_lo != lo || c->plan_hi != hi || s.flat_capped != (s.flat_kernel == 3) ||
+            (s.flat_capped && c->plan_shape != c->shape_version)) {
+            // the third form of K1 wants batches that are also bounded by record volume: the CSR comes
+            // back for that plan (which then depends on the records, not only on the read lengths)
+            const bool capped = s.flat_kernel == 3;
+            std::vector<int64_t> h_off;
+            if (capped) {
+                h_off.resize((size_t)c->n_read + 1);
+                HG_TRY(cuda_check(c, cudaMemcpyAsync(h_off.data(), c->d_read_off, sizeof(int64_t) * h_off.size(), cudaMemcpyDeviceToHost, c->stream), "D2H"));
+                HG_TRY(cuda_check(c, cudaStreamSynchronize(c->stream), "D2H"));
+            }
+            FlatPlan plan;
+            flat_plan(c->h_rlen.data(), capped ? h_off.data() : nullptr, lo, std::max(lo, hi), c->n_read, p->cut_off, capped, &plan);
+            s.flat_capped = capped;
+            const std::vector<int2>& batch = plan.batch;
             s.flat_nbatch = hi > lo ? (int)batch.size() - 1 : 0;
+            s.flat_lo = lo;
+            s.flat_hi = std::max(lo, hi);
             s.flat_bins_total = 0;
             for (const int2& bt : batch) s.flat_bins_total += bt.y;
+            const size_t nb1 = (size_t)std::max(s.flat_nbatch, 1);
             HG_TRY(dev_alloc(c, &s.flat_batch, batch.size(), "flat batches"));
-            HG_TRY(dev_alloc(c, &s.flat_rbase, rbase.size(), "flat read offsets"));
-            HG_TRY(dev_alloc(c, &s.flat_prof, (size_t)std::max(s.flat_nbatch, 1) * kFlatBins, "coverage profiles"));
+            HG_TRY(dev_alloc(c, &s.flat_rbase, plan.rbase.size() + 8, "flat read offsets"));  // + slack, as above
+            HG_TRY(dev_alloc(c, &s.flat_rbatch, plan.rbatch.size(), "flat read batches"));
+            HG_TRY(dev_alloc(c, &s.flat_cpre, plan.cpre.size() + 8, "flat chunk offsets"));
+            HG_TRY(dev_alloc(c, &s.flat_desc, plan.desc.size(), "flat batch descriptors"));
+            HG_TRY(dev_alloc(c, &s.flat_prof, nb1 * kFlatBins, "coverage profiles"));
+            HG_TRY(dev_alloc(c, &s.flat_zmap, nb1 * (kFlatBins / 16), "coverage bit maps"));
+            HG_TRY(dev_alloc(c, &s.flat_cmap, nb1 * (kFlatBins / 16), "coverage bit maps"));
             HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_batch, batch.data(), sizeof(int2) * batch.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
-            HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_rbase, rbase.data(), sizeof(int) * rbase.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
+            HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_rbase, plan.rbase.data(), sizeof(int) * plan.rbase.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
+            HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_rbatch, plan.rbatch.data(), sizeof(int) * plan.rbatch.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
+            HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_cpre, plan.cpre.data(), sizeof(int) * plan.cpre.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
+            HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_desc, plan.desc.data(), sizeof(int4) * plan.desc.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
             // per-read results of the reads outside the planned range: "no pile-up"
             cudaMemsetAsync(s.cov_maxbin, 0xff, sizeof(int) * c->n_read, c->stream);
             cudaMemsetAsync(s.mean_cov, 0xff, sizeof(int) * c->n_read, c->stream);
@@ -407,6 +435,7 @@ static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
             cudaMemsetAsync(s.anno_ref, 0, sizeof(int2) * c->n_read, c->stream);
             HG_TRY(cuda_check(c, cudaStreamSynchronize(c->stream), "flat plan"));  // the vectors go away
             c->plan_reads_version = c->reads_version;
+            c->plan_shape = c->shape_version;
             c->plan_cut_off = p->cut_off;
             c->plan_lo = lo;
             c->plan_hi = hi;
@@ -564,9 +593,10 @@ int hg_debug_warp_sort(hg_ctx* c, int32_t* key_idx, const int32_t* off, int32_t 
 // of batches, or -1 when capacity (in pairs) is too small.
 int hg_debug_flat_plan(const int32_t* rlen, int32_t n_read, int32_t lo, int32_t hi, int32_t cut_off,
                        int32_t* batch_out, int32_t capacity, int32_t* rbase_out) {
-    std::vector<int2> batch;
-    std::vector<int> rbase;
-    flat_plan(rlen, lo, hi, n_read, cut_off, &batch, &rbase);
+    FlatPlan plan;
+    flat_plan(rlen, nullptr, lo, hi, n_read, cut_off, false, &plan);
+    const std::vector<int2>& batch = plan.batch;
+    const std::vector<int>& rbase = plan.rbase;
     if ((int)batch.size() > capacity) return -1;
     for (size_t i = 0; i < batch.size(); i++) {
         batch_out[2 * i] = batch[i].x;
@@ -574,6 +604,25 @@ int hg_debug_flat_plan(const int32_t* rlen, int32_t n_read, int32_t lo, int32_t 
     }
     memcpy(rbase_out, rbase.data(), sizeof(int) * (size_t)n_read);
     return (int)batch.size() - 1;
+}
+
+// The same with the CSR (batches also bounded by record volume): chunk_out gets, per read, the
+// 32-record chunks of the earlier reads of its batch, nchunk_out the chunks per batch.
+int hg_debug_flat_plan2(const int32_t* rlen, const int64_t* read_off, int32_t n_read, int32_t lo, int32_t hi,
+                        int32_t cut_off, int32_t* batch_out, int32_t capacity, int32_t* rbase_out,
+                        int32_t* rbatch_out, int32_t* cpre_out, int32_t* nchunk_out) {
+    FlatPlan plan;
+    flat_plan(rlen, read_off, lo, hi, n_read, cut_off, true, &plan);
+    if ((int)plan.batch.size() > capacity) return -1;
+    for (size_t i = 0; i < plan.batch.size(); i++) {
+        batch_out[2 * i] = plan.batch[i].x;
+        batch_out[2 * i + 1] = plan.batch[i].y;
+    }
+    memcpy(rbase_out, plan.rbase.data(), sizeof(int) * (size_t)n_read);
+    memcpy(rbatch_out, plan.rbatch.data(), sizeof(int) * (size_t)n_read);
+    memcpy(cpre_out, plan.cpre.data(), sizeof(int) * (size_t)n_read);
+    for (size_t i = 0; i + 1 < plan.batch.size(); i++) nchunk_out[i] = plan.desc[2 * i].w;
+    return (int)plan.batch.size() - 1;
 }
 
 int hg_debug_std_sort(int32_t* key_idx, const int32_t* off, int32_t count, int32_t descending) {

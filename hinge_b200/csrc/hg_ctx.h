@@ -52,7 +52,7 @@ struct hg_ctx {
     hg_filter_params fp;
     bool filter_params_set = false, filter_done = false;
     int shape_version = 0, configured_shape = -1;
-    int reads_version = 0, plan_reads_version = -1, plan_cut_off = 0, plan_lo = 0, plan_hi = 0;  // flat K2 plan
+    int reads_version = 0, plan_reads_version = -1, plan_cut_off = 0, plan_lo = 0, plan_hi = 0, plan_shape = -1;  // flat plan
     int keep_cov = 0;
     bool keep_masks = false;  // HG_OPT_KEEP_MASKS
     int anno_pool_hint = 0;   // HG_OPT_ANNO_POOL

@@ -47,10 +47,18 @@ struct FilterScratch {
     int2* flat_batch = nullptr;       // (first read, histogram words in use) per batch (flat_nbatch + 1)
     int* flat_rbase = nullptr;        // per read, first histogram word inside its batch (-1: fallback path)
     uint32_t* flat_prof = nullptr;    // scanned packed profiles, kFlatBins words per batch (K1 -> K2)
+    int* flat_rbatch = nullptr;       // per read: its batch (-1 = outside the planned range)
+    int* flat_cpre = nullptr;         // per read: 32-record chunks of the batch's earlier reads (third form of K1)
+    int4* flat_desc = nullptr;        // per batch, two entries: (first read, reads, words, chunks) (first record lo, hi, records, 0)
+    uint16_t* flat_zmap = nullptr;    // K2: bit maps of the batches' bins (kFlatBins bits per batch each)
+    uint16_t* flat_cmap = nullptr;
+    int flat_lo = 0, flat_hi = 0;     // planned read range
     int flat_nbatch = 0;
     int flat_spread = 8;              // record windows per warp in the scatter (tuning aid)
-    int flat_kernel = 0;              // 0: pick the form of K1 by cut-off and shape, 1: always the first form,
+    int flat_kernel = 0;              // form of K1.  0: first / second by cut-off and shape, 1: first, 3: third
+                                      // (k_profile_tma; first when the columns are not 16-byte aligned),
                                       // 5 / 6: second form compiled for 4 / 6 resident CTAs per SM
+    bool flat_capped = false;         // the plan bounds the batches by record volume (third form)
     double flat_bins_total = 0;       // coverage bins of the planned reads
     float flat_bins_per_record = 0;   // ... per record of the context
     unsigned long long* big_scratch = nullptr;
@@ -74,8 +82,15 @@ void launch_mask_anno(const RecView& rv, const ReadView& rd, const hg_filter_par
                       int r_begin, int r_end, FilterScratch& s, int* cov0, const int64_t* cov0_off,
                       const PeerView& peer, cudaStream_t st);
 // flat kernels (hg_filter_flat.cu): host-side batch plan + launchers of the two phases
-void flat_plan(const int* rlen, int lo, int hi, int n_read, int cut_off, std::vector<int2>* batch,
-               std::vector<int>* rbase);
+struct FlatPlan {
+    std::vector<int2> batch;   // (first read, histogram words in use) per batch, closed by (hi, 0)
+    std::vector<int> rbase;    // per read: first word of its profile inside its batch, -1 = fallback path
+    std::vector<int> rbatch;   // per read: its batch, -1 = outside [lo, hi)
+    std::vector<int> cpre;     // per read: 32-record chunks of the earlier reads of its batch
+    std::vector<int4> desc;    // per batch: (first read, reads, words, chunks) (first record lo, hi, records, 0)
+};
+void flat_plan(const int* rlen, const int64_t* read_off, int lo, int hi, int n_read, int cut_off, bool cap_records,
+               FlatPlan* plan);
 void launch_profile(const RecView& rv, const ReadView& rd, const hg_filter_params& P, int r_begin,
                     int r_end, FilterScratch& s, cudaStream_t st);
 void launch_mask_anno_flat(const RecView& rv, const ReadView& rd, const hg_filter_params& P, int r_begin,

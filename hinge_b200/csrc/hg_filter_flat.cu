@@ -50,6 +50,7 @@ constexpr int kFlatItems = 16;                           // bins per thread and 
 constexpr int kFlatPass = kFlatThreads * kFlatItems;     // bins per scan pass
 constexpr int kFlatWords = kFlatBins + 32;               // histogram words per CTA (+ slack)
 constexpr int kFlatMaps = (kFlatBins + kFlatPass - 1) / kFlatPass * kFlatThreads;  // 16-bit map entries
+constexpr int kSlabRecords = 4096;                       // records of a batch (third form of K1: staged by TMA)
 
 __device__ __forceinline__ uint4 lds128(const uint32_t* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void sts128(uint32_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
@@ -63,16 +64,6 @@ __device__ __forceinline__ int f_hi(uint32_t v) { return (int)v >> 16; }
 // every aligned 4-word group intact and makes those accesses conflict-free.
 __device__ __forceinline__ int sw(int j) { return j ^ ((j >> 3) & 12); }
 
-// Bit `i` of the map <=> entry i (maps are arrays of 32-bit words in shared memory).
-__device__ __forceinline__ uint32_t map_word(const uint32_t* map, int w, int lo, int hi) {
-    // word w restricted to entries in [lo, hi)
-    uint32_t m = map[w];
-    const int b = w << 5;
-    if (lo > b) m &= lo - b >= 32 ? 0u : (0xffffffffu << (lo - b));
-    if (hi < b + 32) m &= hi <= b ? 0u : (0xffffffffu >> (b + 32 - hi));
-    return m;
-}
-
 struct FlatParams {
     const int2* __restrict__ batch;      // nbatch + 1: (first read, histogram words in use) of every batch
     const int* __restrict__ rbase;       // per read: first word of its profile inside its batch, -1 = fallback
@@ -84,8 +75,15 @@ struct FlatParams {
     int* __restrict__ counters1;         // [0] length of big_list (phase 1)
     int* __restrict__ big_list;
     const int* __restrict__ scal;        // [1] = MIN_COV (K2 only)
+    const int* __restrict__ rbatch;      // per read: its batch
+    const int* __restrict__ cpre;        // per read: 32-record chunks of the earlier reads of its batch
+    const int4* __restrict__ desc;       // per batch: (first read, reads, words, chunks) (first record lo, hi, records, 0)
+    uint16_t* __restrict__ zmap;         // K2 bit maps, kFlatMaps 16-bit entries per batch
+    uint16_t* __restrict__ cmap;
+    int p_lo, p_hi;                      // planned read range
+    int nbatch;
     int r_begin, r_end;                  // first / last A-read with records
-    int v2;                              // K1 ran in its second form (k_profile_flat2)
+    int v2;                              // form K1 ran in: 0 first, 1 second (k_profile_flat2), 2 third (k_profile_tma)
 };
 
 // Which 4-record group of a 1024-record tile a thread takes.  With the identity map the 32
@@ -104,15 +102,14 @@ __device__ __forceinline__ int flat_group(int tid) {
 
 // filter.cpp:642-656 (mean over reads >= 5000 bp that have a pile-up) and filter.cpp:552-561
 // (self-match reads; float accumulation in record order), shared by K1 and its fallback.
-__device__ __forceinline__ void finalize_read(const RecView& rv, const ReadView& rd, const FlatParams& F, int read,
-                                              long long sum, int maxbin) {
+__device__ __forceinline__ void finalize_read(const RecView& rv, const FlatParams& F, int read, long long sum,
+                                              int maxbin, int rl, int self_cnt) {
     const int len0 = maxbin + 1;
     const int mean = (int)(sum / (long long)max(1, len0));
-    const int rl = rd.rlen[read];
     F.cov_maxbin[read] = maxbin;
     F.mean_cov[read] = (rl >= 5000 && read >= F.r_begin && read <= F.r_end) ? mean : -1;
     uint8_t f = 0;
-    if (self_count(F.self_cnt[read]) > 0) {
+    if (self_count(self_cnt) > 0) {
         float cov = 0.0f;
         for (int64_t k = rv.read_off[read]; k < rv.read_off[read + 1]; k++) {
             if (rv.bread[k] != read) continue;
@@ -124,6 +121,10 @@ __device__ __forceinline__ void finalize_read(const RecView& rv, const ReadView&
         if ((double)cov > 4.5 && rl > 10000) f |= kFlagSelf;
     }
     F.rflags[read] = f;
+}
+__device__ __forceinline__ void finalize_read(const RecView& rv, const ReadView& rd, const FlatParams& F, int read,
+                                              long long sum, int maxbin) {
+    finalize_read(rv, F, read, sum, maxbin, rd.rlen[read], F.self_cnt[read]);
 }
 
 // ------------------------------------------------------------------ K1
@@ -556,6 +557,393 @@ k_profile_flat2(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
     }
 }
 
+// ------------------------------------------------------------------ K1, third form
+//
+// The first two forms wait on their own global loads (ncu, round 2: long-scoreboard is the top
+// stall, 1.15 eligible warps per scheduler, issue slots 53 % busy) and spend half of their
+// instructions telling which read a record belongs to.  This form is a PERSISTENT CTA that never
+// waits on a global load in its steady state and never looks at `aread`:
+//
+//   staging   the batch's abpos / aepos columns (one contiguous run of <= kSlabRecords records, the
+//             plan sees to that) and its per-read tables (CSR offsets, histogram bases, read lengths,
+//             chunk counts) arrive in shared memory by TMA bulk copies (cp.async.bulk, one elected
+//             thread, completion on an mbarrier) -- issued for batch i + 1 BEFORE batch i is worked
+//             on: two stages, the copy of the next batch always in flight.  The batch descriptors
+//             themselves (32 B) travel one more iteration ahead in registers.
+//   scatter   one warp per 32-record CHUNK of one read (chunks are dealt out in contiguous ranges:
+//             even load, and a read's chunks mostly stay with one warp).  The read is warp-uniform,
+//             so the events that pile up on a read's first / last bins -- every overlap that reaches
+//             an end of the read, about half of all events -- are counted with two warp-wide
+//             reductions (REDUX) into seven per-read counters kept in registers and added once per
+//             read; only the others go through shared-memory atomics.  Sum and maximum for the
+//             profile's mean and length (filter.cpp:642-656) are warp reductions as well.
+//   scan      as in the first form: one block-wide prefix sum over the batch's packed histogram;
+//             the scanned words leave as 256-bit stores (one per thread, fully coalesced).
+//
+// Bytes per record from HBM: 8 (abpos, aepos) instead of 12.
+constexpr int kTmaThreads = 512;
+constexpr int kTmaItems = kFlatBins / kTmaThreads;  // 8 bins per thread in the scan
+constexpr int kTmaTab = kFlatMaxReads + 8;          // table entries per stage (+ alignment slack)
+
+struct __align__(128) TmaStage {
+    int s[kSlabRecords + 8];        // abpos of the batch's records, from the 16-byte boundary below the first
+    int e[kSlabRecords + 8];        // aepos
+    long long off[kTmaTab];         // read_off[f0 & ~1 ...]
+    int base[kTmaTab];              // rbase[f0 & ~3 ...]
+    int rlen[kTmaTab];
+};
+struct __align__(128) TmaShared {
+    TmaStage st[2];
+    uint32_t hist[kFlatWords];
+    int sum[kFlatMaxReads], mx[kFlatMaxReads], mx2[kFlatMaxReads];
+    int o32[kFlatMaxReads + 8];     // first staged record of every read of the batch
+    int blk[(kSlabRecords + 8) / 32 + 4];  // read of the first record of every block of 32 staged records
+    uint32_t wtot[kTmaThreads / 32];
+    unsigned long long full[2];     // mbarriers: stage filled
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// global -> shared bulk copy (TMA, 1-D): 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void st_global_v8(uint32_t* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
+// The histogram of this form is not swizzled: the two LDS.128 per thread of the scan take a 2-way
+// bank conflict (32 extra wavefronts per batch), cheaper than two more instructions in front of
+// each of the ~15 000 atomics of a batch.
+// bin of an event at position x >= -40 on the 40-bp grid: cov_bin(x) for x >= 0, 0 below
+__device__ __forceinline__ unsigned tma_bin(int x) { return (unsigned)(x + kReso) / (unsigned)kReso; }
+
+struct TmaBatch {
+    int f0, nreads, words, chunks;  // desc[2 b]
+    int64_t k0;                     // first record
+    int nrec;
+};
+__device__ __forceinline__ TmaBatch tma_batch(const FlatParams& F, int b) {
+    TmaBatch t;
+    if (b < F.nbatch) {
+        const int4 x = __ldg(F.desc + 2 * (size_t)b), y = __ldg(F.desc + 2 * (size_t)b + 1);
+        t.f0 = x.x; t.nreads = x.y; t.words = x.z; t.chunks = x.w;
+        t.k0 = (int64_t)(((unsigned long long)(unsigned)y.y << 32) | (unsigned)y.x);
+        t.nrec = y.z;
+    } else {
+        t.f0 = 0; t.nreads = 0; t.words = 0; t.chunks = 0; t.k0 = 0; t.nrec = 0;
+    }
+    return t;
+}
+
+// Issued by ONE thread: everything batch `t` needs, into stage `sg`, completion on `bar`.
+__device__ __forceinline__ void tma_issue(const RecView& rv, const ReadView& rd, const FlatParams& F,
+                                          const TmaBatch& t, TmaStage* sg, unsigned long long* bar) {
+    // order the generic-proxy reads of this stage (two iterations ago, behind a CTA barrier) before
+    // the async-proxy writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int fa = t.f0 & ~1, fb = t.f0 & ~3;
+    const uint32_t n_off = (uint32_t)((t.f0 + t.nreads + 1 - fa + 1) & ~1);
+    const uint32_t n_tab = (uint32_t)((t.f0 + t.nreads - fb + 3) & ~3);
+    int64_t ka = 0;
+    uint32_t n4 = 0;
+    int tail = 0;
+    if (t.words > 0 && t.nrec > 0) {
+        ka = t.k0 & ~(int64_t)3;
+        const int span = (int)(t.k0 - ka) + t.nrec;   // records from the aligned start
+        n4 = (uint32_t)((span + 3) & ~3);
+        if (ka + (int64_t)n4 > (rv.novl & ~(int64_t)3)) {  // the array's last records: no 16-byte multiple left
+            n4 = (uint32_t)(span & ~3);
+            tail = span - (int)n4;
+        }
+    }
+    const uint32_t bytes = 8u * n4 + 8u * n_off + 8u * n_tab;
+    mbar_expect_tx(bar, bytes);
+    if (n4) {
+        bulk_g2s(sg->s, rv.abpos + ka, 4u * n4, bar);
+        bulk_g2s(sg->e, rv.aepos + ka, 4u * n4, bar);
+    }
+    bulk_g2s(sg->off, rv.read_off + fa, 8u * n_off, bar);
+    if (n_tab) {
+        bulk_g2s(sg->base, F.rbase + fb, 4u * n_tab, bar);
+        bulk_g2s(sg->rlen, rd.rlen + fb, 4u * n_tab, bar);
+    }
+    for (int i = 0; i < tail; i++) {  // at most once per launch
+        sg->s[n4 + i] = rv.abpos[ka + n4 + i];
+        sg->e[n4 + i] = rv.aepos[ka + n4 + i];
+    }
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 2)
+k_profile_tma(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
+    extern __shared__ __align__(128) unsigned char tma_smem_raw[];
+    TmaShared& sh = *reinterpret_cast<TmaShared*>(tma_smem_raw);
+    constexpr int NW = kTmaThreads / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+    const int C = P.cut_off;
+
+    if (tid == 0) {
+        mbar_init(&sh.full[0], 1);
+        mbar_init(&sh.full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    TmaBatch cur = tma_batch(F, blockIdx.x), nxt = tma_batch(F, blockIdx.x + G);
+    if (tid == 0 && blockIdx.x < F.nbatch) tma_issue(rv, rd, F, cur, &sh.st[0], &sh.full[0]);
+
+    int it = 0;
+    for (int b = blockIdx.x; b < F.nbatch; b += G, it++) {
+        TmaStage& sg = sh.st[it & 1];
+        // ---- the next batch's copies go out first; its descriptor came an iteration ago, the one
+        // after it is requested now
+        if (tid == 0 && b + G < F.nbatch) tma_issue(rv, rd, F, nxt, &sh.st[(it + 1) & 1], &sh.full[(it + 1) & 1]);
+        const TmaBatch nn = tma_batch(F, b + 2 * G);
+        const int nb = cur.words, nreads = cur.nreads;
+        // per-read inputs of the last phase, requested now
+        int my_self = 0;
+        if (tid < nreads) my_self = __ldg(F.self_cnt + cur.f0 + tid);
+
+        // ---- zero (the scan of the previous batch has read the histogram: its barrier lies between)
+        if (nb > 0) {
+            const int nz = min(kFlatWords, (nb + 16 + 3) & ~3);
+            for (int j = tid * 4; j < nz; j += kTmaThreads * 4) sts128(sh.hist + j, make_uint4(0, 0, 0, 0));
+        }
+        if (tid < nreads) {   // kFlatMaxReads <= kTmaThreads: read tid of the batch belongs to thread tid throughout
+            sh.sum[tid] = 0;
+            sh.mx[tid] = -1;
+        }
+
+        // ---- wait for this batch's stage
+        {
+            const uint32_t parity = (uint32_t)(it >> 1) & 1u;
+            if (!mbar_try_wait(&sh.full[it & 1], parity)) {
+                const unsigned long long t0 = global_timer_ns();
+                while (!mbar_try_wait(&sh.full[it & 1], parity))
+                    if (global_timer_ns() - t0 > 2000000000ull) __trap();  // a lost copy must not hang the GPU
+            }
+        }
+        const int d_off = cur.f0 & 1, d_tab = cur.f0 & 3;   // where read f0 sits in the tables
+        const int64_t ka = cur.k0 & ~(int64_t)3;
+
+        // ---- per batch: record offsets of the reads inside the stage, and for every block of 32
+        // staged records the read its first record belongs to (one writer per block); the read's
+        // table entries move to registers (the stage is refilled before the last phase)
+        const int rec_lo = (int)(cur.k0 - ka), rec_hi = rec_lo + cur.nrec;
+        int my_base = -1, my_rl = 0;
+        if (tid == 0) sh.o32[nreads] = rec_hi;   // = read_off[f0 + nreads] - ka: every read of a batch with words fits it
+        if (tid < nreads) {
+            const int lo = (int)(sg.off[d_off + tid] - ka);
+            sh.o32[tid] = lo;
+            my_base = sg.base[d_tab + tid];
+            my_rl = sg.rlen[d_tab + tid];
+            const int hi = (int)(sg.off[d_off + tid + 1] - ka);
+            if (hi > lo && nb > 0) {
+                if (lo == rec_lo) sh.blk[lo >> 5] = tid;
+                for (int m = (lo + 31) >> 5; (m << 5) < hi; m++) sh.blk[m] = tid;
+            }
+        }
+        __syncthreads();
+
+        // ---- scatter (profileCoverage, LAInterface.cpp:4298-4320): flat over the staged records,
+        // four per thread and step (two LDS.128).  Every record is scattered, A == B ones included
+        // (telling them apart would need the bread column): they are taken out again below.
+        if (nb > 0 && cur.nrec > 0) {
+            // The lanes of a warp are spread over eight windows (see flat_group): many records start
+            // in their read's first bin or end in its last one, and the four lanes of a window are all
+            // that can meet on such a word.  A window is WS groups of four records, the batch's groups
+            // divided by eight (a multiple of 8 in 32 .. 64); the position inside the window is rotated
+            // by four groups per window, which keeps the 128-bit loads of a quarter warp on eight
+            // different bank groups.
+            const int NG = (rec_hi + 3) >> 2;
+            const int WS = NG >= 512 ? 64 : max(32, (((NG + 7) >> 3) + 7) & ~7);
+            const int wdw = lane >> 2;
+            int pos = 4 * warp + (lane & 3);
+            const bool busy = pos < WS;
+            pos += 4 * wdw;
+            if (pos >= WS) pos -= WS;
+            for (int g = 4 * (wdw * WS + pos); busy && g < rec_hi; g += 32 * WS) {
+                const int4 vs = *reinterpret_cast<const int4*>(sg.s + g), ve = *reinterpret_cast<const int4*>(sg.e + g);
+                int r0 = sh.blk[g >> 5];
+                int hi0 = sh.o32[r0 + 1];
+                const int kf = max(g, rec_lo);
+                while (kf >= hi0) {   // the read of the group's first record
+                    r0++;
+                    hi0 = sh.o32[r0 + 1];
+                }
+                uint32_t* hb0 = sh.hist + sg.base[d_tab + r0];
+                uint32_t* hb1 = hb0;
+                const int nA = hi0 - g;   // records of the group that belong to read r0 (when all four are in the batch)
+                int r1 = r0;
+                bool simple = g >= rec_lo && g + 4 <= rec_hi;
+                if (simple && nA < 4) {   // a read boundary inside the group: the next read that has records
+                    int hi1;
+                    do {
+                        r1++;
+                        hi1 = sh.o32[r1 + 1];
+                    } while (hi1 <= hi0);
+                    hb1 = sh.hist + sg.base[d_tab + r1];
+                    simple = hi1 >= g + 4;
+                }
+                if (simple) {
+                    // the same code for every lane: records i < nA go to read r0, the others to r1
+                    const int sv[4] = {vs.x, vs.y, vs.z, vs.w}, ev[4] = {ve.x, ve.y, ve.z, ve.w};
+                    int accT = 0, accA = 0, mxA = 0, mxB = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const bool inA = i < nA;
+                        uint32_t* const hb = inA ? hb0 : hb1;
+                        const unsigned q_s = tma_bin(sv[i]), q_e = tma_bin(ev[i]);   // 0 <= abpos < aepos <= rlen (ingest check)
+                        const unsigned b_sc = tma_bin(max(sv[i] + C, -kReso)), b_ec = tma_bin(max(ev[i] - C, -kReso));
+                        atomicAdd(hb + q_s, 1u);
+                        atomicAdd(hb + q_e, 0u - 1u);
+                        atomicAdd(hb + b_sc, 1u << 16);
+                        atomicAdd(hb + b_ec, 0u - (1u << 16));
+                        const int d = (int)q_e - (int)q_s;
+                        accT += d;
+                        accA += inA ? d : 0;
+                        mxA = max(mxA, inA ? (int)q_e : 0);
+                        mxB = max(mxB, inA ? 0 : (int)q_e);
+                    }
+                    atomicAdd(&sh.sum[r0], accA);
+                    atomicMax(&sh.mx[r0], mxA);
+                    if (nA < 4) {
+                        atomicAdd(&sh.sum[r1], accT - accA);
+                        atomicMax(&sh.mx[r1], mxB);
+                    }
+                    continue;
+                }
+                // a group at an end of the batch, or one that touches more than two reads
+                const int sv[4] = {vs.x, vs.y, vs.z, vs.w}, ev[4] = {ve.x, ve.y, ve.z, ve.w};
+                int r = r0, hi = hi0;
+                uint32_t* hb = hb0;
+                int acc = 0, mxq = -1;
+                for (int i = 0; i < 4; i++) {
+                    const int k = g + i;
+                    if (k < rec_lo || k >= rec_hi) continue;
+                    if (k >= hi) {   // next read (reads without records are skipped)
+                        atomicAdd(&sh.sum[r], acc);
+                        atomicMax(&sh.mx[r], mxq);
+                        acc = 0;
+                        mxq = -1;
+                        do {
+                            r++;
+                            hi = sh.o32[r + 1];
+                        } while (k >= hi);
+                        hb = sh.hist + sg.base[d_tab + r];
+                    }
+                    const unsigned q_s = tma_bin(sv[i]), q_e = tma_bin(ev[i]);
+                    const unsigned b_sc = tma_bin(max(sv[i] + C, -kReso)), b_ec = tma_bin(max(ev[i] - C, -kReso));
+                    atomicAdd(hb + q_s, 1u);
+                    atomicAdd(hb + q_e, 0u - 1u);
+                    atomicAdd(hb + b_sc, 1u << 16);
+                    atomicAdd(hb + b_ec, 0u - (1u << 16));
+                    acc += (int)q_e - (int)q_s;
+                    mxq = max(mxq, (int)q_e);
+                }
+                if (mxq >= 0) {
+                    atomicAdd(&sh.sum[r], acc);
+                    atomicMax(&sh.mx[r], mxq);
+                }
+            }
+            // A == B records are inactive (filter.cpp:538-547) and rare; their per-read count comes
+            // from the ingest.  One thread per such read takes their events out again (atomic adds
+            // commute) and finds the maximum without them.
+            if (tid < nreads && self_count(my_self) > 0) {
+                const int read = cur.f0 + tid;
+                const int base = my_base;
+                if (base >= 0) {
+                    int mx = -1, acc = 0;
+                    for (int64_t k = rv.read_off[read]; k < rv.read_off[read + 1]; k++) {
+                        const int as = rv.abpos[k], ae = rv.aepos[k];
+                        const int q_s = as / kReso + 1, q_e = ae / kReso + 1;
+                        if (rv.bread[k] != read) {
+                            mx = max(mx, q_e);
+                            continue;
+                        }
+                        atomicAdd(&sh.hist[base + q_s], 0u - 1u);
+                        atomicAdd(&sh.hist[base + q_e], 1u);
+                        atomicAdd(&sh.hist[base + cov_bin(as + C, kReso)], 0u - (1u << 16));
+                        atomicAdd(&sh.hist[base + cov_bin(ae - C, kReso)], 1u << 16);
+                        acc += q_e - q_s;
+                    }
+                    atomicAdd(&sh.sum[tid], -acc);
+                    sh.mx2[tid] = mx;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- one prefix sum over the whole batch; the scanned words go to HBM for K2
+        if (nb > 0) {
+            uint32_t* const pw = F.prof + (size_t)b * kFlatBins;
+            const int j0 = tid * kTmaItems;
+            uint32_t v[kTmaItems];
+            if (j0 < nb) {
+#pragma unroll
+                for (int q = 0; q < kTmaItems / 4; q++) {
+                    const uint4 x = lds128(sh.hist + j0 + 4 * q);
+                    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+                }
+#pragma unroll
+                for (int i = 1; i < kTmaItems; i++) v[i] += v[i - 1];
+            } else {
+#pragma unroll
+                for (int i = 0; i < kTmaItems; i++) v[i] = 0;
+            }
+            const uint32_t incl = warp_incl_scan(v[kTmaItems - 1]);
+            if (lane == 31) sh.wtot[warp] = incl;
+            __syncthreads();
+            // the 16 warp totals: one more warp-level scan (every warp does its own, no second barrier)
+            uint32_t wt = lane < NW ? sh.wtot[lane] : 0u;
+            wt = warp_incl_scan(wt);
+            const uint32_t wpre = __shfl_sync(0xffffffffu, wt, (warp + 31) & 31);  // inclusive total of warp - 1
+            const uint32_t pre = incl - v[kTmaItems - 1] + (warp > 0 ? wpre : 0u);
+            if (j0 < nb) {
+#pragma unroll
+                for (int i = 0; i < kTmaItems; i++) v[i] += pre;
+                st_global_v8(pw + j0, v);
+            }
+        }
+
+        // ---- per read: length and mean of the cut-off-free profile (filter.cpp:642-656).  No barrier
+        // closes the iteration: what the next one overwrites early (histogram, the other stage's
+        // tables) was last read before the scan's barrier, and a read's sum / maximum are reset by
+        // the thread that reads them here.
+        if (tid < nreads) {
+            const int read = cur.f0 + tid;
+            if (my_base < 0 || nb == 0)
+                F.big_list[atomicAdd(&F.counters1[0], 1)] = read;
+            else
+                finalize_read(rv, F, read, sh.sum[tid], self_count(my_self) > 0 ? sh.mx2[tid] : sh.mx[tid], my_rl, my_self);
+        }
+        cur = nxt;
+        nxt = nn;
+    }
+}
+
 // Fallback of K1 for the reads the flat path cannot take: one warp per read, the same sums
 // straight from the records:  sum_j cov[j] = sum_records (bin(aepos) - bin(abpos)),
 // length = max bin(aepos) + 1.
@@ -582,26 +970,39 @@ k_cov_big(RecView rv, ReadView rd, FlatParams F) {
 }
 
 // ------------------------------------------------------------------ K2
+//
+// Two kernels.  k_mask_bits_flat streams the stored profiles batch by batch and leaves two bits per
+// bin in HBM; k_mask_walk then gives every read ONE THREAD, 32 reads to a warp.  A read's walk is a
+// chain of dependent steps (bit-map words, coverage look-ups behind the annotation candidates); in a
+// single kernel it ran on the first lanes of one warp of the batch's CTA while the CTA's other
+// warps had retired but still held their slots: eight walking warps per SM, 0.61 ms on the long-read
+// set.  Measured alternatives in that form: reads dealt out over the CTA's warps 1.16 ms (the walk
+// is ~1500 instructions, so six instruction streams per CTA cost six times the issue slots), a
+// warp-wide walk (lanes over bit-map words) 0.95 ms.
+
+// Bit i of the word <=> entry 32 w + i; restricted to entries in [lo, hi).
+__device__ __forceinline__ uint32_t map_clip(uint32_t m, int w, int lo, int hi) {
+    const int b = w << 5;
+    if (lo > b) m &= lo - b >= 32 ? 0u : (0xffffffffu << (lo - b));
+    if (hi < b + 32) m &= hi <= b ? 0u : (0xffffffffu >> (b + 32 - hi));
+    return m;
+}
 
 template <bool DUMP>
 __global__ void __launch_bounds__(kFlatThreads, 8)
-k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, MaskAnnoOut out) {
-    __shared__ __align__(16) uint16_t zmap16[kFlatMaps];  // bin has cut-off coverage <= MIN_COV
-    __shared__ __align__(16) uint16_t cmap16[kFlatMaps];  // |cov0[j] - cov0[j-1]| above the smallest threshold
-    const uint32_t* zmap = reinterpret_cast<const uint32_t*>(zmap16);
-    const uint32_t* cmap = reinterpret_cast<const uint32_t*>(cmap16);
-
+k_mask_bits_flat(RecView rv, hg_filter_params P, FlatParams F, MaskAnnoOut out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int2 bt = F.batch[blockIdx.x];
     const int f0 = bt.x, f1 = F.batch[blockIdx.x + 1].x;
     const int MIN_COV = F.scal[1];
-    constexpr int reso = kReso;
     // MIN_COV < 0: runs could cross read boundaries, everything goes the generic way; so do the
     // batches the second form of K1 declined (more records than its 16-bit prefix counts hold)
-    const bool declined = F.v2 && bt.y > 0 && rv.read_off[f1] - rv.read_off[f0] > kV2MaxBatchRecords;
+    const bool declined = F.v2 == 1 && bt.y > 0 && rv.read_off[f1] - rv.read_off[f0] > kV2MaxBatchRecords;
     const int nb = (MIN_COV < 0 || declined) ? 0 : bt.y;
     const int npass = (nb + kFlatPass - 1) / kFlatPass;
     const uint32_t* __restrict__ const pw = F.prof + (size_t)blockIdx.x * kFlatBins;
+    uint16_t* const zmap16 = F.zmap + (size_t)blockIdx.x * kFlatMaps;
+    uint16_t* const cmap16 = F.cmap + (size_t)blockIdx.x * kFlatMaps;
 
     // ---- the two bit maps, flat over the batch's bins.  zero <=> high half <= MIN_COV <=> the
     // word, as a signed integer, is below (MIN_COV + 1) << 16 (the low half is >= 0).
@@ -635,36 +1036,59 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
         zmap16[pass * kFlatThreads + tid] = (uint16_t)zbits;
         cmap16[pass * kFlatThreads + tid] = (uint16_t)cbits;
     }
-    __syncthreads();
 
-    // ---- per read, one thread each.  A read's walk is a chain of dependent steps (bit-map words,
-    // coverage look-ups behind the annotation candidates), so the reads of a batch are dealt out
-    // round-robin over the CTA's WARPS: consecutive thread ids would put a long-read batch's six reads
-    // into one warp -- one instruction stream per CTA, eight per SM -- where this gives six.  (A
-    // warp-wide form of the walk, lanes over bit-map words and candidate bits, was tried on the
-    // long-read set and lost: 0.95 ms against 0.61 ms; the walk is short on parallel work and the
-    // reductions cost more issue slots than they save.)
+    // ---- optional dump of the cut-off-free profiles for .coverage.txt (filter.cpp:599-602)
+    if (DUMP && nb > 0) {
+        for (int read = f0 + warp; read < f1; read += kFlatThreads / 32) {
+            const int base = F.rbase[read];
+            if (base < 0 || rv.read_off[read + 1] - rv.read_off[read] > Packed<uint32_t>::kMaxCount) continue;
+            const int L0 = F.cov_maxbin[read] + 1;
+            int* dst = out.cov0 + out.cov0_off[read];
+            for (int j = lane; j < L0; j += 32) dst[j] = f_lo(__ldg(pw + base + j));
+        }
+    }
+}
+
+constexpr int kWalkThreads = 128;
+
+__global__ void __launch_bounds__(kWalkThreads)
+k_mask_walk(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, MaskAnnoOut out) {
+    const int read = F.p_lo + blockIdx.x * kWalkThreads + threadIdx.x;
+    if (read >= F.p_hi) return;
+    const int bi = F.rbatch[read];
+    if (bi < 0) return;
+    const int MIN_COV = F.scal[1];
+    constexpr int reso = kReso;
+    const int base = F.rbase[read];
+    const int64_t nrec = rv.read_off[read + 1] - rv.read_off[read];
+    bool generic = base < 0 || MIN_COV < 0 || nrec > Packed<uint32_t>::kMaxCount;
+    if (!generic && F.v2 == 1) {  // a batch the second form of K1 declined
+        const int f0 = F.batch[bi].x, f1 = F.batch[bi + 1].x;
+        generic = rv.read_off[f1] - rv.read_off[f0] > kV2MaxBatchRecords;
+    }
+    if (generic) {
+        out.big_list[atomicAdd(&out.counters[3], 1)] = read;
+        return;
+    }
+    const uint32_t* __restrict__ const pw = F.prof + (size_t)bi * kFlatBins;
+    const uint32_t* __restrict__ const zmap = reinterpret_cast<const uint32_t*>(F.zmap + (size_t)bi * kFlatMaps);
+    const uint32_t* __restrict__ const cmap = reinterpret_cast<const uint32_t*>(F.cmap + (size_t)bi * kFlatMaps);
     const int NHR = P.no_hinge_region;
     const int MINT = P.min_repeat_annotation_threshold, MAXT = P.max_repeat_annotation_threshold;
-    constexpr int kWarps = kFlatThreads / 32;
-    for (int slot = lane * kWarps + warp; slot < f1 - f0; slot += kFlatThreads) {
-        const int read = f0 + slot;
-        const int base = F.rbase[read];
-        const int64_t nrec = rv.read_off[read + 1] - rv.read_off[read];
-        if (base < 0 || nb == 0 || nrec > Packed<uint32_t>::kMaxCount) {
-            out.big_list[atomicAdd(&out.counters[3], 1)] = read;
-            continue;
-        }
-        const int nbz = bins_needed(rd.rlen[read], P);
-        const int L0 = F.cov_maxbin[read] + 1;  // length of the cut-off-free profile
-        auto H = [&](int j) { return __ldg(pw + base + j); };  // packed coverage of the read's bin j (L1 hit)
+    const int nbz = bins_needed(rd.rlen[read], P);
+    const int L0 = F.cov_maxbin[read] + 1;  // length of the cut-off-free profile
+    auto H = [&](int j) { return __ldg(pw + base + j); };  // packed coverage of the read's bin j
 
-        // longest run of covered bins (filter.cpp:696-728): the run between two consecutive zeros
-        // p < z scores 40 (z - p - 2); bin 0 acts as a zero; '>' keeps the earliest of the longest
-        int p = base, bestgap = 0, bestz = 0;
-        const int end = base + nbz;
-        for (int w = base >> 5; w <= (end - 1) >> 5; w++) {
-            uint32_t m = map_word(zmap, w, base + 1, end);
+    // longest run of covered bins (filter.cpp:696-728): the run between two consecutive zeros
+    // p < z scores 40 (z - p - 2); bin 0 acts as a zero; '>' keeps the earliest of the longest
+    int p = base, bestgap = 0, bestz = 0;
+    const int end = base + nbz;
+    {
+        const int w1 = (end - 1) >> 5;
+        uint32_t nxt = __ldg(zmap + (base >> 5));
+        for (int w = base >> 5; w <= w1; w++) {
+            uint32_t m = map_clip(nxt, w, base + 1, end);
+            if (w < w1) nxt = __ldg(zmap + w + 1);  // in flight while this word is walked
             while (m) {
                 const int bit = __ffs(m) - 1;
                 const int z = (w << 5) + bit;
@@ -679,187 +1103,208 @@ k_mask_anno_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, Mask
                 m = bit + run >= 32 ? 0u : (m >> (bit + run)) << (bit + run);
             }
         }
-        int maxstart = 0, maxend = 0, msc = 0, mec = 0;
-        if (bestgap >= 3) {
-            const int z = bestz - base, pz = z - bestgap;
-            msc = pz + 1;
-            mec = z - 1;
-            maxstart = reso * (pz + 1);
-            maxend = reso * (z - 1);
+    }
+    int maxstart = 0, maxend = 0, msc = 0, mec = 0;
+    if (bestgap >= 3) {
+        const int z = bestz - base, pz = z - bestgap;
+        msc = pz + 1;
+        mec = z - 1;
+        maxstart = reso * (pz + 1);
+        maxend = reso * (z - 1);
+    }
+
+    // telomere / coverage-imbalance flag (filter.cpp:731-760)
+    uint8_t flags = 0;
+    if (P.delete_telomere) {
+        flags = out.rflags[read] & kFlagSelf;
+        int limit, div;
+        if (mec - msc + 1 > 20) {
+            limit = 10;
+            div = 10;
+        } else {
+            limit = (mec - msc) / 2;
+            div = limit;
         }
-
-        // telomere / coverage-imbalance flag (filter.cpp:731-760)
-        uint8_t flags = 0;
-        if (P.delete_telomere) {
-            flags = out.rflags[read] & kFlagSelf;
-            int limit, div;
-            if (mec - msc + 1 > 20) {
-                limit = 10;
-                div = 10;
-            } else {
-                limit = (mec - msc) / 2;
-                div = limit;
-            }
-            int sc = 0, ec = 0;
-            for (int t = 0; t < limit; t++) {
-                sc += max(f_hi(H(msc + t)), MIN_COV);
-                ec += max(f_hi(H(mec - t)), MIN_COV);
-            }
-            if (div == 0) {
-                sc = 0;
-                ec = 0;
-            } else {
-                sc /= div;
-                ec /= div;
-            }
-            if (sc >= 10 * ec || ec >= 10 * sc) flags |= kFlagCov;
+        int sc = 0, ec = 0;
+        for (int t = 0; t < limit; t++) {
+            sc += max(f_hi(H(msc + t)), MIN_COV);
+            ec += max(f_hi(H(mec - t)), MIN_COV);
         }
+        if (div == 0) {
+            sc = 0;
+            ec = 0;
+        } else {
+            sc /= div;
+            ec /= div;
+        }
+        if (sc >= 10 * ec || ec >= 10 * sc) flags |= kFlagCov;
+    }
 
-        // final mask (filter.cpp:777-788)
-        const int2 q = rd.qvmask[read];
-        int2 mk;
-        if (P.use_qv_mask && P.use_coverage_mask)
-            mk = make_int2(max(maxstart, q.x), min(maxend, q.y));
-        else if (P.use_coverage_mask && !P.use_qv_mask)
-            mk = make_int2(maxstart, maxend);
-        else
-            mk = q;
+    // final mask (filter.cpp:777-788)
+    const int2 q = rd.qvmask[read];
+    int2 mk;
+    if (P.use_qv_mask && P.use_coverage_mask)
+        mk = make_int2(max(maxstart, q.x), min(maxend, q.y));
+    else if (P.use_coverage_mask && !P.use_qv_mask)
+        mk = make_int2(maxstart, maxend);
+    else
+        mk = q;
 
-        // repeat annotation from the coverage gradient (filter.cpp:796-813) + merge pass
-        // (filter.cpp:817-829) as a stream: first count what survives, then write it.
-        // Candidates are bins j < L0 - 2 with 40 j in [mask.start + NHR, mask.end - NHR];
-        // map entry j + 1 flags the jump cov0[j + 1] - cov0[j].
-        const int ja_lo = mk.x + NHR <= 0 ? 0 : (mk.x + NHR + reso - 1) / reso;
-        const int ja_hi = mk.y - NHR < 0 ? -1 : min((mk.y - NHR) / reso, L0 - 3);
-        const int GAP = P.repeat_annotation_gap_threshold;
-        int kept = 0, off = 0;
-        for (int wr = 0; wr < 2; wr++) {
-            int n = 0;
-            unsigned cur = 0;
-            bool have = false;
-            if (ja_hi >= ja_lo) {
-                const int lo = base + ja_lo + 1, hi = base + ja_hi + 2;
-                for (int w = lo >> 5; w <= (hi - 1) >> 5; w++) {
-                    uint32_t m = map_word(cmap, w, lo, hi);
-                    while (m) {
-                        const int bit = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int j = (w << 5) + bit - 1 - base;
-                        const int c0 = f_lo(H(j));
-                        const int g = f_lo(H(j + 1)) - c0;
-                        const int thr = min(max((c0 + MIN_COV) / P.coverage_fraction, MINT), MAXT);
-                        const int type = g > thr ? 1 : (g < -thr ? -1 : 0);
-                        if (type == 0) continue;
-                        const unsigned nxt = ((unsigned)(reso * j) << 2) | (unsigned)(type + 1);
-                        if (!have) {
-                            cur = nxt;
-                            have = true;
-                            continue;
+    // repeat annotation from the coverage gradient (filter.cpp:796-813) + merge pass
+    // (filter.cpp:817-829) as a stream: first count what survives, then write it.
+    // Candidates are bins j < L0 - 2 with 40 j in [mask.start + NHR, mask.end - NHR];
+    // map entry j + 1 flags the jump cov0[j + 1] - cov0[j].
+    const int ja_lo = mk.x + NHR <= 0 ? 0 : (mk.x + NHR + reso - 1) / reso;
+    const int ja_hi = mk.y - NHR < 0 ? -1 : min((mk.y - NHR) / reso, L0 - 3);
+    const int GAP = P.repeat_annotation_gap_threshold;
+    int kept = 0, off = 0;
+    for (int wr = 0; wr < 2; wr++) {
+        int n = 0;
+        unsigned cur = 0;
+        bool have = false;
+        if (ja_hi >= ja_lo) {
+            const int lo = base + ja_lo + 1, hi = base + ja_hi + 2;
+            const int w1 = (hi - 1) >> 5;
+            uint32_t nxt = __ldg(cmap + (lo >> 5));
+            for (int w = lo >> 5; w <= w1; w++) {
+                uint32_t m = map_clip(nxt, w, lo, hi);
+                if (w < w1) nxt = __ldg(cmap + w + 1);
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int j = (w << 5) + bit - 1 - base;
+                    const int c0 = f_lo(H(j));
+                    const int g = f_lo(H(j + 1)) - c0;
+                    const int thr = min(max((c0 + MIN_COV) / P.coverage_fraction, MINT), MAXT);
+                    const int type = g > thr ? 1 : (g < -thr ? -1 : 0);
+                    if (type == 0) continue;
+                    const unsigned nx = ((unsigned)(reso * j) << 2) | (unsigned)(type + 1);
+                    if (!have) {
+                        cur = nx;
+                        have = true;
+                        continue;
+                    }
+                    const int ct = (int)(cur & 3u) - 1;
+                    const int gap = (int)(nx >> 2) - (int)(cur >> 2);
+                    if (ct == 1 && type == 1 && gap < GAP) {
+                        continue;   // +1,+1 close together: the later one goes
+                    } else if (ct == -1 && type == -1 && gap < GAP) {
+                        cur = nx;   // -1,-1 close together: the earlier one goes
+                    } else {
+                        if (wr) {
+                            out.anno_pool[off + n] = make_int2((int)(cur >> 2), (int)(cur & 3u) - 1);
+                            out.hinge_keep[off + n] = 0;
                         }
-                        const int ct = (int)(cur & 3u) - 1;
-                        const int gap = (int)(nxt >> 2) - (int)(cur >> 2);
-                        if (ct == 1 && type == 1 && gap < GAP) {
-                            continue;   // +1,+1 close together: the later one goes
-                        } else if (ct == -1 && type == -1 && gap < GAP) {
-                            cur = nxt;  // -1,-1 close together: the earlier one goes
-                        } else {
-                            if (wr) {
-                                out.anno_pool[off + n] = make_int2((int)(cur >> 2), (int)(cur & 3u) - 1);
-                                out.hinge_keep[off + n] = 0;
-                            }
-                            n++;
-                            cur = nxt;
-                        }
+                        n++;
+                        cur = nx;
                     }
                 }
             }
-            if (have) {
-                if (wr) {
-                    out.anno_pool[off + n] = make_int2((int)(cur >> 2), (int)(cur & 3u) - 1);
-                    out.hinge_keep[off + n] = 0;
-                }
-                n++;
-            }
-            if (wr == 0) {
-                kept = n;
-                if (kept == 0) break;
-                off = atomicAdd(&out.counters[0], kept);
-                if (off + kept > out.anno_cap) {
-                    atomicExch(&out.counters[2], 1);
-                    off = -1;
-                    break;
-                }
-            }
         }
-
-        // hinge pre-test: mean coverage near both mask ends (filter.cpp:842-865); its outcome
-        // only matters for reads that carry annotations
-        bool skip_hinges = false;
-        if (kept > 0) {
-            int cs = 0, ns = 0, ce = 0, ne = 0;
-            int jlo = mk.x <= 0 ? 0 : (mk.x + reso - 1) / reso;  // bins with mk.x <= 40 j <= mk.x + NHR
-            int jhi = mk.x + NHR < 0 ? -1 : min((mk.x + NHR) / reso, L0 - 1);
-            for (int j = jlo; j <= jhi; j++) {
-                cs += f_lo(H(j));
-                ns++;
+        if (have) {
+            if (wr) {
+                out.anno_pool[off + n] = make_int2((int)(cur >> 2), (int)(cur & 3u) - 1);
+                out.hinge_keep[off + n] = 0;
             }
-            jlo = mk.y - NHR <= 0 ? 0 : (mk.y - NHR + reso - 1) / reso;  // mk.y - NHR <= 40 j <= mk.y
-            jhi = mk.y < 0 ? -1 : min(mk.y / reso, L0 - 1);
-            for (int j = jlo; j <= jhi; j++) {
-                ce += f_lo(H(j));
-                ne++;
-            }
-            // float on purpose: 0/0 = NaN makes the '< 10' test false (filter.cpp:861-865)
-            const float avg_end = __fdiv_rn((float)ce, (float)ne);
-            const float avg_start = __fdiv_rn((float)cs, (float)ns);
-            skip_hinges = fabsf(__fsub_rn(avg_end, avg_start)) < 10.0f;
+            n++;
         }
-
-        store_mask(out, read, mk);
-        out.cmask[read] = make_int2(msc, mec);
-        out.rflags[read] = flags | (skip_hinges ? kFlagSkipHinge : 0);
-        out.anno_ref[read] = make_int2(off, kept);
-        if (kept > 0 && !skip_hinges && off >= 0)
-            push_work_item(out, read, rv.read_off[read], (int)nrec, mk, off, kept);
-    }
-
-    // ---- optional dump of the cut-off-free profiles for .coverage.txt (filter.cpp:599-602)
-    if (DUMP && nb > 0) {
-        for (int read = f0 + warp; read < f1; read += kFlatThreads / 32) {
-            const int base = F.rbase[read];
-            if (base < 0 || rv.read_off[read + 1] - rv.read_off[read] > Packed<uint32_t>::kMaxCount) continue;
-            const int L0 = F.cov_maxbin[read] + 1;
-            int* dst = out.cov0 + out.cov0_off[read];
-            for (int j = lane; j < L0; j += 32) dst[j] = f_lo(__ldg(pw + base + j));
+        if (wr == 0) {
+            kept = n;
+            if (kept == 0) break;
+            off = atomicAdd(&out.counters[0], kept);
+            if (off + kept > out.anno_cap) {
+                atomicExch(&out.counters[2], 1);
+                off = -1;
+                break;
+            }
         }
     }
+
+    // hinge pre-test: mean coverage near both mask ends (filter.cpp:842-865); its outcome
+    // only matters for reads that carry annotations
+    bool skip_hinges = false;
+    if (kept > 0) {
+        int cs = 0, ns = 0, ce = 0, ne = 0;
+        int jlo = mk.x <= 0 ? 0 : (mk.x + reso - 1) / reso;  // bins with mk.x <= 40 j <= mk.x + NHR
+        int jhi = mk.x + NHR < 0 ? -1 : min((mk.x + NHR) / reso, L0 - 1);
+        for (int j = jlo; j <= jhi; j++) {
+            cs += f_lo(H(j));
+            ns++;
+        }
+        jlo = mk.y - NHR <= 0 ? 0 : (mk.y - NHR + reso - 1) / reso;  // mk.y - NHR <= 40 j <= mk.y
+        jhi = mk.y < 0 ? -1 : min(mk.y / reso, L0 - 1);
+        for (int j = jlo; j <= jhi; j++) {
+            ce += f_lo(H(j));
+            ne++;
+        }
+        // float on purpose: 0/0 = NaN makes the '< 10' test false (filter.cpp:861-865)
+        const float avg_end = __fdiv_rn((float)ce, (float)ne);
+        const float avg_start = __fdiv_rn((float)cs, (float)ns);
+        skip_hinges = fabsf(__fsub_rn(avg_end, avg_start)) < 10.0f;
+    }
+
+    store_mask(out, read, mk);
+    out.cmask[read] = make_int2(msc, mec);
+    out.rflags[read] = flags | (skip_hinges ? kFlagSkipHinge : 0);
+    out.anno_ref[read] = make_int2(off, kept);
+    if (kept > 0 && !skip_hinges && off >= 0)
+        push_work_item(out, read, rv.read_off[read], (int)nrec, mk, off, kept);
 }
 
 // ------------------------------------------------------------------ host side
 
-// Greedy packing of the reads [lo, hi) into batches of at most kFlatBins histogram words and
-// kFlatMaxReads reads.
-//   batch  (first read, words in use) per batch, closed by (hi, 0)
-//   rbase  per read: first word of its profile inside its batch; -1 = fallback path
-void flat_plan(const int* rlen, int lo, int hi, int n_read, int cut_off, std::vector<int2>* batch,
-               std::vector<int>* rbase) {
-    batch->clear();
-    rbase->assign((size_t)n_read, -1);
-    int used = 0;
+// Greedy packing of the reads [lo, hi) into batches of at most kFlatBins histogram words,
+// kFlatMaxReads reads and -- with cap_records -- kSlabRecords records (what the third form of K1
+// stages in shared memory per batch).  A read that is too long or too deep for a batch goes to
+// the per-read fallbacks (rbase = -1) and is a batch of its own (words = 0), which reports it.
+void flat_plan(const int* rlen, const int64_t* read_off, int lo, int hi, int n_read, int cut_off, bool cap_records,
+               FlatPlan* plan) {
+    const int64_t max_recs = cap_records && read_off ? kSlabRecords : (int64_t)1 << 60;
+    plan->batch.clear();
+    plan->desc.clear();
+    plan->rbase.assign((size_t)n_read, -1);
+    plan->rbatch.assign((size_t)n_read, -1);
+    plan->cpre.assign((size_t)n_read + 1, 0);
+    int used = 0, chunks = 0;
+    int64_t recs = 0;
+    bool open = false, solitary = false;
+    auto close = [&](int r_end) {
+        if (!open) return;
+        const int f0 = plan->batch.back().x;
+        const int64_t k0 = read_off ? read_off[f0] : 0;
+        plan->desc.push_back(make_int4(f0, r_end - f0, plan->batch.back().y, chunks));
+        plan->desc.push_back(make_int4((int)(k0 & 0xffffffffll), (int)(k0 >> 32), (int)recs, 0));
+        open = false;
+    };
     for (int r = lo; r < hi; r++) {
         const int nbz = bins_needed(rlen[r], cut_off);
-        const bool fits = nbz <= kFlatBins;  // otherwise fallback; still belongs to a batch, which reports it
-        if (batch->empty() || (fits && used + nbz > kFlatBins) || r - batch->back().x >= kFlatMaxReads) {
-            batch->push_back(make_int2(r, 0));
+        const int64_t nrec = read_off ? read_off[r + 1] - read_off[r] : 0;
+        const bool fits = nbz <= kFlatBins && nrec <= max_recs;
+        if (!open || solitary || !fits || used + nbz > kFlatBins || recs + nrec > max_recs ||
+            r - plan->batch.back().x >= kFlatMaxReads) {
+            close(r);
+            plan->batch.push_back(make_int2(r, 0));
+            open = true;
+            solitary = !fits;
             used = 0;
+            chunks = 0;
+            recs = 0;
         }
+        plan->rbatch[r] = (int)plan->batch.size() - 1;
+        plan->cpre[r] = chunks;
         if (!fits) continue;
-        (*rbase)[r] = used;
+        plan->rbase[r] = used;
         used += nbz;
-        batch->back().y = used;
+        recs += nrec;
+        chunks += (int)((nrec + 31) >> 5);
+        plan->batch.back().y = used;
     }
-    if (batch->empty()) batch->push_back(make_int2(lo, 0));
-    batch->push_back(make_int2(hi, 0));
+    if (!open) {
+        plan->batch.push_back(make_int2(lo, 0));
+        open = true;
+    }
+    close(hi);
+    plan->batch.push_back(make_int2(hi, 0));
 }
 
 // The second form of K1 is written for the nominal cut-off (300: every INI the reference ships).
@@ -868,15 +1313,22 @@ void flat_plan(const int* rlen, int lo, int hi, int n_read, int cut_off, std::ve
 // the 62 M-record N(3500,1500) set, a wash); with long reads (3 bins per record on the
 // N(24000,8000) set) the first form is faster (0.92 vs 1.14 ms).  flat_bins_per_record is set
 // when the batch plan is made.
+// The third form (k_profile_tma) needs 16-byte aligned columns for its bulk copies.
+static bool use_v3(const FilterScratch& s, const RecView& rv) {
+    if (s.flat_kernel != 3 || !s.flat_capped) return false;
+    return ((reinterpret_cast<uintptr_t>(rv.abpos) | reinterpret_cast<uintptr_t>(rv.aepos)) & 15) == 0;
+}
+
 static bool use_v2(const FilterScratch& s, const hg_filter_params& P) {
-    if (s.flat_kernel == 1 || P.cut_off != kV2CutOff) return false;
+    if (s.flat_kernel == 1 || s.flat_kernel == 3 || P.cut_off != kV2CutOff) return false;
     if (s.flat_kernel >= 5) return true;
     return s.flat_bins_per_record < 1.5f;
 }
 
-static FlatParams flat_params(const FilterScratch& s, const hg_filter_params& P, int r_begin, int r_end) {
+static FlatParams flat_params(const FilterScratch& s, const hg_filter_params& P, const RecView& rv, int r_begin,
+                              int r_end) {
     FlatParams F;
-    F.v2 = use_v2(s, P) ? 1 : 0;
+    F.v2 = use_v3(s, rv) ? 2 : use_v2(s, P) ? 1 : 0;
     F.batch = s.flat_batch;
     F.rbase = s.flat_rbase;
     F.self_cnt = s.self_cnt;
@@ -887,6 +1339,14 @@ static FlatParams flat_params(const FilterScratch& s, const hg_filter_params& P,
     F.counters1 = s.counters1;
     F.big_list = s.big_list;
     F.scal = s.scal;
+    F.rbatch = s.flat_rbatch;
+    F.cpre = s.flat_cpre;
+    F.desc = s.flat_desc;
+    F.zmap = s.flat_zmap;
+    F.cmap = s.flat_cmap;
+    F.p_lo = s.flat_lo;
+    F.p_hi = s.flat_hi;
+    F.nbatch = s.flat_nbatch;
     F.r_begin = r_begin;
     F.r_end = r_end;
     return F;
@@ -895,14 +1355,19 @@ static FlatParams flat_params(const FilterScratch& s, const hg_filter_params& P,
 // Phase 1 of the stage: both coverage profiles of every owned read, their lengths and means.
 void launch_profile(const RecView& rv, const ReadView& rd, const hg_filter_params& P, int r_begin,
                     int r_end, FilterScratch& s, cudaStream_t st) {
-    const FlatParams F = flat_params(s, P, r_begin, r_end);
+    const FlatParams F = flat_params(s, P, rv, r_begin, r_end);
     // the counters of both phases; per-read results of reads outside the planned range were
     // cleared when the plan was made (hg_capi.cu)
     cudaMemsetAsync(s.counters, 0, sizeof(int) * 16, st);
     const int grid = s.flat_nbatch;
     if (grid <= 0) return;
     g_launches += 2;
-    if (F.v2) {
+    if (F.v2 == 2) {
+        // persistent: two CTAs per SM, batches strided over them; function attributes are per device
+        const int smem = (int)sizeof(TmaShared);
+        cudaFuncSetAttribute(k_profile_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        k_profile_tma<<<std::min(grid, 2 * s.num_sms), kTmaThreads, smem, st>>>(rv, rd, P, F);
+    } else if (F.v2) {
         // tuning aids: resident CTAs per SM the compiler aims for (registers), scatter spread
         if (s.flat_kernel == 5) k_profile_flat2<8, 4><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
         else if (s.flat_kernel == 6) k_profile_flat2<8, 6><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F);
@@ -924,14 +1389,17 @@ void launch_profile(const RecView& rv, const ReadView& rd, const hg_filter_param
 // for the reads it reports is launched by launch_mask_anno, hg_filter.cu).
 void launch_mask_anno_flat(const RecView& rv, const ReadView& rd, const hg_filter_params& P, int r_begin,
                            int r_end, FilterScratch& s, const MaskAnnoOut& out, cudaStream_t st) {
-    const FlatParams F = flat_params(s, P, r_begin, r_end);
+    const FlatParams F = flat_params(s, P, rv, r_begin, r_end);
     const int grid = s.flat_nbatch;
     if (grid <= 0) return;
-    g_launches += 1;
+    g_launches += 2;
     if (out.cov0)
-        k_mask_anno_flat<true><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F, out);
+        k_mask_bits_flat<true><<<grid, kFlatThreads, 0, st>>>(rv, P, F, out);
     else
-        k_mask_anno_flat<false><<<grid, kFlatThreads, 0, st>>>(rv, rd, P, F, out);
+        k_mask_bits_flat<false><<<grid, kFlatThreads, 0, st>>>(rv, P, F, out);
+    const int nreads = s.flat_hi - s.flat_lo;
+    if (nreads > 0)
+        k_mask_walk<<<(nreads + kWalkThreads - 1) / kWalkThreads, kWalkThreads, 0, st>>>(rv, rd, P, F, out);
 }
 
 }  // namespace hg

@@ -138,9 +138,16 @@ struct EarlyContext {
     hg_ctx* ctx = nullptr;
     int rc = HG_OK;
     bool started = false;
+    double create_ms = 0;
     void start() {
         started = true;
-        worker = std::thread([this]() { rc = hg_ctx_create(0, nullptr, &ctx); });
+        worker = std::thread([this]() {
+            struct timespec a, b;
+            clock_gettime(CLOCK_MONOTONIC, &a);
+            rc = hg_ctx_create(0, nullptr, &ctx);
+            clock_gettime(CLOCK_MONOTONIC, &b);
+            create_ms = 1e3 * (double)(b.tv_sec - a.tv_sec) + 1e-6 * (double)(b.tv_nsec - a.tv_nsec);
+        });
     }
     int take(hg_ctx** out) {
         if (!started) return hg_ctx_create(0, nullptr, out);
@@ -201,6 +208,7 @@ int open_context(const ReadDB& db, const LasFile& las, bool with_trace, hg_ctx**
     PhaseTimer timer;
     int rc = g_early.take(ctx);
     timer.lap("  wait for CUDA context");
+    timer.note("  (context creation, thread)", g_early.create_ms, "ms");
     if (rc != HG_OK) {
         fprintf(stderr, "hinge_b200: cannot create a CUDA context (status %d)\n", rc);
         return rc;

@@ -50,11 +50,12 @@ enum hg_option {
                                  as the reference's part loop does (filter.cpp:534,884-889) */
     HG_OPT_ANNO_POOL = 6,     /* initial capacity of the annotation pool (entries; default 2 per owned read + 64 K);
                                  a pool that turns out too small is grown and the stage rerun (HG_RETRY_POOL) */
-    HG_OPT_PROFILE_KERNEL = 4 /* tuning aid: 0 = pick the form of the coverage-profile kernel by cut_off and
-                                 data shape (20-bp start/end histogram for the nominal cut_off 300 when
-                                 records outnumber coverage bins), 1 = always the four-event 40-bp form,
-                                 5 / 6 = always the 20-bp form, compiled for 4 / 6 resident CTAs per SM
-                                 (default: 5) */
+    HG_OPT_PROFILE_KERNEL = 4 /* tuning aid, form of the coverage-profile kernel: 0 = picked by cut_off and data
+                                 shape (20-bp start/end histogram for the nominal cut_off 300 when records
+                                 outnumber coverage bins, else the four-event 40-bp form), 1 = always the
+                                 four-event form, 3 = the persistent TMA-staged form (bulk copies of the abpos /
+                                 aepos columns into shared memory, batches bounded by record volume),
+                                 5 / 6 = always the 20-bp form, compiled for 4 / 6 resident CTAs per SM */
 };
 
 enum hg_buffer { /* per-read device arrays a sharded run exchanges between phases */

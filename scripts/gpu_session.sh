@@ -34,7 +34,7 @@ import json;d=json.load(open('$OUT/${TAG}_bench_k1old.json'));print('c5',d['ms_p
       timeout 900 python -m pytest tests/test_gpu_filter_api.py tests/test_gpu_edge_cases.py tests/test_gpu_filter_cli.py -m gpu -x -q > $OUT/${TAG}_pytest_filter.log 2>&1
       echo "pytest (filter) exit $?" | tee -a $OUT/${TAG}_pytest_filter.log; tail -5 $OUT/${TAG}_pytest_filter.log ;;
     variants)
-      for V in 0 5 6; do
+      for V in ${VARIANTS:-1 2 0}; do
         timeout 600 python bench.py --profile-kernel $V $SHORT > $OUT/${TAG}_bench_v$V.json 2> $OUT/${TAG}_bench_v$V.err
         echo "variant $V exit $?"
         python -c "
@@ -95,6 +95,12 @@ d=json.load(open('$OUT/${TAG}_bench_n$NG.json')); print('c5 value %.4g ms %.4f'%
           -o $OUT/${TAG}_k_profile_flat2_$CFG python bench.py --config $CFG --also "" $SHORT > $OUT/${TAG}_ncu_k1_$CFG.log 2>&1
         echo "ncu k_profile_flat2 $CFG exit $?"
       done ;;
+    ncu_one)
+      # NCU_K=<kernel regex> NCU_CFG=c3|c5 [NCU_ARGS="--profile-kernel 1"]
+      K=${NCU_K:-k_profile_tma}; CFG=${NCU_CFG:-c3}
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^$K" -s 4 -c 1 -f \
+        -o $OUT/${TAG}_${K}_$CFG python bench.py --config $CFG --also "" $SHORT ${NCU_ARGS:-} > $OUT/${TAG}_ncu_${K}_$CFG.log 2>&1
+      echo "ncu $K $CFG exit $?" ;;
     ncu_k4)
       for K in k_hinge_exact_warp k_hinge_call; do
         timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^$K" -s 4 -c 1 -f \

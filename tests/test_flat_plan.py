@@ -62,6 +62,64 @@ def test_plan_invariants(built, case):
             assert rbase[r] == pos, "profiles are laid end to end"
             pos += int(nbz[r])
         assert pos == used and used <= K_BINS
+        if any(nbz[r] > K_BINS for r in range(f0, f1)):
+            assert f1 - f0 == 1 and used == 0, "a read that fits no batch is a batch of its own"
         # greedy: the next read did not fit (or the read-count limit closed the batch)
-        if f1 < hi and nbz[f1] <= K_BINS:
+        elif f1 < hi and nbz[f1] <= K_BINS:
             assert used + nbz[f1] > K_BINS or f1 - f0 == K_READS
+
+
+K_SLAB = 4096
+
+
+def _plan2(rlen, read_off, lo, hi, cut_off):
+    from hinge_b200._lib import lib
+    lib.hg_debug_flat_plan2.restype = C.c_int
+    lib.hg_debug_flat_plan2.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rlen = np.ascontiguousarray(rlen, np.int32)
+    read_off = np.ascontiguousarray(read_off, np.int64)
+    n = len(rlen)
+    cap = n + 2
+    batch = np.zeros((cap, 2), np.int32)
+    rbase, rbatch, cpre, nchunk = (np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32),
+                                   np.zeros(cap, np.int32))
+    nb = lib.hg_debug_flat_plan2(rlen.ctypes.data, read_off.ctypes.data, n, lo, hi, cut_off, batch.ctypes.data, cap,
+                                 rbase.ctypes.data, rbatch.ctypes.data, cpre.ctypes.data, nchunk.ctypes.data)
+    assert nb >= 0
+    return batch[:nb + 1], rbase, rbatch, cpre, nchunk[:nb]
+
+
+@pytest.mark.parametrize("case", ["pacbio", "deep", "empty_reads"])
+def test_plan_bounded_by_records(built, case):
+    """With the CSR the batches are also bounded by kSlabRecords records (what the TMA-staged form of the
+    profile kernel holds in shared memory); deeper pile-ups are batches of their own on the generic path."""
+    rng = np.random.default_rng(11)
+    n, cut_off = 6000, 300
+    rlen = np.maximum(1000, rng.normal(3500, 1500, n)).astype(np.int32)
+    if case == "pacbio":
+        nrec = rng.poisson(90, n)
+    elif case == "deep":
+        nrec = rng.poisson(400, n)
+        nrec[[5, 700, 701, 5999]] = [5000, 4097, 4096, 20000]
+    else:
+        nrec = rng.poisson(60, n) * (rng.random(n) < 0.5)
+    read_off = np.concatenate([[0], np.cumsum(nrec)]).astype(np.int64)
+    lo, hi = 10, n - 5
+    batch, rbase, rbatch, cpre, nchunk = _plan2(rlen, read_off, lo, hi, cut_off)
+    nbz = _bins(rlen.astype(np.int64), cut_off)
+    first = batch[:, 0]
+    assert first[0] == lo and first[-1] == hi and np.all(np.diff(first) > 0)
+    assert np.all(rbatch[:lo] == -1) and np.all(rbatch[hi:] == -1)
+    for b in range(len(batch) - 1):
+        f0, f1, used = int(first[b]), int(first[b + 1]), int(batch[b, 1])
+        assert np.all(rbatch[f0:f1] == b)
+        fit = (nbz[f0:f1] <= K_BINS) & (nrec[f0:f1] <= K_SLAB)
+        if not fit.all():
+            assert f1 - f0 == 1 and used == 0 and rbase[f0] == -1 and nchunk[b] == 0
+            continue
+        assert used == nbz[f0:f1].sum() <= K_BINS and nrec[f0:f1].sum() <= K_SLAB and f1 - f0 <= K_READS
+        chunks = (nrec[f0:f1] + 31) // 32
+        assert np.array_equal(cpre[f0:f1], np.concatenate([[0], np.cumsum(chunks)[:-1]])) and nchunk[b] == chunks.sum()
+        if f1 < hi and nbz[f1] <= K_BINS and nrec[f1] <= K_SLAB:
+            assert (used + nbz[f1] > K_BINS or nrec[f0:f1].sum() + nrec[f1] > K_SLAB or f1 - f0 == K_READS)

@@ -35,6 +35,24 @@ def _tiling(rng, n_read, rlen, genome, cov_step):
     return recs
 
 
+TMA_CASES = {"test_reads_without_overlaps_and_self_overlaps", "test_very_deep_pileups_take_the_fallbacks",
+             "test_long_read_and_overlaps_inside_one_bin", "test_many_tiny_reads_per_batch",
+             "test_reads_just_under_and_over_the_batch_capacity",
+             "test_batch_with_more_records_than_the_prefix_counts_hold"}
+
+
+@pytest.fixture(params=["default", "tma"], autouse=True)
+def profile_kernel_form(request, monkeypatch):
+    """The edge cases that bear on the batch plan run twice: with the default forms of the coverage-profile
+    kernel and with the TMA-staged persistent one (HINGE_B200_PROFILE_KERNEL=3, read by the executables)."""
+    if request.param == "tma":
+        if request.node.originalname not in TMA_CASES:
+            pytest.skip("default form only")
+        monkeypatch.setenv("HINGE_B200_PROFILE_KERNEL", "3")
+    else:
+        monkeypatch.delenv("HINGE_B200_PROFILE_KERNEL", raising=False)
+
+
 def test_many_overlaps_per_pair_and_ties(built, tmp_path):
     rng = np.random.default_rng(1)
     n = 60

@@ -51,13 +51,26 @@ def test_filter_arrays_match_oracle(built):
 
 def test_both_forms_of_the_profile_kernel_match_oracle(built):
     """HG_OPT_PROFILE_KERNEL = 1 forces the four-event 40-bp form of K1 (the one that also serves
-    cut-offs off the 20-bp grid); the default picks the 20-bp start / end histogram."""
+    cut-offs off the 20-bp grid), 3 the TMA-staged persistent form; the default picks the 20-bp
+    start / end histogram here."""
     from hinge_b200 import api
 
     kw = dict(genome_len=500000, coverage=45.0, seed=78, n_families=4)
-    for form in (0, 1):
+    for form in (0, 1, 3):
         got, want, summ = _run_both(built, kw, options=[(api.HG_OPT_PROFILE_KERNEL, form)])
         _assert_equal(got, want, summ)
+
+
+def test_tma_staged_profile_kernel_on_long_reads(built):
+    """HG_OPT_PROFILE_KERNEL = 3: the persistent form of K1 that stages the abpos / aepos columns and the
+    per-read tables of a batch in shared memory with TMA bulk copies (batches bounded by record volume,
+    deeper pile-ups on the generic path), on the long-read shape with repeat-induced deep pile-ups."""
+    from hinge_b200 import api
+
+    got, want, summ = _run_both(built, dict(genome_len=3000000, coverage=40.0, read_mean=24000, read_sd=8000,
+                                           read_min=2000, seed=99, frag_prob=1.2, n_families=12),
+                                options=[(api.HG_OPT_PROFILE_KERNEL, 3)])
+    _assert_equal(got, want, summ)
 
 
 def test_c5_shaped_long_reads_with_fragmented_alignments(built):
