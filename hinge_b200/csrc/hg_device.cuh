@@ -209,14 +209,17 @@ __device__ __forceinline__ void store_mask(const MaskAnnoOut& out, int read, int
 // work item itself (one 48-byte read instead of read id -> offsets / mask / annotation ref ->
 // annotations): (read, pile-up size, first record lo, hi) (mask.x, mask.y, first annotation,
 // annotations) (pos0, type0, pos1, type1: the first two annotations, most reads have no more)
-__device__ __forceinline__ void push_work_item(const MaskAnnoOut& out, int read, int64_t o0, int np, int2 mk,
-                                               int off, int kept) {
-    const int slot = atomicAdd(&out.counters[1], 1);
+__device__ __forceinline__ void write_work_item(const MaskAnnoOut& out, int slot, int read, int64_t o0, int np,
+                                                int2 mk, int off, int kept) {
     const int2 a0 = out.anno_pool[off], a1 = kept > 1 ? out.anno_pool[off + 1] : make_int2(0, 0);
     int4* it = out.work_items + 3 * (size_t)slot;
     it[0] = make_int4(read, np, (int)(o0 & 0xffffffffll), (int)(o0 >> 32));
     it[1] = make_int4(mk.x, mk.y, off, kept);
     it[2] = make_int4(a0.x, a0.y, a1.x, a1.y);
+}
+__device__ __forceinline__ void push_work_item(const MaskAnnoOut& out, int read, int64_t o0, int np, int2 mk,
+                                               int off, int kept) {
+    write_work_item(out, atomicAdd(&out.counters[1], 1), read, o0, np, mk, off, kept);
 }
 
 // Histogram words one read needs: every event bin of both profiles (cut-off of either

@@ -54,6 +54,18 @@ constexpr int kSlabRecords = 4096;                       // records of a batch (
 
 __device__ __forceinline__ uint4 lds128(const uint32_t* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void sts128(uint32_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+// 256-bit store (sm_100: STG.E.ENL2.256): a thread's eight consecutive profile words fill a whole 32-byte
+// sector, where four 128-bit stores 64 B apart leave every sector half written per request
+__device__ __forceinline__ void st_global_v8(uint32_t* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const uint32_t* p, uint32_t* v) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
 __device__ __forceinline__ int f_lo(uint32_t v) { return (int)(v & 0xffffu); }   // after the scan: cov0 >= 0
 __device__ __forceinline__ int f_hi(uint32_t v) { return (int)v >> 16; }
 
@@ -279,11 +291,7 @@ k_profile_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
 #pragma unroll
             for (int i = 0; i < kFlatItems; i++) v[i] += pre;
 #pragma unroll
-            for (int q = 0; q < kFlatItems / 4; q++) {
-                const uint4 x = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                sts128(hist + ((j0 + 4 * q) ^ sx), x);
-                *reinterpret_cast<uint4*>(pw + j0 + 4 * q) = x;
-            }
+            for (int q = 0; q < kFlatItems / 8; q++) st_global_v8(pw + j0 + 8 * q, v + 8 * q);
         }
     }
     __syncthreads();
@@ -506,9 +514,7 @@ k_profile_flat2(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
         uint32_t* const pw = F.prof + (size_t)blockIdx.x * kFlatBins;
         if (mine) {
 #pragma unroll
-            for (int v = 0; v < kFlatItems / 4; v++)
-                *reinterpret_cast<uint4*>(pw + q0 + 4 * v) =
-                    make_uint4(word[4 * v], word[4 * v + 1], word[4 * v + 2], word[4 * v + 3]);
+            for (int v = 0; v < kFlatItems / 8; v++) st_global_v8(pw + q0 + 8 * v, word + 8 * v);
         }
 
         // ---- T = exclusive prefix sum of cov0 over the batch, into shared memory (swizzled like the
@@ -625,11 +631,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void st_global_v8(uint32_t* p, const uint32_t* v) {
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
-                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }
 
@@ -1014,10 +1015,7 @@ k_mask_bits_flat(RecView rv, hg_filter_params P, FlatParams F, MaskAnnoOut out) 
         uint32_t v[kFlatItems];
         if (j0 < nb) {
 #pragma unroll
-            for (int q = 0; q < kFlatItems / 4; q++) {
-                const uint4 x = __ldg(reinterpret_cast<const uint4*>(pw + j0 + 4 * q));
-                v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-            }
+            for (int q = 0; q < kFlatItems / 8; q++) ld_global_nc_v8(pw + j0 + 8 * q, v + 8 * q);
         } else {
 #pragma unroll
             for (int i = 0; i < kFlatItems; i++) v[i] = 0;
@@ -1050,132 +1048,54 @@ k_mask_bits_flat(RecView rv, hg_filter_params P, FlatParams F, MaskAnnoOut out) 
 }
 
 constexpr int kWalkThreads = 128;
+constexpr int kWalkFetch = 4;   // bit-map words in flight per thread
 
-__global__ void __launch_bounds__(kWalkThreads)
-k_mask_walk(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, MaskAnnoOut out) {
-    const int read = F.p_lo + blockIdx.x * kWalkThreads + threadIdx.x;
-    if (read >= F.p_hi) return;
-    const int bi = F.rbatch[read];
-    if (bi < 0) return;
-    const int MIN_COV = F.scal[1];
+// Per-read state of the walk between its phases.
+struct WalkRead {
+    const uint32_t* pw;     // the batch's packed profiles
+    const uint32_t* cmap;
+    int base, L0, ja_lo, ja_hi, MIN_COV;
+};
+
+// Repeat annotation from the coverage gradient (filter.cpp:796-813) + merge pass (filter.cpp:817-829)
+// as a stream over the flagged bins; WRITE = false counts what survives, WRITE = true stores it.
+// Candidates are bins j < L0 - 2 with 40 j in [mask.start + NHR, mask.end - NHR]; map entry j + 1
+// flags the jump cov0[j + 1] - cov0[j].
+template <bool WRITE>
+__device__ __forceinline__ int walk_annotations(const WalkRead& w, const hg_filter_params& P, const MaskAnnoOut& out,
+                                                int off) {
     constexpr int reso = kReso;
-    const int base = F.rbase[read];
-    const int64_t nrec = rv.read_off[read + 1] - rv.read_off[read];
-    bool generic = base < 0 || MIN_COV < 0 || nrec > Packed<uint32_t>::kMaxCount;
-    if (!generic && F.v2 == 1) {  // a batch the second form of K1 declined
-        const int f0 = F.batch[bi].x, f1 = F.batch[bi + 1].x;
-        generic = rv.read_off[f1] - rv.read_off[f0] > kV2MaxBatchRecords;
-    }
-    if (generic) {
-        out.big_list[atomicAdd(&out.counters[3], 1)] = read;
-        return;
-    }
-    const uint32_t* __restrict__ const pw = F.prof + (size_t)bi * kFlatBins;
-    const uint32_t* __restrict__ const zmap = reinterpret_cast<const uint32_t*>(F.zmap + (size_t)bi * kFlatMaps);
-    const uint32_t* __restrict__ const cmap = reinterpret_cast<const uint32_t*>(F.cmap + (size_t)bi * kFlatMaps);
-    const int NHR = P.no_hinge_region;
     const int MINT = P.min_repeat_annotation_threshold, MAXT = P.max_repeat_annotation_threshold;
-    const int nbz = bins_needed(rd.rlen[read], P);
-    const int L0 = F.cov_maxbin[read] + 1;  // length of the cut-off-free profile
-    auto H = [&](int j) { return __ldg(pw + base + j); };  // packed coverage of the read's bin j
-
-    // longest run of covered bins (filter.cpp:696-728): the run between two consecutive zeros
-    // p < z scores 40 (z - p - 2); bin 0 acts as a zero; '>' keeps the earliest of the longest
-    int p = base, bestgap = 0, bestz = 0;
-    const int end = base + nbz;
-    {
-        const int w1 = (end - 1) >> 5;
-        uint32_t nxt = __ldg(zmap + (base >> 5));
-        for (int w = base >> 5; w <= w1; w++) {
-            uint32_t m = map_clip(nxt, w, base + 1, end);
-            if (w < w1) nxt = __ldg(zmap + w + 1);  // in flight while this word is walked
-            while (m) {
-                const int bit = __ffs(m) - 1;
-                const int z = (w << 5) + bit;
-                if (z - p > bestgap) {
-                    bestgap = z - p;
-                    bestz = z;
-                }
-                // the zeros that follow z back to back each have gap 1: skip them in one go
-                const uint32_t t = ~(m >> bit);                     // bit 0 clear
-                const int run = t ? __ffs(t) - 1 : 32 - bit;        // consecutive zeros from z on
-                p = z + run - 1;
-                m = bit + run >= 32 ? 0u : (m >> (bit + run)) << (bit + run);
-            }
-        }
-    }
-    int maxstart = 0, maxend = 0, msc = 0, mec = 0;
-    if (bestgap >= 3) {
-        const int z = bestz - base, pz = z - bestgap;
-        msc = pz + 1;
-        mec = z - 1;
-        maxstart = reso * (pz + 1);
-        maxend = reso * (z - 1);
-    }
-
-    // telomere / coverage-imbalance flag (filter.cpp:731-760)
-    uint8_t flags = 0;
-    if (P.delete_telomere) {
-        flags = out.rflags[read] & kFlagSelf;
-        int limit, div;
-        if (mec - msc + 1 > 20) {
-            limit = 10;
-            div = 10;
-        } else {
-            limit = (mec - msc) / 2;
-            div = limit;
-        }
-        int sc = 0, ec = 0;
-        for (int t = 0; t < limit; t++) {
-            sc += max(f_hi(H(msc + t)), MIN_COV);
-            ec += max(f_hi(H(mec - t)), MIN_COV);
-        }
-        if (div == 0) {
-            sc = 0;
-            ec = 0;
-        } else {
-            sc /= div;
-            ec /= div;
-        }
-        if (sc >= 10 * ec || ec >= 10 * sc) flags |= kFlagCov;
-    }
-
-    // final mask (filter.cpp:777-788)
-    const int2 q = rd.qvmask[read];
-    int2 mk;
-    if (P.use_qv_mask && P.use_coverage_mask)
-        mk = make_int2(max(maxstart, q.x), min(maxend, q.y));
-    else if (P.use_coverage_mask && !P.use_qv_mask)
-        mk = make_int2(maxstart, maxend);
-    else
-        mk = q;
-
-    // repeat annotation from the coverage gradient (filter.cpp:796-813) + merge pass
-    // (filter.cpp:817-829) as a stream: first count what survives, then write it.
-    // Candidates are bins j < L0 - 2 with 40 j in [mask.start + NHR, mask.end - NHR];
-    // map entry j + 1 flags the jump cov0[j + 1] - cov0[j].
-    const int ja_lo = mk.x + NHR <= 0 ? 0 : (mk.x + NHR + reso - 1) / reso;
-    const int ja_hi = mk.y - NHR < 0 ? -1 : min((mk.y - NHR) / reso, L0 - 3);
     const int GAP = P.repeat_annotation_gap_threshold;
-    int kept = 0, off = 0;
-    for (int wr = 0; wr < 2; wr++) {
-        int n = 0;
-        unsigned cur = 0;
-        bool have = false;
-        if (ja_hi >= ja_lo) {
-            const int lo = base + ja_lo + 1, hi = base + ja_hi + 2;
-            const int w1 = (hi - 1) >> 5;
-            uint32_t nxt = __ldg(cmap + (lo >> 5));
-            for (int w = lo >> 5; w <= w1; w++) {
-                uint32_t m = map_clip(nxt, w, lo, hi);
-                if (w < w1) nxt = __ldg(cmap + w + 1);
+    int n = 0;
+    unsigned cur = 0;
+    bool have = false;
+    if (w.ja_hi >= w.ja_lo) {
+        const int lo = w.base + w.ja_lo + 1, hi = w.base + w.ja_hi + 2;
+        const int w1 = (hi - 1) >> 5;
+        const int wf = lo >> 5;
+        const uint32_t mf = 0xffffffffu << (lo & 31), ml = 0xffffffffu >> (31 - ((hi - 1) & 31));  // clips of the first / last word
+        for (int w0 = wf; w0 <= w1; w0 += kWalkFetch) {
+            uint32_t buf[kWalkFetch], any = 0;
+#pragma unroll
+            for (int i = 0; i < kWalkFetch; i++) {
+                buf[i] = w0 + i <= w1 ? __ldg(w.cmap + w0 + i) : 0u;
+                any |= buf[i];
+            }
+            if (any == 0) continue;   // most words flag nothing
+#pragma unroll
+            for (int i = 0; i < kWalkFetch; i++) {
+                const int wd = w0 + i;
+                uint32_t m = buf[i];
+                if (wd == wf) m &= mf;
+                if (wd == w1) m &= ml;
                 while (m) {
                     const int bit = __ffs(m) - 1;
                     m &= m - 1;
-                    const int j = (w << 5) + bit - 1 - base;
-                    const int c0 = f_lo(H(j));
-                    const int g = f_lo(H(j + 1)) - c0;
-                    const int thr = min(max((c0 + MIN_COV) / P.coverage_fraction, MINT), MAXT);
+                    const int j = (wd << 5) + bit - 1 - w.base;
+                    const int c0 = f_lo(__ldg(w.pw + w.base + j));
+                    const int g = f_lo(__ldg(w.pw + w.base + j + 1)) - c0;
+                    const int thr = min(max((c0 + w.MIN_COV) / P.coverage_fraction, MINT), MAXT);
                     const int type = g > thr ? 1 : (g < -thr ? -1 : 0);
                     if (type == 0) continue;
                     const unsigned nx = ((unsigned)(reso * j) << 2) | (unsigned)(type + 1);
@@ -1191,7 +1111,7 @@ k_mask_walk(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, MaskAnnoO
                     } else if (ct == -1 && type == -1 && gap < GAP) {
                         cur = nx;   // -1,-1 close together: the earlier one goes
                     } else {
-                        if (wr) {
+                        if (WRITE) {
                             out.anno_pool[off + n] = make_int2((int)(cur >> 2), (int)(cur & 3u) - 1);
                             out.hinge_keep[off + n] = 0;
                         }
@@ -1201,54 +1121,213 @@ k_mask_walk(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, MaskAnnoO
                 }
             }
         }
-        if (have) {
-            if (wr) {
-                out.anno_pool[off + n] = make_int2((int)(cur >> 2), (int)(cur & 3u) - 1);
-                out.hinge_keep[off + n] = 0;
-            }
-            n++;
+    }
+    if (have) {
+        if (WRITE) {
+            out.anno_pool[off + n] = make_int2((int)(cur >> 2), (int)(cur & 3u) - 1);
+            out.hinge_keep[off + n] = 0;
         }
-        if (wr == 0) {
-            kept = n;
-            if (kept == 0) break;
-            off = atomicAdd(&out.counters[0], kept);
-            if (off + kept > out.anno_cap) {
-                atomicExch(&out.counters[2], 1);
-                off = -1;
-                break;
-            }
+        n++;
+    }
+    return n;
+}
+
+// One thread per read, 32 reads to a warp.  Pool space for the annotations and slots of the hinge work
+// list are claimed ONCE PER WARP (prefix sums over the lanes' demands, one atomic by lane 0): a quarter
+// of a million single-address atomics with return values would otherwise take as long as the walk.
+__global__ void __launch_bounds__(kWalkThreads)
+k_mask_walk(RecView rv, ReadView rd, hg_filter_params P, FlatParams F, MaskAnnoOut out) {
+    const int lane = threadIdx.x & 31;
+    const int read = F.p_lo + blockIdx.x * kWalkThreads + threadIdx.x;
+    const int MIN_COV = F.scal[1];
+    constexpr int reso = kReso;
+    const int NHR = P.no_hinge_region;
+    bool act = read < F.p_hi;
+    const int bi = act ? F.rbatch[read] : -1;
+    act = act && bi >= 0;
+    int64_t nrec = 0;
+    WalkRead w;
+    w.pw = nullptr; w.cmap = nullptr; w.base = -1; w.L0 = 0; w.ja_lo = 0; w.ja_hi = -1; w.MIN_COV = MIN_COV;
+    if (act) {
+        w.base = F.rbase[read];
+        nrec = rv.read_off[read + 1] - rv.read_off[read];
+        bool generic = w.base < 0 || MIN_COV < 0 || nrec > Packed<uint32_t>::kMaxCount;
+        if (!generic && F.v2 == 1) {  // a batch the second form of K1 declined
+            const int f0 = F.batch[bi].x, f1 = F.batch[bi + 1].x;
+            generic = rv.read_off[f1] - rv.read_off[f0] > kV2MaxBatchRecords;
+        }
+        if (generic) {
+            out.big_list[atomicAdd(&out.counters[3], 1)] = read;
+            act = false;
         }
     }
 
-    // hinge pre-test: mean coverage near both mask ends (filter.cpp:842-865); its outcome
-    // only matters for reads that carry annotations
-    bool skip_hinges = false;
-    if (kept > 0) {
-        int cs = 0, ns = 0, ce = 0, ne = 0;
-        int jlo = mk.x <= 0 ? 0 : (mk.x + reso - 1) / reso;  // bins with mk.x <= 40 j <= mk.x + NHR
-        int jhi = mk.x + NHR < 0 ? -1 : min((mk.x + NHR) / reso, L0 - 1);
-        for (int j = jlo; j <= jhi; j++) {
-            cs += f_lo(H(j));
-            ns++;
+    // ---- phase 1: mask, telomere flag, number of annotations
+    int2 mk = make_int2(0, 0);
+    int msc = 0, mec = 0, kept = 0;
+    uint8_t flags = 0;
+    if (act) {
+        const int base = w.base;
+        w.pw = F.prof + (size_t)bi * kFlatBins;
+        w.cmap = reinterpret_cast<const uint32_t*>(F.cmap + (size_t)bi * kFlatMaps);
+        const uint32_t* __restrict__ const zmap = reinterpret_cast<const uint32_t*>(F.zmap + (size_t)bi * kFlatMaps);
+        const int nbz = bins_needed(rd.rlen[read], P);
+        w.L0 = F.cov_maxbin[read] + 1;  // length of the cut-off-free profile
+        auto H = [&](int j) { return __ldg(w.pw + base + j); };  // packed coverage of the read's bin j
+
+        // longest run of covered bins (filter.cpp:696-728): the run between two consecutive zeros
+        // p < z scores 40 (z - p - 2); bin 0 acts as a zero; '>' keeps the earliest of the longest
+        int p = base, bestgap = 0, bestz = 0;
+        const int end = base + nbz;
+        {
+            // the map words of a read are fetched kWalkFetch at a time (independent loads)
+            const int w1 = (end - 1) >> 5, wf = (base + 1) >> 5;
+            const uint32_t mf = 0xffffffffu << ((base + 1) & 31), ml = 0xffffffffu >> (31 - ((end - 1) & 31));
+            for (int w0 = wf; w0 <= w1; w0 += kWalkFetch) {
+                uint32_t buf[kWalkFetch], any = 0;
+#pragma unroll
+                for (int i = 0; i < kWalkFetch; i++) {
+                    buf[i] = w0 + i <= w1 ? __ldg(zmap + w0 + i) : 0u;
+                    any |= buf[i];
+                }
+                if (any == 0) continue;   // a covered stretch: no zeros in these words
+#pragma unroll
+                for (int i = 0; i < kWalkFetch; i++) {
+                    const int wd = w0 + i;
+                    uint32_t m = buf[i];
+                    if (wd == wf) m &= mf;
+                    if (wd == w1) m &= ml;
+                    while (m) {
+                        const int bit = __ffs(m) - 1;
+                        const int z = (wd << 5) + bit;
+                        if (z - p > bestgap) {
+                            bestgap = z - p;
+                            bestz = z;
+                        }
+                        // the zeros that follow z back to back each have gap 1: skip them in one go
+                        const uint32_t t = ~(m >> bit);                     // bit 0 clear
+                        const int run = t ? __ffs(t) - 1 : 32 - bit;        // consecutive zeros from z on
+                        p = z + run - 1;
+                        m = bit + run >= 32 ? 0u : (m >> (bit + run)) << (bit + run);
+                    }
+                }
+            }
         }
-        jlo = mk.y - NHR <= 0 ? 0 : (mk.y - NHR + reso - 1) / reso;  // mk.y - NHR <= 40 j <= mk.y
-        jhi = mk.y < 0 ? -1 : min(mk.y / reso, L0 - 1);
-        for (int j = jlo; j <= jhi; j++) {
-            ce += f_lo(H(j));
-            ne++;
+        int maxstart = 0, maxend = 0;
+        if (bestgap >= 3) {
+            const int z = bestz - base, pz = z - bestgap;
+            msc = pz + 1;
+            mec = z - 1;
+            maxstart = reso * (pz + 1);
+            maxend = reso * (z - 1);
         }
-        // float on purpose: 0/0 = NaN makes the '< 10' test false (filter.cpp:861-865)
-        const float avg_end = __fdiv_rn((float)ce, (float)ne);
-        const float avg_start = __fdiv_rn((float)cs, (float)ns);
-        skip_hinges = fabsf(__fsub_rn(avg_end, avg_start)) < 10.0f;
+
+        // telomere / coverage-imbalance flag (filter.cpp:731-760)
+        if (P.delete_telomere) {
+            flags = out.rflags[read] & kFlagSelf;
+            int limit, div;
+            if (mec - msc + 1 > 20) {
+                limit = 10;
+                div = 10;
+            } else {
+                limit = (mec - msc) / 2;
+                div = limit;
+            }
+            int sc = 0, ec = 0;
+            for (int t = 0; t < limit; t++) {
+                sc += max(f_hi(H(msc + t)), MIN_COV);
+                ec += max(f_hi(H(mec - t)), MIN_COV);
+            }
+            if (div == 0) {
+                sc = 0;
+                ec = 0;
+            } else {
+                sc /= div;
+                ec /= div;
+            }
+            if (sc >= 10 * ec || ec >= 10 * sc) flags |= kFlagCov;
+        }
+
+        // final mask (filter.cpp:777-788)
+        const int2 q = rd.qvmask[read];
+        if (P.use_qv_mask && P.use_coverage_mask)
+            mk = make_int2(max(maxstart, q.x), min(maxend, q.y));
+        else if (P.use_coverage_mask && !P.use_qv_mask)
+            mk = make_int2(maxstart, maxend);
+        else
+            mk = q;
+
+        w.ja_lo = mk.x + NHR <= 0 ? 0 : (mk.x + NHR + reso - 1) / reso;
+        w.ja_hi = mk.y - NHR < 0 ? -1 : min((mk.y - NHR) / reso, w.L0 - 3);
+        kept = walk_annotations<false>(w, P, out, 0);
     }
 
-    store_mask(out, read, mk);
-    out.cmask[read] = make_int2(msc, mec);
-    out.rflags[read] = flags | (skip_hinges ? kFlagSkipHinge : 0);
-    out.anno_ref[read] = make_int2(off, kept);
-    if (kept > 0 && !skip_hinges && off >= 0)
-        push_work_item(out, read, rv.read_off[read], (int)nrec, mk, off, kept);
+    // ---- pool space for the warp's annotations: one atomic
+    int off = 0;
+    {
+        int incl = kept;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int first = 0;
+        if (total > 0) {
+            if (lane == 0) first = atomicAdd(&out.counters[0], total);
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if (first + total > out.anno_cap) {   // the host grows the pool and reruns the stage
+                if (lane == 0) atomicExch(&out.counters[2], 1);
+                first = -1;
+            }
+        }
+        off = first < 0 ? -1 : first + incl - kept;
+    }
+
+    // ---- phase 2: the annotations, the hinge pre-test, the read's results
+    bool push = false;
+    if (act) {
+        if (kept > 0 && off >= 0) walk_annotations<true>(w, P, out, off);
+        // hinge pre-test: mean coverage near both mask ends (filter.cpp:842-865); its outcome
+        // only matters for reads that carry annotations
+        bool skip_hinges = false;
+        if (kept > 0) {
+            auto H = [&](int j) { return __ldg(w.pw + w.base + j); };
+            int cs = 0, ns = 0, ce = 0, ne = 0;
+            int jlo = mk.x <= 0 ? 0 : (mk.x + reso - 1) / reso;  // bins with mk.x <= 40 j <= mk.x + NHR
+            int jhi = mk.x + NHR < 0 ? -1 : min((mk.x + NHR) / reso, w.L0 - 1);
+            for (int j = jlo; j <= jhi; j++) {
+                cs += f_lo(H(j));
+                ns++;
+            }
+            jlo = mk.y - NHR <= 0 ? 0 : (mk.y - NHR + reso - 1) / reso;  // mk.y - NHR <= 40 j <= mk.y
+            jhi = mk.y < 0 ? -1 : min(mk.y / reso, w.L0 - 1);
+            for (int j = jlo; j <= jhi; j++) {
+                ce += f_lo(H(j));
+                ne++;
+            }
+            // float on purpose: 0/0 = NaN makes the '< 10' test false (filter.cpp:861-865)
+            const float avg_end = __fdiv_rn((float)ce, (float)ne);
+            const float avg_start = __fdiv_rn((float)cs, (float)ns);
+            skip_hinges = fabsf(__fsub_rn(avg_end, avg_start)) < 10.0f;
+        }
+        store_mask(out, read, mk);
+        out.cmask[read] = make_int2(msc, mec);
+        out.rflags[read] = flags | (skip_hinges ? kFlagSkipHinge : 0);
+        out.anno_ref[read] = make_int2(kept > 0 ? off : 0, kept);
+        push = kept > 0 && !skip_hinges && off >= 0;
+    }
+
+    // ---- slots of the hinge work list: one atomic per warp
+    {
+        const unsigned m = __ballot_sync(0xffffffffu, push);
+        if (m) {
+            int first = 0;
+            if (lane == 0) first = atomicAdd(&out.counters[1], __popc(m));
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if (push) write_work_item(out, first + __popc(m & ((1u << lane) - 1u)), read, rv.read_off[read], (int)nrec, mk, off, kept);
+        }
+    }
 }
 
 // ------------------------------------------------------------------ host side

@@ -80,19 +80,22 @@ __device__ Match classify_record(const RecView& rv, const int* __restrict__ rlen
     const int a100 = m.as / 100;
     const int ia_s = m.as >= EA.x ? 0 : max(1, (EA.x + 99) / 100 - a100);   // EA.x > as >= 0 here
     const int ia_e = EA.y < m.as ? -1 : (EA.y < 0 ? -1 : max(0, min(inner, EA.y / 100 - a100)));
-    int start_idx = npts, end_idx = 0;
-    bool have_start = false;
     // the final point (idx npts - 1): the match's own end
     const int fa = m.ae, fb = m.comp ? m.bs : m.be;
     const int fu = sign * fb;
     const bool end_final = fa <= EA.y && fu <= u_e;
-    bool end_alive = true;
-    int u = sign * (m.comp ? m.be : m.bs), u_start = 0, u_end = 0;
+    const int u0 = sign * (m.comp ? m.be : m.bs);
     const uint8_t* __restrict__ t8 = rv.trace + toff;
     const uint16_t* __restrict__ t16 = reinterpret_cast<const uint16_t*>(rv.trace + toff);
     const bool wide = rv.tbytes != 1;
-    // four trace values are fetched side by side (the exits depend on the values, so a one-at-a-time
-    // loop is a chain of load latencies: a third of this kernel's stall samples, ncu round 2)
+    // Both tests are monotone along the walk (start: false ... false true ... true, end: true ... true
+    // false ... false), so the walk only COUNTS: n_s points before the start, n_e points that pass the
+    // end test, and u at the first / last such point is a running min / max.  Four trace values are
+    // fetched side by side and the exits are tested once per four points (the exits depend on the
+    // values: a one-at-a-time loop is a chain of load latencies); what the extra points of the last
+    // group may add is taken back below.  About a dozen instructions per point.
+    int n_s = 0, n_e = 0, seen = 0;
+    int u = u0, u_start = 0x7fffffff, u_end = -0x7fffffff - 1;
     bool done = false;
     for (int idx0 = 0; idx0 <= inner && !done; idx0 += 4) {
         int d[4];
@@ -101,30 +104,32 @@ __device__ Match classify_record(const RecView& rv, const int* __restrict__ rlen
             const int idx = idx0 + i;
             d[i] = (idx > 0 && idx <= inner) ? (wide ? (int)t16[2 * idx - 1] : (int)t8[2 * idx - 1]) : 0;
         }
+        const int rs = ia_s - idx0, re = ia_e - idx0, rn = inner - idx0;   // the index tests, relative to the group
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const int idx = idx0 + i;
-            if (idx > inner) break;
             u += d[i];
-            if (!have_start && idx >= ia_s && u >= u_s) {
-                start_idx = idx;
-                u_start = u;
-                have_start = true;
-            }
-            if (end_alive) {
-                if (idx <= ia_e && u <= u_e) {
-                    end_idx = idx;
-                    u_end = u;
-                } else {
-                    end_alive = false;
-                }
-            }
-            if (end_final ? have_start : !end_alive) {
-                done = true;
-                break;
-            }
+            const bool in = i <= rn;
+            const bool s_ok = in && i >= rs && u >= u_s;
+            const bool e_ok = in && i <= re && u <= u_e;
+            n_s += (in && !s_ok) ? 1 : 0;
+            n_e += e_ok ? 1 : 0;
+            u_start = min(u_start, s_ok ? u : 0x7fffffff);
+            u_end = max(u_end, e_ok ? u : -0x7fffffff - 1);
         }
+        seen = min(idx0 + 4, inner + 1);
+        // the reference's walk would stop at the first point where this holds
+        done = end_final ? n_s < seen : n_e < seen;
     }
+    bool have_start = n_s < seen;
+    int start_idx = have_start ? n_s : npts;
+    // without a final end point the reference's walk stops at the first point that fails the end test
+    // (index n_e): a start behind that point was never seen
+    if (!end_final && n_e < seen && start_idx > n_e) {
+        have_start = false;
+        start_idx = npts;
+    }
+    int end_idx = n_e > 0 ? n_e - 1 : 0;
+    if (n_e == 0) u_end = 0;
     if (have_start) {
         m.eas = start_idx == 0 ? m.as : (a100 + start_idx) * 100;
         if (!m.comp) m.ebs = u_start; else m.ebe = -u_start;

@@ -40,6 +40,12 @@ import json;d=json.load(open('$OUT/${TAG}_bench_k1old.json'));print('c5',d['ms_p
         python -c "
 import json;d=json.load(open('$OUT/${TAG}_bench_v$V.json'));print('c5',round(d['ms_per_step'],4),{k:round(v,4) for k,v in d['kernel_ms'].items()},round(d['roofline']['frac'],3));print('c3',round(d['c3']['ms_per_step'],4),{k:round(v,4) for k,v in d['c3']['kernel_ms'].items()},round(d['c3']['roofline']['frac'],3))"
       done ;;
+    spreads)
+      for S in ${SPREADS:-1 4 16}; do
+        timeout 600 python bench.py --config c5 --also "" --spread $S --profile-kernel 1 $SHORT > $OUT/${TAG}_bench_s$S.json 2> $OUT/${TAG}_bench_s$S.err
+        python -c "
+import json;d=json.load(open('$OUT/${TAG}_bench_s$S.json'));print('spread $S c5',round(d['ms_per_step'],4),{k:round(v,4) for k,v in d['kernel_ms'].items()})"
+      done ;;
     down)
       for CFG in c3 c5; do
         HINGE_B200_TIMING=1 timeout 900 python bench.py --config $CFG --also "" --steps 3 --e2e-steps 1 --no-cpu-baseline --no-verify > $OUT/${TAG}_down_$CFG.json 2> $OUT/${TAG}_down_$CFG.err
@@ -111,6 +117,20 @@ d=json.load(open('$OUT/${TAG}_bench_n$NG.json')); print('c5 value %.4g ms %.4f'%
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^k_classify_reads" -s 1 -c 1 -f \
         -o $OUT/${TAG}_k_classify_reads_c3 python bench.py --config c3 --also "" --steps 2 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-verify > $OUT/${TAG}_ncu_k_classify_reads.log 2>&1
       echo "ncu k_classify_reads exit $?" ;;
+    ncu_final)
+      # the kernels of a filter step on both workloads, one launch each (steady state: -s skips the warm-up)
+      for SPEC in "k_profile_flat2 c3" "k_profile_flat c5" "k_mask_bits_flat c5" "k_mask_walk c5" "k_mask_bits_flat c3" \
+                  "k_mask_walk c3" "k_hinge_call c5" "k_hinge_exact_warp c5" "k_hinge_call c3"; do
+        set -- $SPEC; K=$1; CFG=$2
+        timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^$K\b" -s 4 -c 1 -f \
+          -o $OUT/${TAG}_${K}_$CFG python bench.py --config $CFG --also "" $SHORT > $OUT/${TAG}_ncu_${K}_$CFG.log 2>&1
+        echo "ncu $K $CFG exit $?"
+      done
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^k_profile_tma" -s 4 -c 1 -f \
+        -o $OUT/${TAG}_k_profile_tma_c3 python bench.py --config c3 --also "" --profile-kernel 3 $SHORT > $OUT/${TAG}_ncu_k_profile_tma_c3.log 2>&1
+      echo "ncu k_profile_tma c3 exit $?"
+      timeout 600 python bench.py --profile-kernel 3 $SHORT > $OUT/${TAG}_bench_tma.json 2> $OUT/${TAG}_bench_tma.err
+      echo "bench (TMA form of K1) exit $?" ;;
     ncu_all)
       for K in k_mask_anno_flat k_hinge_call k_hinge_exact_warp k_profile_flat; do
         timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^$K" -s 4 -c 1 -f \

@@ -108,8 +108,10 @@ def launch_table(path, title):
     return "\n".join(lines) + "\n"
 
 
-ALIAS = {"k_mask_anno_flat": "mask_anno", "k_profile_flat": "profile", "k_profile_flat2": "profile",
-         "k_hinge_call": "hinge_call"}
+# kernel -> the bench line's kernel group (traffic.json holds DRAM bytes per launch and workload; a group
+# of several kernels gets the sum of its captured members)
+ALIAS = {"k_mask_bits_flat": "mask_anno", "k_mask_walk": "mask_anno", "k_profile_flat": "profile",
+         "k_profile_flat2": "profile", "k_hinge_call": "hinge_call"}
 
 
 def main():
@@ -138,8 +140,13 @@ def main():
                     rd = float(d["dram__bytes_read.sum"][0].replace(",", "")) * SCALE[d["dram__bytes_read.sum"][1]]
                     wr = float(d["dram__bytes_write.sum"][0].replace(",", "")) * SCALE[d["dram__bytes_write.sum"][1]]
                     if kname in ALIAS and cfg:
-                        traffic.setdefault(cfg, {})[ALIAS[kname]] = rd + wr
-                        traffic[cfg][ALIAS[kname] + "_source"] = name
+                        t = traffic.setdefault(cfg, {})
+                        parts = t.setdefault(ALIAS[kname] + "_kernels", {})
+                        if not isinstance(parts, dict):
+                            parts = t[ALIAS[kname] + "_kernels"] = {}
+                        parts[kname] = rd + wr
+                        t[ALIAS[kname]] = sum(parts.values())
+                        t[ALIAS[kname] + "_source"] = "%s_*_%s_ncu.txt" % (dst, cfg)
                 except (KeyError, ValueError):
                     pass
         elif "launches" in base and base.endswith(".csv"):
