@@ -117,12 +117,12 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, interval_ms=20):
         self.rows = []
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", str(interval_ms)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -208,7 +208,9 @@ def file_to_file(p, steps, warmup, with_cli):
             # clocks are sampled over this timed region too; the running nvidia-smi also keeps the driver
             # attached to the GPU between the runs (on a box without persistence mode every process start
             # would otherwise pay the driver's own cold start, ~0.7 s, which is not the executable's doing)
-            sampler = ClockSampler(0)
+            # (sampled every 250 ms only: NVML queries at the 20 ms rate of the kernel-timed region contend with
+            # the creation of the executable's CUDA context and were seen to double it, scripts/cli_probe.py)
+            sampler = ClockSampler(0, interval_ms=250)
             time.sleep(0.3)
             for _ in range(3):
                 t0 = time.perf_counter()
@@ -493,9 +495,9 @@ class Bench:
             # (24 B + two gathers per record near the annotation) touches a few per cent of that
             n_anno = np.diff(result["anno_off"][a_lo:a_hi + 1])
             k4 = float((n_anno * pile).sum()) * 4.0 + 48.0 * float((n_anno > 0).sum())
-            # the TMA-staged form of K1 (default) reads abpos / aepos only: 8 B per record; K2 also writes and
-            # reads back two bits per bin (its two kernels' bit maps)
-            rec_b = 12.0 if args.profile_kernel in (1, 2, 5, 6) else 8.0
+            # the TMA-staged form of K1 (--profile-kernel 3) reads abpos / aepos only: 8 B per record; K2 also
+            # writes and reads back two bits per bin (its two kernels' bit maps)
+            rec_b = 8.0 if args.profile_kernel == 3 else 12.0
             kbytes = {"profile": rec_b * novl + 4.0 * bins + 39.0 * owned, "mask_anno": 4.5 * bins + 60.0 * owned,
                       "hinge_call": k4}
             dom = max(kbytes, key=lambda k: kavg[k])
