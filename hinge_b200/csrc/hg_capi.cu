@@ -133,7 +133,7 @@ void hg_ctx_destroy(hg_ctx* c) {
     cudaFree(c->d_rlen); cudaFree(c->d_qvmask); cudaFree(c->d_read_off); cudaFree(c->d_err);
     FilterScratch& s = c->fs;
     cudaFree(s.cov_maxbin); cudaFree(s.self_cnt); cudaFree(s.flat_prof);
-    cudaFree(s.flat_rbatch); cudaFree(s.flat_cpre); cudaFree(s.flat_desc); cudaFree(s.flat_zmap); cudaFree(s.flat_cmap);
+    cudaFree(s.flat_rbatch); cudaFree(s.flat_desc); cudaFree(s.flat_zmap); cudaFree(s.flat_cmap);
     if (!c->ext_mean_cov) cudaFree(s.mean_cov);
     if (!c->ext_mask) cudaFree(s.mask);
     for (int i = 0; i < hg_ctx::kMarks; i++)
@@ -416,7 +416,6 @@ static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
             HG_TRY(dev_alloc(c, &s.flat_batch, batch.size(), "flat batches"));
             HG_TRY(dev_alloc(c, &s.flat_rbase, plan.rbase.size() + 8, "flat read offsets"));  // + slack, as above
             HG_TRY(dev_alloc(c, &s.flat_rbatch, plan.rbatch.size(), "flat read batches"));
-            HG_TRY(dev_alloc(c, &s.flat_cpre, plan.cpre.size() + 8, "flat chunk offsets"));
             HG_TRY(dev_alloc(c, &s.flat_desc, plan.desc.size(), "flat batch descriptors"));
             HG_TRY(dev_alloc(c, &s.flat_prof, nb1 * kFlatBins, "coverage profiles"));
             HG_TRY(dev_alloc(c, &s.flat_zmap, nb1 * (kFlatBins / 16), "coverage bit maps"));
@@ -424,7 +423,6 @@ static int configure_filter(hg_ctx* c, const hg_filter_params* p) {
             HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_batch, batch.data(), sizeof(int2) * batch.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
             HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_rbase, plan.rbase.data(), sizeof(int) * plan.rbase.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
             HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_rbatch, plan.rbatch.data(), sizeof(int) * plan.rbatch.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
-            HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_cpre, plan.cpre.data(), sizeof(int) * plan.cpre.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
             HG_TRY(cuda_check(c, cudaMemcpyAsync(s.flat_desc, plan.desc.data(), sizeof(int4) * plan.desc.size(), cudaMemcpyHostToDevice, c->stream), "H2D"));
             // per-read results of the reads outside the planned range: "no pile-up"
             cudaMemsetAsync(s.cov_maxbin, 0xff, sizeof(int) * c->n_read, c->stream);
@@ -606,11 +604,10 @@ int hg_debug_flat_plan(const int32_t* rlen, int32_t n_read, int32_t lo, int32_t 
     return (int)batch.size() - 1;
 }
 
-// The same with the CSR (batches also bounded by record volume): chunk_out gets, per read, the
-// 32-record chunks of the earlier reads of its batch, nchunk_out the chunks per batch.
+// The same with the CSR (batches also bounded by record volume): nrec_out gets the records per batch.
 int hg_debug_flat_plan2(const int32_t* rlen, const int64_t* read_off, int32_t n_read, int32_t lo, int32_t hi,
                         int32_t cut_off, int32_t* batch_out, int32_t capacity, int32_t* rbase_out,
-                        int32_t* rbatch_out, int32_t* cpre_out, int32_t* nchunk_out) {
+                        int32_t* rbatch_out, int32_t* nrec_out) {
     FlatPlan plan;
     flat_plan(rlen, read_off, lo, hi, n_read, cut_off, true, &plan);
     if ((int)plan.batch.size() > capacity) return -1;
@@ -620,8 +617,7 @@ int hg_debug_flat_plan2(const int32_t* rlen, const int64_t* read_off, int32_t n_
     }
     memcpy(rbase_out, plan.rbase.data(), sizeof(int) * (size_t)n_read);
     memcpy(rbatch_out, plan.rbatch.data(), sizeof(int) * (size_t)n_read);
-    memcpy(cpre_out, plan.cpre.data(), sizeof(int) * (size_t)n_read);
-    for (size_t i = 0; i + 1 < plan.batch.size(); i++) nchunk_out[i] = plan.desc[2 * i].w;
+    for (size_t i = 0; i + 1 < plan.batch.size(); i++) nrec_out[i] = plan.desc[2 * i + 1].z;
     return (int)plan.batch.size() - 1;
 }
 

@@ -48,8 +48,7 @@ struct FilterScratch {
     int* flat_rbase = nullptr;        // per read, first histogram word inside its batch (-1: fallback path)
     uint32_t* flat_prof = nullptr;    // scanned packed profiles, kFlatBins words per batch (K1 -> K2)
     int* flat_rbatch = nullptr;       // per read: its batch (-1 = outside the planned range)
-    int* flat_cpre = nullptr;         // per read: 32-record chunks of the batch's earlier reads (third form of K1)
-    int4* flat_desc = nullptr;        // per batch, two entries: (first read, reads, words, chunks) (first record lo, hi, records, 0)
+    int4* flat_desc = nullptr;        // per batch, two entries: (first read, reads, words, 0) (first record lo, hi, records, 0)
     uint16_t* flat_zmap = nullptr;    // K2: bit maps of the batches' bins (kFlatBins bits per batch each)
     uint16_t* flat_cmap = nullptr;
     int flat_lo = 0, flat_hi = 0;     // planned read range
@@ -86,8 +85,7 @@ struct FlatPlan {
     std::vector<int2> batch;   // (first read, histogram words in use) per batch, closed by (hi, 0)
     std::vector<int> rbase;    // per read: first word of its profile inside its batch, -1 = fallback path
     std::vector<int> rbatch;   // per read: its batch, -1 = outside [lo, hi)
-    std::vector<int> cpre;     // per read: 32-record chunks of the earlier reads of its batch
-    std::vector<int4> desc;    // per batch: (first read, reads, words, chunks) (first record lo, hi, records, 0)
+    std::vector<int4> desc;    // per batch: (first read, reads, words, 0) (first record lo, hi, records, 0)
 };
 void flat_plan(const int* rlen, const int64_t* read_off, int lo, int hi, int n_read, int cut_off, bool cap_records,
                FlatPlan* plan);

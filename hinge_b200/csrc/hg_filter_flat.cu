@@ -88,8 +88,7 @@ struct FlatParams {
     int* __restrict__ big_list;
     const int* __restrict__ scal;        // [1] = MIN_COV (K2 only)
     const int* __restrict__ rbatch;      // per read: its batch
-    const int* __restrict__ cpre;        // per read: 32-record chunks of the earlier reads of its batch
-    const int4* __restrict__ desc;       // per batch: (first read, reads, words, chunks) (first record lo, hi, records, 0)
+    const int4* __restrict__ desc;       // per batch: (first read, reads, words, 0) (first record lo, hi, records, 0)
     uint16_t* __restrict__ zmap;         // K2 bit maps, kFlatMaps 16-bit entries per batch
     uint16_t* __restrict__ cmap;
     int p_lo, p_hi;                      // planned read range
@@ -566,27 +565,27 @@ k_profile_flat2(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
 // ------------------------------------------------------------------ K1, third form
 //
 // The first two forms wait on their own global loads (ncu, round 2: long-scoreboard is the top
-// stall, 1.15 eligible warps per scheduler, issue slots 53 % busy) and spend half of their
-// instructions telling which read a record belongs to.  This form is a PERSISTENT CTA that never
-// waits on a global load in its steady state and never looks at `aread`:
+// stall, 1.15 eligible warps per scheduler, issue slots 53 % busy).  This form is a PERSISTENT CTA
+// that never waits on a global load in its steady state and never looks at `aread`:
 //
 //   staging   the batch's abpos / aepos columns (one contiguous run of <= kSlabRecords records, the
-//             plan sees to that) and its per-read tables (CSR offsets, histogram bases, read lengths,
-//             chunk counts) arrive in shared memory by TMA bulk copies (cp.async.bulk, one elected
-//             thread, completion on an mbarrier) -- issued for batch i + 1 BEFORE batch i is worked
-//             on: two stages, the copy of the next batch always in flight.  The batch descriptors
-//             themselves (32 B) travel one more iteration ahead in registers.
-//   scatter   one warp per 32-record CHUNK of one read (chunks are dealt out in contiguous ranges:
-//             even load, and a read's chunks mostly stay with one warp).  The read is warp-uniform,
-//             so the events that pile up on a read's first / last bins -- every overlap that reaches
-//             an end of the read, about half of all events -- are counted with two warp-wide
-//             reductions (REDUX) into seven per-read counters kept in registers and added once per
-//             read; only the others go through shared-memory atomics.  Sum and maximum for the
-//             profile's mean and length (filter.cpp:642-656) are warp reductions as well.
+//             plan sees to that) and its per-read tables (CSR offsets, histogram bases, read lengths)
+//             arrive in shared memory by TMA bulk copies (cp.async.bulk, one elected thread,
+//             completion on an mbarrier) -- issued for batch i + 1 BEFORE batch i is worked on: two
+//             stages, the copy of the next batch always in flight.  The batch descriptors themselves
+//             (32 B) travel one more iteration ahead in registers.
+//   scatter   flat over the staged records, four per thread (two LDS.128); a record's read comes
+//             from the staged CSR (a per-batch table gives the read of every 32nd record), the code
+//             is the same for every lane also where a group of four crosses a read boundary.  Events
+//             as in the first form: four packed +-1 per record.
 //   scan      as in the first form: one block-wide prefix sum over the batch's packed histogram;
 //             the scanned words leave as 256-bit stores (one per thread, fully coalesced).
 //
-// Bytes per record from HBM: 8 (abpos, aepos) instead of 12.
+// Bytes per record from HBM: 8 (abpos, aepos) instead of 12.  Measured: correct, long-scoreboard stalls
+// gone, and still SLOWER than the other two forms (0.39 vs 0.32 ms on the short-read set, 1.05 vs 0.78 ms
+// on the long-read set): two 512-thread CTAs per SM (107 KB of staging each) whose phases cannot overlap
+// the way five to seven small CTAs do, and the four-event scatter on the same shared-memory data pipe
+// (DESIGN.md section 4a).  Kept as a tested variant (HG_OPT_PROFILE_KERNEL = 3), not the default.
 constexpr int kTmaThreads = 512;
 constexpr int kTmaItems = kFlatBins / kTmaThreads;  // 8 bins per thread in the scan
 constexpr int kTmaTab = kFlatMaxReads + 8;          // table entries per stage (+ alignment slack)
@@ -641,7 +640,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ unsigned tma_bin(int x) { return (unsigned)(x + kReso) / (unsigned)kReso; }
 
 struct TmaBatch {
-    int f0, nreads, words, chunks;  // desc[2 b]
+    int f0, nreads, words;          // desc[2 b]
     int64_t k0;                     // first record
     int nrec;
 };
@@ -649,11 +648,11 @@ __device__ __forceinline__ TmaBatch tma_batch(const FlatParams& F, int b) {
     TmaBatch t;
     if (b < F.nbatch) {
         const int4 x = __ldg(F.desc + 2 * (size_t)b), y = __ldg(F.desc + 2 * (size_t)b + 1);
-        t.f0 = x.x; t.nreads = x.y; t.words = x.z; t.chunks = x.w;
+        t.f0 = x.x; t.nreads = x.y; t.words = x.z;
         t.k0 = (int64_t)(((unsigned long long)(unsigned)y.y << 32) | (unsigned)y.x);
         t.nrec = y.z;
     } else {
-        t.f0 = 0; t.nreads = 0; t.words = 0; t.chunks = 0; t.k0 = 0; t.nrec = 0;
+        t.f0 = 0; t.nreads = 0; t.words = 0; t.k0 = 0; t.nrec = 0;
     }
     return t;
 }
@@ -1343,15 +1342,14 @@ void flat_plan(const int* rlen, const int64_t* read_off, int lo, int hi, int n_r
     plan->desc.clear();
     plan->rbase.assign((size_t)n_read, -1);
     plan->rbatch.assign((size_t)n_read, -1);
-    plan->cpre.assign((size_t)n_read + 1, 0);
-    int used = 0, chunks = 0;
+    int used = 0;
     int64_t recs = 0;
     bool open = false, solitary = false;
     auto close = [&](int r_end) {
         if (!open) return;
         const int f0 = plan->batch.back().x;
         const int64_t k0 = read_off ? read_off[f0] : 0;
-        plan->desc.push_back(make_int4(f0, r_end - f0, plan->batch.back().y, chunks));
+        plan->desc.push_back(make_int4(f0, r_end - f0, plan->batch.back().y, 0));
         plan->desc.push_back(make_int4((int)(k0 & 0xffffffffll), (int)(k0 >> 32), (int)recs, 0));
         open = false;
     };
@@ -1366,16 +1364,13 @@ void flat_plan(const int* rlen, const int64_t* read_off, int lo, int hi, int n_r
             open = true;
             solitary = !fits;
             used = 0;
-            chunks = 0;
             recs = 0;
         }
         plan->rbatch[r] = (int)plan->batch.size() - 1;
-        plan->cpre[r] = chunks;
         if (!fits) continue;
         plan->rbase[r] = used;
         used += nbz;
         recs += nrec;
-        chunks += (int)((nrec + 31) >> 5);
         plan->batch.back().y = used;
     }
     if (!open) {
@@ -1419,7 +1414,6 @@ static FlatParams flat_params(const FilterScratch& s, const hg_filter_params& P,
     F.big_list = s.big_list;
     F.scal = s.scal;
     F.rbatch = s.flat_rbatch;
-    F.cpre = s.flat_cpre;
     F.desc = s.flat_desc;
     F.zmap = s.flat_zmap;
     F.cmap = s.flat_cmap;

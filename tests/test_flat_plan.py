@@ -76,18 +76,17 @@ def _plan2(rlen, read_off, lo, hi, cut_off):
     from hinge_b200._lib import lib
     lib.hg_debug_flat_plan2.restype = C.c_int
     lib.hg_debug_flat_plan2.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     rlen = np.ascontiguousarray(rlen, np.int32)
     read_off = np.ascontiguousarray(read_off, np.int64)
     n = len(rlen)
     cap = n + 2
     batch = np.zeros((cap, 2), np.int32)
-    rbase, rbatch, cpre, nchunk = (np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32),
-                                   np.zeros(cap, np.int32))
+    rbase, rbatch, nrec_b = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(cap, np.int32)
     nb = lib.hg_debug_flat_plan2(rlen.ctypes.data, read_off.ctypes.data, n, lo, hi, cut_off, batch.ctypes.data, cap,
-                                 rbase.ctypes.data, rbatch.ctypes.data, cpre.ctypes.data, nchunk.ctypes.data)
+                                 rbase.ctypes.data, rbatch.ctypes.data, nrec_b.ctypes.data)
     assert nb >= 0
-    return batch[:nb + 1], rbase, rbatch, cpre, nchunk[:nb]
+    return batch[:nb + 1], rbase, rbatch, nrec_b[:nb]
 
 
 @pytest.mark.parametrize("case", ["pacbio", "deep", "empty_reads"])
@@ -106,7 +105,7 @@ def test_plan_bounded_by_records(built, case):
         nrec = rng.poisson(60, n) * (rng.random(n) < 0.5)
     read_off = np.concatenate([[0], np.cumsum(nrec)]).astype(np.int64)
     lo, hi = 10, n - 5
-    batch, rbase, rbatch, cpre, nchunk = _plan2(rlen, read_off, lo, hi, cut_off)
+    batch, rbase, rbatch, nrec_b = _plan2(rlen, read_off, lo, hi, cut_off)
     nbz = _bins(rlen.astype(np.int64), cut_off)
     first = batch[:, 0]
     assert first[0] == lo and first[-1] == hi and np.all(np.diff(first) > 0)
@@ -116,10 +115,9 @@ def test_plan_bounded_by_records(built, case):
         assert np.all(rbatch[f0:f1] == b)
         fit = (nbz[f0:f1] <= K_BINS) & (nrec[f0:f1] <= K_SLAB)
         if not fit.all():
-            assert f1 - f0 == 1 and used == 0 and rbase[f0] == -1 and nchunk[b] == 0
+            assert f1 - f0 == 1 and used == 0 and rbase[f0] == -1 and nrec_b[b] == 0
             continue
         assert used == nbz[f0:f1].sum() <= K_BINS and nrec[f0:f1].sum() <= K_SLAB and f1 - f0 <= K_READS
-        chunks = (nrec[f0:f1] + 31) // 32
-        assert np.array_equal(cpre[f0:f1], np.concatenate([[0], np.cumsum(chunks)[:-1]])) and nchunk[b] == chunks.sum()
+        assert nrec_b[b] == nrec[f0:f1].sum(), "the batch descriptor carries its record count"
         if f1 < hi and nbz[f1] <= K_BINS and nrec[f1] <= K_SLAB:
             assert (used + nbz[f1] > K_BINS or nrec[f0:f1].sum() + nrec[f1] > K_SLAB or f1 - f0 == K_READS)
