@@ -158,10 +158,15 @@ k_profile_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
     // ---- the batch's records: four per thread and step
     const int64_t k_begin = nb > 0 ? rv.read_off[f0] : 0, k_end = nb > 0 ? rv.read_off[f1] : 0;
     const int64_t g0 = k_begin & ~(int64_t)3;
-    const int grp = flat_group<SPREAD>(tid) * 4;
+    // full steps spread the lanes over record windows (flat_group); the last, partial step of a batch
+    // takes the records in thread order, so that only the warps that still have records run its body
+    const int grp_spread = flat_group<SPREAD>(tid) * 4, grp_tail = tid * 4;
+    auto grp_of = [&](int64_t kb) { return k_end - kb >= kFlatThreads * 4 ? grp_spread : grp_tail; };
     int4 va = make_int4(-1, -1, -1, -1), vs = make_int4(0, 0, 0, 0), ve = vs;
     auto load4 = [&](int64_t k) {
-        if (k >= k_begin && k + 4 <= k_end) {
+        if (k >= k_end) {
+            va = make_int4(-1, -1, -1, -1);
+        } else if (k >= k_begin && k + 4 <= k_end) {
             va = __ldg(reinterpret_cast<const int4*>(rv.aread + k));
             vs = __ldg(reinterpret_cast<const int4*>(rv.abpos + k));
             ve = __ldg(reinterpret_cast<const int4*>(rv.aepos + k));
@@ -180,7 +185,7 @@ k_profile_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
             ve = make_int4(e[0], e[1], e[2], e[3]);
         }
     };
-    if (g0 < k_end) load4(g0 + grp);  // in flight while the histogram is cleared
+    if (g0 < k_end) load4(g0 + grp_of(g0));  // in flight while the histogram is cleared
 
     // ---- zero
     for (int j = tid * 4; j < npass * kFlatPass + 16 && j < kFlatWords; j += kFlatThreads * 4)
@@ -198,7 +203,7 @@ k_profile_flat(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
     for (int64_t kb = g0; kb < k_end; kb += kFlatThreads * 4) {
         const int a[4] = {va.x, va.y, va.z, va.w}, s[4] = {vs.x, vs.y, vs.z, vs.w};
         const int e[4] = {ve.x, ve.y, ve.z, ve.w};
-        if (kb + kFlatThreads * 4 < k_end) load4(kb + kFlatThreads * 4 + grp);
+        if (kb + kFlatThreads * 4 < k_end) load4(kb + kFlatThreads * 4 + grp_of(kb + kFlatThreads * 4));
         // records are sorted by A-read: in most groups one lookup of the read's base serves all four
         const int base0 = a[0] >= 0 ? __ldg(F.rbase + a[0]) : -1;
         int cur = -1, acc = 0, mx = -1;  // run of records of one read inside this group
@@ -371,10 +376,14 @@ k_profile_flat2(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
     if (nb > 0) {
         // ---- the batch's records: four per thread and step (abpos / aepos; aread for the base)
         const int64_t g0 = k_begin & ~(int64_t)3;
-        const int grp = flat_group<SPREAD>(tid) * 4;
+        // (lane mapping of full steps and of the last, partial one: see the first form)
+        const int grp_spread = flat_group<SPREAD>(tid) * 4, grp_tail = tid * 4;
+        auto grp_of = [&](int64_t kb) { return k_end - kb >= kFlatThreads * 4 ? grp_spread : grp_tail; };
         int4 va = make_int4(-1, -1, -1, -1), vs = make_int4(0, 0, 0, 0), ve = vs;
         auto load4 = [&](int64_t k) {
-            if (k >= k_begin && k + 4 <= k_end) {
+            if (k >= k_end) {
+                va = make_int4(-1, -1, -1, -1);
+            } else if (k >= k_begin && k + 4 <= k_end) {
                 va = __ldg(reinterpret_cast<const int4*>(rv.aread + k));
                 vs = __ldg(reinterpret_cast<const int4*>(rv.abpos + k));
                 ve = __ldg(reinterpret_cast<const int4*>(rv.aepos + k));
@@ -393,7 +402,7 @@ k_profile_flat2(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
                 ve = make_int4(e[0], e[1], e[2], e[3]);
             }
         };
-        if (g0 < k_end) load4(g0 + grp);  // in flight while the histogram is cleared
+        if (g0 < k_end) load4(g0 + grp_of(g0));  // in flight while the histogram is cleared
 
         // ---- zero (swh permutes inside aligned 256-word blocks)
         const int nzero = min((2 * nb + 255) & ~255, 2 * kFlatBins);
@@ -404,7 +413,7 @@ k_profile_flat2(RecView rv, ReadView rd, hg_filter_params P, FlatParams F) {
         for (int64_t kb = g0; kb < k_end; kb += kFlatThreads * 4) {
             const int a[4] = {va.x, va.y, va.z, va.w}, s[4] = {vs.x, vs.y, vs.z, vs.w};
             const int e[4] = {ve.x, ve.y, ve.z, ve.w};
-            if (kb + kFlatThreads * 4 < k_end) load4(kb + kFlatThreads * 4 + grp);
+            if (kb + kFlatThreads * 4 < k_end) load4(kb + kFlatThreads * 4 + grp_of(kb + kFlatThreads * 4));
             // records are sorted by A-read: in most groups one lookup of the read's base serves all four
             const int base0 = a[0] >= 0 ? __ldg(F.rbase + a[0]) : -1;
 #pragma unroll
