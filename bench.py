@@ -80,6 +80,8 @@ def parse_args():
     ap.add_argument("--sample-mb", type=float, default=None, help="genome size of the file-to-file / CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--sync-steps", action="store_true", help="one blocking hg_filter per timed step instead of "
+                    "hg_filter_enqueue back to back + one hg_filter_finish")
     ap.add_argument("--spread", type=int, default=None, help="HG_OPT_SCATTER_SPREAD (tuning aid)")
     ap.add_argument("--profile-kernel", type=int, default=None, help="HG_OPT_PROFILE_KERNEL (tuning aid)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -443,15 +445,30 @@ class Bench:
         launches0 = api.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ktimes = {}
+        # The timed steps are enqueued back to back (hg_filter_enqueue: the launches of one stage) and waited
+        # for once (hg_filter_finish), the way a caller works through the parts of a .las; with the NCCL
+        # exchange the host takes part in every step, so there each step is a full hg_filter.
+        queued = (world == 1 or arrays.exchange == "peer") and not args.sync_steps
         ev0.record(self.stream)
-        for _ in range(args.steps):
-            summary = run_stage()
-            for k, v in ctx.filter_kernel_times().items():
-                ktimes.setdefault(k, []).append(v)
-        ev1.record(self.stream)
+        if queued:
+            for _ in range(args.steps):
+                ctx.filter_enqueue(params)
+            ev1.record(self.stream)
+            rc, summary = ctx.filter_finish()
+            if rc != 0:
+                raise RuntimeError("hg_filter_finish: status %d" % rc)
+        else:
+            for _ in range(args.steps):
+                summary = run_stage()
+            ev1.record(self.stream)
         self.barrier()
         launches = api.launch_count() - launches0
         ms_total = self.max_over_ranks(ev0.elapsed_time(ev1))
+        # per-kernel device times (CUDA events between the launches): a few more steps, one at a time
+        for _ in range(min(args.steps, 5)):
+            summary = run_stage()
+            for k, v in ctx.filter_kernel_times().items():
+                ktimes.setdefault(k, []).append(v)
         clocks = sampler.stop() if sampler else None
         total_ovl = self.sum_over_ranks(float(novl))
         ms_step = ms_total / args.steps
@@ -514,6 +531,8 @@ class Bench:
                            "l2": "inputs (%.0f MB of records on rank 0) exceed the 126 MB L2" % (28.0 * novl / 1e6),
                            "parallelism": "reads sharded by A-read id x%d, balanced on record volume; exchange: %s"
                            % (world, "none" if world == 1 else arrays.exchange),
+                           "steps": "enqueued back to back (hg_filter_enqueue), one hg_filter_finish" if queued
+                           else "one blocking hg_filter per step",
                            "cov_est": int(summary.cov_est), "annotations_rank0": int(summary.n_annotations),
                            "hinges_rank0": int(result["hinge_keep"].sum()),
                            "exact_order_annotations_rank0": int(summary.n_exact_order),

@@ -75,6 +75,8 @@ PROTOTYPES = {
     "hg_filter_phase1": (C.c_int, [vp, C.POINTER(FilterParamsC)]),
     "hg_filter_phase2": (C.c_int, [vp]),
     "hg_filter_phase3": (C.c_int, [vp, C.POINTER(FilterSummaryC)]),
+    "hg_filter_enqueue": (C.c_int, [vp, C.POINTER(FilterParamsC)]),
+    "hg_filter_finish": (C.c_int, [vp, C.POINTER(FilterSummaryC)]),
     "hg_filter_fetch": (C.c_int, [vp] + [vp] * 7),
     "hg_filter_coverage": (C.c_int, [vp, vp, vp, i64p]),
     "hg_maximal": (C.c_int, [vp, C.POINTER(LayoutParamsC), vp, vp, vp, f32p]),

@@ -136,6 +136,15 @@ class Context:
         rc = self._check(lib.hg_filter_phase3(self._h, C.byref(s)), "hg_filter_phase3")
         return rc, s
 
+    def filter_enqueue(self, params):
+        """Launches the stage and returns (no wait); filter_finish() waits for the run enqueued last."""
+        self._check(lib.hg_filter_enqueue(self._h, C.byref(params)), "hg_filter_enqueue")
+
+    def filter_finish(self):
+        s = FilterSummaryC()
+        rc = self._check(lib.hg_filter_finish(self._h, C.byref(s)), "hg_filter_finish")
+        return rc, s
+
     def filter_fetch(self, n_annotations):
         n = self.n_read
         out = {

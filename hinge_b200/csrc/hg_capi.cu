@@ -505,16 +505,35 @@ int hg_filter_phase2(hg_ctx* c) {
     return cuda_check(c, cudaGetLastError(), "filter phase 2");
 }
 
-int hg_filter_phase3(hg_ctx* c, hg_filter_summary* out) {
+// The launches of phase 3; nothing waits for them here.
+static int filter_phase3_launch(hg_ctx* c) {
     if (!c || !c->filter_params_set) return set_err(c, HG_ERR_ARG, "phase3 before phase1");
     cudaSetDevice(c->device);
     cudaStream_t st = c->stream;
-    FilterScratch& s = c->fs;
     c->mark(5);
-    launch_hinge_call(c->rec_view(), c->read_view(), c->fp, s, c->peer, st);
+    launch_hinge_call(c->rec_view(), c->read_view(), c->fp, c->fs, c->peer, st);
     c->mark(6);
     cudaEventRecord(c->ev1, st);
-    HG_TRY(cuda_check(c, cudaGetLastError(), "filter phase 3"));
+    return cuda_check(c, cudaGetLastError(), "filter phase 3");
+}
+
+int hg_filter_enqueue(hg_ctx* c, const hg_filter_params* p) {
+    HG_TRY(hg_filter_phase1(c, p));
+    HG_TRY(hg_filter_phase2(c));
+    return filter_phase3_launch(c);
+}
+
+int hg_filter_phase3(hg_ctx* c, hg_filter_summary* out) {
+    HG_TRY(filter_phase3_launch(c));
+    return hg_filter_finish(c, out);
+}
+
+// Waits for the stage (the last one enqueued) and reads its counters back.
+int hg_filter_finish(hg_ctx* c, hg_filter_summary* out) {
+    if (!c || !c->filter_params_set) return set_err(c, HG_ERR_ARG, "hg_filter_finish before a filter run");
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    FilterScratch& s = c->fs;
     int cnt[16], scal[8];
     HG_TRY(cuda_check(c, cudaMemcpyAsync(cnt, s.counters, sizeof cnt, cudaMemcpyDeviceToHost, st), "D2H"));
     HG_TRY(cuda_check(c, cudaMemcpyAsync(scal, s.scal, sizeof scal, cudaMemcpyDeviceToHost, st), "D2H"));

@@ -137,6 +137,14 @@ d=json.load(open('$OUT/${TAG}_bench_n$NG.json')); print('c5 value %.4g ms %.4f'%
           -o $OUT/${TAG}_${K}_c5 python bench.py --config c5 --also "" $SHORT > $OUT/${TAG}_ncu_${K}.log 2>&1
         echo "ncu $K exit $?"
       done ;;
+    sanitize2)
+      # memcheck and racecheck of one small filter run (smoke) with the default forms of K1 and with the TMA-staged one
+      for TOOL in memcheck racecheck; do
+        for PK in 0 3; do
+          HINGE_B200_PROFILE_KERNEL=$PK timeout 900 compute-sanitizer --tool $TOOL python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_${TOOL}_pk$PK.log 2>&1
+          echo "$TOOL (profile kernel $PK) exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard" $OUT/${TAG}_${TOOL}_pk$PK.log | tail -3
+        done
+      done ;;
     sanitize)
       timeout 900 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_memcheck_smoke.log 2>&1
       echo "memcheck exit $?"; tail -3 $OUT/${TAG}_memcheck_smoke.log ;;

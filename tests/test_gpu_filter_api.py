@@ -73,6 +73,35 @@ def test_tma_staged_profile_kernel_on_long_reads(built):
     _assert_equal(got, want, summ)
 
 
+def test_enqueued_runs_match_oracle(built):
+    """hg_filter_enqueue three times back to back (no wait in between), one hg_filter_finish: the results
+    are those of one hg_filter."""
+    import hgsynth
+    import oraclelib
+    from hinge_b200 import api
+
+    s = hgsynth.Synth(genome_len=500000, coverage=45.0, seed=78, n_families=4)
+    s.generate(want_trace=False, threads=4)
+    cols = {k: v.copy() for k, v in s.cols().items()}
+    rlen, qv_off, qv = s.rlen.copy(), s.qv_off.copy(), s.qv.copy()
+    orc = oraclelib.Oracle(rlen, qv_off, qv, 100, cols)
+    want = orc.filter()
+    orc.close()
+    ctx = api.Context(0)
+    ctx.set_reads(rlen, qv_off, qv, 100)
+    ctx.set_overlaps(len(cols["aread"]), cols)
+    params = api.FilterParams()
+    ctx.filter(params)  # sizes the annotation pool
+    for _ in range(3):
+        ctx.filter_enqueue(params)
+    rc, summ = ctx.filter_finish()
+    assert rc == 0
+    got = ctx.filter_fetch(int(summ.n_annotations))
+    ctx.close()
+    s.close()
+    _assert_equal(got, want, summ)
+
+
 def test_c5_shaped_long_reads_with_fragmented_alignments(built):
     """BASELINE configs[4] shape at 1/40 of its size: reads N(24000, 8000) (~600 coverage bins and ~200
     records each, ~6 reads per batch of the flat kernels), most pairs reported as two or three local
