@@ -117,6 +117,13 @@ d=json.load(open('$OUT/${TAG}_bench_n$NG.json')); print('c5 value %.4g ms %.4f'%
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^k_classify_reads" -s 1 -c 1 -f \
         -o $OUT/${TAG}_k_classify_reads_c3 python bench.py --config c3 --also "" --steps 2 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-verify > $OUT/${TAG}_ncu_k_classify_reads.log 2>&1
       echo "ncu k_classify_reads exit $?" ;;
+    ncu_k1final)
+      for SPEC in "k_profile_flat2 c3" "k_profile_flat c5"; do
+        set -- $SPEC; K=$1; CFG=$2
+        timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^$K\\b" -s 4 -c 1 -f \
+          -o $OUT/${TAG}_${K}_$CFG python bench.py --config $CFG --also "" $SHORT > $OUT/${TAG}_ncu_${K}_$CFG.log 2>&1
+        echo "ncu $K $CFG exit $?"
+      done ;;
     ncu_final)
       # the kernels of a filter step on both workloads, one launch each (steady state: -s skips the warm-up)
       for SPEC in "k_profile_flat2 c3" "k_profile_flat c5" "k_mask_bits_flat c5" "k_mask_walk c5" "k_mask_bits_flat c3" \
