@@ -446,7 +446,7 @@ class Bench:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ktimes = {}
         # The timed steps are enqueued back to back (hg_filter_enqueue: the launches of one stage) and waited
-        # for once (hg_filter_finish), the way a caller works through the parts of a .las; with the NCCL
+        # for once (hg_filter_finish): device time of K stages without K host round trips; with the NCCL
         # exchange the host takes part in every step, so there each step is a full hg_filter.
         queued = (world == 1 or arrays.exchange == "peer") and not args.sync_steps
         ev0.record(self.stream)

@@ -173,8 +173,8 @@ int hg_filter_phase1(hg_ctx* ctx, const hg_filter_params* params); /* -> HG_BUF_
 int hg_filter_phase2(hg_ctx* ctx);                                 /* -> HG_BUF_MASK_PACKED / HG_BUF_MASK   */
 int hg_filter_phase3(hg_ctx* ctx, hg_filter_summary* out);         /* hinge calls        */
 
-/* hg_filter without the wait at its end, for callers that run the stage on one batch after the other
- * (the parts of a split .las, the shards of a queue): hg_filter_enqueue only launches -- phase 1, 2 and 3
+/* hg_filter without the wait at its end, for callers that have host work to overlap or run the stage
+ * several times on resident records: hg_filter_enqueue only launches -- phase 1, 2 and 3
  * of a context that owns all reads or exchanges through peer memory (hg_peer_connect) --, hg_filter_finish
  * waits for the stage enqueued last and returns its summary (HG_RETRY_POOL as from hg_filter_phase3).
  * hg_filter == enqueue; finish (+ the rerun after HG_RETRY_POOL). */
