@@ -110,6 +110,28 @@ def host_threads(world=1):
     return max(1, (os.cpu_count() or 8) // max(1, world))
 
 
+def bind_to_gpu_numa(torch, index):
+    """Ranks of a multi-GPU run stay on the cores of their GPU's NUMA node, so that the pinned host buffers
+    of the end-to-end leg (first touch) and the copies out of them are local to the GPU's PCIe root."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 # ----------------------------------------------------------------------------- clocks
 
 
@@ -368,6 +390,7 @@ class Bench:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group("nccl", device_id=self.dev)
         self.stream = torch.cuda.current_stream()
+        self.numa = bind_to_gpu_numa(torch, self.local) if self.world > 1 else None
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             self.peak, self.peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -547,7 +570,7 @@ class Bench:
                 "filter_scan": {"bytes_per_overlap": 32, "gbs": 32.0 * novl / (ms_step * 1e-3) / 1e9,
                                 "frac_of_peak": 32.0 * novl / (ms_step * 1e-3) / 1e9 / self.peak},
                 "e2e_arrays": {"value": total_ovl / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                               "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s},
+                               "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s, "numa_node_rank0": self.numa},
                 "parity": parity, "gpu_launches": int(launches), "clocks": clocks,
             }
             if downstream and world == 1:
