@@ -91,6 +91,7 @@ PROTOTYPES = {
     "hg_main_filter": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "hg_main_maximal": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "hg_main_layout": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
+    "hg_main_exit_after": (None, [C.c_int]),
 }
 
 MISSING = []

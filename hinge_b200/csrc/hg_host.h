@@ -52,6 +52,8 @@ int open_context(const ReadDB& db, const LasFile& las, bool with_trace, hg_ctx**
 // load_inputs starts the creation of the CUDA context on a side thread; every error return between
 // load_inputs and open_context must give it back (joins the thread, destroys the context)
 void drop_early_context();
+// hg_ctx_destroy, unless the process is about to exit anyway (hg_main_exit_after)
+void release_context(hg_ctx* ctx);
 
 }  // namespace hg
 #endif

@@ -183,7 +183,7 @@ extern "C" int hg_main_maximal(int argc, char** argv) {
         return 1;
     }
     timer.lap("hg_maximal");
-    hg_ctx_destroy(ctx);
+    release_context(ctx);
     touch(a.prefix + ".homologous.txt");  // maximal.cpp:515-517 reopens (truncates) these
     touch(a.prefix + ".filtered.fasta");
     TextOut fmax(a.prefix + ".max"), fcont(a.prefix + ".contained.txt");
@@ -368,7 +368,7 @@ extern "C" int hg_main_layout(int argc, char** argv) {
         fclose(sk);
         printf("[hinge_b200] %lld edges, %.3f ms on device\n", (long long)n_edges, ms);
     }
-    hg_ctx_destroy(ctx);
+    release_context(ctx);
     timer.lap("write output files + destroy");
     return g_out_failed ? 1 : 0;
 }

@@ -271,6 +271,10 @@ int hg_layout_phase3(hg_ctx* ctx, const uint8_t* alive_all, const hg_graph_rec* 
 int hg_main_filter(int argc, char** argv);
 int hg_main_maximal(int argc, char** argv);
 int hg_main_layout(int argc, char** argv);
+/* For a process that exits right after one hg_main_* call (the `hinge` executable): leave the CUDA context
+ * and its allocations to the process exit instead of tearing them down one by one (the results are on the
+ * host by then; the driver reclaims everything).  Off by default: a library user keeps clean teardown. */
+void hg_main_exit_after(int on);
 
 #ifdef __cplusplus
 }
