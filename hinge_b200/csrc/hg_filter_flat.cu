@@ -22,18 +22,21 @@
 //               every read boundary: no segmentation needed.  The scanned words go to HBM
 //               (4 B per bin, about 4 B per record) for K2.
 //     per read  profile length and mean coverage (filter.cpp:642-656), self-overlap flag.
-//   K2 k_mask_anno_flat  (after the median) streams the stored profiles: bit maps of bins whose
-//     cut-off coverage is <= MIN_COV ("zeros") and of bins where the coverage jumps by more
-//     than the smallest annotation threshold, then one thread per read walks its slice of the
-//     maps: longest covered run (filter.cpp:696-728), mask, telomere flag, repeat annotations
-//     with the streaming form of the merge pass (filter.cpp:796-829), hinge pre-test
-//     (filter.cpp:842-865).
+//   K2 (after the median), two kernels:
+//     k_mask_bits_flat  streams the stored profiles and leaves two bits per bin in HBM: bins whose
+//       cut-off coverage is <= MIN_COV ("zeros") and bins where the coverage jumps by more than the
+//       smallest annotation threshold
+//     k_mask_walk       one thread per read walks its slice of the maps: longest covered run
+//       (filter.cpp:696-728), mask, telomere flag, repeat annotations with the streaming form of the
+//       merge pass (filter.cpp:796-829), hinge pre-test (filter.cpp:842-865)
 //
-// K1 is bound by the shared-memory data pipe (ncu: l1tex data-pipe wavefronts > 70 % of peak,
-// ~4 wavefronts per ATOMS on random bins is what the banks give), so everything else in it is
-// kept conflict-free (sw) and the global accesses wide.  Tried and measured on B200, K2 of the
-// previous form alone: match.any aggregation of equal bins 0.84 ms, ballot aggregation of the
-// hot bins 0.54 ms, none 0.40 ms, + lane spreading 0.365 ms, + swizzle and prefetch 0.34 ms.
+// K1 is bound by the shared-memory data pipe (ncu: l1tex data-pipe wavefronts > 70 % of peak; ~3
+// wavefronts per ATOMS on random bins is what the banks give, same-address lanes of a +1 are merged
+// by the hardware (ATOMS.POPC.INC), those of other addends are not), so everything else in it is kept
+// conflict-free (sw) and the global accesses wide (128-bit loads, 256-bit stores).  Tried and
+// measured on B200 on the way: match.any aggregation of equal bins 0.84 ms, ballot aggregation of the
+// hot bins 0.54 ms, none 0.40 ms, + lane spreading 0.365 ms, + swizzle and prefetch 0.34 ms, + 256-bit
+// stores 0.32 ms (short-read set).  A third, TMA-staged form of K1 follows the two flat ones.
 //
 // Reads longer than kFlatBins bins and pile-ups deeper than the 16-bit halves can count go
 // to per-read fallbacks (k_cov_big here, k_mask_anno_big in hg_filter.cu); so does everything
