@@ -61,7 +61,7 @@ import json;d=json.load(open('$OUT/${TAG}_down_$CFG.json'));print(d.get('downstr
         --log-file $OUT/${TAG}_launches_down.csv python bench.py --config c3 --also "" --steps 1 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-verify > $OUT/${TAG}_launches_down.log 2>&1
       echo "launch list (downstream) exit $?" ;;
     ncu_down)
-      for K in k_classify_reads k_layout_pairs k_order_candidates k_hinge_exact_warp; do
+      for K in ${NCU_DOWN:-k_classify_reads k_layout_pairs k_order_candidates k_hinge_exact_warp}; do
         timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^$K" -s 1 -c 1 -f \
           -o $OUT/${TAG}_${K}_c3 python bench.py --config c3 --also "" --steps 2 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-verify > $OUT/${TAG}_ncu_${K}.log 2>&1
         echo "ncu $K exit $?"
